@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the GLARE hot path (BASELINE.json metric: 600x400 images/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl glare|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One step = one pass of the whole inference path (cond-encoder -> inverse flow -> VQ lookup -> VQGAN decoder
+-> AFT/DCN decoder) over one batch of 15 synthetic LOL-eval-shape images (400x600, reflect-padded to 420x620
+as infer_dataset_lol.py:124 does) per GPU -- BASELINE.json configs[1].  Images shard across ranks with no
+data-path collective; the only NCCL call is the final all_gather of the outputs (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = through GlareEnhancer.enhance with
+pinned host uint8 buffers (H2D + pre/post-processing + D2H inside the timed region), `roofline` = the dominant
+kernel of libglare_b200.so timed live with CUDA events, `cpu_baseline` = the CPU oracle port on the host cores.
+`--impl reference` times the reference algorithm's CPU path (the oracle port: the reference is Python and
+/root/reference does not exist on the GPU box) with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "600x400 images/sec (LOL eval15 shape, batch 15 per GPU)"
+H, W, BATCH = 400, 600, 15
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tensor": p["bf16_tflops_sustained"], "tensor_burst": p["bf16_tflops"], "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor": 1400.0, "tensor_burst": 1590.0, "src": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.p, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.p.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(batch, seed):
+    from glare_b200 import synth
+    lq, gt = synth.synth_images(batch, H, W, seed=seed)
+    return lq, gt
+
+
+def cpu_oracle_step(sd_g, sd_v, lr_one):
+    from oracle import glare_oracle as O
+    t0 = time.perf_counter()
+    O.glare_infer(sd_g, sd_v, lr_one)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference algorithm (oracle port) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from glare_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd_g, sd_v = synth.synth_state_dict("netG", 0), synth.synth_state_dict("vqgan", 0)
+    lq, _ = synth_batch(1, 0)
+    lr = synth.preprocess(synth.pad_lol(lq))
+    budget = float(os.environ.get("GLARE_BENCH_CPU_BUDGET_S", "200"))
+    t_start = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_step(sd_g, sd_v, lr)
+    times = []
+    while len(times) < args.steps and (not times or time.perf_counter() - t_start + times[-1] < budget):
+        times.append(cpu_oracle_step(sd_g, sd_v, lr))
+    ips = len(times) / sum(times)
+    sample = "1 image (420x620 padded) of the 15-image batch per step; %d of %d requested steps inside a %.0f s budget" % (
+        len(times), args.steps, budget)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": len(times),
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "LOL eval15-shape inference 600x400 (padded 420x620), fp32, CPU oracle port of the reference path",
+                       "batch_per_step": 1},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="glare", choices=["glare", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--dense", default=os.environ.get("GLARE_DENSE", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from glare_b200 import ops, synth
+    from glare_b200.api import GlareEnhancer
+    from glare_b200.dense import make_dense
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sd_g, sd_v = synth.synth_state_dict("netG", 0), synth.synth_state_dict("vqgan", 0)
+    dense = make_dense(args.dense)
+    enh = GlareEnhancer(sd_g, sd_v, device=dev, pad="lol", dense=dense)
+    eng = enh.engine
+    B = args.batch
+    lq, gt = synth_batch(B, seed=rank)
+    host_u8 = (lq.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
+    host_out = torch.empty_like(host_u8).pin_memory()
+    lr_dev, box = enh.preprocess(host_u8.to(dev))
+    lr_dev = lr_dev.contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    gather = torch.empty((world * B, 3) + tuple(lr_dev.shape[2:]), device=dev) if world > 1 else None
+
+    def step():
+        out = eng.infer(lr_dev)
+        if world > 1:
+            dist.all_gather_into_tensor(gather, out)
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+        flush.zero_()
+    warm = max(args.warmup, 3)
+
+    # ---- device-resident throughput (`value`) + live per-kernel timers for the roofline
+    eng.timers = {}
+    n0 = ops.LAUNCHES
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        flush.zero_()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.LAUNCHES - n0
+    timers, eng.timers = eng.timers, None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers
+    for _ in range(2):
+        enh.enhance(host_u8, out=host_out)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        enh.enhance(host_u8, out=host_out)
+        flush.zero_()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": host_u8.numel(),
+           "d2h_bytes_per_step": host_out.numel()}
+
+    if rank == 0:
+        pk = peaks()
+        roof = dense.roofline(timers, eng, B, lr_dev.shape, pk)
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            one = lr_dev[:1].cpu()
+            dt = cpu_oracle_step(sd_g, sd_v, one)
+            cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "1 image (420x620 padded) of the 15-image batch, CPU oracle port, %d torch threads, %.1f s" % (cores, dt)}
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": dense.dtype_name, "data": "synthetic",
+                "config": {"workload": "LOL eval15-shape batch inference: 15 images 600x400 (reflect-padded to 420x620) per GPU per step",
+                           "batch_per_gpu": B, "dense_backend": dense.name, "parallelism": "images sharded, dp%d" % world,
+                           "l2": "256 MiB buffer written between timed iterations (L2 flush); activations per step exceed L2"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "peaks": pk["src"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,8 +4,12 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+// exported C-ABI symbol (the library is built with -fvisibility=hidden)
+#define GLARE_API extern "C" __attribute__((visibility("default")))
+
 #define GLARE_OK 0
 #define GLARE_ERR_BAD_ARG (-1)
+#define GLARE_ERR_UNSUPPORTED (-2)
 
 // Every C-ABI entry point returns 0 or a cudaError_t (positive) / GLARE_ERR_* (negative).
 #define GLARE_CHECK_LAUNCH()                                  \

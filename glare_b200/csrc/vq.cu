@@ -128,10 +128,14 @@ vq_argmin_gather_kernel(const float* __restrict__ z,        // [B,3,hw]
                 }
                 idx_out[t] = bi_;
                 const float4 c = s_cb[bi_];
+                // quantize.py:298 straight-through estimator, evaluated in fp32 exactly as the reference does:
+                // z_q = z + (e - z)  (two roundings; differs from e in the last bit for some tokens)
+                const float* zb = z + bi * 3 * hw;
+                const float a = zb[p], b = zb[hw + p], c3 = zb[2 * (long long)hw + p];
                 float* q = zq_out + bi * 3 * hw;
-                q[p] = c.x;
-                q[hw + p] = c.y;
-                q[2 * (long long)hw + p] = c.z;
+                q[p] = __fadd_rn(a, __fsub_rn(c.x, a));
+                q[hw + p] = __fadd_rn(b, __fsub_rn(c.y, b));
+                q[2 * (long long)hw + p] = __fadd_rn(c3, __fsub_rn(c.z, c3));
             }
         }
         __syncthreads();
@@ -143,14 +147,14 @@ vq_argmin_gather_kernel(const float* __restrict__ z,        // [B,3,hw]
 
 using namespace glare;
 
-extern "C" int glare_vq_pack_codebook_f32(const float* codebook, int K, float* packed_out, cudaStream_t stream) {
+GLARE_API int glare_vq_pack_codebook_f32(const float* codebook, int K, float* packed_out, cudaStream_t stream) {
     if (!codebook || !packed_out || K <= 0) return GLARE_ERR_BAD_ARG;
     vq_pack_codebook_kernel<<<(K + 255) / 256, 256, 0, stream>>>(codebook, reinterpret_cast<float4*>(packed_out), K);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
 
-extern "C" int glare_vq_argmin_gather_f32(const float* z_nchw, const float* packed_codebook, int B, int hw, int K,
+GLARE_API int glare_vq_argmin_gather_f32(const float* z_nchw, const float* packed_codebook, int B, int hw, int K,
                                           long long* idx_out, float* zq_nchw_out, cudaStream_t stream) {
     if (!z_nchw || !packed_codebook || !idx_out || !zq_nchw_out || B < 0 || hw < 0 || K <= 0) return GLARE_ERR_BAD_ARG;
     const long long N = (long long)B * hw;

@@ -1,0 +1,233 @@
+"""GLARE inference engine on one B200: the hot path of VQLLFLOWDeformable.reverse_flow
+(VQLLFLOWDeformable_arch.py:222-250), state-dict driven, kernels from libglare_b200.so.
+
+    cond-encoder (ConditionEncoder.py:46-55) -> inverse flow (FlowUpsamplerNet.py:290-326) -> VQ lookup
+    (quantize.py:271-312) -> VQGAN decoder features (VQModel_arch.py:81-91) -> AFT decoder with DCNv2 warps
+    (deformableDecoder_arch.py:525-576)
+
+The engine consumes the reference's checkpoints unchanged (``net_G.pth`` / ``vqgan.pkl`` state-dict keys).
+It is CUDA-only by construction: there is no CPU path and no PyTorch re-implementation of the VQ, flow-step
+or DCN operators to fall back to.
+
+Dense operators (3x3 / 1x1 convolutions, GroupNorm+swish, attention) go through the ``dense`` backend object:
+``TorchDense`` (cuDNN / cuBLAS library calls, the recompiled-library baseline) or ``glare_b200.dense_tc``
+(tcgen05 implicit-GEMM kernels) -- chosen explicitly by the caller, never silently.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import flow as flowmod
+from . import ops
+
+
+class TorchDense:
+    """Library (cuDNN/cuBLAS) implementation of the dense operators, fp32 or bf16.  This is the baseline the
+    hand-written tensor-core path is measured against, and the dense backend of the first bring-up."""
+    name = "torch-library"
+
+    def __init__(self, dtype=torch.float32, allow_tf32=False):
+        self.dtype = dtype
+        self.allow_tf32 = allow_tf32
+
+    def _ctx(self):
+        torch.backends.cudnn.allow_tf32 = self.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
+
+    def conv2d(self, x, w, b=None, stride=1, padding=1):
+        self._ctx()
+        return F.conv2d(x.to(self.dtype), w.to(self.dtype), None if b is None else b.to(self.dtype), stride=stride,
+                        padding=padding)
+
+    def gn_swish(self, x, gamma, beta, swish=True):
+        y = F.group_norm(x.float(), 32, gamma, beta, eps=1e-6)       # encoder_decoder.py:34-35
+        if swish:
+            y = y * torch.sigmoid(y)                                 # encoder_decoder.py:29-31
+        return y.to(self.dtype)
+
+    def attention(self, q, k, v):
+        """single-head attention over h*w tokens, d = C (encoder_decoder.py:176-187); q,k,v [B,C,h,w]"""
+        self._ctx()
+        B, C, h, w = q.shape
+        out = torch.empty_like(q)
+        for b in range(B):                       # the N x N score matrix is materialised per sample (1 GB at 105x155)
+            qb = q[b].reshape(C, h * w).t()
+            s = torch.mm(qb, k[b].reshape(C, h * w)) * (int(C) ** (-0.5))
+            s = torch.softmax(s.float(), dim=1).to(q.dtype)
+            out[b] = torch.mm(v[b].reshape(C, h * w), s.t()).reshape(C, h, w)
+        return out
+
+
+class _Timed:
+    """CUDA-event bracket on the current stream around one named operator (used by bench.py for the roofline)."""
+
+    def __init__(self, timers, name):
+        self.timers, self.name = timers, name
+
+    def __enter__(self):
+        if self.timers is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.timers is not None:
+            self.e1.record()
+            self.timers.setdefault(self.name, []).append((self.e0, self.e1))
+
+
+class GlareEngine:
+    def __init__(self, sd_g, sd_vq, device="cuda:0", dense=None, per_sample_ratio=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("glare_b200.GlareEngine needs a CUDA device (B200 / sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        self.dense = dense if dense is not None else TorchDense()
+        self.per_sample_ratio = per_sample_ratio
+        self.timers = None        # bench.py sets a dict: name -> [(start_event, end_event), ...]
+        self.g = {k: v.to(self.device, torch.float32).contiguous() for k, v in sd_g.items()
+                  if not k.startswith(("flowUpsamplerNet.f.", "deformable_decoder.scale", "deformable_decoder.bias",
+                                       "deformable_decoder.enc", "deformable_decoder.conv_out"))}
+        self.v = {k: v.to(self.device, torch.float32).contiguous() for k, v in sd_vq.items()
+                  if k.startswith(("quantize.", "post_quant_conv.", "decoder."))}
+        with torch.cuda.device(self.device):
+            self.flow_plan = flowmod.FlowPlan(sd_g, self.device)
+            self.codebook_packed = ops.vq_pack_codebook(self.v["quantize.embedding.weight"])
+            self.dcn_w = {i: ops.dcn_pack_weight(self.g["deformable_decoder.warp.%d.dcn.weight" % i]) for i in (0, 1)}
+
+    def _timed(self, name):
+        return _Timed(self.timers, name)
+
+    # ------------------------------------------------------------------ taming blocks (encoder_decoder.py)
+    def _conv(self, sd, p, x, stride=1, padding=1):
+        return self.dense.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
+
+    def _gn(self, sd, p, x, swish=True):
+        return self.dense.gn_swish(x, sd[p + ".weight"], sd[p + ".bias"], swish)
+
+    def resnet_block(self, sd, p, x):
+        """ResnetBlock.forward   encoder_decoder.py:117-137"""
+        h = self._conv(sd, p + ".conv1", self._gn(sd, p + ".norm1", x))
+        h = self._conv(sd, p + ".conv2", self._gn(sd, p + ".norm2", h))
+        if (p + ".nin_shortcut.weight") in sd:
+            x = self._conv(sd, p + ".nin_shortcut", x, padding=0)
+        return x + h
+
+    def attn_block(self, sd, p, x):
+        """AttnBlock.forward   encoder_decoder.py:168-192"""
+        hn = self._gn(sd, p + ".norm", x, swish=False)
+        q = self._conv(sd, p + ".q", hn, padding=0)
+        k = self._conv(sd, p + ".k", hn, padding=0)
+        v = self._conv(sd, p + ".v", hn, padding=0)
+        o = self.dense.attention(q, k, v)
+        return x + self._conv(sd, p + ".proj_out", o, padding=0)
+
+    def downsample(self, sd, p, x):
+        """encoder_decoder.py:68-72"""
+        return self._conv(sd, p + ".conv", F.pad(x, (0, 1, 0, 1)), stride=2, padding=0)
+
+    def upsample(self, sd, p, x):
+        """encoder_decoder.py:49-53"""
+        return self._conv(sd, p + ".conv", F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+    def cond_encoder(self, x, p="RRDB"):
+        """ConEncoder1.forward   ConditionEncoder.py:46-55 (Encoder.forward encoder_decoder.py:406-442)"""
+        sd, e = self.g, p + ".encoder"
+        h = self._conv(sd, e + ".conv_in", x)
+        mid = []
+        for lvl in range(3):
+            for blk in range(2):
+                h = self.resnet_block(sd, "%s.down.%d.block.%d" % (e, lvl, blk), h)
+                if ("%s.down.%d.attn.%d.q.weight" % (e, lvl, blk)) in sd:
+                    h = self.attn_block(sd, "%s.down.%d.attn.%d" % (e, lvl, blk), h)
+            if lvl != 2:
+                mid.append(h)
+                h = self.downsample(sd, "%s.down.%d.downsample" % (e, lvl), h)
+        h = self.resnet_block(sd, e + ".mid.block_1", h)
+        h = self.attn_block(sd, e + ".mid.attn_1", h)
+        h = self.resnet_block(sd, e + ".mid.block_2", h)
+        enc = self._conv(sd, e + ".conv_out", self._gn(sd, e + ".norm_out", h)).float()
+        return {"cond_feat": torch.sigmoid(self._conv(sd, p + ".cond_conv.0", enc).float()),
+                "color_map": self._conv(sd, p + ".color_conv", enc).float(), "mid_feat": mid}
+
+    def _decoder_trunk(self, sd, p, z):
+        h = self._conv(sd, p + ".conv_in", z)
+        h = self.resnet_block(sd, p + ".mid.block_1", h)
+        h = self.attn_block(sd, p + ".mid.attn_1", h)
+        return self.resnet_block(sd, p + ".mid.block_2", h)
+
+    def vq_decoder_features(self, zq, p="decoder"):
+        """VQModel.decode after the quantizer (VQModel_arch.py:88-90, encoder_decoder.py:515-551)"""
+        sd = self.v
+        h = self._decoder_trunk(sd, p, self._conv(sd, "post_quant_conv", zq, padding=0))
+        feats = []
+        for lvl in (2, 1, 0):
+            for blk in range(3):
+                h = self.resnet_block(sd, "%s.up.%d.block.%d" % (p, lvl, blk), h)
+                if lvl == 2:
+                    h = self.attn_block(sd, "%s.up.%d.attn.%d" % (p, lvl, blk), h)
+            if lvl != 2:
+                feats.append(h)
+            if lvl != 0:
+                h = self.upsample(sd, "%s.up.%d.upsample" % (p, lvl), h)
+        return feats
+
+    # ------------------------------------------------------------------ AFT / DCN (deformableDecoder_arch.py)
+    def warp_block(self, i, x_vq, h):
+        """WarpBlock.forward (:285-290) + DCNv2Pack.forward (:141-152)"""
+        sd, p = self.g, "deformable_decoder.warp.%d" % i
+        feat = self._conv(sd, p + ".offset", torch.cat([x_vq, h], dim=1))
+        out = self._conv(sd, p + ".dcn.conv_offset", feat).float()
+        o1, o2, m = torch.chunk(out, 3, dim=1)
+        offset = torch.cat((o1, o2), dim=1)
+        mask = torch.sigmoid(m)
+        x_vq = x_vq.float().contiguous()
+        with self._timed("dcn%d" % i):
+            return ops.modulated_deform_conv(x_vq, offset, mask, sd[p + ".dcn.weight"], sd[p + ".dcn.bias"], 1, 1, 1, 1, 4,
+                                             packed_weight=self.dcn_w[i])
+
+    def aft_decoder(self, z, vq_feats, enc_feats, p="deformable_decoder"):
+        """MultiScaleDecoder2.forward   deformableDecoder_arch.py:525-576"""
+        sd = self.g
+        h = self._decoder_trunk(sd, p, z)
+        for lvl in (2, 1, 0):
+            for blk in range(3):
+                h = self.resnet_block(sd, "%s.up.%d.block.%d" % (p, lvl, blk), h)
+                if lvl == 2:
+                    h = self.attn_block(sd, "%s.up.%d.attn.%d" % (p, lvl, blk), h)
+            if lvl != 2:
+                mixf = torch.sigmoid(sd["%s.mix.%d.w" % (p, 1 - lvl)])
+                h = enc_feats[lvl] * mixf + h * (1 - mixf)                       # Mix.forward :587-590
+                x_vq = self.warp_block(1 - lvl, vq_feats[1 - lvl], h).to(h.dtype)
+                if self.per_sample_ratio:
+                    # :567 reduces over the whole batch but the reference only ever runs batch 1; per-sample
+                    # means keep that behaviour for any batch size / sharding (DESIGN.md "batch coupling")
+                    ratio = h.float().mean(dim=(1, 2, 3), keepdim=True) / x_vq.float().mean(dim=(1, 2, 3), keepdim=True)
+                else:
+                    ratio = h.float().mean() / x_vq.float().mean()
+                h = h + x_vq * ratio.to(h.dtype)
+            if lvl != 0:
+                h = self.upsample(sd, "%s.up.%d.upsample" % (p, lvl), h)
+        return self._conv(sd, p + ".residual_conv", self._gn(sd, p + ".norm_out", h)).float()
+
+    # ------------------------------------------------------------------ stages
+    def flow_decode(self, z, ft, trace=None):
+        return flowmod.decode(self.flow_plan, z, ft, lambda x, w: self.dense.conv2d(x, w).float(), trace=trace)[0]
+
+    def vector_quantize(self, z):
+        with self._timed("vq"):
+            idx, zq = ops.vq_lookup(z, self.codebook_packed)
+        return zq, idx
+
+    @torch.no_grad()
+    def infer(self, lr, stages=None):
+        """lr [B,3,H,W] = log(clamp(x + 1e-3)) (infer_unpaired.py:121-122), H and W multiples of 4... returns RGB [B,3,H,W] fp32."""
+        with torch.cuda.device(self.device):
+            lr = lr.to(self.device, torch.float32)
+            enc = self.cond_encoder(lr)
+            z = self.flow_decode(enc["color_map"], enc["cond_feat"])
+            zq, idx = self.vector_quantize(z)
+            vq_feats = self.vq_decoder_features(zq)
+            out = self.aft_decoder(z, vq_feats, enc["mid_feat"])
+        if stages is not None:
+            stages.update(cond_feat=enc["cond_feat"], color_map=enc["color_map"], mid0=enc["mid_feat"][0], mid1=enc["mid_feat"][1],
+                          z_flow=z, z_q=zq, idx=idx, vq_feat1=vq_feats[0], vq_feat0=vq_feats[1], out=out)
+        return out

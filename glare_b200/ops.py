@@ -1,0 +1,97 @@
+"""Operator-level wrappers: allocate outputs with torch, call the C ABI on the current stream.
+
+Signatures follow the reference operators they replace (cited per function; paths relative to
+/root/reference/code/models/modules).
+"""
+import torch
+
+from . import _lib
+from ._lib import f32c, lib, ptr, require_cuda, stream
+
+LAUNCHES = 0          # kernels of libglare_b200.so launched by this process (every C-ABI call below launches exactly one)
+
+
+def check(code, what):
+    global LAUNCHES
+    _lib.check(code, what)
+    LAUNCHES += 1
+
+
+# ------------------------------------------------------------------------------------------- VQ
+def vq_pack_codebook(codebook):
+    """codebook [K,3] -> packed [K,4] {e0,e1,e2,|e|^2}  (|e|^2 rounded as quantize.py:281 does on CPU)."""
+    require_cuda(codebook)
+    cb = f32c(codebook)
+    if cb.dim() != 2 or cb.shape[1] != 3:
+        raise ValueError("VQ kernel supports e_dim == 3 (LOL.yml network_VQGAN embed_dim); got %s" % (tuple(cb.shape),))
+    packed = torch.empty((cb.shape[0], 4), device=cb.device, dtype=torch.float32)
+    check(lib().glare_vq_pack_codebook_f32(ptr(cb), cb.shape[0], ptr(packed), stream()), "glare_vq_pack_codebook_f32")
+    return packed
+
+
+def vq_lookup(z, packed_codebook):
+    """VectorQuantizer2.forward core (quantize.py:276-301): z [B,3,h,w] -> (indices int64 [B*h*w], z_q [B,3,h,w])."""
+    require_cuda(z, packed_codebook)
+    z = f32c(z)
+    if z.dim() != 4 or z.shape[1] != 3:
+        raise ValueError("expected z [B,3,h,w], got %s" % (tuple(z.shape),))
+    B, _, h, w = z.shape
+    idx = torch.empty((B * h * w,), device=z.device, dtype=torch.int64)
+    zq = torch.empty_like(z)
+    check(lib().glare_vq_argmin_gather_f32(ptr(z), ptr(packed_codebook), B, h * w, packed_codebook.shape[0], ptr(idx),
+                                           ptr(zq), stream()), "glare_vq_argmin_gather_f32")
+    return idx, zq
+
+
+# ------------------------------------------------------------------------------------------- DCN
+def dcn_pack_weight(weight):
+    """[Cout,C,kh,kw] -> [kh*kw][C][Cout] (once per weight update)."""
+    require_cuda(weight)
+    w = f32c(weight)
+    Co, C, kh, kw = w.shape
+    out = torch.empty((kh * kw, C, Co), device=w.device, dtype=torch.float32)
+    check(lib().glare_dcn_pack_weight_f32(ptr(w), Co, C, kh, kw, ptr(out), stream()), "glare_dcn_pack_weight_f32")
+    return out
+
+
+def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                          deformable_groups=1, packed_weight=None):
+    """ModulatedDeformConvFunction.forward (ops/dcn/deform_conv.py:124-153), same argument order and meaning.
+    Inference only (no autograd graph is recorded)."""
+    if not input.is_cuda:
+        raise NotImplementedError            # deform_conv.py:143-144
+    require_cuda(offset, mask, weight, bias)
+    if groups != 1:
+        raise NotImplementedError("groups != 1 is not used by GLARE (deformableDecoder_arch.py:151-152)")
+    x, offset, mask = f32c(input), f32c(offset), f32c(mask)
+    B, C, H, W = x.shape
+    Co, Cw, kh, kw = weight.shape
+    if Cw != C:
+        raise ValueError("weight expects %d input channels, input has %d" % (Cw, C))
+    Ho = (H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
+    Wo = (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
+    if tuple(offset.shape) != (B, deformable_groups * 2 * kh * kw, Ho, Wo):
+        raise ValueError("offset shape %s != %s" % (tuple(offset.shape), (B, deformable_groups * 2 * kh * kw, Ho, Wo)))
+    if tuple(mask.shape) != (B, deformable_groups * kh * kw, Ho, Wo):
+        raise ValueError("mask shape %s != %s" % (tuple(mask.shape), (B, deformable_groups * kh * kw, Ho, Wo)))
+    if packed_weight is None:
+        packed_weight = dcn_pack_weight(weight)
+    y = x.new_empty((B, Co, Ho, Wo))
+    b = f32c(bias) if bias is not None else None
+    check(lib().glare_dcnv2_fwd_f32(ptr(x), ptr(offset), ptr(mask), ptr(packed_weight), ptr(b), B, C, H, W, Co, kh, kw,
+                                    stride, padding, dilation, deformable_groups, ptr(y), stream()), "glare_dcnv2_fwd_f32")
+    return y
+
+
+# ------------------------------------------------------------------------------------------- flow
+def flow_cond_tail(p, p_batch_stride, p_step_stride, nets, n_steps, nout, B, h, w, out, out_batch_stride, out_step_stride):
+    require_cuda(p, nets, out)
+    check(lib().glare_flow_cond_tail_f32(ptr(p), p_batch_stride, p_step_stride, ptr(nets), n_steps, nout, B, h, w, ptr(out),
+                                         out_batch_stride, out_step_stride, stream()), "glare_flow_cond_tail_f32")
+
+
+def flow_step(direction, coupling, z_in, z_out, pA, pA_batch_stride, hF, hF_batch_stride, netA, pw, logdet=None):
+    require_cuda(z_in, z_out, pA, hF, netA, pw, logdet)
+    B, _, h, w = z_in.shape
+    check(lib().glare_flow_step_f32(direction, 1 if coupling else 0, ptr(z_in), ptr(z_out), ptr(pA), pA_batch_stride, ptr(hF),
+                                    hF_batch_stride, ptr(netA), ptr(pw), B, h, w, ptr(logdet), stream()), "glare_flow_step_f32")

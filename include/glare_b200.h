@@ -1,0 +1,105 @@
+/*
+ * glare_b200.h -- C ABI of libglare_b200.so: the B200 (sm_100a) kernels behind GLARE's hot path.
+ *
+ * This is the drop-in boundary.  The reference's only native plug-in is the pybind11 torch extension
+ * `deform_conv_ext` (code/models/modules/ops/dcn/src/deform_conv_ext.cpp:150-164); every other operator on
+ * the path is a Python nn.Module calling ATen.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/code/models/modules unless stated).  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference adds at each of those call sites.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes/strides (in elements), the CUDA stream to launch on.
+ *     No torch / ATen types, no global mutable state, re-entrant, asynchronous w.r.t. the host
+ *     (deform_conv_cuda.cpp launches on at::cuda::getCurrentCUDAStream(); the caller passes that stream).
+ *   - the caller allocates every output (deform_conv.py:147 `input.new_empty(shape)` convention).
+ *   - return value: 0 = launched; < 0 = GLARE_ERR_* argument error (nothing launched); > 0 = cudaError_t.
+ *     (the reference only printf()s launch errors, deform_conv_cuda_kernel.cu:794-798; here the Python shim
+ *     raises RuntimeError on any non-zero code.)
+ *   - tensors are dense and contiguous in the layout stated per function (the reference TORCH_CHECKs
+ *     contiguity, deform_conv_cuda.cpp:497-498).
+ */
+#ifndef GLARE_B200_H_
+#define GLARE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define GLARE_OK 0
+#define GLARE_ERR_BAD_ARG (-1)
+#define GLARE_ERR_UNSUPPORTED (-2)
+
+#define GLARE_ABI_VERSION 1
+int glare_abi_version(void);
+/* static string for a return code of this library (GLARE_ERR_* or cudaError_t) */
+const char* glare_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (1) VectorQuantizer2.forward -- quantize.py:271-312
+ *     d = |z|^2 + |e|^2 - 2 z.e (:280-282), argmin (:284, lowest index among equal minima), embedding
+ *     gather (:285), straight-through z_q = z + (e - z) (:298), NCHW<->NHWC rearranges (:276, :301) fused.
+ *     Indices are bit-exact w.r.t. the reference's CPU fp32 evaluation order.
+ * ---------------------------------------------------------------------------------------------------- */
+/* codebook [K,3] fp32 -> packed [K,4] = {e0,e1,e2,|e|^2}; run once per codebook */
+int glare_vq_pack_codebook_f32(const float* codebook, int K, float* packed_out, cudaStream_t stream);
+/* z [B,3,hw] fp32 (NCHW) -> idx int64 [B*hw] in (b,y,x) order, z_q [B,3,hw] fp32 (NCHW) */
+int glare_vq_argmin_gather_f32(const float* z_nchw, const float* packed_codebook, int B, int hw, int K,
+                               long long* idx_out, float* zq_nchw_out, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (2) FlowStep.normal_flow / reverse_flow -- FlowStep.py:75-119, with ActNorm2d (FlowActNorms.py:48-100),
+ *     InvertibleConv1x1 (Permutations.py:21-59) and CondAffineSeparatedAndCond
+ *     (FlowAffineCouplingsAblation.py:50-151; NN = flow.py:13-70 Conv2d/Conv2dZeros) fused into one launch.
+ *
+ *     The first 3x3 conv of each coupling net is linear; its conditioning-feature part ("pre-activation
+ *     planes": 64 channels per net) is produced by the dense conv path for all steps at once, see DESIGN.md.
+ *
+ *     Packed net block (GLARE_FLOW_NET_FLOATS floats, built by glare_b200.flow.pack_net):
+ *       [0,576)      w1z  [64][9]      first-layer weights of the z1 input channel (zeros for NN_F)
+ *       [576,640)    b1   [64]         ActNorm bias          [640,704)   s1 = exp(ActNorm logs)
+ *       [704,4800)   w2t  [64 in][64 out]                    1x1 conv, transposed
+ *       [4800,4864)  b2                                      [4864,4928) s2
+ *       [4928,9536)  w3   [64][9][8]   last 3x3 conv, output channel padded to 8
+ *       [9536,9544)  b3   [8]                                [9544,9552) s3 = exp(3 * logs)
+ *     Pointwise block (16 floats): M[9] row-major (W in normal_flow, fp64-inverted W^-1 in reverse_flow),
+ *       ActNorm bias[3], ActNorm scale[3] (exp(logs) normal / exp(-logs) reverse), pad.
+ * ---------------------------------------------------------------------------------------------------- */
+#define GLARE_FLOW_NET_FLOATS 9552
+#define GLARE_FLOW_PW_FLOATS 16
+int glare_flow_net_floats(void);
+/* NN tail (ActNorm+ReLU, 1x1+ActNorm+ReLU, 3x3 -> nout in {4,6}) of n_steps nets in one launch; used for
+ * NN_F = feature_extract (FlowAffineCouplingsAblation.py:121-128) of every step, which never sees z.
+ * p[b][s][64][h*w] and out[b][s][nout][h*w] are addressed through the element strides given. */
+int glare_flow_cond_tail_f32(const float* p, long long p_batch_stride, long long p_step_stride, const float* nets,
+                             int n_steps, int nout, int B, int h, int w, float* out, long long out_batch_stride,
+                             long long out_step_stride, cudaStream_t stream);
+/* One FlowStep.  direction 0 = normal_flow, 1 = reverse_flow; coupling 0 = "noCoupling" step.
+ * z_in/z_out [B,3,h,w] (must not alias); pA [b][64][h*w] = NN_A first-layer pre-activations from ft;
+ * hF [b][6][h*w] = NN_F output; logdet [B] or NULL receives += sum(log scale) (negated in reverse). */
+int glare_flow_step_f32(int direction, int coupling, const float* z_in, float* z_out, const float* pA,
+                        long long pA_batch_stride, const float* hF, long long hF_batch_stride, const float* netA,
+                        const float* pw, int B, int h, int w, float* logdet, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (3) modulated_deform_conv_forward -- ops/dcn/src/deform_conv_ext.cpp:52-147 (pybind signature),
+ *     deform_conv_cuda.cpp:490-569 (host loop), deform_conv_cuda_kernel.cu:571-633 (im2col kernel).
+ *     x [B,C,H,W]; offset [B, dg*2*kh*kw, Ho, Wo]; mask [B, dg*kh*kw, Ho, Wo]; y [B,Cout,Ho,Wo]; groups = 1
+ *     (the only value GLARE uses, deformableDecoder_arch.py:151-152).  No `columns` / `ones` scratch.
+ * ---------------------------------------------------------------------------------------------------- */
+/* weight [Cout,C,kh,kw] -> packed [kh*kw][C][Cout]; run once per weight update */
+int glare_dcn_pack_weight_f32(const float* weight, int Cout, int C, int kh, int kw, float* packed_out,
+                              cudaStream_t stream);
+int glare_dcnv2_fwd_f32(const float* x, const float* offset, const float* mask, const float* packed_weight,
+                        const float* bias_or_null, int B, int C, int H, int W, int Cout, int kh, int kw, int stride,
+                        int pad, int dil, int deformable_groups, float* y, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLARE_B200_H_ */

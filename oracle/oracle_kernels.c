@@ -48,9 +48,10 @@ void glare_oracle_vq_f32(const float *z, const float *codebook, int B, int hw, i
             }
             idx_out[(size_t)b * hw + p] = besti;
             float *q = zq_out + (size_t)b * 3 * hw;
-            q[p] = codebook[3 * besti];
-            q[hw + p] = codebook[3 * besti + 1];
-            q[2 * hw + p] = codebook[3 * besti + 2];
+            /* quantize.py:298 straight-through: z_q = z + (z_q - z).detach(), evaluated in fp32 */
+            q[p] = t0 + (codebook[3 * besti] - t0);
+            q[hw + p] = t1 + (codebook[3 * besti + 1] - t1);
+            q[2 * hw + p] = t2 + (codebook[3 * besti + 2] - t2);
             if (dmin_out) dmin_out[(size_t)b * hw + p] = best;
         }
     }

@@ -1,0 +1,97 @@
+"""GPU parity: modulated deformable conv forward through the C ABI vs the golden (torchvision == literal
+restatement of the reference CUDA kernel, PIN_REPORT) and the C oracle.  fp32 path tolerance 1e-4 abs/rel."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dcn(x, off, msk, w, b, dg=4, stride=1, pad=1, dil=1):
+    from glare_b200 import ops
+    y = ops.modulated_deform_conv(x.cuda(), off.cuda(), msk.cuda(), w.cuda(), None if b is None else b.cuda(), stride, pad, dil, 1, dg)
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def test_golden(glare_lib):
+    g = {k: torch.from_numpy(v) for k, v in load_golden("dcn").items()}
+    y = _dcn(g["x"], g["offset"], g["mask"], g["weight"], g["bias"])
+    assert torch.allclose(y, g["y"], atol=1e-5, rtol=1e-5), float((y - g["y"]).abs().max())
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, C, Cout, H, W, dg, with_bias
+    (1, 4, 4, 1, 1, 4, True), (2, 8, 12, 5, 7, 4, False), (1, 32, 130, 13, 17, 4, True), (1, 64, 64, 23, 19, 2, True),
+    (2, 128, 128, 30, 41, 4, True), (1, 256, 256, 16, 24, 4, True)])
+def test_against_oracle(glare_lib, cfg):
+    from oracle import glare_oracle as O
+    B, C, Co, H, W, dg, wb = cfg
+    g = torch.Generator().manual_seed(C * 7 + H)
+    x = torch.randn((B, C, H, W), generator=g)
+    off = torch.randn((B, dg * 18, H, W), generator=g) * 3.0
+    off[0, :, 0, 0] = 1000.0
+    off[0, 1::2, H - 1, W - 1] = -0.75
+    msk = torch.sigmoid(torch.randn((B, dg * 9, H, W), generator=g))
+    w = torch.randn((Co, C, 3, 3), generator=g) / (3.0 * C ** 0.5)
+    b = torch.randn((Co,), generator=g) if wb else None
+    y = _dcn(x, off, msk, w, b, dg)
+    y_o = O.modulated_deform_conv(x, off, msk, w, b, dg=dg)
+    assert torch.allclose(y, y_o, atol=1e-4, rtol=1e-4), float((y - y_o).abs().max())
+
+
+def test_stride_dilation_against_oracle(glare_lib):
+    from oracle import glare_oracle as O
+    g = torch.Generator().manual_seed(9)
+    B, C, Co, H, W, dg = 1, 8, 8, 11, 14, 2
+    x = torch.randn((B, C, H, W), generator=g)
+    Ho, Wo = (H + 2 * 2 - (2 * 2 + 1)) // 2 + 1, (W + 2 * 2 - (2 * 2 + 1)) // 2 + 1
+    off = torch.randn((B, dg * 18, Ho, Wo), generator=g) * 1.5
+    msk = torch.sigmoid(torch.randn((B, dg * 9, Ho, Wo), generator=g))
+    w = torch.randn((Co, C, 3, 3), generator=g) * 0.2
+    y = _dcn(x, off, msk, w, None, dg, stride=2, pad=2, dil=2)
+    y_o = O.modulated_deform_conv(x, off, msk, w, None, stride=2, padding=2, dilation=2, dg=dg)
+    assert torch.allclose(y, y_o, atol=1e-4, rtol=1e-4)
+
+
+def test_zero_offset_is_masked_conv_full_size(glare_lib):
+    """known answer at the AFT scale-1 shape (128ch @ 420x620): offsets 0, mask 0.5 -> 0.5 * conv2d"""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((1, 128, 420, 620), generator=g).cuda()
+    w = (torch.randn((128, 128, 3, 3), generator=g) / 34.0).cuda()
+    b = torch.randn((128,), generator=g).cuda()
+    off = torch.zeros((1, 72, 420, 620), device="cuda")
+    msk = torch.full((1, 36, 420, 620), 0.5, device="cuda")
+    from glare_b200 import ops
+    y = ops.modulated_deform_conv(x, off, msk, w, b, 1, 1, 1, 1, 4)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = 0.5 * F.conv2d(x, w, None, padding=1) + b.view(1, -1, 1, 1)
+    assert float((y - ref).abs().max()) < 2e-4
+
+
+def test_linearity_in_input_full_size(glare_lib):
+    """size-independent property at the AFT scale-0 shape (256ch @ 210x310): DCN is linear in x for fixed offsets"""
+    from glare_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    B, C, H, W = 1, 256, 210, 310
+    x1 = torch.randn((B, C, H, W), generator=g).cuda()
+    x2 = torch.randn((B, C, H, W), generator=g).cuda()
+    off = (torch.randn((B, 72, H, W), generator=g) * 4).cuda()
+    msk = torch.sigmoid(torch.randn((B, 36, H, W), generator=g)).cuda()
+    w = (torch.randn((C, C, 3, 3), generator=g) / 48.0).cuda()
+    pk = ops.dcn_pack_weight(w)
+    f = lambda x: ops.modulated_deform_conv(x, off, msk, w, None, 1, 1, 1, 1, 4, packed_weight=pk)
+    lhs = f(2.0 * x1 - 3.0 * x2)
+    rhs = 2.0 * f(x1) - 3.0 * f(x2)
+    assert float((lhs - rhs).abs().max()) < 1e-3
+
+
+def test_bad_shapes_raise(glare_lib):
+    from glare_b200 import ops
+    x = torch.zeros((1, 8, 4, 4), device="cuda")
+    with pytest.raises(ValueError):
+        ops.modulated_deform_conv(x, torch.zeros((1, 10, 4, 4), device="cuda"), torch.zeros((1, 36, 4, 4), device="cuda"),
+                                  torch.zeros((8, 8, 3, 3), device="cuda"), None, 1, 1, 1, 1, 4)

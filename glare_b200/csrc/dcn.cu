@@ -168,6 +168,7 @@ GLARE_API int glare_dcn_pack_weight_f32(const float* weight, int Cout, int C, in
 GLARE_API int glare_dcnv2_fwd_f32(const float* x, const float* offset, const float* mask, const float* packed_weight,
                                    const float* bias_or_null, int B, int C, int H, int W, int Cout, int kh, int kw,
                                    int stride, int pad, int dil, int deformable_groups, float* y, cudaStream_t stream) {
+    if (B == 0) return GLARE_OK;
     if (!x || !offset || !mask || !packed_weight || !y) return GLARE_ERR_BAD_ARG;
     if (B < 0 || C <= 0 || H <= 0 || W <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0 || dil <= 0 ||
         deformable_groups <= 0 || C % deformable_groups != 0)

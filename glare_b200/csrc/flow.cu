@@ -323,8 +323,9 @@ GLARE_API int glare_flow_net_floats(void) { return NET_FLOATS; }
 GLARE_API int glare_flow_cond_tail_f32(const float* p, long long p_batch_stride, long long p_step_stride,
                                         const float* nets, int n_steps, int nout, int B, int h, int w, float* out,
                                         long long out_batch_stride, long long out_step_stride, cudaStream_t stream) {
-    if (!p || !nets || !out || B < 0 || h < 0 || w < 0 || n_steps < 0 || (nout != 4 && nout != 6)) return GLARE_ERR_BAD_ARG;
+    if (B < 0 || h < 0 || w < 0 || n_steps < 0 || (nout != 4 && nout != 6)) return GLARE_ERR_BAD_ARG;
     if (B == 0 || h == 0 || w == 0 || n_steps == 0) return GLARE_OK;
+    if (!p || !nets || !out) return GLARE_ERR_BAD_ARG;
     if (B > 65535 || n_steps > 65535) return GLARE_ERR_BAD_ARG;
     FlowArgs a{};
     a.p = p; a.p_bs = p_batch_stride; a.p_ss = p_step_stride;
@@ -342,9 +343,9 @@ GLARE_API int glare_flow_step_f32(int direction, int coupling, const float* z_in
                                    long long pA_batch_stride, const float* hF, long long hF_batch_stride,
                                    const float* netA, const float* pw, int B, int h, int w, float* logdet,
                                    cudaStream_t stream) {
-    if (!z_in || !z_out || !pw || z_in == z_out || B < 0 || h < 0 || w < 0 || (direction != 0 && direction != 1))
-        return GLARE_ERR_BAD_ARG;
+    if (B < 0 || h < 0 || w < 0 || (direction != 0 && direction != 1)) return GLARE_ERR_BAD_ARG;
     if (B == 0 || h == 0 || w == 0) return GLARE_OK;
+    if (!z_in || !z_out || !pw || z_in == z_out) return GLARE_ERR_BAD_ARG;
     if (!coupling) {
         const long long hw = (long long)h * w, n = (long long)B * hw;
         const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);

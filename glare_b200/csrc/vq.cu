@@ -156,9 +156,10 @@ GLARE_API int glare_vq_pack_codebook_f32(const float* codebook, int K, float* pa
 
 GLARE_API int glare_vq_argmin_gather_f32(const float* z_nchw, const float* packed_codebook, int B, int hw, int K,
                                           long long* idx_out, float* zq_nchw_out, cudaStream_t stream) {
-    if (!z_nchw || !packed_codebook || !idx_out || !zq_nchw_out || B < 0 || hw < 0 || K <= 0) return GLARE_ERR_BAD_ARG;
+    if (B < 0 || hw < 0 || K <= 0) return GLARE_ERR_BAD_ARG;
     const long long N = (long long)B * hw;
-    if (N == 0) return GLARE_OK;
+    if (N == 0) return GLARE_OK;                     // empty batch: nothing to launch (pointers may be null)
+    if (!z_nchw || !packed_codebook || !idx_out || !zq_nchw_out) return GLARE_ERR_BAD_ARG;
     // tokens per thread: 4 when there is enough work to fill the chip, else spread thinner
     const int TPT = (N >= (long long)kNumSMs * 128) ? 4 : (N >= (long long)kNumSMs * 64 ? 2 : 1);
     const int tile_tokens = 32 * TPT;

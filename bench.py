@@ -186,6 +186,8 @@ def main():
 
     # ---- device-resident throughput (`value`) + live per-kernel timers for the roofline
     eng.timers = {}
+    if hasattr(dense, "timers"):
+        dense.timers = {}
     n0 = ops.LAUNCHES
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -202,6 +204,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = ops.LAUNCHES - n0
     timers, eng.timers = eng.timers, None
+    if hasattr(dense, "timers"):
+        dense.last_timers, dense.last_steps, dense.timers = dense.timers, args.steps, None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -240,7 +244,8 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": dense.dtype_name, "data": "synthetic",
                 "config": {"workload": "LOL eval15-shape batch inference: 15 images 600x400 (reflect-padded to 420x620) per GPU per step",
-                           "batch_per_gpu": B, "dense_backend": dense.name, "parallelism": "images sharded, dp%d" % world,
+                           "batch_per_gpu": B, "dense_backend": dense.name,
+                           "library_fallbacks_per_run": getattr(dense, "fallbacks", None), "parallelism": "images sharded, dp%d" % world,
                            "l2": "256 MiB buffer written between timed iterations (L2 flush); activations per step exceed L2"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "peaks": pk["src"]}

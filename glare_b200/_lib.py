@@ -17,10 +17,16 @@ SIGNATURES = {
     "glare_vq_pack_codebook_f32": [_vp, _i, _vp, _vp],
     "glare_vq_argmin_gather_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "glare_flow_net_floats": [],
-    "glare_flow_cond_tail_f32": [_vp, _ll, _ll, _vp, _i, _i, _i, _i, _i, _vp, _ll, _ll, _vp],
-    "glare_flow_step_f32": [_i, _i, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "glare_flow_cond_tail_f32": [_vp, _ll, _ll, _ll, _ll, _vp, _i, _i, _i, _i, _i, _vp, _ll, _ll, _vp],
+    "glare_flow_step_f32": [_i, _i, _vp, _vp, _vp, _ll, _ll, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp],
     "glare_dcn_pack_weight_f32": [_vp, _i, _i, _i, _i, _vp, _vp],
     "glare_dcnv2_fwd_f32": [_vp, _vp, _vp, _vp, _vp] + [_i] * 11 + [_vp, _vp],
+    "glare_conv_tc_elem_bytes": [_i],
+    "glare_conv_pack_weight": [_i, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "glare_conv_prep_act": [_i, _vp, _ll, _vp, _vp, _vp],
+    "glare_conv2d_nhwc_tc": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "glare_gn_stats_nhwc_f32": [_vp, _i, _ll, _i, _i, _vp, _vp],
+    "glare_gn_apply_nhwc": [_i, _vp, _vp, _vp, _vp, ctypes.c_float, _i, _i, _ll, _i, _i, _vp, _vp, _vp],
 }
 _RESTYPES = {"glare_error_string": ctypes.c_char_p}
 

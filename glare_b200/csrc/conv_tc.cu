@@ -1,0 +1,402 @@
+// Dense 3x3 / 1x1 convolution (stride 1, "same" padding) as an implicit GEMM on the 5th-gen tensor cores.
+//
+// Replaces the cuDNN calls behind the reference's nn.Conv2d on the hot path: ResnetBlock.conv1/conv2
+// (encoder_decoder.py:88-115), Upsample.conv (:38-53), AttnBlock q/k/v/proj_out (:146-165), nin_shortcut,
+// WarpBlock.offset / DCNv2Pack.conv_offset (deformableDecoder_arch.py:282, deform_conv.py:352-371) and the
+// hoisted first layers of the flow coupling nets (flow.py:13-52).
+//
+//   y[n,h,w,co] = bias[co] + residual[n,h,w,co] + sum_{dy,dx,ci} x[n,h+dy-p,w+dx-p,ci] * W[co,dy,dx,ci]
+//
+// Layout: activations NHWC (channels innermost = GEMM K contiguous), weights [Cout][kh*kw][Cin] (K-major).
+// Mapping (one CTA per SM, persistent over output tiles):
+//   M = 128 output pixels (TH x TW patch of one image), N = BN output channels, K = taps x Cin.
+//   warp 0   TMA producer: per (tap, 128-byte K chunk) one 4-D tiled load of the shifted activation patch --
+//            out-of-image rows/columns are zero-filled by the TMA unit, which IS the conv zero padding -- and
+//            one 2-D load of the weight slab, both SWIZZLE_128B, landing on an mbarrier (full[stage]).
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16 bf16 / 8 tf32) from shared-memory
+//            descriptors into a TMEM accumulator; tcgen05.commit frees the stage (empty[stage]) and publishes
+//            the finished accumulator (tmem_full[acc]).  Two accumulators (2 x BN TMEM columns) let the
+//            epilogue of tile i overlap the MMAs of tile i+1.
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers, + bias (+ residual), 128-byte NHWC stores.
+// Precision modes: 0 = bf16 operands, 1 = tf32 operands (fp32 storage), 2 = 3xTF32 (x = hi + lo split of both
+// operands, D += A_hi B_hi + A_lo B_hi + A_hi B_lo) which restores ~fp32 accuracy for the fp32 configuration.
+// Accumulation is fp32 in TMEM in every mode.
+#include <cuda.h>
+
+#include "tc.cuh"
+
+namespace glare {
+
+constexpr int CT_THREADS = 192;
+constexpr int CT_A_BYTES = 128 * 128;     // 128 pixels x 128-byte K chunk
+
+struct ConvTcArgs {
+    const float* bias;       // [Cout] or null
+    const float* residual;   // NHWC [B,H,W,Cout] or null
+    float* y;                // NHWC [B,H,W,Cout]
+    int B, H, W, Cin, Cout, ksize, pad, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;
+    int total_tiles;
+};
+
+template <int MODE, int BN>
+struct ConvCfg {
+    static constexpr bool X3 = MODE == 2;
+    static constexpr bool TF32 = MODE >= 1;
+    static constexpr int BKE = TF32 ? 32 : 64;                 // elements per 128-byte K chunk
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = (CT_A_BYTES + B_BYTES) * (X3 ? 2 : 1);
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 1024 /*static*/;
+    static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_COLS = 2 * BN;                   // 128 / 256 / 512: powers of two >= 32
+    static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;
+};
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const ConvTcArgs a) {
+    using Cfg = ConvCfg<MODE, BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* const smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (Cfg::X3) {
+            tma_prefetch_desc(&tmAlo);
+            tma_prefetch_desc(&tmBlo);
+        }
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar[0], 1);
+        mbar_init(&tmem_full_bar[1], 1);
+        mbar_init(&tmem_empty_bar[0], 128);
+        mbar_init(&tmem_empty_bar[1], 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&s_tmem_base, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    const int k_iters = a.ksize * a.ksize * a.kchunks;
+    const int tiles_per_block = a.B * a.tiles_y * a.tiles_x;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int nb = tile / tiles_per_block;
+                int r = tile - nb * tiles_per_block;
+                const int n = r / (a.tiles_y * a.tiles_x);
+                r -= n * a.tiles_y * a.tiles_x;
+                const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+                const int y0 = ty * a.TH - a.pad, x0 = tx * a.TW - a.pad;
+                for (int tap = 0; tap < a.ksize * a.ksize; ++tap) {
+                    const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
+                    for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                        uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                        tma_load_4d(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
+                        tma_load_2d(st + CT_A_BYTES, &tmB, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN);
+                        if (Cfg::X3) {
+                            uint8_t* lo = st + CT_A_BYTES + Cfg::B_BYTES;
+                            tma_load_4d(lo, &tmAlo, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
+                            tma_load_2d(lo + CT_A_BYTES, &tmBlo, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(Cfg::TF32 ? 2 : 1, 128, BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait_bounded(&tmem_empty_bar[as], aph ^ 1);        // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int ki = 0; ki < k_iters; ++ki, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait_bounded(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)s * Cfg::STAGE_BYTES;
+                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + CT_A_BYTES);
+                    const uint64_t dal = umma_desc_sw128(sa + CT_A_BYTES + Cfg::B_BYTES);
+                    const uint64_t dbl = umma_desc_sw128(sa + 2 * CT_A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {                       // 4 x 32-byte K steps inside the 128-byte swizzle row
+                        const uint64_t adv = (uint64_t)(j * 2);        // +32 bytes in 16-byte units
+                        umma_ss<Cfg::TF32>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
+                        if (Cfg::X3) {
+                            umma_ss<true>(d_tmem, dal + adv, db + adv, idesc, 1u);
+                            umma_ss<true>(d_tmem, da + adv, dbl + adv, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);                         // stage reusable once these MMAs retire
+                }
+                umma_commit(&tmem_full_bar[as]);                        // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue warps (TMEM -> registers -> NHWC global) =====================
+        const int q = warp & 3;                                          // TMEM lane quadrant this warp may access
+        const int m = q * 32 + lane;                                     // accumulator row = pixel inside the tile
+        const int py = m / a.TW, px = m - py * a.TW;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+            const int nb = tile / tiles_per_block;
+            int r = tile - nb * tiles_per_block;
+            const int n = r / (a.tiles_y * a.tiles_x);
+            r -= n * a.tiles_y * a.tiles_x;
+            const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+            const int gy = ty * a.TH + py, gx = tx * a.TW + px;
+            const bool valid = gy < a.H && gx < a.W;
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait_bounded(&tmem_full_bar[as], aph);
+            tc_fence_after();
+            const long long pix = ((long long)n * a.H + gy) * a.W + gx;
+            float* yrow = a.y + pix * a.Cout;
+            const float* rrow = a.residual ? a.residual + pix * a.Cout : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c0, v);
+                tmem_ld_wait();
+                const int co = nb * BN + c0;
+                if (valid && co < a.Cout) {
+                    if (co + 32 <= a.Cout) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o;
+                            o.x = __uint_as_float(v[j]);
+                            o.y = __uint_as_float(v[j + 1]);
+                            o.z = __uint_as_float(v[j + 2]);
+                            o.w = __uint_as_float(v[j + 3]);
+                            if (a.bias) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            }
+                            if (rrow) {
+                                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + co + j));
+                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                            }
+                            *reinterpret_cast<float4*>(yrow + co + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (co + j < a.Cout) {
+                                float o = __uint_as_float(v[j]);
+                                if (a.bias) o += __ldg(a.bias + co + j);
+                                if (rrow) o += __ldg(rrow + co + j);
+                                yrow[co + j] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---- weight / activation packing ---------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// OIHW fp32 -> [Cout][kh*kw][Cin]; mode 0: bf16; mode 1: fp32 (tensor core truncates to tf32); mode 2: hi (low 13
+// mantissa bits cleared) + lo = w - hi (exact in fp32)
+__global__ void conv_pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kk, int mode,
+                                        void* __restrict__ out_hi, float* __restrict__ out_lo) {
+    const long long n = (long long)Cout * Cin * kk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        const long long r = i / Cin;
+        const int t = (int)(r % kk), co = (int)(r / kk);
+        const float v = w[((long long)co * Cin + ci) * kk + t];
+        if (mode == 0) {
+            reinterpret_cast<__nv_bfloat16*>(out_hi)[i] = __float2bfloat16_rn(v);
+        } else if (mode == 1) {
+            reinterpret_cast<float*>(out_hi)[i] = v;
+        } else {
+            const float h = tf32_hi(v);
+            reinterpret_cast<float*>(out_hi)[i] = h;
+            out_lo[i] = v - h;
+        }
+    }
+}
+
+// elementwise operand preparation for activations that do not come out of the GroupNorm kernel
+__global__ void conv_prep_act_kernel(const float4* __restrict__ x, long long n4, int mode, void* __restrict__ out_hi,
+                                     float4* __restrict__ out_lo) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        if (mode == 0) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&a);
+            o.y = *reinterpret_cast<uint32_t*>(&b);
+            reinterpret_cast<uint2*>(out_hi)[i] = o;
+        } else {
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            reinterpret_cast<float4*>(out_hi)[i] = h;
+            out_lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int make_act_map(CUtensorMap* m, const void* ptr, bool bf16, int B, int H, int W, int C, int TH, int TW) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GLARE_ERR_UNSUPPORTED;
+    const cuuint64_t es = bf16 ? 2 : 4;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
+}
+
+static int make_w_map(CUtensorMap* m, const void* ptr, bool bf16, int Cout, int K, int BN) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GLARE_ERR_UNSUPPORTED;
+    const cuuint64_t es = bf16 ? 2 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * es};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
+}
+
+template <int MODE, int BN>
+static int launch_conv(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
+                       const ConvTcArgs& a, cudaStream_t stream) {
+    using Cfg = ConvCfg<MODE, BN>;
+    static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
+    GLARE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
+    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+    conv_tc_kernel<MODE, BN><<<grid, CT_THREADS, Cfg::SMEM_DYN, stream>>>(tA, tAl, tB, tBl, a);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+}  // namespace glare
+
+using namespace glare;
+
+// bytes per element of the packed operand for a precision mode (0 bf16, 1 tf32, 2 3xtf32)
+GLARE_API int glare_conv_tc_elem_bytes(int mode) { return mode == 0 ? 2 : 4; }
+
+GLARE_API int glare_conv_pack_weight(int mode, const float* w_oihw, int Cout, int Cin, int ksize, void* out_hi, void* out_lo,
+                                     cudaStream_t stream) {
+    if (!w_oihw || !out_hi || (mode == 2 && !out_lo) || mode < 0 || mode > 2 || Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3))
+        return GLARE_ERR_BAD_ARG;
+    const long long n = (long long)Cout * Cin * ksize * ksize;
+    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    conv_pack_weight_kernel<<<grid, 256, 0, stream>>>(w_oihw, Cout, Cin, ksize * ksize, mode, out_hi, reinterpret_cast<float*>(out_lo));
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// fp32 activations -> tensor-core operand(s): mode 0 bf16 copy, mode 2 tf32 hi/lo split (mode 1 needs no preparation)
+GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* out_hi, void* out_lo, cudaStream_t stream) {
+    if (n < 0 || (mode != 0 && mode != 2) || (n & 3)) return GLARE_ERR_BAD_ARG;
+    if (n == 0) return GLARE_OK;
+    if (!x || !out_hi || (mode == 2 && !out_lo)) return GLARE_ERR_BAD_ARG;
+    const long long n4 = n / 4;
+    const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    conv_prep_act_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), n4, mode, out_hi, reinterpret_cast<float4*>(out_lo));
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// x / x_lo: NHWC [B,H,W,Cin] (bf16 for mode 0, fp32 otherwise; x_lo only for mode 2); w / w_lo: packed by
+// glare_conv_pack_weight; bias [Cout] / residual NHWC [B,H,W,Cout] fp32 or NULL; y NHWC fp32.
+GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                                   const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                                   cudaStream_t stream) {
+    if (mode < 0 || mode > 2 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!x || !w || !y || (mode == 2 && (!x_lo || !w_lo))) return GLARE_ERR_BAD_ARG;
+    const int bke = mode == 0 ? 64 : 32;
+    if (Cin % bke != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return GLARE_ERR_BAD_ARG;
+    ConvTcArgs a{};
+    a.bias = bias; a.residual = residual; a.y = y;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.pad = ksize / 2;
+    a.TH = 8; a.TW = 16;
+    a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
+    a.kchunks = Cin / bke;
+    const int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+    a.n_blocks = (Cout + BN - 1) / BN;
+    const long long total = (long long)a.n_blocks * B * a.tiles_y * a.tiles_x;
+    if (total > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
+    a.total_tiles = (int)total;
+    CUtensorMap tA, tAl, tB, tBl;
+    int rc;
+    const bool bf = mode == 0;
+    if ((rc = make_act_map(&tA, x, bf, B, H, W, Cin, a.TH, a.TW)) != GLARE_OK) return rc;
+    if ((rc = make_w_map(&tB, w, bf, Cout, ksize * ksize * Cin, BN)) != GLARE_OK) return rc;
+    tAl = tA; tBl = tB;
+    if (mode == 2) {
+        if ((rc = make_act_map(&tAl, x_lo, false, B, H, W, Cin, a.TH, a.TW)) != GLARE_OK) return rc;
+        if ((rc = make_w_map(&tBl, w_lo, false, Cout, ksize * ksize * Cin, BN)) != GLARE_OK) return rc;
+    }
+#define GLARE_CONV_DISPATCH(M)                                                            \
+    do {                                                                                  \
+        if (BN == 256) return launch_conv<M, 256>(tA, tAl, tB, tBl, a, stream);           \
+        if (BN == 128) return launch_conv<M, 128>(tA, tAl, tB, tBl, a, stream);           \
+        return launch_conv<M, 64>(tA, tAl, tB, tBl, a, stream);                           \
+    } while (0)
+    if (mode == 0) GLARE_CONV_DISPATCH(0);
+    if (mode == 1) GLARE_CONV_DISPATCH(1);
+    GLARE_CONV_DISPATCH(2);
+#undef GLARE_CONV_DISPATCH
+}

@@ -47,7 +47,7 @@ enum { FLOW_RAW = 0, FLOW_INV = 1, FLOW_FWD = 2 };
 
 struct FlowArgs {
     const float* p;          // pre-activation planes of this net: [b][step][64][h*w] through the strides below
-    long long p_bs, p_ss;
+    long long p_bs, p_ss, p_cs, p_ps;   // batch / step / channel / pixel strides (NCHW planes: cs = h*w, ps = 1; NHWC: cs = 1, ps = C)
     const float* net;        // packed nets, one per step
     long long net_ss;
     float* out;              // RAW: [b][step][nout][h*w]
@@ -128,13 +128,13 @@ __global__ void __launch_bounds__(FLOW_THREADS, 2) flow_tail_kernel(const FlowAr
 #pragma unroll
         for (int t = 0; t < 9; ++t) zc[t] = s_z1[(r + t / 3) * 20 + (c + t % 3)];
     }
-    const float* pb = a.p + (long long)b * a.p_bs + (long long)step * a.p_ss + (in_img ? pix : 0);
+    const float* pb = a.p + (long long)b * a.p_bs + (long long)step * a.p_ss + (in_img ? pix * a.p_ps : 0);
     mbar_wait(&bar, 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < FLOW_C; c0 += 8) {
         float pv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pv[j] = in_img ? __ldg(pb + (long long)(c0 + j) * hw) : 0.f;
+        for (int j = 0; j < 8; ++j) pv[j] = in_img ? __ldg(pb + (long long)(c0 + j) * a.p_cs) : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float v = pv[j];
@@ -321,14 +321,14 @@ GLARE_API int glare_flow_net_floats(void) { return NET_FLOATS; }
 
 // NN tail for `n_steps` nets at once (used for NN_F of all coupling steps: it never sees z).
 GLARE_API int glare_flow_cond_tail_f32(const float* p, long long p_batch_stride, long long p_step_stride,
-                                        const float* nets, int n_steps, int nout, int B, int h, int w, float* out,
+                                        long long p_chan_stride, long long p_pix_stride, const float* nets, int n_steps, int nout, int B, int h, int w, float* out,
                                         long long out_batch_stride, long long out_step_stride, cudaStream_t stream) {
     if (B < 0 || h < 0 || w < 0 || n_steps < 0 || (nout != 4 && nout != 6)) return GLARE_ERR_BAD_ARG;
     if (B == 0 || h == 0 || w == 0 || n_steps == 0) return GLARE_OK;
     if (!p || !nets || !out) return GLARE_ERR_BAD_ARG;
     if (B > 65535 || n_steps > 65535) return GLARE_ERR_BAD_ARG;
     FlowArgs a{};
-    a.p = p; a.p_bs = p_batch_stride; a.p_ss = p_step_stride;
+    a.p = p; a.p_bs = p_batch_stride; a.p_ss = p_step_stride; a.p_cs = p_chan_stride; a.p_ps = p_pix_stride;
     a.net = nets; a.net_ss = NET_FLOATS;
     a.out = out; a.out_bs = out_batch_stride; a.out_ss = out_step_stride;
     a.B = B; a.h = h; a.w = w; a.tiles_x = (w + FLOW_TILE - 1) / FLOW_TILE;
@@ -340,7 +340,7 @@ GLARE_API int glare_flow_cond_tail_f32(const float* p, long long p_batch_stride,
 // incremented by the data-dependent terms only (sum log scale; negated in reverse); the constant
 // ActNorm / invconv terms are added by the caller (they depend only on the weights).
 GLARE_API int glare_flow_step_f32(int direction, int coupling, const float* z_in, float* z_out, const float* pA,
-                                   long long pA_batch_stride, const float* hF, long long hF_batch_stride,
+                                   long long pA_batch_stride, long long pA_chan_stride, long long pA_pix_stride, const float* hF, long long hF_batch_stride,
                                    const float* netA, const float* pw, int B, int h, int w, float* logdet,
                                    cudaStream_t stream) {
     if (B < 0 || h < 0 || w < 0 || (direction != 0 && direction != 1)) return GLARE_ERR_BAD_ARG;
@@ -356,7 +356,7 @@ GLARE_API int glare_flow_step_f32(int direction, int coupling, const float* z_in
     }
     if (!pA || !hF || !netA || B > 65535) return GLARE_ERR_BAD_ARG;
     FlowArgs a{};
-    a.p = pA; a.p_bs = pA_batch_stride; a.p_ss = 0;
+    a.p = pA; a.p_bs = pA_batch_stride; a.p_ss = 0; a.p_cs = pA_chan_stride; a.p_ps = pA_pix_stride;
     a.net = netA; a.net_ss = 0;
     a.z_in = z_in; a.z_out = z_out;
     a.hF = hF; a.hF_bs = hF_batch_stride;

@@ -1,0 +1,140 @@
+// GroupNorm(32, eps=1e-6) + swish for NHWC activations, producing the tensor-core operand of the next conv.
+//
+// Replaces reference encoder_decoder.py:34-35 (Normalize = GroupNorm(num_groups=32, eps=1e-6, affine)) and
+// :29-31 (nonlinearity x*sigmoid(x)) as used by ResnetBlock.forward (:117-137), AttnBlock.forward (:168-171,
+// no swish) and the norm_out heads (:435-442, :546-550).  HBM-bound: one read for the statistics, one read +
+// one operand write for the apply pass (the conv that follows consumes the operand through TMA).
+//   stats : per (sample, group) sum and sum of squares, accumulated in fp64 (no E[x^2]-E[x]^2 cancellation issue)
+//   apply : y = (x - mean) * rstd * gamma + beta ; y *= sigmoid(y) ; emitted as bf16 | fp32 | tf32 hi+lo split
+#include "common.cuh"
+
+namespace glare {
+
+constexpr int GN_THREADS = 256;
+
+// x [B][HW][C]; grid (chunks, B); stats [B][G][2] (pre-zeroed)
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, long long HW, int C, int G,
+                                                              double* __restrict__ stats) {
+    __shared__ double s_sum[64], s_sq[64];
+    const int b = blockIdx.y;
+    const int c4n = C >> 2;                          // float4 columns per pixel
+    const int rows = GN_THREADS / c4n;               // pixels processed per CTA pass (C <= 1024)
+    const int my_c4 = threadIdx.x % c4n, my_row = threadIdx.x / c4n;
+    if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+    __syncthreads();
+    double s = 0.0, q = 0.0;
+    if (my_row < rows) {
+        const long long per = (HW + gridDim.x - 1) / gridDim.x;
+        const long long p0 = (long long)blockIdx.x * per, p1 = (p0 + per < HW) ? p0 + per : HW;
+        const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * HW * C);
+        for (long long p = p0 + my_row; p < p1; p += rows) {
+            const float4 v = __ldg(xb + p * c4n + my_c4);
+            s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+            q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        }
+        const int g = (my_c4 * 4) / (C / G);
+        atomicAdd(&s_sum[g], s);
+        atomicAdd(&s_sq[g], q);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2], s_sum[threadIdx.x]);
+        atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    }
+}
+
+__device__ __forceinline__ float tf32_hi_n(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// OUT: 0 = bf16, 1 = fp32, 2 = tf32 hi + lo
+template <int OUT>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, int swish, long long HW, int C, int G,
+                                                              void* __restrict__ out_hi, float* __restrict__ out_lo) {
+    extern __shared__ float s_ab[];                  // [C] rstd*gamma, [C] beta, [C] mean for this sample
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    const double cnt = (double)HW * cpg;
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        const int g = c / cpg;
+        const double mean = stats[((long long)b * G + g) * 2] / cnt;
+        double var = stats[((long long)b * G + g) * 2 + 1] / cnt - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        s_ab[c] = gamma[c] * rstd;
+        s_ab[C + c] = beta[c];
+        s_ab[2 * C + c] = (float)mean;
+    }
+    __syncthreads();
+    const int c4n = C >> 2;
+    const long long n4 = HW * c4n;
+    const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * HW * C);
+    const long long base4 = (long long)b * n4;
+    for (long long i = (long long)blockIdx.x * GN_THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * GN_THREADS) {
+        const int c = (int)(i % c4n) * 4;
+        const float4 v = __ldg(xb + i);
+        float y[4] = {fmaf(v.x - s_ab[2 * C + c], s_ab[c], s_ab[C + c]), fmaf(v.y - s_ab[2 * C + c + 1], s_ab[c + 1], s_ab[C + c + 1]),
+                      fmaf(v.z - s_ab[2 * C + c + 2], s_ab[c + 2], s_ab[C + c + 2]),
+                      fmaf(v.w - s_ab[2 * C + c + 3], s_ab[c + 3], s_ab[C + c + 3])};
+        if (swish) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.0f + expf(-y[k]));
+        }
+        if (OUT == 0) {
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(y[0], y[1]), a1 = __floats2bfloat162_rn(y[2], y[3]);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&a0);
+            o.y = *reinterpret_cast<uint32_t*>(&a1);
+            reinterpret_cast<uint2*>(out_hi)[base4 + i] = o;
+        } else if (OUT == 1) {
+            reinterpret_cast<float4*>(out_hi)[base4 + i] = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+            const float4 h = make_float4(tf32_hi_n(y[0]), tf32_hi_n(y[1]), tf32_hi_n(y[2]), tf32_hi_n(y[3]));
+            reinterpret_cast<float4*>(out_hi)[base4 + i] = h;
+            reinterpret_cast<float4*>(out_lo)[base4 + i] = make_float4(y[0] - h.x, y[1] - h.y, y[2] - h.z, y[3] - h.w);
+        }
+    }
+}
+
+}  // namespace glare
+
+using namespace glare;
+
+// x NHWC [B,HW,C] fp32 -> stats [B][G][2] fp64 (sum, sum of squares); stats is overwritten.
+GLARE_API int glare_gn_stats_nhwc_f32(const float* x, int B, long long HW, int C, int G, double* stats, cudaStream_t stream) {
+    if (B < 0 || HW < 0 || C <= 0 || G <= 0 || G > 64 || C % G != 0 || (C & 3) || C > 1024 || ((C / G) & 3)) return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!x || !stats || B > 65535) return GLARE_ERR_BAD_ARG;
+    GLARE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)B * G, stream));
+    if (HW == 0) return GLARE_OK;
+    const int rows = GN_THREADS / (C / 4);
+    long long chunks = (HW + (long long)rows * 16 - 1) / ((long long)rows * 16);      // >= 16 pixels per thread row
+    const long long cap = (148 * 8 + B - 1) / B;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    gn_stats_kernel<<<dim3((unsigned)chunks, (unsigned)B), GN_THREADS, 0, stream>>>(x, HW, C, G, stats);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// out_mode 0: bf16 -> out_hi; 1: fp32 -> out_hi; 2: tf32 hi -> out_hi, lo -> out_lo.  swish != 0 applies x*sigmoid(x).
+GLARE_API int glare_gn_apply_nhwc(int out_mode, const float* x, const double* stats, const float* gamma, const float* beta,
+                                  float eps, int swish, int B, long long HW, int C, int G, void* out_hi, void* out_lo,
+                                  cudaStream_t stream) {
+    if (out_mode < 0 || out_mode > 2 || B < 0 || HW < 0 || C <= 0 || G <= 0 || C % G != 0 || (C & 3) || C > 1024) return GLARE_ERR_BAD_ARG;
+    if (B == 0 || HW == 0) return GLARE_OK;
+    if (!x || !stats || !gamma || !beta || !out_hi || (out_mode == 2 && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
+    const long long n4 = HW * (C / 4);
+    long long blocks = (n4 + GN_THREADS * 4 - 1) / (GN_THREADS * 4);
+    const long long cap = (148 * 16 + B - 1) / B;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const dim3 grid((unsigned)blocks, (unsigned)B);
+    const size_t smem = 3 * (size_t)C * sizeof(float);
+    float* lo = reinterpret_cast<float*>(out_lo);
+    if (out_mode == 0) gn_apply_kernel<0><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
+    else if (out_mode == 1) gn_apply_kernel<1><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
+    else gn_apply_kernel<2><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}

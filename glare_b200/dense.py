@@ -41,8 +41,125 @@ class _TorchBackend(TorchDense):
                 "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None, "ms_per_step": tot_ms, "peak_source": pk["src"]}
 
 
+class Operand:
+    """Tensor-core operand of a conv: NHWC ``hi`` (+ ``lo`` for the 3xTF32 split) of a logical [B,C,H,W] activation."""
+
+    def __init__(self, mode, hi, lo, B, C, H, W):
+        self.mode, self.hi, self.lo, self.B, self.C, self.H, self.W = mode, hi, lo, B, C, H, W
+
+    def dense(self):
+        """fp32 logical-NCHW (channels_last) value of the operand: hi + lo is exact for the tf32 split"""
+        v = self.hi.float() if self.lo is None else self.hi + self.lo
+        return v.view(self.B, self.H, self.W, self.C).permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    """logical [B,C,H,W] fp32 tensor -> the same storage viewed as contiguous NHWC (converting layout if needed)"""
+    if x.dtype != torch.float32:
+        x = x.float()
+    if not x.is_contiguous(memory_format=torch.channels_last) or (x.shape[1] > 1 and x.stride(1) != 1):
+        x = x.contiguous(memory_format=torch.channels_last)
+    return x.permute(0, 2, 3, 1)
+
+
+class TcDense:
+    """tcgen05 implicit-GEMM convolutions + fused GroupNorm/swish operand kernels (libglare_b200.so).
+
+    mode 0 bf16 operands, 1 tf32, 2 3xTF32 (~fp32).  Shapes the kernel does not cover (3-channel heads, the two
+    stride-2 downsample convs; < 2.5 % of the FLOPs) and the attention matmuls go to the cuDNN/cuBLAS library
+    backend ``self.lib`` -- listed in ``self.fallbacks`` so the bench can report them."""
+
+    def __init__(self, mode):
+        from . import ops
+        self.ops = ops
+        self.mode = mode
+        self.name = {0: "tcgen05-bf16", 1: "tcgen05-tf32", 2: "tcgen05-3xtf32"}[mode]
+        self.dtype_name = {0: "bf16", 1: "tf32", 2: "fp32 (3xTF32 tensor-core emulation, fp32 accumulate)"}[mode]
+        self.lib = TorchDense(torch.float32, allow_tf32=(mode != 2))
+        self.bke = 64 if mode == 0 else 32
+        self._w = {}
+        self.fallbacks = {}
+        self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
+        self.last_timers, self.last_steps = None, 1
+
+    def _weights(self, w):
+        key = (w.data_ptr(), tuple(w.shape))
+        if key not in self._w:
+            self._w[key] = self.ops.conv_pack_weight(self.mode, w)
+        return self._w[key]
+
+    def _supported(self, Cin, w, stride, padding):
+        ks = w.shape[2]
+        return (w.shape[2] == w.shape[3] and ks in (1, 3) and stride == 1 and padding == ks // 2 and Cin % self.bke == 0
+                and w.shape[0] % 4 == 0)
+
+    def conv2d(self, x, w, b=None, stride=1, padding=1, residual=None):
+        Cin = x.C if isinstance(x, Operand) else x.shape[1]
+        if not self._supported(Cin, w, stride, padding):
+            key = "conv %dx%d %d->%d s%d" % (w.shape[2], w.shape[3], Cin, w.shape[0], stride)
+            self.fallbacks[key] = self.fallbacks.get(key, 0) + 1
+            xd = x.dense() if isinstance(x, Operand) else x
+            y = self.lib.conv2d(xd.contiguous(memory_format=torch.channels_last), w, b, stride=stride, padding=padding)
+            return y if residual is None else y + residual
+        if isinstance(x, Operand):
+            op = x
+        else:
+            xn = _nhwc(x)
+            B, H, W, C = xn.shape
+            hi, lo = self.ops.conv_prep_act(self.mode, xn)
+            op = Operand(self.mode, hi, lo, B, C, H, W)
+        w_hi, w_lo = self._weights(w)
+        res = _nhwc(residual) if residual is not None else None
+        Cout, ks = w.shape[0], w.shape[2]
+        if self.timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        y = self.ops.conv2d_nhwc_tc(self.mode, op.hi, op.lo, w_hi, w_lo, b, res, op.B, op.H, op.W, op.C, Cout, ks)
+        if self.timers is not None:
+            e1.record()
+            self.timers.setdefault("conv_tc", []).append((e0, e1, 2.0 * op.B * op.H * op.W * op.C * Cout * ks * ks))
+        return y.permute(0, 3, 1, 2)
+
+    def gn_swish(self, x, gamma, beta, swish=True):
+        C = x.shape[1]
+        if C % 128 != 0:
+            self.fallbacks["groupnorm C=%d" % C] = self.fallbacks.get("groupnorm C=%d" % C, 0) + 1
+            return self.lib.gn_swish(x, gamma, beta, swish)
+        xn = _nhwc(x)
+        B, H, W, _ = xn.shape
+        stats = self.ops.gn_stats(xn, B, H * W, C)
+        hi, lo = self.ops.gn_apply(self.mode, xn, stats, gamma, beta, swish, B, H * W, C)
+        return Operand(self.mode, hi, lo, B, C, H, W)
+
+    def attention(self, q, k, v):
+        self.fallbacks["attention bmm+softmax (library)"] = self.fallbacks.get("attention bmm+softmax (library)", 0) + 1
+        return self.lib.attention(q, k, v)
+
+    def roofline(self, timers, eng, B, lr_shape, pk):
+        """Dominant kernel: conv_tc_kernel (all tensor-core conv launches of one step).  Algorithmic work =
+        2*Cin*Cout*k*k FLOP per output pixel, summed over the launches; the 3xTF32 mode issues 3 MMAs
+        per algorithmic MAC, the roofline counts the algorithmic ones."""
+        ev = (self.last_timers or {}).get("conv_tc", [])
+        if not ev:
+            return None
+        ms = sum(a.elapsed_time(b) for a, b, _ in ev)
+        fl = sum(f for _, _, f in ev)
+        steps = max(1, self.last_steps)
+        ach = fl / (ms / 1e3) / 1e12
+        return {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step, mode %s)" % (len(ev) // steps, self.name),
+                "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+                "traffic": None, "ms_per_step": ms / steps, "algorithmic_tflop_per_step": fl / steps / 1e12,
+                "peak_source": pk["src"] + " (cuBLAS bf16 sustained)"}
+
+
 def make_dense(name="auto"):
-    if name in ("auto", "torch-fp32"):
+    if name in ("auto", "tc-3xtf32"):
+        return TcDense(2)
+    if name == "tc-tf32":
+        return TcDense(1)
+    if name == "tc-bf16":
+        return TcDense(0)
+    if name == "torch-fp32":
         return _TorchBackend(torch.float32)
     if name == "torch-tf32":
         b = _TorchBackend(torch.float32, allow_tf32=True)

@@ -33,10 +33,11 @@ class TorchDense:
         torch.backends.cudnn.allow_tf32 = self.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
 
-    def conv2d(self, x, w, b=None, stride=1, padding=1):
+    def conv2d(self, x, w, b=None, stride=1, padding=1, residual=None):
         self._ctx()
-        return F.conv2d(x.to(self.dtype), w.to(self.dtype), None if b is None else b.to(self.dtype), stride=stride,
-                        padding=padding)
+        y = F.conv2d(x.to(self.dtype), w.to(self.dtype), None if b is None else b.to(self.dtype), stride=stride,
+                     padding=padding)
+        return y if residual is None else y + residual
 
     def gn_swish(self, x, gamma, beta, swish=True):
         y = F.group_norm(x.float(), 32, gamma, beta, eps=1e-6)       # encoder_decoder.py:34-35
@@ -97,8 +98,8 @@ class GlareEngine:
         return _Timed(self.timers, name)
 
     # ------------------------------------------------------------------ taming blocks (encoder_decoder.py)
-    def _conv(self, sd, p, x, stride=1, padding=1):
-        return self.dense.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
+    def _conv(self, sd, p, x, stride=1, padding=1, residual=None):
+        return self.dense.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding, residual=residual)
 
     def _gn(self, sd, p, x, swish=True):
         return self.dense.gn_swish(x, sd[p + ".weight"], sd[p + ".bias"], swish)
@@ -106,10 +107,9 @@ class GlareEngine:
     def resnet_block(self, sd, p, x):
         """ResnetBlock.forward   encoder_decoder.py:117-137"""
         h = self._conv(sd, p + ".conv1", self._gn(sd, p + ".norm1", x))
-        h = self._conv(sd, p + ".conv2", self._gn(sd, p + ".norm2", h))
         if (p + ".nin_shortcut.weight") in sd:
             x = self._conv(sd, p + ".nin_shortcut", x, padding=0)
-        return x + h
+        return self._conv(sd, p + ".conv2", self._gn(sd, p + ".norm2", h), residual=x)      # x + h fused in the epilogue
 
     def attn_block(self, sd, p, x):
         """AttnBlock.forward   encoder_decoder.py:168-192"""
@@ -118,7 +118,7 @@ class GlareEngine:
         k = self._conv(sd, p + ".k", hn, padding=0)
         v = self._conv(sd, p + ".v", hn, padding=0)
         o = self.dense.attention(q, k, v)
-        return x + self._conv(sd, p + ".proj_out", o, padding=0)
+        return self._conv(sd, p + ".proj_out", o, padding=0, residual=x)
 
     def downsample(self, sd, p, x):
         """encoder_decoder.py:68-72"""

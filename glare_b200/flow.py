@@ -89,8 +89,17 @@ def precompute(plan, ft, conv2d):
     P = conv2d(ft, plan.w_pre)
     hw = h * w
     hF = torch.empty((B, n * 6, h, w), device=ft.device, dtype=torch.float32)
-    ops.flow_cond_tail(P[:, 64:], n * 128 * hw, 128 * hw, plan.nets_f, n, 6, B, h, w, hF, n * 6 * hw, 6 * hw)
+    ops.flow_cond_tail(P[:, 64:], plane_strides(P, True), plan.nets_f, n, 6, B, h, w, hF, n * 6 * hw, 6 * hw)
     return P, hF
+
+
+def plane_strides(P, with_step):
+    """element strides of the pre-activation tensor P [B, 24*128, h, w] in whatever dense layout the conv path
+    produced (NCHW planes or channels_last): (batch, [step,] channel, pixel)"""
+    sb, sc, sh, sw = P.stride()
+    if sh != sw * P.shape[3]:
+        raise ValueError("pre-activation planes must be dense over (h, w)")
+    return (sb, 128 * sc, sc, sw) if with_step else (sb, sc, sw)
 
 
 def decode(plan, z, ft, conv2d, logdet=None, trace=None):
@@ -105,10 +114,10 @@ def decode(plan, z, ft, conv2d, logdet=None, trace=None):
         coupling = s not in NO_COUPLING_STEPS
         if coupling:
             ci = COUPLING_STEPS.index(s)
-            ops.flow_step(1, True, bufs[cur], bufs[nxt], P[:, ci * 128:], n * 128 * hw, hF[:, ci * 6:], n * 6 * hw,
+            ops.flow_step(1, True, bufs[cur], bufs[nxt], P[:, ci * 128:], plane_strides(P, False), hF[:, ci * 6:], n * 6 * hw,
                           plan.nets_a[ci], plan.pw_inv[s], logdet)
         else:
-            ops.flow_step(1, False, bufs[cur], bufs[nxt], None, 0, None, 0, None, plan.pw_inv[s], None)
+            ops.flow_step(1, False, bufs[cur], bufs[nxt], None, (0, 0, 0), None, 0, None, plan.pw_inv[s], None)
         if logdet is not None:
             logdet -= (plan.ld_const[s, 0] + plan.ld_const[s, 1]) * float(hw)
         if trace is not None:
@@ -133,10 +142,10 @@ def encode(plan, gt, ft, conv2d, logdet=None):
         logdet += plan.ld_const[s, 1] * float(hw)
         if coupling:
             ci = COUPLING_STEPS.index(s)
-            ops.flow_step(0, True, bufs[cur], bufs[nxt], P[:, ci * 128:], n * 128 * hw, hF[:, ci * 6:], n * 6 * hw,
+            ops.flow_step(0, True, bufs[cur], bufs[nxt], P[:, ci * 128:], plane_strides(P, False), hF[:, ci * 6:], n * 6 * hw,
                           plan.nets_a[ci], plan.pw_fwd[s], logdet)
         else:
-            ops.flow_step(0, False, bufs[cur], bufs[nxt], None, 0, None, 0, None, plan.pw_fwd[s], None)
+            ops.flow_step(0, False, bufs[cur], bufs[nxt], None, (0, 0, 0), None, 0, None, plan.pw_fwd[s], None)
         cur, nxt = nxt, (2 if nxt == 1 else 1)
     return bufs[cur], logdet
 

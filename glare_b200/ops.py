@@ -84,14 +84,70 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
 
 
 # ------------------------------------------------------------------------------------------- flow
-def flow_cond_tail(p, p_batch_stride, p_step_stride, nets, n_steps, nout, B, h, w, out, out_batch_stride, out_step_stride):
+def flow_cond_tail(p, p_strides, nets, n_steps, nout, B, h, w, out, out_batch_stride, out_step_stride):
+    """p_strides = (batch, step, channel, pixel) element strides of the pre-activation planes"""
     require_cuda(p, nets, out)
-    check(lib().glare_flow_cond_tail_f32(ptr(p), p_batch_stride, p_step_stride, ptr(nets), n_steps, nout, B, h, w, ptr(out),
-                                         out_batch_stride, out_step_stride, stream()), "glare_flow_cond_tail_f32")
+    check(lib().glare_flow_cond_tail_f32(ptr(p), p_strides[0], p_strides[1], p_strides[2], p_strides[3], ptr(nets), n_steps, nout,
+                                         B, h, w, ptr(out), out_batch_stride, out_step_stride, stream()), "glare_flow_cond_tail_f32")
 
 
-def flow_step(direction, coupling, z_in, z_out, pA, pA_batch_stride, hF, hF_batch_stride, netA, pw, logdet=None):
+def flow_step(direction, coupling, z_in, z_out, pA, pA_strides, hF, hF_batch_stride, netA, pw, logdet=None):
+    """pA_strides = (batch, channel, pixel) element strides"""
     require_cuda(z_in, z_out, pA, hF, netA, pw, logdet)
     B, _, h, w = z_in.shape
-    check(lib().glare_flow_step_f32(direction, 1 if coupling else 0, ptr(z_in), ptr(z_out), ptr(pA), pA_batch_stride, ptr(hF),
-                                    hF_batch_stride, ptr(netA), ptr(pw), B, h, w, ptr(logdet), stream()), "glare_flow_step_f32")
+    check(lib().glare_flow_step_f32(direction, 1 if coupling else 0, ptr(z_in), ptr(z_out), ptr(pA), pA_strides[0], pA_strides[1],
+                                    pA_strides[2], ptr(hF), hF_batch_stride, ptr(netA), ptr(pw), B, h, w, ptr(logdet), stream()),
+          "glare_flow_step_f32")
+
+
+# ------------------------------------------------------------------------------------------- dense convs / GroupNorm
+MODE_BF16, MODE_TF32, MODE_TF32X3 = 0, 1, 2
+
+
+def conv_pack_weight(mode, w_oihw):
+    """OIHW fp32 -> (hi, lo|None) packed [Cout][kh*kw][Cin] operands for glare_conv2d_nhwc_tc"""
+    require_cuda(w_oihw)
+    w = f32c(w_oihw)
+    Co, Ci, kh, kw = w.shape
+    dt = torch.bfloat16 if mode == MODE_BF16 else torch.float32
+    hi = torch.empty((Co, kh * kw, Ci), device=w.device, dtype=dt)
+    lo = torch.empty_like(hi) if mode == MODE_TF32X3 else None
+    check(lib().glare_conv_pack_weight(mode, ptr(w), Co, Ci, kh, ptr(hi), ptr(lo), stream()), "glare_conv_pack_weight")
+    return hi, lo
+
+
+def conv_prep_act(mode, x_nhwc):
+    """fp32 NHWC activations -> (hi, lo|None) operands (mode 1 passes the tensor through)"""
+    require_cuda(x_nhwc)
+    if mode == MODE_TF32:
+        return x_nhwc, None
+    hi = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=torch.bfloat16 if mode == MODE_BF16 else torch.float32)
+    lo = torch.empty_like(hi) if mode == MODE_TF32X3 else None
+    check(lib().glare_conv_prep_act(mode, ptr(x_nhwc), x_nhwc.numel(), ptr(hi), ptr(lo), stream()), "glare_conv_prep_act")
+    return hi, lo
+
+
+def conv2d_nhwc_tc(mode, x_hi, x_lo, w_hi, w_lo, bias, residual, B, H, W, Cin, Cout, ksize, out=None):
+    """x_* NHWC [B,H,W,Cin] operands, w_* packed; returns y NHWC [B,H,W,Cout] fp32"""
+    require_cuda(x_hi, x_lo, w_hi, w_lo, bias, residual)
+    y = out if out is not None else torch.empty((B, H, W, Cout), device=x_hi.device, dtype=torch.float32)
+    check(lib().glare_conv2d_nhwc_tc(mode, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(residual), ptr(y), B, H, W, Cin,
+                                     Cout, ksize, stream()), "glare_conv2d_nhwc_tc")
+    return y
+
+
+def gn_stats(x_nhwc, B, HW, C, G=32):
+    require_cuda(x_nhwc)
+    stats = torch.empty((B, G, 2), device=x_nhwc.device, dtype=torch.float64)
+    check(lib().glare_gn_stats_nhwc_f32(ptr(x_nhwc), B, HW, C, G, ptr(stats), stream()), "glare_gn_stats_nhwc_f32")
+    return stats
+
+
+def gn_apply(out_mode, x_nhwc, stats, gamma, beta, swish, B, HW, C, G=32, eps=1e-6):
+    """-> (hi, lo|None) with hi bf16 (mode 0) / fp32 (mode 1) / tf32-hi (mode 2), same NHWC shape as x"""
+    require_cuda(x_nhwc, stats, gamma, beta)
+    hi = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=torch.bfloat16 if out_mode == 0 else torch.float32)
+    lo = torch.empty_like(hi) if out_mode == 2 else None
+    check(lib().glare_gn_apply_nhwc(out_mode, ptr(x_nhwc), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if swish else 0, B, HW, C, G,
+                                    ptr(hi), ptr(lo), stream()), "glare_gn_apply_nhwc")
+    return hi, lo

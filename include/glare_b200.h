@@ -75,15 +75,16 @@ int glare_vq_argmin_gather_f32(const float* z_nchw, const float* packed_codebook
 int glare_flow_net_floats(void);
 /* NN tail (ActNorm+ReLU, 1x1+ActNorm+ReLU, 3x3 -> nout in {4,6}) of n_steps nets in one launch; used for
  * NN_F = feature_extract (FlowAffineCouplingsAblation.py:121-128) of every step, which never sees z.
- * p[b][s][64][h*w] and out[b][s][nout][h*w] are addressed through the element strides given. */
-int glare_flow_cond_tail_f32(const float* p, long long p_batch_stride, long long p_step_stride, const float* nets,
-                             int n_steps, int nout, int B, int h, int w, float* out, long long out_batch_stride,
+ * p is addressed as p[b*batch_stride + s*step_stride + c*chan_stride + pixel*pix_stride] (NCHW planes: chan_stride = h*w,
+ * pix_stride = 1; NHWC: chan_stride = 1, pix_stride = channels); out[b][s][nout][h*w] through its two strides. */
+int glare_flow_cond_tail_f32(const float* p, long long p_batch_stride, long long p_step_stride, long long p_chan_stride,
+                             long long p_pix_stride, const float* nets, int n_steps, int nout, int B, int h, int w, float* out, long long out_batch_stride,
                              long long out_step_stride, cudaStream_t stream);
 /* One FlowStep.  direction 0 = normal_flow, 1 = reverse_flow; coupling 0 = "noCoupling" step.
  * z_in/z_out [B,3,h,w] (must not alias); pA [b][64][h*w] = NN_A first-layer pre-activations from ft;
  * hF [b][6][h*w] = NN_F output; logdet [B] or NULL receives += sum(log scale) (negated in reverse). */
 int glare_flow_step_f32(int direction, int coupling, const float* z_in, float* z_out, const float* pA,
-                        long long pA_batch_stride, const float* hF, long long hF_batch_stride, const float* netA,
+                        long long pA_batch_stride, long long pA_chan_stride, long long pA_pix_stride, const float* hF, long long hF_batch_stride, const float* netA,
                         const float* pw, int B, int h, int w, float* logdet, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
@@ -98,6 +99,33 @@ int glare_dcn_pack_weight_f32(const float* weight, int Cout, int C, int kh, int 
 int glare_dcnv2_fwd_f32(const float* x, const float* offset, const float* mask, const float* packed_weight,
                         const float* bias_or_null, int B, int C, int H, int W, int Cout, int kh, int kw, int stride,
                         int pad, int dil, int deformable_groups, float* y, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (4) Dense convolutions on tcgen05 tensor cores -- the cuDNN calls behind nn.Conv2d in ResnetBlock
+ *     (encoder_decoder.py:88-115), Upsample.conv (:38-53), AttnBlock q/k/v/proj_out (:146-165), nin_shortcut,
+ *     WarpBlock.offset / conv_offset (deformableDecoder_arch.py:282) and the flow nets' first layers (flow.py:13-52).
+ *     3x3 (pad 1) or 1x1, stride 1.  Activations NHWC, weights packed [Cout][kh*kw][Cin].
+ *     mode 0 = bf16 operands, 1 = tf32, 2 = 3xTF32 (hi/lo split operands, ~fp32 accuracy); fp32 accumulate.
+ *     Requires Cin % 64 == 0 (mode 0) / Cin % 32 == 0 (modes 1,2) and Cout % 4 == 0, else GLARE_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------------------- */
+int glare_conv_tc_elem_bytes(int mode);
+/* OIHW fp32 -> packed operand(s); out_lo only for mode 2 */
+int glare_conv_pack_weight(int mode, const float* w_oihw, int Cout, int Cin, int ksize, void* out_hi, void* out_lo,
+                           cudaStream_t stream);
+/* fp32 activations (n elements, n % 4 == 0) -> bf16 copy (mode 0) or tf32 hi/lo split (mode 2) */
+int glare_conv_prep_act(int mode, const float* x, long long n, void* out_hi, void* out_lo, cudaStream_t stream);
+int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                         const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                         cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (5) Normalize = GroupNorm(32, eps 1e-6) (+ swish) -- encoder_decoder.py:29-35 as used by ResnetBlock.forward
+ *     (:117-137), AttnBlock.forward (:168-171) and the norm_out heads.  NHWC fp32 in; the apply pass emits the
+ *     tensor-core operand of the following conv (out_mode 0 bf16, 1 fp32, 2 tf32 hi + lo).
+ * ---------------------------------------------------------------------------------------------------- */
+int glare_gn_stats_nhwc_f32(const float* x, int B, long long HW, int C, int G, double* stats, cudaStream_t stream);
+int glare_gn_apply_nhwc(int out_mode, const float* x, const double* stats, const float* gamma, const float* beta, float eps,
+                        int swish, int B, long long HW, int C, int G, void* out_hi, void* out_lo, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,89 @@
+"""GPU parity: tcgen05 implicit-GEMM convolution and the GroupNorm/swish operand kernels through the C ABI,
+against cuDNN fp32 (TF32 off) on the same inputs.  Tolerances: 3xTF32 2e-5 relative to the output scale
+(fp32-grade), TF32 3e-3, bf16 exact-product check against bf16-rounded operands 2e-4."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # B, H, W, Cin, Cout, ks
+    (1, 8, 16, 64, 64, 3),        # exactly one tile
+    (1, 8, 16, 64, 64, 1),
+    (2, 13, 21, 128, 128, 3),     # ragged tiles, halo across tile borders
+    (1, 24, 40, 256, 256, 3),     # BN = 256
+    (1, 17, 33, 512, 512, 3),
+    (1, 9, 20, 512, 256, 3),
+    (1, 26, 39, 256, 108, 3),     # conv_offset: Cout not a multiple of the N tile
+    (1, 12, 20, 64, 3072, 3),     # flow pre-pass
+    (2, 15, 19, 512, 512, 1),     # attention q/k/v/proj
+    (1, 5, 7, 128, 256, 1),       # nin_shortcut
+    (1, 105, 155, 128, 128, 3),   # many tiles per CTA: exercises the persistent loop, both TMEM accumulators, stage wrap
+]
+
+
+def _ref(x, w, b, res, ks):
+    torch.backends.cudnn.allow_tf32 = False
+    y = F.conv2d(x, w, b, padding=ks // 2)
+    return y if res is None else y + res
+
+
+@pytest.mark.parametrize("mode", [2, 1, 0])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_against_cudnn_fp32(glare_lib, shape, mode):
+    from glare_b200 import ops
+    B, H, W, Ci, Co, ks = shape
+    g = torch.Generator().manual_seed(Ci + Co + H)
+    x = torch.randn((B, Ci, H, W), generator=g).cuda()
+    w = (torch.randn((Co, Ci, ks, ks), generator=g) / (ks * Ci ** 0.5)).cuda()
+    b = torch.randn((Co,), generator=g).cuda()
+    res = torch.randn((B, Co, H, W), generator=g).cuda()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    rn = res.permute(0, 2, 3, 1).contiguous()
+    w_hi, w_lo = ops.conv_pack_weight(mode, w)
+    x_hi, x_lo = ops.conv_prep_act(mode, xn)
+    y = ops.conv2d_nhwc_tc(mode, x_hi, x_lo, w_hi, w_lo, b, rn, B, H, W, Ci, Co, ks).permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    if mode == 0:
+        ref = _ref(x.bfloat16().float(), w.bfloat16().float(), b, res, ks)
+        tol = 2e-4
+    else:
+        ref = _ref(x, w, b, res, ks)
+        tol = 2e-5 if mode == 2 else 3e-3
+    err = float((y - ref).abs().max())
+    assert err < tol * max(1.0, float(ref.abs().max())), (shape, mode, err)
+    # no bias / no residual path
+    y2 = ops.conv2d_nhwc_tc(mode, x_hi, x_lo, w_hi, w_lo, None, None, B, H, W, Ci, Co, ks).permute(0, 3, 1, 2)
+    ref2 = ref - b.view(1, -1, 1, 1) - res
+    assert float((y2 - ref2).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+
+
+def test_unsupported_shapes_are_refused(glare_lib):
+    from glare_b200 import ops
+    x = torch.zeros((1, 4, 4, 3), device="cuda")
+    w = torch.zeros((64, 9, 3), device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.conv2d_nhwc_tc(1, x, None, w, None, None, None, 1, 4, 4, 3, 64, 3)
+
+
+@pytest.mark.parametrize("C,H,W,B", [(128, 9, 14, 2), (256, 31, 17, 1), (512, 105, 155, 1), (128, 420, 620, 1)])
+@pytest.mark.parametrize("swish", [True, False])
+def test_groupnorm_swish_operands(glare_lib, C, H, W, B, swish):
+    from glare_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn((B, C, H, W), generator=g) * 2.0 + 3.0).cuda()          # large mean: stresses the variance computation
+    gamma = (1 + 0.1 * torch.randn((C,), generator=g)).cuda()
+    beta = (0.1 * torch.randn((C,), generator=g)).cuda()
+    ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    if swish:
+        ref = ref * torch.sigmoid(ref)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    stats = ops.gn_stats(xn, B, H * W, C)
+    for mode, tol in ((2, 2e-6), (1, 2e-6), (0, 1e-2)):
+        hi, lo = ops.gn_apply(mode, xn, stats, gamma, beta, swish, B, H * W, C)
+        val = hi.double() if lo is None else hi.double() + lo.double()
+        err = float((val.permute(0, 3, 1, 2) - ref).abs().max())
+        assert err < tol * max(1.0, float(ref.abs().max())), (mode, err)
+        if mode == 2:
+            assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0      # hi is an exact tf32 value

@@ -31,11 +31,11 @@ def _single_step(plan, s, z, ft, direction):
     ld = torch.zeros(B, device=z.device)
     pw = (plan.pw_inv if direction == 1 else plan.pw_fwd)[s]
     if s in flow.NO_COUPLING_STEPS:
-        ops.flow_step(direction, False, z, out, None, 0, None, 0, None, pw, None)
+        ops.flow_step(direction, False, z, out, None, (0, 0, 0), None, 0, None, pw, None)
     else:
         P, hF = flow.precompute(plan, ft, _conv)
         ci = flow.COUPLING_STEPS.index(s)
-        ops.flow_step(direction, True, z, out, P[:, ci * 128:], n * 128 * hw, hF[:, ci * 6:], n * 6 * hw, plan.nets_a[ci], pw, ld)
+        ops.flow_step(direction, True, z, out, P[:, ci * 128:], flow.plane_strides(P, False), hF[:, ci * 6:], n * 6 * hw, plan.nets_a[ci], pw, ld)
     sign = -1.0 if direction == 1 else 1.0
     ld = ld + sign * (plan.ld_const[s, 0] + plan.ld_const[s, 1]) * float(hw)
     torch.cuda.synchronize()
@@ -104,11 +104,11 @@ def test_empty_batch(plan):
     from glare_b200 import ops
     z = torch.zeros((0, 3, 8, 8), device="cuda")
     out = torch.empty_like(z)
-    ops.flow_step(1, False, z, out, None, 0, None, 0, None, plan.pw_inv[0], None)
+    ops.flow_step(1, False, z, out, None, (0, 0, 0), None, 0, None, plan.pw_inv[0], None)
 
 
 def test_aliasing_is_rejected(plan):
     from glare_b200 import ops
     z = torch.zeros((1, 3, 8, 8), device="cuda")
     with pytest.raises(RuntimeError):
-        ops.flow_step(1, False, z, z, None, 0, None, 0, None, plan.pw_inv[0], None)
+        ops.flow_step(1, False, z, z, None, (0, 0, 0), None, 0, None, plan.pw_inv[0], None)

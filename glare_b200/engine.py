@@ -77,7 +77,7 @@ class _Timed:
 
 
 class GlareEngine:
-    def __init__(self, sd_g, sd_vq, device="cuda:0", dense=None, per_sample_ratio=True):
+    def __init__(self, sd_g, sd_vq, device="cuda:0", dense=None, per_sample_ratio=True, flow=True, decoders=True):
         if not torch.cuda.is_available():
             raise RuntimeError("glare_b200.GlareEngine needs a CUDA device (B200 / sm_100a); there is no CPU path")
         self.device = torch.device(device)
@@ -88,11 +88,13 @@ class GlareEngine:
                   if not k.startswith(("flowUpsamplerNet.f.", "deformable_decoder.scale", "deformable_decoder.bias",
                                        "deformable_decoder.enc", "deformable_decoder.conv_out"))}
         self.v = {k: v.to(self.device, torch.float32).contiguous() for k, v in sd_vq.items()
-                  if k.startswith(("quantize.", "post_quant_conv.", "decoder."))}
+                  if k.startswith(("quantize.", "post_quant_conv.", "decoder.", "encoder.", "quant_conv."))}
         with torch.cuda.device(self.device):
-            self.flow_plan = flowmod.FlowPlan(sd_g, self.device)
-            self.codebook_packed = ops.vq_pack_codebook(self.v["quantize.embedding.weight"])
-            self.dcn_w = {i: ops.dcn_pack_weight(self.g["deformable_decoder.warp.%d.dcn.weight" % i]) for i in (0, 1)}
+            self.flow_plan = flowmod.FlowPlan(sd_g, self.device) if flow and "flowUpsamplerNet.layers.0.actnorm.bias" in sd_g else None
+            self.codebook_packed = (ops.vq_pack_codebook(self.v["quantize.embedding.weight"])
+                                    if "quantize.embedding.weight" in self.v else None)
+            self.dcn_w = {i: ops.dcn_pack_weight(self.g["deformable_decoder.warp.%d.dcn.weight" % i]) for i in (0, 1)
+                          if decoders and ("deformable_decoder.warp.%d.dcn.weight" % i) in self.g}
 
     def _timed(self, name):
         return _Timed(self.timers, name)
@@ -128,9 +130,20 @@ class GlareEngine:
         """encoder_decoder.py:49-53"""
         return self._conv(sd, p + ".conv", F.interpolate(x, scale_factor=2.0, mode="nearest"))
 
+    def vqgan_encode(self, x):
+        """VQModel.encode (VQModel_arch.py:74-79): Encoder + quant_conv"""
+        x = x.to(self.device, torch.float32)
+        return self._conv(self.v, "quant_conv", self._encoder(self.v, "encoder", x)[0], padding=0).float()
+
     def cond_encoder(self, x, p="RRDB"):
-        """ConEncoder1.forward   ConditionEncoder.py:46-55 (Encoder.forward encoder_decoder.py:406-442)"""
-        sd, e = self.g, p + ".encoder"
+        """ConEncoder1.forward   ConditionEncoder.py:46-55"""
+        sd = self.g
+        enc, mid = self._encoder(sd, p + ".encoder", x)
+        return {"cond_feat": torch.sigmoid(self._conv(sd, p + ".cond_conv.0", enc).float()),
+                "color_map": self._conv(sd, p + ".color_conv", enc).float(), "mid_feat": mid}
+
+    def _encoder(self, sd, e, x):
+        """Encoder.forward(mid_feat=True)   encoder_decoder.py:406-442"""
         h = self._conv(sd, e + ".conv_in", x)
         mid = []
         for lvl in range(3):
@@ -144,9 +157,7 @@ class GlareEngine:
         h = self.resnet_block(sd, e + ".mid.block_1", h)
         h = self.attn_block(sd, e + ".mid.attn_1", h)
         h = self.resnet_block(sd, e + ".mid.block_2", h)
-        enc = self._conv(sd, e + ".conv_out", self._gn(sd, e + ".norm_out", h)).float()
-        return {"cond_feat": torch.sigmoid(self._conv(sd, p + ".cond_conv.0", enc).float()),
-                "color_map": self._conv(sd, p + ".color_conv", enc).float(), "mid_feat": mid}
+        return self._conv(sd, e + ".conv_out", self._gn(sd, e + ".norm_out", h)).float(), mid
 
     def _decoder_trunk(self, sd, p, z):
         h = self._conv(sd, p + ".conv_in", z)
@@ -211,6 +222,9 @@ class GlareEngine:
     # ------------------------------------------------------------------ stages
     def flow_decode(self, z, ft, trace=None):
         return flowmod.decode(self.flow_plan, z, ft, lambda x, w: self.dense.conv2d(x, w).float(), trace=trace)[0]
+
+    def flow_encode(self, gt, ft, logdet=None):
+        return flowmod.encode(self.flow_plan, gt, ft, lambda x, w: self.dense.conv2d(x, w).float(), logdet=logdet)
 
     def vector_quantize(self, z):
         with self._timed("vq"):

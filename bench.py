@@ -248,7 +248,8 @@ def main():
                            "library_fallbacks_per_run": getattr(dense, "fallbacks", None), "parallelism": "images sharded, dp%d" % world,
                            "l2": "256 MiB buffer written between timed iterations (L2 flush); activations per step exceed L2"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "peaks": pk["src"]}
+                "peaks": pk["src"],
+                "breakdown_ms_per_step": dense.breakdown(timers, args.steps) if hasattr(dense, "breakdown") else None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,157 @@
+// AttnBlock core (reference encoder_decoder.py:176-187): w = softmax(q^T k * C^-0.5, dim=keys); h = v w^T.
+// Single head, d = C = 512, N = h*w tokens (16 275 at 600x400).  The two matmuls run on the tcgen05 GEMM path
+// (conv_tc.cu, per-sample weights: S = Q K^T with W = K[n]; O = P V with W = V[n]^T); this file holds the
+// memory-bound pieces in between, written so that each N x N matrix is touched once per pass:
+//   attn_softmax_rows : reads one band of S (fp32), applies the C^-0.5 scale and the row softmax, and emits P
+//                       directly as the tensor-core operand of the second GEMM (bf16 | fp32 | tf32 hi+lo), zero
+//                       in the padded key columns.
+//   attn_transpose_v  : V [N][C] (NHWC) -> V^T [C][Np] operand(s), zero padded keys.
+// The score matrix is processed in bands of query rows sized to stay L2-resident (glare_b200/dense.py).
+#include "common.cuh"
+
+namespace glare {
+
+__device__ __forceinline__ float tf32_hi_a(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <int OUT>
+__global__ void __launch_bounds__(256) attn_softmax_rows_kernel(const float* __restrict__ S, long long lds, int n_keys,
+                                                                int n_pad, float scale, void* __restrict__ out_hi,
+                                                                float* __restrict__ out_lo, long long ldp) {
+    __shared__ float s_red[8];
+    __shared__ float s_bcast;
+    const long long row = blockIdx.x;
+    const float* s = S + row * lds;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // pass 1: max of the scaled logits (row stays in L1/L2 for the next passes)
+    float m = -INFINITY;
+    for (int i = tid * 4; i < n_keys; i += 1024) {
+        if (i + 3 < n_keys) {
+            const float4 v = *reinterpret_cast<const float4*>(s + i);
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) );
+        } else {
+            for (int j = i; j < n_keys; ++j) m = fmaxf(m, s[j]);
+        }
+    }
+    // scale > 0, so max(scale * s) = scale * max(s); the reference multiplies first (encoder_decoder.py:181-182)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float t = s_red[0];
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, s_red[i]);
+        s_bcast = t * scale;
+    }
+    __syncthreads();
+    const float mx = s_bcast;
+    // pass 2: sum of exp
+    float sum = 0.f;
+    for (int i = tid * 4; i < n_keys; i += 1024) {
+        if (i + 3 < n_keys) {
+            const float4 v = *reinterpret_cast<const float4*>(s + i);
+            sum += expf(v.x * scale - mx) + expf(v.y * scale - mx) + expf(v.z * scale - mx) + expf(v.w * scale - mx);
+        } else {
+            for (int j = i; j < n_keys; ++j) sum += expf(s[j] * scale - mx);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_red[i];
+        s_bcast = 1.0f / t;
+    }
+    __syncthreads();
+    const float inv = s_bcast;
+    // pass 3: normalise and emit the operand (n_pad is a multiple of 4)
+    for (int i = tid * 4; i < n_pad; i += 1024) {
+        float p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = (i + j < n_keys) ? expf(s[i + j] * scale - mx) * inv : 0.f;
+        const long long o = row * ldp + i;
+        if (OUT == 0) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(p[0], p[1]), b = __floats2bfloat162_rn(p[2], p[3]);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&a);
+            u.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + o) = u;
+        } else if (OUT == 1) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = make_float4(p[0], p[1], p[2], p[3]);
+        } else {
+            const float4 h = make_float4(tf32_hi_a(p[0]), tf32_hi_a(p[1]), tf32_hi_a(p[2]), tf32_hi_a(p[3]));
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = h;
+            *reinterpret_cast<float4*>(out_lo + o) = make_float4(p[0] - h.x, p[1] - h.y, p[2] - h.z, p[3] - h.w);
+        }
+    }
+}
+
+// v [B][N][C] fp32 -> vt [B][C][Np] operand(s); 32x32 tiles through shared memory
+template <int OUT>
+__global__ void __launch_bounds__(256) attn_transpose_v_kernel(const float* __restrict__ v, int N, int C, int Np,
+                                                               void* __restrict__ out_hi, float* __restrict__ out_lo) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+    const float* vb = v + (long long)b * N * C;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r, c = c0 + tx;
+        tile[r][tx] = (n < N && c < C) ? __ldg(vb + (long long)n * C + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, n = n0 + tx;
+        if (c < C && n < Np) {
+            const float x = tile[tx][r];
+            const long long o = ((long long)b * C + c) * Np + n;
+            if (OUT == 0) reinterpret_cast<__nv_bfloat16*>(out_hi)[o] = __float2bfloat16_rn(x);
+            else if (OUT == 1) reinterpret_cast<float*>(out_hi)[o] = x;
+            else {
+                const float h = tf32_hi_a(x);
+                reinterpret_cast<float*>(out_hi)[o] = h;
+                out_lo[o] = x - h;
+            }
+        }
+    }
+}
+
+}  // namespace glare
+
+using namespace glare;
+
+// S [rows][lds] fp32 logits (first n_keys columns valid) -> P [rows][ldp] operand (out_mode 0 bf16, 1 fp32, 2 tf32 hi+lo),
+// P = softmax(scale * S) over the keys, zero in columns [n_keys, n_pad).
+GLARE_API int glare_attn_softmax_rows(int out_mode, const float* S, long long rows, long long lds, int n_keys, int n_pad, float scale,
+                                      void* out_hi, void* out_lo, long long ldp, cudaStream_t stream) {
+    if (out_mode < 0 || out_mode > 2 || rows < 0 || n_keys <= 0 || n_pad < n_keys || (n_pad & 3) || (lds & 3) || (ldp & 3) || lds < n_keys ||
+        ldp < n_pad || scale <= 0.f)
+        return GLARE_ERR_BAD_ARG;
+    if (rows == 0) return GLARE_OK;
+    if (!S || !out_hi || (out_mode == 2 && !out_lo) || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
+    float* lo = reinterpret_cast<float*>(out_lo);
+    if (out_mode == 0) attn_softmax_rows_kernel<0><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+    else if (out_mode == 1) attn_softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+    else attn_softmax_rows_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// v NHWC [B][N][C] fp32 -> V^T [B][C][Np] operand(s) (zero for keys >= N)
+GLARE_API int glare_attn_transpose_v(int out_mode, const float* v, int B, int N, int C, int Np, void* out_hi, void* out_lo,
+                                     cudaStream_t stream) {
+    if (out_mode < 0 || out_mode > 2 || B < 0 || N <= 0 || C <= 0 || Np < N) return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!v || !out_hi || (out_mode == 2 && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
+    dim3 grid((Np + 31) / 32, (C + 31) / 32, B);
+    float* lo = reinterpret_cast<float*>(out_lo);
+    if (out_mode == 0) attn_transpose_v_kernel<0><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
+    else if (out_mode == 1) attn_transpose_v_kernel<1><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
+    else attn_transpose_v_kernel<2><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}

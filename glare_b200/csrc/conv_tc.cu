@@ -36,6 +36,8 @@ struct ConvTcArgs {
     float* y;                // NHWC [B,H,W,Cout]
     int B, H, W, Cin, Cout, ksize, pad, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;
     int total_tiles;
+    int w_batched;           // weights differ per sample (3rd tensor-map coordinate = n): attention S = Q K^T, O = P V
+    long long ldy;           // output row (pixel) stride in elements, >= Cout
 };
 
 template <int MODE, int BN>
@@ -91,15 +93,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = s_tmem_base;
 
     const int k_iters = a.ksize * a.ksize * a.kchunks;
-    const int tiles_per_block = a.B * a.tiles_y * a.tiles_x;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int nb = tile / tiles_per_block;
-                int r = tile - nb * tiles_per_block;
+                const int nb = tile % a.n_blocks;                       // N blocks fastest: CTAs running together share the A tile in L2
+                int r = tile / a.n_blocks;
                 const int n = r / (a.tiles_y * a.tiles_x);
                 r -= n * a.tiles_y * a.tiles_x;
                 const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
@@ -113,11 +114,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                         tma_load_4d(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
-                        tma_load_2d(st + CT_A_BYTES, &tmB, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN);
+                        const int wn = a.w_batched ? n : 0;
+                        tma_load_3d(st + CT_A_BYTES, &tmB, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN, wn);
                         if (Cfg::X3) {
                             uint8_t* lo = st + CT_A_BYTES + Cfg::B_BYTES;
                             tma_load_4d(lo, &tmAlo, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
-                            tma_load_2d(lo + CT_A_BYTES, &tmBlo, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN);
+                            tma_load_3d(lo + CT_A_BYTES, &tmBlo, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN, wn);
                         }
                     }
                 }
@@ -163,8 +165,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int py = m / a.TW, px = m - py * a.TW;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
-            const int nb = tile / tiles_per_block;
-            int r = tile - nb * tiles_per_block;
+            const int nb = tile % a.n_blocks;
+            int r = tile / a.n_blocks;
             const int n = r / (a.tiles_y * a.tiles_x);
             r -= n * a.tiles_y * a.tiles_x;
             const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
@@ -174,7 +176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait_bounded(&tmem_full_bar[as], aph);
             tc_fence_after();
             const long long pix = ((long long)n * a.H + gy) * a.W + gx;
-            float* yrow = a.y + pix * a.Cout;
+            float* yrow = a.y + pix * a.ldy;
             const float* rrow = a.residual ? a.residual + pix * a.Cout : nullptr;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -301,15 +303,15 @@ static int make_act_map(CUtensorMap* m, const void* ptr, bool bf16, int B, int H
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-static int make_w_map(CUtensorMap* m, const void* ptr, bool bf16, int Cout, int K, int BN) {
+static int make_w_map(CUtensorMap* m, const void* ptr, bool bf16, int Cout, int K, int BN, int n_w, long long w_batch_stride) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return GLARE_ERR_UNSUPPORTED;
     const cuuint64_t es = bf16 ? 2 : 4;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)K * es};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, (cuuint64_t)n_w};
+    cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)(n_w > 1 ? w_batch_stride : (long long)K * Cout) * es};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
@@ -359,14 +361,28 @@ GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* o
 
 // x / x_lo: NHWC [B,H,W,Cin] (bf16 for mode 0, fp32 otherwise; x_lo only for mode 2); w / w_lo: packed by
 // glare_conv_pack_weight; bias [Cout] / residual NHWC [B,H,W,Cout] fp32 or NULL; y NHWC fp32.
+GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
+                                      const float* bias, const float* residual, float* y, int B, int H, int W, int Cin, int Cout,
+                                      int ksize, long long ldy, long long w_batch_stride, cudaStream_t stream);
+
 GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                                    const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                                    cudaStream_t stream) {
+    return glare_conv2d_nhwc_tc_ex(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, Cin, Cout, ksize, Cout, 0, stream);
+}
+
+// Extended form: ldy = output pixel stride in elements (>= Cout, multiple of 4); w_batch_stride != 0 selects per-sample
+// weights w[n] = w + n * w_batch_stride elements (the two attention GEMMs: S = Q K^T with W = K[n], O = P V with
+// W = V[n]^T -- encoder_decoder.py:176-187).  residual must be null when ldy != Cout.
+GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
+                                      const float* bias, const float* residual, float* y, int B, int H, int W, int Cin, int Cout,
+                                      int ksize, long long ldy, long long w_batch_stride, cudaStream_t stream) {
+    if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
     if (mode < 0 || mode > 2 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
     if (!x || !w || !y || (mode == 2 && (!x_lo || !w_lo))) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
-    if (Cin % bke != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
+    if (Cin % bke != 0 || (Cout % 4 != 0 && ldy == Cout)) return GLARE_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return GLARE_ERR_BAD_ARG;
     ConvTcArgs a{};
     a.bias = bias; a.residual = residual; a.y = y;
@@ -379,15 +395,18 @@ GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, co
     const long long total = (long long)a.n_blocks * B * a.tiles_y * a.tiles_x;
     if (total > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
     a.total_tiles = (int)total;
+    a.ldy = ldy;
+    a.w_batched = w_batch_stride != 0 ? 1 : 0;
+    const int n_w = a.w_batched ? B : 1;
     CUtensorMap tA, tAl, tB, tBl;
     int rc;
     const bool bf = mode == 0;
     if ((rc = make_act_map(&tA, x, bf, B, H, W, Cin, a.TH, a.TW)) != GLARE_OK) return rc;
-    if ((rc = make_w_map(&tB, w, bf, Cout, ksize * ksize * Cin, BN)) != GLARE_OK) return rc;
+    if ((rc = make_w_map(&tB, w, bf, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
     tAl = tA; tBl = tB;
     if (mode == 2) {
         if ((rc = make_act_map(&tAl, x_lo, false, B, H, W, Cin, a.TH, a.TW)) != GLARE_OK) return rc;
-        if ((rc = make_w_map(&tBl, w_lo, false, Cout, ksize * ksize * Cin, BN)) != GLARE_OK) return rc;
+        if ((rc = make_w_map(&tBl, w_lo, false, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
     }
 #define GLARE_CONV_DISPATCH(M)                                                            \
     do {                                                                                  \

@@ -41,6 +41,23 @@ class _TorchBackend(TorchDense):
                 "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None, "ms_per_step": tot_ms, "peak_source": pk["src"]}
 
 
+class _Bracket:
+    """CUDA-event bracket (current stream) recorded into a timers dict: name -> [(e0, e1, algorithmic_flops)]"""
+
+    def __init__(self, timers, name, flops=0.0):
+        self.timers, self.name, self.flops = timers, name, flops
+
+    def __enter__(self):
+        if self.timers is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.timers is not None:
+            self.e1.record()
+            self.timers.setdefault(self.name, []).append((self.e0, self.e1, self.flops))
+
+
 class Operand:
     """Tensor-core operand of a conv: NHWC ``hi`` (+ ``lo`` for the 3xTF32 split) of a logical [B,C,H,W] activation."""
 
@@ -79,8 +96,13 @@ class TcDense:
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
+        self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
+        self.attn_band_rows = 8        # query rows (image rows) per band; multiple of the 8x16 pixel tile
         self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
         self.last_timers, self.last_steps = None, 1
+
+    def _t(self, name, flops=0.0):
+        return _Bracket(self.timers, name, flops)
 
     def _weights(self, w):
         key = (w.data_ptr(), tuple(w.shape))
@@ -98,26 +120,23 @@ class TcDense:
         if not self._supported(Cin, w, stride, padding):
             key = "conv %dx%d %d->%d s%d" % (w.shape[2], w.shape[3], Cin, w.shape[0], stride)
             self.fallbacks[key] = self.fallbacks.get(key, 0) + 1
-            xd = x.dense() if isinstance(x, Operand) else x
-            y = self.lib.conv2d(xd.contiguous(memory_format=torch.channels_last), w, b, stride=stride, padding=padding)
-            return y if residual is None else y + residual
+            with self._t("conv_library_fallback"):
+                xd = x.dense() if isinstance(x, Operand) else x
+                y = self.lib.conv2d(xd.contiguous(memory_format=torch.channels_last), w, b, stride=stride, padding=padding)
+                return y if residual is None else y + residual
         if isinstance(x, Operand):
             op = x
         else:
-            xn = _nhwc(x)
-            B, H, W, C = xn.shape
-            hi, lo = self.ops.conv_prep_act(self.mode, xn)
-            op = Operand(self.mode, hi, lo, B, C, H, W)
+            with self._t("prep_act"):
+                xn = _nhwc(x)
+                B, H, W, C = xn.shape
+                hi, lo = self.ops.conv_prep_act(self.mode, xn)
+                op = Operand(self.mode, hi, lo, B, C, H, W)
         w_hi, w_lo = self._weights(w)
         res = _nhwc(residual) if residual is not None else None
         Cout, ks = w.shape[0], w.shape[2]
-        if self.timers is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        y = self.ops.conv2d_nhwc_tc(self.mode, op.hi, op.lo, w_hi, w_lo, b, res, op.B, op.H, op.W, op.C, Cout, ks)
-        if self.timers is not None:
-            e1.record()
-            self.timers.setdefault("conv_tc", []).append((e0, e1, 2.0 * op.B * op.H * op.W * op.C * Cout * ks * ks))
+        with self._t("conv_tc", 2.0 * op.B * op.H * op.W * op.C * Cout * ks * ks):
+            y = self.ops.conv2d_nhwc_tc(self.mode, op.hi, op.lo, w_hi, w_lo, b, res, op.B, op.H, op.W, op.C, Cout, ks)
         return y.permute(0, 3, 1, 2)
 
     def gn_swish(self, x, gamma, beta, swish=True):
@@ -125,15 +144,57 @@ class TcDense:
         if C % 128 != 0:
             self.fallbacks["groupnorm C=%d" % C] = self.fallbacks.get("groupnorm C=%d" % C, 0) + 1
             return self.lib.gn_swish(x, gamma, beta, swish)
-        xn = _nhwc(x)
-        B, H, W, _ = xn.shape
-        stats = self.ops.gn_stats(xn, B, H * W, C)
-        hi, lo = self.ops.gn_apply(self.mode, xn, stats, gamma, beta, swish, B, H * W, C)
+        with self._t("groupnorm"):
+            xn = _nhwc(x)
+            B, H, W, _ = xn.shape
+            stats = self.ops.gn_stats(xn, B, H * W, C)
+            hi, lo = self.ops.gn_apply(self.mode, xn, stats, gamma, beta, swish, B, H * W, C)
         return Operand(self.mode, hi, lo, B, C, H, W)
 
     def attention(self, q, k, v):
-        self.fallbacks["attention bmm+softmax (library)"] = self.fallbacks.get("attention bmm+softmax (library)", 0) + 1
-        return self.lib.attention(q, k, v)
+        """AttnBlock core (encoder_decoder.py:176-187) on the tcgen05 GEMM path: per sample and per band of query rows
+        S = Q K^T (W = K[n]) -> fused scale + row softmax emitting the operand P -> O = P V (W = V[n]^T)."""
+        C = q.shape[1]
+        if self.attn_impl == "library" or C % self.bke != 0:
+            self.fallbacks["attention bmm+softmax (library)"] = self.fallbacks.get("attention bmm+softmax (library)", 0) + 1
+            with self._t("attention"):
+                return self.lib.attention(q, k, v)
+        ops = self.ops
+        with self._t("attention"):
+            qn, kn, vn = _nhwc(q), _nhwc(k), _nhwc(v)
+            B, h, w, _ = qn.shape
+            N = h * w
+            Np = (N + 63) // 64 * 64
+            q_hi, q_lo = ops.conv_prep_act(self.mode, qn)
+            k_hi, k_lo = ops.conv_prep_act(self.mode, kn)                 # K[n] as GEMM weights [N][C]
+            vt_hi, vt_lo = ops.attn_transpose_v(self.mode, vn, B, N, C, Np)
+            out = torch.empty((B, h, w, C), device=q.device, dtype=torch.float32)
+            band = self.attn_band_rows
+            rows_max = min(band, h) * w
+            S = torch.empty((rows_max, Np), device=q.device, dtype=torch.float32)
+            p_hi = torch.empty((rows_max, Np), device=q.device, dtype=q_hi.dtype)
+            p_lo = torch.empty_like(p_hi) if self.mode == 2 else None
+            scale = float(int(C) ** (-0.5))
+            for b in range(B):
+                for r0 in range(0, h, band):
+                    r1 = min(h, r0 + band)
+                    bh = r1 - r0
+                    ops.conv2d_nhwc_tc_ex(self.mode, q_hi[b, r0:r1], None if q_lo is None else q_lo[b, r0:r1], k_hi[b],
+                                          None if k_lo is None else k_lo[b], S, 1, bh, w, C, N, Np, 0)
+                    ops.attn_softmax_rows(self.mode, S, bh * w, Np, N, Np, scale, p_hi, p_lo, Np)
+                    ops.conv2d_nhwc_tc_ex(self.mode, p_hi, p_lo, vt_hi[b], None if vt_lo is None else vt_lo[b], out[b, r0:r1],
+                                          1, bh, w, Np, C, C, 0)
+            if self.timers is not None:
+                self.timers.setdefault("attention_flops", []).append((None, None, 4.0 * B * N * N * C))
+        return out.permute(0, 3, 1, 2)
+
+    def breakdown(self, eng_timers, steps):
+        out = {}
+        for src in (self.last_timers or {}, eng_timers or {}):
+            for k, ev in src.items():
+                if ev and ev[0][0] is not None:
+                    out[k] = round(sum(e[0].elapsed_time(e[1]) for e in ev) / max(1, steps), 2)
+        return out
 
     def roofline(self, timers, eng, B, lr_shape, pk):
         """Dominant kernel: conv_tc_kernel (all tensor-core conv launches of one step).  Algorithmic work =
@@ -153,6 +214,11 @@ class TcDense:
 
 
 def make_dense(name="auto"):
+    if name.endswith("+libattn"):
+        d = make_dense(name[:-len("+libattn")])
+        d.attn_impl = "library"
+        d.name += "+library-attention"
+        return d
     if name in ("auto", "tc-3xtf32"):
         return TcDense(2)
     if name == "tc-tf32":

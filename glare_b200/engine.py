@@ -221,7 +221,8 @@ class GlareEngine:
 
     # ------------------------------------------------------------------ stages
     def flow_decode(self, z, ft, trace=None):
-        return flowmod.decode(self.flow_plan, z, ft, lambda x, w: self.dense.conv2d(x, w).float(), trace=trace)[0]
+        with self._timed("flow_total"):
+            return flowmod.decode(self.flow_plan, z, ft, lambda x, w: self.dense.conv2d(x, w).float(), trace=trace)[0]
 
     def flow_encode(self, gt, ft, logdet=None):
         return flowmod.encode(self.flow_plan, gt, ft, lambda x, w: self.dense.conv2d(x, w).float(), logdet=logdet)

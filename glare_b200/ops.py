@@ -136,6 +136,29 @@ def conv2d_nhwc_tc(mode, x_hi, x_lo, w_hi, w_lo, bias, residual, B, H, W, Cin, C
     return y
 
 
+def conv2d_nhwc_tc_ex(mode, x_hi, x_lo, w_hi, w_lo, y, B, H, W, Cin, Cout, ldy, w_batch_stride):
+    """1x1 GEMM form with an output pixel stride and per-sample weights (attention); writes into ``y``"""
+    require_cuda(x_hi, x_lo, w_hi, w_lo, y)
+    check(lib().glare_conv2d_nhwc_tc_ex(mode, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), None, None, ptr(y), B, H, W, Cin, Cout, 1,
+                                        ldy, w_batch_stride, stream()), "glare_conv2d_nhwc_tc_ex")
+    return y
+
+
+def attn_softmax_rows(mode, S, rows, lds, n_keys, n_pad, scale, out_hi, out_lo, ldp):
+    require_cuda(S, out_hi, out_lo)
+    check(lib().glare_attn_softmax_rows(mode, ptr(S), rows, lds, n_keys, n_pad, scale, ptr(out_hi), ptr(out_lo), ldp, stream()),
+          "glare_attn_softmax_rows")
+
+
+def attn_transpose_v(mode, v_nhwc, B, N, C, Np):
+    require_cuda(v_nhwc)
+    dt = torch.bfloat16 if mode == MODE_BF16 else torch.float32
+    hi = torch.empty((B, C, Np), device=v_nhwc.device, dtype=dt)
+    lo = torch.empty_like(hi) if mode == MODE_TF32X3 else None
+    check(lib().glare_attn_transpose_v(mode, ptr(v_nhwc), B, N, C, Np, ptr(hi), ptr(lo), stream()), "glare_attn_transpose_v")
+    return hi, lo
+
+
 def gn_stats(x_nhwc, B, HW, C, G=32):
     require_cuda(x_nhwc)
     stats = torch.empty((B, G, 2), device=x_nhwc.device, dtype=torch.float64)

@@ -118,6 +118,23 @@ int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* 
                          const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                          cudaStream_t stream);
 
+/* extended form: ldy = output pixel stride (elements, >= Cout, % 4 == 0); w_batch_stride != 0 -> per-sample weights
+ * w + n * w_batch_stride (the attention GEMMs S = Q K^T and O = P V, encoder_decoder.py:176-187) */
+int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                            const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize, long long ldy,
+                            long long w_batch_stride, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (4b) AttnBlock core -- encoder_decoder.py:176-187: softmax(q^T k * C^-0.5) and h = v w^T around the two GEMMs above.
+ * ---------------------------------------------------------------------------------------------------- */
+/* S [rows][lds] fp32 logits -> P [rows][ldp] = softmax(scale*S[:, :n_keys]) as operand (0 bf16 | 1 fp32 | 2 tf32 hi+lo),
+ * zero in [n_keys, n_pad) */
+int glare_attn_softmax_rows(int out_mode, const float* S, long long rows, long long lds, int n_keys, int n_pad, float scale,
+                            void* out_hi, void* out_lo, long long ldp, cudaStream_t stream);
+/* v NHWC [B][N][C] fp32 -> V^T [B][C][Np] operand(s) */
+int glare_attn_transpose_v(int out_mode, const float* v, int B, int N, int C, int Np, void* out_hi, void* out_lo,
+                           cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * (5) Normalize = GroupNorm(32, eps 1e-6) (+ swish) -- encoder_decoder.py:29-35 as used by ResnetBlock.forward
  *     (:117-137), AttnBlock.forward (:168-171) and the norm_out heads.  NHWC fp32 in; the apply pass emits the

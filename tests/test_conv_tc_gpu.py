@@ -87,3 +87,27 @@ def test_groupnorm_swish_operands(glare_lib, C, H, W, B, swish):
         assert err < tol * max(1.0, float(ref.abs().max())), (mode, err)
         if mode == 2:
             assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0      # hi is an exact tf32 value
+
+
+@pytest.mark.parametrize("mode,tol", [(2, 2e-5), (1, 3e-3), (0, 2e-2)])
+@pytest.mark.parametrize("shape", [(1, 512, 9, 14), (2, 512, 24, 21), (1, 512, 105, 155)])
+def test_attention_gemm_path(glare_lib, shape, mode, tol):
+    """AttnBlock core (encoder_decoder.py:176-187) through the tcgen05 GEMMs + fused softmax kernel vs an fp64 evaluation"""
+    from glare_b200.dense import TcDense
+    B, C, h, w = shape
+    g = torch.Generator().manual_seed(h * w)
+    q = torch.randn((B, C, h, w), generator=g).cuda()
+    k = torch.randn((B, C, h, w), generator=g).cuda()
+    v = torch.randn((B, C, h, w), generator=g).cuda()
+    d = TcDense(mode)
+    out = d.attention(q, k, v)
+    torch.cuda.synchronize()
+    N = h * w
+    ref = torch.empty((B, C, N), dtype=torch.float64, device="cuda")
+    for b in range(B):
+        qq, kk, vv = q[b].reshape(C, N).double(), k[b].reshape(C, N).double(), v[b].reshape(C, N).double()
+        for i0 in range(0, N, 4096):                         # query chunks: keep the fp64 score matrix small
+            s = torch.softmax(qq[:, i0:i0 + 4096].t() @ kk * (int(C) ** -0.5), dim=1)
+            ref[b, :, i0:i0 + 4096] = vv @ s.t()
+    err = float((out.reshape(B, C, N).double() - ref).abs().max())
+    assert err < tol * max(1.0, float(ref.abs().max())), (shape, mode, err)

@@ -390,9 +390,12 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
     a.TH = 8; a.TW = 16;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
     a.kchunks = Cin / bke;
-    const int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+    // N tile: as wide as Cout allows, narrowed while the launch would leave SMs without a tile (short-M GEMMs: O = P V)
+    int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+    const long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
+    while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
     a.n_blocks = (Cout + BN - 1) / BN;
-    const long long total = (long long)a.n_blocks * B * a.tiles_y * a.tiles_x;
+    const long long total = (long long)a.n_blocks * m_tiles;
     if (total > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
     a.total_tiles = (int)total;
     a.ldy = ldy;

@@ -1,0 +1,352 @@
+// DCNv2Pack.forward tail on tensor cores: chunk/cat/sigmoid of the conv_offset output + modulated deformable 3x3 conv.
+//
+// Replaces reference deformableDecoder_arch.py:141-152 (o1,o2,mask = chunk(conv_offset(feat)); offset = cat(o1,o2);
+// mask = sigmoid(mask); modulated_deform_conv(...)) and ops/dcn/src/deform_conv_cuda.cpp:490-569 +
+// deform_conv_cuda_kernel.cu:467-497,571-633 for the configuration GLARE uses: 3x3, stride 1, pad 1, dilation 1,
+// groups 1, deformable_groups dg (4).  The general fp32 operator stays in dcn.cu.
+//
+//   y[n,h,w,co] = bias[co] + sum_{g,t,c in g} W[co,c,t] * sigmoid(m[g,t]) * bilinear(x[n,:,:,c], (h,w) - 1 + t + off[g,t])
+//
+// Same persistent tcgen05 implicit-GEMM skeleton as conv_tc.cu (M = 8x16 pixel tile, N = BN output channels, TMEM
+// double-buffered accumulator, TMA for the weight operand), but the A operand is PRODUCED in shared memory by four
+// sampler warps instead of loaded by TMA: per (group, tap, 128-byte channel chunk) each 8-lane group gathers the four
+// bilinear corners of one pixel as whole 128-byte NHWC channel lines (L1-cached, coalesced), blends them with the
+// corner weights x mask (geometry computed once per (pixel, group, tap) for all channels of the chunk), and stores the
+// operand row in the SWIZZLE_128B pattern the UMMA descriptor expects (16-byte chunk j of row r lives at chunk
+// j ^ (r & 7)); fence.proxy.async + mbarrier publish the stage to the MMA thread.  No `columns` buffer, no separate
+// offset/mask tensors; the 3xTF32 hi/lo split is taken directly from the fp32 sample.
+// Layouts: x NHWC fp32 [B,H,W,C]; om = raw conv_offset output NHWC fp32 [B,H,W,3*dg*9] (channels [0,18dg) offsets in the
+// reference's (g, tap, {dh,dw}) order, [18dg,27dg) mask logits); weights packed [Cout][9][C] (glare_conv_pack_weight).
+#include <cuda.h>
+
+#include "tc.cuh"
+
+namespace glare {
+
+constexpr int DT_THREADS = 320;           // warp 0 TMA(weights), 1 MMA, 2-5 epilogue, 6-9 samplers
+constexpr int DT_A_BYTES = 128 * 128;
+
+struct DcnTcArgs {
+    const float* x;
+    const float* om;
+    const float* bias;
+    float* y;
+    int B, H, W, C, Cout, dg, cpg, TH, TW, tiles_x, tiles_y, n_blocks, kchunks_per_tap;   // kchunks_per_tap = chunks per (g, tap)
+    int total_tiles;
+};
+
+template <int MODE, int BN>
+struct DcnCfg {
+    static constexpr bool X3 = MODE == 2;
+    static constexpr bool TF32 = MODE >= 1;
+    static constexpr int BKE = TF32 ? 32 : 64;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = (DT_A_BYTES + B_BYTES) * (X3 ? 2 : 1);
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+    static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;
+};
+
+__device__ __forceinline__ float tf32_hi_d(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(DT_THREADS, 1)
+dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const DcnTcArgs a) {
+    using Cfg = DcnCfg<MODE, BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* const smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmB);
+        if (Cfg::X3) tma_prefetch_desc(&tmBlo);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1 + 128);          // weight TMA (expect_tx) + 128 sampler threads
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar[0], 1);
+        mbar_init(&tmem_full_bar[1], 1);
+        mbar_init(&tmem_empty_bar[0], 128);
+        mbar_init(&tmem_empty_bar[1], 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&s_tmem_base, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+    const int k_iters = a.dg * 9 * a.kchunks_per_tap;
+    const int tiles_xy = a.tiles_y * a.tiles_x;
+
+    if (warp == 0) {
+        // ===================== weight TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int nb = tile % a.n_blocks;
+                for (int g = 0; g < a.dg; ++g)
+                    for (int tap = 0; tap < 9; ++tap)
+                        for (int kc = 0; kc < a.kchunks_per_tap; ++kc, ++it) {
+                            const int s = it % STAGES;
+                            const uint32_t ph = (it / STAGES) & 1;
+                            mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                            uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                            const int kcoord = tap * a.C + g * a.cpg + kc * Cfg::BKE;
+                            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * (Cfg::X3 ? 2 : 1));
+                            tma_load_3d(st + DT_A_BYTES, &tmB, &full_bar[s], kcoord, nb * BN, 0);
+                            if (Cfg::X3) tma_load_3d(st + 2 * DT_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], kcoord, nb * BN, 0);
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(Cfg::TF32 ? 2 : 1, 128, BN);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait_bounded(&tmem_empty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int ki = 0; ki < k_iters; ++ki, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait_bounded(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)s * Cfg::STAGE_BYTES;
+                    const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + DT_A_BYTES);
+                    const uint64_t dal = umma_desc_sw128(sa + DT_A_BYTES + Cfg::B_BYTES);
+                    const uint64_t dbl = umma_desc_sw128(sa + 2 * DT_A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t adv = (uint64_t)(j * 2);
+                        umma_ss<Cfg::TF32>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
+                        if (Cfg::X3) {
+                            umma_ss<true>(d_tmem, dal + adv, db + adv, idesc, 1u);
+                            umma_ss<true>(d_tmem, da + adv, dbl + adv, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int py = m / a.TW, px = m - py * a.TW;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+            const int nb = tile % a.n_blocks;
+            int r = tile / a.n_blocks;
+            const int n = r / tiles_xy;
+            r -= n * tiles_xy;
+            const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+            const int gy = ty * a.TH + py, gx = tx * a.TW + px;
+            const bool valid = gy < a.H && gx < a.W;
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait_bounded(&tmem_full_bar[as], aph);
+            tc_fence_after();
+            float* yrow = a.y + (((long long)n * a.H + gy) * a.W + gx) * a.Cout;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c0, v);
+                tmem_ld_wait();
+                const int co = nb * BN + c0;
+                if (valid && co < a.Cout) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (co + j + 4 <= a.Cout) {
+                            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                   __uint_as_float(v[j + 3]));
+                            if (a.bias) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            }
+                            *reinterpret_cast<float4*>(yrow + co + j) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[as]);
+        }
+    } else {
+        // ===================== samplers: produce the A operand =====================
+        const int sw = warp - 6;                       // 0..3: rows [32 sw, 32 sw + 32) of the tile
+        const int sub = lane >> 3, j = lane & 7;       // 4 pixels per step, 8 lanes x 16 bytes per operand row
+        constexpr int CPL = Cfg::TF32 ? 4 : 8;         // channels per lane per stage
+        const int om_c = 27 * a.dg;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            int r = tile / a.n_blocks;
+            const int n = r / tiles_xy;
+            r -= n * tiles_xy;
+            const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+            const float* xn = a.x + (long long)n * a.H * a.W * a.C;
+            for (int g = 0; g < a.dg; ++g)
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ti = tap / 3, tj = tap - ti * 3;
+                    for (int kc = 0; kc < a.kchunks_per_tap; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                        uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                        const int cbase = g * a.cpg + kc * Cfg::BKE + j * CPL;
+#pragma unroll 2
+                        for (int step = 0; step < 8; ++step) {
+                            const int m = sw * 32 + step * 4 + sub;
+                            const int py = m / a.TW, px = m - py * a.TW;
+                            const int gy = ty * a.TH + py, gx = tx * a.TW + px;
+                            float acc[CPL];
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+                            if (gy < a.H && gx < a.W) {
+                                const float* omp = a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c;
+                                const float oh = __ldg(omp + g * 18 + 2 * tap), ow = __ldg(omp + g * 18 + 2 * tap + 1);
+                                const float mk = 1.0f / (1.0f + expf(-__ldg(omp + 18 * a.dg + g * 9 + tap)));
+                                const float h_im = (float)(gy - 1 + ti) + oh, w_im = (float)(gx - 1 + tj) + ow;   // .cu:607-612
+                                if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {            // .cu:618
+                                    const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
+                                    const int hh = hl + 1, wh = wl + 1;
+                                    const float lh = h_im - hl, lw = w_im - wl, uh = 1.f - lh, uw = 1.f - lw;
+                                    const float cw[4] = {uh * uw * mk, uh * lw * mk, lh * uw * mk, lh * lw * mk};
+                                    const bool ok[4] = {hl >= 0 && wl >= 0, hl >= 0 && wh <= a.W - 1, hh <= a.H - 1 && wl >= 0,
+                                                        hh <= a.H - 1 && wh <= a.W - 1};
+                                    const int cy[4] = {hl, hl, hh, hh}, cx[4] = {wl, wh, wl, wh};
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        if (ok[k]) {
+                                            const float4* p = reinterpret_cast<const float4*>(xn + ((long long)cy[k] * a.W + cx[k]) * a.C + cbase);
+#pragma unroll
+                                            for (int v4 = 0; v4 < CPL / 4; ++v4) {
+                                                const float4 xv = __ldg(p + v4);
+                                                acc[4 * v4 + 0] = fmaf(cw[k], xv.x, acc[4 * v4 + 0]);
+                                                acc[4 * v4 + 1] = fmaf(cw[k], xv.y, acc[4 * v4 + 1]);
+                                                acc[4 * v4 + 2] = fmaf(cw[k], xv.z, acc[4 * v4 + 2]);
+                                                acc[4 * v4 + 3] = fmaf(cw[k], xv.w, acc[4 * v4 + 3]);
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            const uint32_t off = (uint32_t)m * 128u + (uint32_t)((j ^ (m & 7)) << 4);     // SWIZZLE_128B
+                            if (!Cfg::TF32) {
+                                __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[0], acc[1]), b1 = __floats2bfloat162_rn(acc[2], acc[3]);
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[CPL - 4], acc[CPL - 3]),
+                                               b3 = __floats2bfloat162_rn(acc[CPL - 2], acc[CPL - 1]);
+                                uint4 u;
+                                u.x = *reinterpret_cast<uint32_t*>(&b0); u.y = *reinterpret_cast<uint32_t*>(&b1);
+                                u.z = *reinterpret_cast<uint32_t*>(&b2); u.w = *reinterpret_cast<uint32_t*>(&b3);
+                                *reinterpret_cast<uint4*>(st + off) = u;
+                            } else if (!Cfg::X3) {
+                                *reinterpret_cast<float4*>(st + off) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                            } else {
+                                const float4 h = make_float4(tf32_hi_d(acc[0]), tf32_hi_d(acc[1]), tf32_hi_d(acc[2]), tf32_hi_d(acc[3]));
+                                *reinterpret_cast<float4*>(st + off) = h;
+                                *reinterpret_cast<float4*>(st + DT_A_BYTES + Cfg::B_BYTES + off) =
+                                    make_float4(acc[0] - h.x, acc[1] - h.y, acc[2] - h.z, acc[3] - h.w);
+                            }
+                        }
+                        fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                        mbar_arrive(&full_bar[s]);
+                    }
+                }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+typedef CUresult (*EncodeTiledFnD)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_w_map_d(CUtensorMap* m, const void* ptr, bool bf16, int Cout, int K, int BN) {
+    static EncodeTiledFnD enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return GLARE_ERR_UNSUPPORTED;
+        enc = reinterpret_cast<EncodeTiledFnD>(p);
+    }
+    const cuuint64_t es = bf16 ? 2 : 4;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)K * Cout * es};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
+}
+
+template <int MODE, int BN>
+static int launch_dcn_tc(const CUtensorMap& tB, const CUtensorMap& tBl, const DcnTcArgs& a, cudaStream_t stream) {
+    using Cfg = DcnCfg<MODE, BN>;
+    static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
+    GLARE_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
+    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+    dcn_tc_kernel<MODE, BN><<<grid, DT_THREADS, Cfg::SMEM_DYN, stream>>>(tB, tBl, a);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+}  // namespace glare
+
+using namespace glare;
+
+// x NHWC fp32 [B,H,W,C]; offmask = raw conv_offset output NHWC fp32 [B,H,W,27*dg]; w / w_lo packed by
+// glare_conv_pack_weight(mode, weight[Cout,C,3,3]); y NHWC fp32 [B,H,W,Cout].  3x3, stride 1, pad 1, dilation 1, groups 1.
+GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float* offmask, const void* w, const void* w_lo,
+                                           const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout,
+                                           int deformable_groups, cudaStream_t stream) {
+    if (mode < 0 || mode > 2 || B < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || deformable_groups <= 0) return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!x || !offmask || !w || !y || (mode == 2 && !w_lo)) return GLARE_ERR_BAD_ARG;
+    const int bke = mode == 0 ? 64 : 32;
+    if (C % deformable_groups != 0 || (C / deformable_groups) % bke != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
+    DcnTcArgs a{};
+    a.x = x; a.om = offmask; a.bias = bias_or_null; a.y = y;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.dg = deformable_groups; a.cpg = C / deformable_groups;
+    a.TH = 8; a.TW = 16;
+    a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
+    a.kchunks_per_tap = a.cpg / bke;
+    int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+    const long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
+    while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
+    a.n_blocks = (Cout + BN - 1) / BN;
+    const long long total = m_tiles * a.n_blocks;
+    if (total > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
+    a.total_tiles = (int)total;
+    CUtensorMap tB, tBl;
+    int rc;
+    if ((rc = make_w_map_d(&tB, w, mode == 0, Cout, 9 * C, BN)) != GLARE_OK) return rc;
+    tBl = tB;
+    if (mode == 2 && (rc = make_w_map_d(&tBl, w_lo, false, Cout, 9 * C, BN)) != GLARE_OK) return rc;
+#define GLARE_DCN_DISPATCH(M)                                                 \
+    do {                                                                      \
+        if (BN == 256) return launch_dcn_tc<M, 256>(tB, tBl, a, stream);      \
+        if (BN == 128) return launch_dcn_tc<M, 128>(tB, tBl, a, stream);      \
+        return launch_dcn_tc<M, 64>(tB, tBl, a, stream);                      \
+    } while (0)
+    if (mode == 0) GLARE_DCN_DISPATCH(0);
+    if (mode == 1) GLARE_DCN_DISPATCH(1);
+    GLARE_DCN_DISPATCH(2);
+#undef GLARE_DCN_DISPATCH
+}

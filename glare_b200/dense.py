@@ -96,6 +96,7 @@ class TcDense:
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
+        self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
         self.attn_band_rows = 8        # query rows (image rows) per band; multiple of the 8x16 pixel tile
         self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
@@ -150,6 +151,19 @@ class TcDense:
             stats = self.ops.gn_stats(xn, B, H * W, C)
             hi, lo = self.ops.gn_apply(self.mode, xn, stats, gamma, beta, swish, B, H * W, C)
         return Operand(self.mode, hi, lo, B, C, H, W)
+
+    def dcn_pack(self, x, offmask_raw, weight, bias, dg):
+        """DCNv2Pack.forward after conv_offset (deformableDecoder_arch.py:141-152): x [B,C,H,W], raw conv_offset output
+        [B,27*dg,H,W] -> y [B,Cout,H,W].  None when the shape is outside the tensor-core kernel's coverage."""
+        C, Cout = x.shape[1], weight.shape[0]
+        if tuple(weight.shape[2:]) != (3, 3) or C % dg or (C // dg) % self.bke or Cout % 4 or not self.dcn_tc:
+            return None
+        with self._t("dcn_tc", 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * C * Cout * 9):
+            xn, on = _nhwc(x), _nhwc(offmask_raw)
+            B, H, W, _ = xn.shape
+            w_hi, w_lo = self._weights(weight)
+            y = self.ops.dcnv2_pack_fwd_nhwc_tc(self.mode, xn, on, w_hi, w_lo, bias, B, H, W, C, Cout, dg)
+        return y.permute(0, 3, 1, 2)
 
     def attention(self, q, k, v):
         """AttnBlock core (encoder_decoder.py:176-187) on the tcgen05 GEMM path: per sample and per band of query rows

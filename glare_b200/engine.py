@@ -187,6 +187,10 @@ class GlareEngine:
         sd, p = self.g, "deformable_decoder.warp.%d" % i
         feat = self._conv(sd, p + ".offset", torch.cat([x_vq, h], dim=1))
         out = self._conv(sd, p + ".dcn.conv_offset", feat).float()
+        if hasattr(self.dense, "dcn_pack"):
+            y = self.dense.dcn_pack(x_vq.float(), out, sd[p + ".dcn.weight"], sd[p + ".dcn.bias"], 4)
+            if y is not None:
+                return y
         o1, o2, m = torch.chunk(out, 3, dim=1)
         offset = torch.cat((o1, o2), dim=1)
         mask = torch.sigmoid(m)

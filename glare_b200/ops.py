@@ -136,6 +136,15 @@ def conv2d_nhwc_tc(mode, x_hi, x_lo, w_hi, w_lo, bias, residual, B, H, W, Cin, C
     return y
 
 
+def dcnv2_pack_fwd_nhwc_tc(mode, x_nhwc, offmask_nhwc, w_hi, w_lo, bias, B, H, W, C, Cout, dg):
+    """DCNv2Pack tail (deformableDecoder_arch.py:141-152) on tensor cores; returns y NHWC [B,H,W,Cout] fp32"""
+    require_cuda(x_nhwc, offmask_nhwc, w_hi, w_lo, bias)
+    y = torch.empty((B, H, W, Cout), device=x_nhwc.device, dtype=torch.float32)
+    check(lib().glare_dcnv2_pack_fwd_nhwc_tc(mode, ptr(x_nhwc), ptr(offmask_nhwc), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(y), B, H, W, C,
+                                             Cout, dg, stream()), "glare_dcnv2_pack_fwd_nhwc_tc")
+    return y
+
+
 def conv2d_nhwc_tc_ex(mode, x_hi, x_lo, w_hi, w_lo, y, B, H, W, Cin, Cout, ldy, w_batch_stride):
     """1x1 GEMM form with an output pixel stride and per-sample weights (attention); writes into ``y``"""
     require_cuda(x_hi, x_lo, w_hi, w_lo, y)

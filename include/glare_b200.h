@@ -100,6 +100,13 @@ int glare_dcnv2_fwd_f32(const float* x, const float* offset, const float* mask, 
                         const float* bias_or_null, int B, int C, int H, int W, int Cout, int kh, int kw, int stride,
                         int pad, int dil, int deformable_groups, float* y, cudaStream_t stream);
 
+/* DCNv2Pack.forward tail on tensor cores (deformableDecoder_arch.py:141-152): consumes the RAW conv_offset output
+ * (chunk / cat / sigmoid fused), x and offmask NHWC fp32, weights packed by glare_conv_pack_weight, y NHWC fp32.
+ * 3x3, stride 1, pad 1, dilation 1, groups 1; (C / deformable_groups) % 64 == 0 (mode 0) or % 32 == 0 (modes 1, 2). */
+int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float* offmask, const void* w, const void* w_lo,
+                                 const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout,
+                                 int deformable_groups, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * (4) Dense convolutions on tcgen05 tensor cores -- the cuDNN calls behind nn.Conv2d in ResnetBlock
  *     (encoder_decoder.py:88-115), Upsample.conv (:38-53), AttnBlock q/k/v/proj_out (:146-165), nin_shortcut,

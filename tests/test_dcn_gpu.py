@@ -95,3 +95,30 @@ def test_bad_shapes_raise(glare_lib):
     with pytest.raises(ValueError):
         ops.modulated_deform_conv(x, torch.zeros((1, 10, 4, 4), device="cuda"), torch.zeros((1, 36, 4, 4), device="cuda"),
                                   torch.zeros((8, 8, 3, 3), device="cuda"), None, 1, 1, 1, 1, 4)
+
+
+@pytest.mark.parametrize("mode,tol", [(2, 5e-5), (1, 5e-3), (0, 3e-2)])
+@pytest.mark.parametrize("cfg", [(1, 128, 128, 8, 16), (2, 128, 128, 19, 27), (1, 256, 256, 33, 41), (1, 128, 128, 105, 155)])
+def test_tensor_core_dcn_pack_against_fp32_kernel(glare_lib, cfg, mode, tol):
+    """dcn_tc.cu (sampled A operand + tcgen05) vs the fp32 FMA kernel (itself checked against the oracle above),
+    from the RAW conv_offset output: chunk / cat / sigmoid fused (deformableDecoder_arch.py:141-152)"""
+    from glare_b200 import ops
+    from glare_b200.dense import TcDense
+    B, C, Co, H, W = cfg
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn((B, C, H, W), generator=g).cuda()
+    raw = torch.randn((B, 108, H, W), generator=g)
+    raw[:, :72] *= 3.0
+    raw[0, :72, 0, 0] = 500.0                      # far outside
+    raw[0, 0:72:2, H - 1, W - 1] = -0.75           # straddles the border
+    raw = raw.cuda()
+    w = (torch.randn((Co, C, 3, 3), generator=g) / (3.0 * C ** 0.5)).cuda()
+    b = torch.randn((Co,), generator=g).cuda()
+    o1, o2, m = torch.chunk(raw, 3, dim=1)
+    ref = ops.modulated_deform_conv(x, torch.cat((o1, o2), 1), torch.sigmoid(m), w, b, 1, 1, 1, 1, 4)
+    d = TcDense(mode)
+    y = d.dcn_pack(x.contiguous(memory_format=torch.channels_last), raw.contiguous(memory_format=torch.channels_last), w, b, 4)
+    torch.cuda.synchronize()
+    assert y is not None
+    err = float((y - ref).abs().max())
+    assert err < tol * max(1.0, float(ref.abs().max())), (cfg, mode, err)

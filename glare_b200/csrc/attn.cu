@@ -88,6 +88,86 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(const float* __r
     }
 }
 
+// Same contract, one pass over S: the row (<= 256 threads x 64 values) lives in registers between the max, the
+// exponentials (evaluated once) and the normalised operand write.
+template <int OUT>
+__global__ void __launch_bounds__(256) attn_softmax_rows_reg_kernel(const float* __restrict__ S, long long lds, int n_keys,
+                                                                    int n_pad, float scale, void* __restrict__ out_hi,
+                                                                    float* __restrict__ out_lo, long long ldp) {
+    __shared__ float s_red[8];
+    __shared__ float s_bcast;
+    const long long row = blockIdx.x;
+    const float4* s4 = reinterpret_cast<const float4*>(S + row * lds);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4 v[16];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = (tid + 256 * i) * 4;
+        float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (e < n_keys) {
+            t = __ldg(s4 + tid + 256 * i);                              // lds % 4 == 0, padded columns are readable
+            if (e + 1 >= n_keys) t.y = -INFINITY;
+            if (e + 2 >= n_keys) t.z = -INFINITY;
+            if (e + 3 >= n_keys) t.w = -INFINITY;
+        }
+        v[i] = t;
+        m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float t = s_red[0];
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, s_red[i]);
+        s_bcast = t * scale;
+    }
+    __syncthreads();
+    const float mx = s_bcast;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        v[i].x = expf(v[i].x * scale - mx);                             // exp(-inf) = 0 for masked / padded columns
+        v[i].y = expf(v[i].y * scale - mx);
+        v[i].z = expf(v[i].z * scale - mx);
+        v[i].w = expf(v[i].w * scale - mx);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_red[i];
+        s_bcast = 1.0f / t;
+    }
+    __syncthreads();
+    const float inv = s_bcast;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = (tid + 256 * i) * 4;
+        if (e >= n_pad) continue;
+        const float p0 = v[i].x * inv, p1 = v[i].y * inv, p2 = v[i].z * inv, p3 = v[i].w * inv;
+        const long long o = row * ldp + e;
+        if (OUT == 0) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(p0, p1), b = __floats2bfloat162_rn(p2, p3);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&a);
+            u.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + o) = u;
+        } else if (OUT == 1) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = make_float4(p0, p1, p2, p3);
+        } else {
+            const float4 h = make_float4(tf32_hi_a(p0), tf32_hi_a(p1), tf32_hi_a(p2), tf32_hi_a(p3));
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = h;
+            *reinterpret_cast<float4*>(out_lo + o) = make_float4(p0 - h.x, p1 - h.y, p2 - h.z, p3 - h.w);
+        }
+    }
+}
+
 // v [B][N][C] fp32 -> vt [B][C][Np] operand(s); 32x32 tiles through shared memory
 template <int OUT>
 __global__ void __launch_bounds__(256) attn_transpose_v_kernel(const float* __restrict__ v, int N, int C, int Np,
@@ -134,6 +214,13 @@ GLARE_API int glare_attn_softmax_rows(int out_mode, const float* S, long long ro
     if (rows == 0) return GLARE_OK;
     if (!S || !out_hi || (out_mode == 2 && !out_lo) || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
     float* lo = reinterpret_cast<float*>(out_lo);
+    if (n_pad <= 256 * 64) {                         // whole row in registers: one pass over S (N = 16 275 at 600x400)
+        if (out_mode == 0) attn_softmax_rows_reg_kernel<0><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+        else if (out_mode == 1) attn_softmax_rows_reg_kernel<1><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+        else attn_softmax_rows_reg_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+        GLARE_CHECK_LAUNCH();
+        return GLARE_OK;
+    }
     if (out_mode == 0) attn_softmax_rows_kernel<0><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
     else if (out_mode == 1) attn_softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
     else attn_softmax_rows_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);

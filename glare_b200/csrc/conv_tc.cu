@@ -22,6 +22,7 @@
 // operands, D += A_hi B_hi + A_lo B_hi + A_hi B_lo) which restores ~fp32 accuracy for the fp32 configuration.
 // Accumulation is fp32 in TMEM in every mode.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc.cuh"
 
@@ -38,6 +39,7 @@ struct ConvTcArgs {
     int total_tiles;
     int w_batched;           // weights differ per sample (3rd tensor-map coordinate = n): attention S = Q K^T, O = P V
     long long ldy;           // output row (pixel) stride in elements, >= Cout
+    int tma_store;           // epilogue: registers -> swizzled smem staging -> TMA tiled store (else per-thread float4 stores)
 };
 
 template <int MODE, int BN>
@@ -47,17 +49,19 @@ struct ConvCfg {
     static constexpr int BKE = TF32 ? 32 : 64;                 // elements per 128-byte K chunk
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = (CT_A_BYTES + B_BYTES) * (X3 ? 2 : 1);
-    static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 1024 /*static*/;
+    static constexpr int STAGING_BYTES = 2 * 128 * 128;        // epilogue staging: two 128-pixel x 32-fp32 chunks
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 1024 /*static*/ - STAGING_BYTES;
     static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BN;                   // 128 / 256 / 512: powers of two >= 32
-    static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;
+    static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
 };
 
 template <int MODE, int BN>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const ConvTcArgs a) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ CUtensorMap tmY, const ConvTcArgs a) {
     using Cfg = ConvCfg<MODE, BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_dyn[];
@@ -71,6 +75,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmY);
         if (Cfg::X3) {
             tma_prefetch_desc(&tmAlo);
             tma_prefetch_desc(&tmBlo);
@@ -159,11 +164,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue warps (TMEM -> registers -> NHWC global) =====================
+        // ===================== epilogue warps (TMEM -> registers -> [smem -> TMA store |] NHWC global) =====================
         const int q = warp & 3;                                          // TMEM lane quadrant this warp may access
         const int m = q * 32 + lane;                                     // accumulator row = pixel inside the tile
         const int py = m / a.TW, px = m - py * a.TW;
-        uint32_t tcount = 0;
+        const bool issuer = threadIdx.x == 64;                           // first epilogue thread issues the TMA stores
+        uint8_t* const staging = smem_al + (size_t)STAGES * Cfg::STAGE_BYTES;
+        uint32_t tcount = 0, chunk_id = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
             const int nb = tile % a.n_blocks;
             int r = tile / a.n_blocks;
@@ -177,48 +184,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const long long pix = ((long long)n * a.H + gy) * a.W + gx;
             float* yrow = a.y + pix * a.ldy;
-            const float* rrow = a.residual ? a.residual + pix * a.Cout : nullptr;
+            const float* rrow = (a.residual && valid) ? a.residual + pix * a.Cout : nullptr;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c0, v);
                 tmem_ld_wait();
+                if (c0 + 32 >= BN) {                                     // accumulator fully read: hand it back to the MMA thread
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty_bar[as]);
+                }
                 const int co = nb * BN + c0;
-                if (valid && co < a.Cout) {
-                    if (co + 32 <= a.Cout) {
+                if (co >= a.Cout) continue;                              // uniform over the CTA
+                float o[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o;
-                            o.x = __uint_as_float(v[j]);
-                            o.y = __uint_as_float(v[j + 1]);
-                            o.z = __uint_as_float(v[j + 2]);
-                            o.w = __uint_as_float(v[j + 3]);
-                            if (a.bias) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
-                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                            }
-                            if (rrow) {
-                                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + co + j));
-                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                            }
-                            *reinterpret_cast<float4*>(yrow + co + j) = o;
+                for (int j = 0; j < 32; j += 4) {
+                    o[j] = __uint_as_float(v[j]); o[j + 1] = __uint_as_float(v[j + 1]);
+                    o[j + 2] = __uint_as_float(v[j + 2]); o[j + 3] = __uint_as_float(v[j + 3]);
+                    if (co + j + 4 <= a.Cout) {
+                        if (a.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
+                            o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
                         }
-                    } else {
+                        if (rrow) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + co + j));
+                            o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+                        }
+                    }
+                }
+                if (a.tma_store) {
+                    uint8_t* buf = staging + (chunk_id & 1) * (128 * 128);
+                    named_bar_sync(1, 128);                              // issuer has seen the previous store of this buffer drain
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (co + j < a.Cout) {
-                                float o = __uint_as_float(v[j]);
-                                if (a.bias) o += __ldg(a.bias + co + j);
-                                if (rrow) o += __ldg(rrow + co + j);
-                                yrow[co + j] = o;
-                            }
+                    for (int j = 0; j < 8; ++j)                          // SWIZZLE_128B: 16-byte chunk j of row m at chunk j ^ (m & 7)
+                        *reinterpret_cast<float4*>(buf + m * 128 + ((j ^ (m & 7)) << 4)) =
+                            make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    fence_proxy_async();
+                    named_bar_sync(2, 128);
+                    if (issuer) {
+                        tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH, n);   // clips pixels / channels outside the tensor
+                        tma_store_commit();
+                        tma_store_wait_read<1>();                        // the other staging buffer is free again
+                    }
+                    ++chunk_id;
+                } else if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (co + j + 4 <= a.Cout) *reinterpret_cast<float4*>(yrow + co + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (co + j + e < a.Cout) yrow[co + j + e] = o[j + e];
                         }
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[as]);
         }
+        if (issuer) tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -317,14 +339,27 @@ static int make_w_map(CUtensorMap* m, const void* ptr, bool bf16, int Cout, int 
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
+static int make_out_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int Cout, long long ldy, int TH, int TW) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GLARE_ERR_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)W * ldy * 4, (cuuint64_t)H * W * ldy * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
+}
+
 template <int MODE, int BN>
 static int launch_conv(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
-                       const ConvTcArgs& a, cudaStream_t stream) {
+                       const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
     using Cfg = ConvCfg<MODE, BN>;
     static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
     GLARE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
     const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    conv_tc_kernel<MODE, BN><<<grid, CT_THREADS, Cfg::SMEM_DYN, stream>>>(tA, tAl, tB, tBl, a);
+    conv_tc_kernel<MODE, BN><<<grid, CT_THREADS, Cfg::SMEM_DYN, stream>>>(tA, tAl, tB, tBl, tY, a);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -401,8 +436,13 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
     a.ldy = ldy;
     a.w_batched = w_batch_stride != 0 ? 1 : 0;
     const int n_w = a.w_batched ? B : 1;
-    CUtensorMap tA, tAl, tB, tBl;
+    CUtensorMap tA, tAl, tB, tBl, tY;
     int rc;
+    {
+        static const bool direct = getenv("GLARE_CONV_DIRECT_STORE") != nullptr;   // A/B switch for profiling only
+        a.tma_store = (!direct && Cout >= 32) ? 1 : 0;
+    }
+    if ((rc = make_out_map(&tY, y, B, H, W, Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0;
     if ((rc = make_act_map(&tA, x, bf, B, H, W, Cin, a.TH, a.TW)) != GLARE_OK) return rc;
     if ((rc = make_w_map(&tB, w, bf, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
@@ -413,9 +453,9 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
     }
 #define GLARE_CONV_DISPATCH(M)                                                            \
     do {                                                                                  \
-        if (BN == 256) return launch_conv<M, 256>(tA, tAl, tB, tBl, a, stream);           \
-        if (BN == 128) return launch_conv<M, 128>(tA, tAl, tB, tBl, a, stream);           \
-        return launch_conv<M, 64>(tA, tAl, tB, tBl, a, stream);                           \
+        if (BN == 256) return launch_conv<M, 256>(tA, tAl, tB, tBl, tY, a, stream);       \
+        if (BN == 128) return launch_conv<M, 128>(tA, tAl, tB, tBl, tY, a, stream);       \
+        return launch_conv<M, 64>(tA, tAl, tB, tBl, tY, a, stream);                       \
     } while (0)
     if (mode == 0) GLARE_CONV_DISPATCH(0);
     if (mode == 1) GLARE_CONV_DISPATCH(1);

@@ -98,7 +98,7 @@ class TcDense:
         self.fallbacks = {}
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
-        self.attn_band_rows = 8        # query rows (image rows) per band; multiple of the 8x16 pixel tile
+        self.attn_s_budget = 3 << 29   # bytes of fp32 score matrix materialised per pass (1.5 GiB)
         self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
         self.last_timers, self.last_steps = None, 1
 
@@ -183,7 +183,9 @@ class TcDense:
             k_hi, k_lo = ops.conv_prep_act(self.mode, kn)                 # K[n] as GEMM weights [N][C]
             vt_hi, vt_lo = ops.attn_transpose_v(self.mode, vn, B, N, C, Np)
             out = torch.empty((B, h, w, C), device=q.device, dtype=torch.float32)
-            band = self.attn_band_rows
+            # query rows per pass: the whole sample when its score matrix fits the budget (tile-filling GEMMs matter more
+            # than L2 residency of S: the P V GEMM needs >= 74 M-tiles to give every SM a 128x256 tile), else 8-row multiples
+            band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
             rows_max = min(band, h) * w
             S = torch.empty((rows_max, Np), device=q.device, dtype=torch.float32)
             p_hi = torch.empty((rows_max, Np), device=q.device, dtype=q_hi.dtype)

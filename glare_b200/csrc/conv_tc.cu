@@ -35,7 +35,8 @@ struct ConvTcArgs {
     const float* bias;       // [Cout] or null
     const float* residual;   // NHWC [B,H,W,Cout] or null
     float* y;                // NHWC [B,H,W,Cout]
-    int B, H, W, Cin, Cout, ksize, pad, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;
+    int B, H, W, Cin, Cout, ksize, pad, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;   // H, W: OUTPUT size
+    int stride;              // 1, or 2 (Downsample: zero pad right/bottom, pad = 0; the TMA box walks the input with stride 2)
     int total_tiles;
     int w_batched;           // weights differ per sample (3rd tensor-map coordinate = n): attention S = Q K^T, O = P V
     long long ldy;           // output row (pixel) stride in elements, >= Cout
@@ -109,7 +110,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int n = r / (a.tiles_y * a.tiles_x);
                 r -= n * a.tiles_y * a.tiles_x;
                 const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-                const int y0 = ty * a.TH - a.pad, x0 = tx * a.TW - a.pad;
+                const int y0 = ty * a.TH * a.stride - a.pad, x0 = tx * a.TW * a.stride - a.pad;
                 for (int tap = 0; tap < a.ksize * a.ksize; ++tap) {
                     const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
                     for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
@@ -311,14 +312,15 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_act_map(CUtensorMap* m, const void* ptr, bool bf16, int B, int H, int W, int C, int TH, int TW) {
+static int make_act_map(CUtensorMap* m, const void* ptr, bool bf16, int B, int H, int W, int C, int TH, int TW, int stride) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return GLARE_ERR_UNSUPPORTED;
     const cuuint64_t es = bf16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
-    cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)TW, (cuuint32_t)TH, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // traversal stride s: the box spans TW*s x TH*s input pixels and delivers every s-th one -> TW x TH rows in smem
+    cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)(TW * stride), (cuuint32_t)(TH * stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -396,14 +398,24 @@ GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* o
 
 // x / x_lo: NHWC [B,H,W,Cin] (bf16 for mode 0, fp32 otherwise; x_lo only for mode 2); w / w_lo: packed by
 // glare_conv_pack_weight; bias [Cout] / residual NHWC [B,H,W,Cout] fp32 or NULL; y NHWC fp32.
-GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
-                                      const float* bias, const float* residual, float* y, int B, int H, int W, int Cin, int Cout,
-                                      int ksize, long long ldy, long long w_batch_stride, cudaStream_t stream);
+static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                          const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, int ksize,
+                          int stride, int pad, long long ldy, long long w_batch_stride, cudaStream_t stream);
 
 GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                                    const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                                    cudaStream_t stream) {
-    return glare_conv2d_nhwc_tc_ex(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, Cin, Cout, ksize, Cout, 0, stream);
+    if (ksize != 1 && ksize != 3) return GLARE_ERR_BAD_ARG;
+    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, H, W, Cin, Cout, ksize, 1, ksize / 2, Cout, 0, stream);
+}
+
+// Downsample.forward (encoder_decoder.py:68-72): zero pad (0,1,0,1) then 3x3 stride-2 conv, pad 0.  x NHWC [B,Hin,Win,Cin];
+// y NHWC [B,Hout,Wout,Cout] with Hout = (Hin + 1 - 3) / 2 + 1.  The padding is the TMA unit's out-of-bounds zero fill.
+GLARE_API int glare_conv2d_nhwc_tc_down2(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
+                                         const float* bias, float* y, int B, int Hin, int Win, int Cin, int Cout, cudaStream_t stream) {
+    if (Hin < 2 || Win < 2) return GLARE_ERR_BAD_ARG;
+    const int Ho = (Hin + 1 - 3) / 2 + 1, Wo = (Win + 1 - 3) / 2 + 1;
+    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, Hin, Win, Ho, Wo, Cin, Cout, 3, 2, 0, Cout, 0, stream);
 }
 
 // Extended form: ldy = output pixel stride in elements (>= Cout, multiple of 4); w_batch_stride != 0 selects per-sample
@@ -412,6 +424,14 @@ GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, co
 GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
                                       const float* bias, const float* residual, float* y, int B, int H, int W, int Cin, int Cout,
                                       int ksize, long long ldy, long long w_batch_stride, cudaStream_t stream) {
+    if (ksize != 1 && ksize != 3) return GLARE_ERR_BAD_ARG;
+    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, H, W, Cin, Cout, ksize, 1, ksize / 2, ldy, w_batch_stride,
+                          stream);
+}
+
+static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                          const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, int ksize,
+                          int stride, int pad, long long ldy, long long w_batch_stride, cudaStream_t stream) {
     if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
     if (mode < 0 || mode > 2 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
@@ -421,7 +441,7 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return GLARE_ERR_BAD_ARG;
     ConvTcArgs a{};
     a.bias = bias; a.residual = residual; a.y = y;
-    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.pad = ksize / 2;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.pad = pad; a.stride = stride;
     a.TH = 8; a.TW = 16;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
     a.kchunks = Cin / bke;
@@ -444,11 +464,11 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
     }
     if ((rc = make_out_map(&tY, y, B, H, W, Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0;
-    if ((rc = make_act_map(&tA, x, bf, B, H, W, Cin, a.TH, a.TW)) != GLARE_OK) return rc;
+    if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
     if ((rc = make_w_map(&tB, w, bf, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
     tAl = tA; tBl = tB;
     if (mode == 2) {
-        if ((rc = make_act_map(&tAl, x_lo, false, B, H, W, Cin, a.TH, a.TW)) != GLARE_OK) return rc;
+        if ((rc = make_act_map(&tAl, x_lo, false, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
         if ((rc = make_w_map(&tBl, w_lo, false, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
     }
 #define GLARE_CONV_DISPATCH(M)                                                            \

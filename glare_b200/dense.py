@@ -5,6 +5,7 @@
 ``make_dense("auto")``        the best hand-written backend available in the built library, else torch-fp32
 """
 import torch
+import torch.nn.functional as F
 
 from .engine import TorchDense
 
@@ -96,6 +97,7 @@ class TcDense:
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
+        self.cover_all = True          # 3-channel convs (channel-padded) and stride-2 Downsample convs on the tcgen05 kernel too
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
         self.attn_s_budget = 3 << 29   # bytes of fp32 score matrix materialised per pass (1.5 GiB)
@@ -105,39 +107,64 @@ class TcDense:
     def _t(self, name, flops=0.0):
         return _Bracket(self.timers, name, flops)
 
-    def _weights(self, w):
-        key = (w.data_ptr(), tuple(w.shape))
+    def _weights(self, w, pad_c=0):
+        key = (w.data_ptr(), tuple(w.shape), pad_c)
         if key not in self._w:
-            self._w[key] = self.ops.conv_pack_weight(self.mode, w)
+            wp = F.pad(w, (0, 0, 0, 0, 0, pad_c)) if pad_c else w            # zero input channels up to the K chunk
+            self._w[key] = self.ops.conv_pack_weight(self.mode, wp)
         return self._w[key]
 
-    def _supported(self, Cin, w, stride, padding):
-        ks = w.shape[2]
-        return (w.shape[2] == w.shape[3] and ks in (1, 3) and stride == 1 and padding == ks // 2 and Cin % self.bke == 0
-                and w.shape[0] % 4 == 0)
+    def _operand(self, x):
+        """logical [B,C,H,W] fp32 tensor -> Operand, input channels zero-padded to a multiple of the 128-byte K chunk"""
+        if isinstance(x, Operand):
+            return x, 0
+        with self._t("prep_act"):
+            xn = _nhwc(x)
+            pad_c = (-xn.shape[3]) % self.bke
+            if pad_c:
+                xn = F.pad(xn, (0, pad_c))
+            B, H, W, C = xn.shape
+            hi, lo = self.ops.conv_prep_act(self.mode, xn)
+        return Operand(self.mode, hi, lo, B, C, H, W), pad_c
+
+    def _library(self, key, x, w, b, stride, padding, residual):
+        self.fallbacks[key] = self.fallbacks.get(key, 0) + 1
+        with self._t("conv_library_fallback"):
+            xd = x.dense() if isinstance(x, Operand) else x
+            y = self.lib.conv2d(xd.contiguous(memory_format=torch.channels_last), w, b, stride=stride, padding=padding)
+            return y if residual is None else y + residual
 
     def conv2d(self, x, w, b=None, stride=1, padding=1, residual=None):
         Cin = x.C if isinstance(x, Operand) else x.shape[1]
-        if not self._supported(Cin, w, stride, padding):
-            key = "conv %dx%d %d->%d s%d" % (w.shape[2], w.shape[3], Cin, w.shape[0], stride)
-            self.fallbacks[key] = self.fallbacks.get(key, 0) + 1
-            with self._t("conv_library_fallback"):
-                xd = x.dense() if isinstance(x, Operand) else x
-                y = self.lib.conv2d(xd.contiguous(memory_format=torch.channels_last), w, b, stride=stride, padding=padding)
-                return y if residual is None else y + residual
-        if isinstance(x, Operand):
-            op = x
-        else:
-            with self._t("prep_act"):
-                xn = _nhwc(x)
-                B, H, W, C = xn.shape
-                hi, lo = self.ops.conv_prep_act(self.mode, xn)
-                op = Operand(self.mode, hi, lo, B, C, H, W)
-        w_hi, w_lo = self._weights(w)
-        res = _nhwc(residual) if residual is not None else None
         Cout, ks = w.shape[0], w.shape[2]
-        with self._t("conv_tc", 2.0 * op.B * op.H * op.W * op.C * Cout * ks * ks):
+        shape_ok = w.shape[2] == w.shape[3] and ks in (1, 3) and stride == 1 and padding == ks // 2
+        native = Cin % self.bke == 0 and Cout % 4 == 0
+        if not shape_ok or not (native or self.cover_all):
+            return self._library("conv %dx%d %d->%d s%d" % (ks, ks, Cin, Cout, stride), x, w, b, stride, padding, residual)
+        op, pad_c = self._operand(x)
+        w_hi, w_lo = self._weights(w, pad_c)
+        flops = 2.0 * op.B * op.H * op.W * Cin * Cout * ks * ks
+        if Cout % 4:                                   # 3-channel heads: padded output pixel stride, sliced view returned
+            ldy = (Cout + 3) // 4 * 4
+            y = torch.empty((op.B, op.H, op.W, ldy), device=op.hi.device, dtype=torch.float32)
+            with self._t("conv_tc", flops):
+                self.ops.conv2d_nhwc_tc_ex(self.mode, op.hi, op.lo, w_hi, w_lo, y, op.B, op.H, op.W, op.C, Cout, ldy, 0, bias=b, ksize=ks)
+            y = y[..., :Cout].permute(0, 3, 1, 2)
+            return y if residual is None else y + residual
+        res = _nhwc(residual) if residual is not None else None
+        with self._t("conv_tc", flops):
             y = self.ops.conv2d_nhwc_tc(self.mode, op.hi, op.lo, w_hi, w_lo, b, res, op.B, op.H, op.W, op.C, Cout, ks)
+        return y.permute(0, 3, 1, 2)
+
+    def downsample_conv(self, x, w, b=None):
+        """Downsample.forward (encoder_decoder.py:68-72): pad (0,1,0,1) + 3x3 stride-2 conv, padding by TMA zero fill"""
+        if not self.cover_all or tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4:
+            return None
+        op, pad_c = self._operand(x)
+        w_hi, w_lo = self._weights(w, pad_c)
+        Ho, Wo = (op.H - 2) // 2 + 1, (op.W - 2) // 2 + 1
+        with self._t("conv_tc", 2.0 * op.B * Ho * Wo * x.shape[1] * w.shape[0] * 9):
+            y = self.ops.conv2d_nhwc_tc_down2(self.mode, op.hi, op.lo, w_hi, w_lo, b, op.B, op.H, op.W, op.C, w.shape[0])
         return y.permute(0, 3, 1, 2)
 
     def gn_swish(self, x, gamma, beta, swish=True):

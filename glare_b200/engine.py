@@ -124,6 +124,10 @@ class GlareEngine:
 
     def downsample(self, sd, p, x):
         """encoder_decoder.py:68-72"""
+        if hasattr(self.dense, "downsample_conv"):
+            y = self.dense.downsample_conv(x, sd[p + ".conv.weight"], sd.get(p + ".conv.bias"))
+            if y is not None:
+                return y
         return self._conv(sd, p + ".conv", F.pad(x, (0, 1, 0, 1)), stride=2, padding=0)
 
     def upsample(self, sd, p, x):

@@ -145,11 +145,21 @@ def dcnv2_pack_fwd_nhwc_tc(mode, x_nhwc, offmask_nhwc, w_hi, w_lo, bias, B, H, W
     return y
 
 
-def conv2d_nhwc_tc_ex(mode, x_hi, x_lo, w_hi, w_lo, y, B, H, W, Cin, Cout, ldy, w_batch_stride):
-    """1x1 GEMM form with an output pixel stride and per-sample weights (attention); writes into ``y``"""
-    require_cuda(x_hi, x_lo, w_hi, w_lo, y)
-    check(lib().glare_conv2d_nhwc_tc_ex(mode, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), None, None, ptr(y), B, H, W, Cin, Cout, 1,
-                                        ldy, w_batch_stride, stream()), "glare_conv2d_nhwc_tc_ex")
+def conv2d_nhwc_tc_down2(mode, x_hi, x_lo, w_hi, w_lo, bias, B, Hin, Win, Cin, Cout):
+    """Downsample.forward (encoder_decoder.py:68-72) -> y NHWC [B,Ho,Wo,Cout] fp32"""
+    require_cuda(x_hi, x_lo, w_hi, w_lo, bias)
+    Ho, Wo = (Hin - 2) // 2 + 1, (Win - 2) // 2 + 1
+    y = torch.empty((B, Ho, Wo, Cout), device=x_hi.device, dtype=torch.float32)
+    check(lib().glare_conv2d_nhwc_tc_down2(mode, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(y), B, Hin, Win, Cin, Cout,
+                                           stream()), "glare_conv2d_nhwc_tc_down2")
+    return y
+
+
+def conv2d_nhwc_tc_ex(mode, x_hi, x_lo, w_hi, w_lo, y, B, H, W, Cin, Cout, ldy, w_batch_stride, bias=None, ksize=1):
+    """form with an output pixel stride and per-sample weights (attention GEMMs, Cout % 4 != 0 heads); writes into ``y``"""
+    require_cuda(x_hi, x_lo, w_hi, w_lo, y, bias)
+    check(lib().glare_conv2d_nhwc_tc_ex(mode, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(bias), None, ptr(y), B, H, W, Cin, Cout,
+                                        ksize, ldy, w_batch_stride, stream()), "glare_conv2d_nhwc_tc_ex")
     return y
 
 

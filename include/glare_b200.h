@@ -125,6 +125,9 @@ int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* 
                          const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                          cudaStream_t stream);
 
+/* Downsample.forward (encoder_decoder.py:68-72): zero pad right/bottom by 1 + 3x3 stride-2 conv; y NHWC [B,(Hin-2)/2+1,(Win-2)/2+1,Cout] */
+int glare_conv2d_nhwc_tc_down2(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                               float* y, int B, int Hin, int Win, int Cin, int Cout, cudaStream_t stream);
 /* extended form: ldy = output pixel stride (elements, >= Cout, % 4 == 0); w_batch_stride != 0 -> per-sample weights
  * w + n * w_batch_stride (the attention GEMMs S = Q K^T and O = P V, encoder_decoder.py:176-187) */
 int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,

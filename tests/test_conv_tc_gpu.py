@@ -111,3 +111,29 @@ def test_attention_gemm_path(glare_lib, shape, mode, tol):
             ref[b, :, i0:i0 + 4096] = vv @ s.t()
     err = float((out.reshape(B, C, N).double() - ref).abs().max())
     assert err < tol * max(1.0, float(ref.abs().max())), (shape, mode, err)
+
+
+@pytest.mark.parametrize("mode,tol", [(2, 2e-5), (1, 3e-3), (0, 2e-2)])
+def test_dense_backend_covers_small_channel_and_stride2_convs(glare_lib, mode, tol):
+    """TcDense: 3-channel convs (channels zero-padded to the K chunk, 3-channel heads through a padded pixel stride) and
+    Downsample (encoder_decoder.py:68-72: pad (0,1,0,1) + stride 2) on the tcgen05 kernel, vs cuDNN fp32"""
+    from glare_b200.dense import TcDense
+    torch.backends.cudnn.allow_tf32 = False
+    d = TcDense(mode)
+    g = torch.Generator().manual_seed(17)
+    for (Ci, Co, H, W, ks) in [(3, 128, 21, 30, 3), (512, 3, 13, 19, 3), (3, 3, 9, 11, 1), (3, 64, 16, 16, 3)]:
+        x = torch.randn((2, Ci, H, W), generator=g).cuda()
+        w = (torch.randn((Co, Ci, ks, ks), generator=g) / (ks * Ci ** 0.5)).cuda()
+        b = torch.randn((Co,), generator=g).cuda()
+        y = d.conv2d(x, w, b, stride=1, padding=ks // 2)
+        ref = F.conv2d(x, w, b, padding=ks // 2)
+        assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max())), (Ci, Co, ks)
+    for (C, Co, H, W) in [(128, 128, 20, 31), (256, 256, 21, 30), (128, 128, 420, 620)]:
+        x = torch.randn((1, C, H, W), generator=g).cuda()
+        w = (torch.randn((Co, C, 3, 3), generator=g) / (3 * C ** 0.5)).cuda()
+        b = torch.randn((Co,), generator=g).cuda()
+        y = d.downsample_conv(x, w, b)
+        ref = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+        assert y.shape == ref.shape
+        assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max())), (C, H, W)
+    assert not d.fallbacks

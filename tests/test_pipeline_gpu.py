@@ -83,3 +83,21 @@ def test_reduced_precision_backends_psnr(glare_lib, sd_g, sd_v, backend, min_agr
     dpsnr = abs(O.psnr(out.clamp(0, 1), gt) - O.psnr(ref.clamp(0, 1), gt))
     print("%s: idx agree %.4f dPSNR %.4f dB max pixel diff %.4g" % (backend, agree, dpsnr, float((out - ref).abs().max())))
     assert agree >= min_agree and dpsnr < 0.1
+
+
+def test_stage2_forward_nll_against_reference(glare_lib):
+    """BASELINE config 4 (stage-2 flow training), forward half: z and the per-sample NLL of LLFlowVQGAN2.normal_flow
+    (LLFlowVQGAN2_arch.py:75-122) against the reference's own outputs (tests/golden/stage2.npz)."""
+    from glare_b200 import flow, synth
+    from glare_b200.dense import make_dense
+    from glare_b200.engine import GlareEngine
+    g = load_golden("stage2")
+    sd2 = synth.synth_state_dict("netG_stage2", 0)
+    assert synth.state_fingerprint(sd2) == pytest.approx(float(g["fingerprint_stage2"]), rel=1e-12)
+    eng = GlareEngine(sd2, {}, device="cuda:0", dense=make_dense("tc-3xtf32"), decoders=False)
+    lr = torch.from_numpy(g["lr"]).cuda()
+    enc = eng.cond_encoder(lr)
+    z, logdet = eng.flow_encode(torch.from_numpy(g["gt_latent"]).cuda(), enc["cond_feat"])
+    nll = flow.gaussian_nll(z, enc["color_map"], logdet)
+    assert torch.allclose(z.cpu(), torch.from_numpy(g["z"]), atol=2e-4, rtol=2e-5)
+    assert torch.allclose(nll.cpu(), torch.from_numpy(g["nll"]), atol=1e-4, rtol=1e-5)

@@ -176,7 +176,7 @@ def main():
     def step():
         out = eng.infer(lr_dev)
         if world > 1:
-            dist.all_gather_into_tensor(gather, out)
+            dist.all_gather_into_tensor(gather, out.contiguous())
         return out
 
     for _ in range(max(args.warmup, 3)):

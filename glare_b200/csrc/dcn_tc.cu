@@ -8,8 +8,8 @@
 //   y[n,h,w,co] = bias[co] + sum_{g,t,c in g} W[co,c,t] * sigmoid(m[g,t]) * bilinear(x[n,:,:,c], (h,w) - 1 + t + off[g,t])
 //
 // Same persistent tcgen05 implicit-GEMM skeleton as conv_tc.cu (M = 8x16 pixel tile, N = BN output channels, TMEM
-// double-buffered accumulator, TMA for the weight operand), but the A operand is PRODUCED in shared memory by four
-// sampler warps instead of loaded by TMA: per (group, tap, 128-byte channel chunk) each 8-lane group gathers the four
+// double-buffered accumulator, TMA for the weight operand), but the A operand is PRODUCED in shared memory by eight
+// sampler warps instead of loaded by TMA: per (tap, 128-byte channel chunk) each 8-lane group gathers the four
 // bilinear corners of one pixel as whole 128-byte NHWC channel lines (L1-cached, coalesced), blends them with the
 // corner weights x mask (geometry computed once per (pixel, group, tap) for all channels of the chunk), and stores the
 // operand row in the SWIZZLE_128B pattern the UMMA descriptor expects (16-byte chunk j of row r lives at chunk
@@ -23,7 +23,7 @@
 
 namespace glare {
 
-constexpr int DT_THREADS = 320;           // warp 0 TMA(weights), 1 MMA, 2-5 epilogue, 6-9 samplers
+constexpr int DT_THREADS = 448;           // warp 0 TMA(weights), 1 MMA, 2-5 epilogue, 6-13 samplers (two groups of four)
 constexpr int DT_A_BYTES = 128 * 128;
 
 struct DcnTcArgs {
@@ -31,7 +31,7 @@ struct DcnTcArgs {
     const float* om;
     const float* bias;
     float* y;
-    int B, H, W, C, Cout, dg, cpg, TH, TW, tiles_x, tiles_y, n_blocks, kchunks_per_tap;   // kchunks_per_tap = chunks per (g, tap)
+    int B, H, W, C, Cout, dg, cpg, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;   // kchunks = C / BKE channel chunks per tap
     int total_tiles;
 };
 
@@ -83,7 +83,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
-    const int k_iters = a.dg * 9 * a.kchunks_per_tap;
+    const int k_iters = 9 * a.kchunks;
     const int tiles_xy = a.tiles_y * a.tiles_x;
 
     if (warp == 0) {
@@ -92,18 +92,17 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int nb = tile % a.n_blocks;
-                for (int g = 0; g < a.dg; ++g)
-                    for (int tap = 0; tap < 9; ++tap)
-                        for (int kc = 0; kc < a.kchunks_per_tap; ++kc, ++it) {
-                            const int s = it % STAGES;
-                            const uint32_t ph = (it / STAGES) & 1;
-                            mbar_wait_bounded(&empty_bar[s], ph ^ 1);
-                            uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                            const int kcoord = tap * a.C + g * a.cpg + kc * Cfg::BKE;
-                            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * (Cfg::X3 ? 2 : 1));
-                            tma_load_3d(st + DT_A_BYTES, &tmB, &full_bar[s], kcoord, nb * BN, 0);
-                            if (Cfg::X3) tma_load_3d(st + 2 * DT_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], kcoord, nb * BN, 0);
-                        }
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                        uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                        const int kcoord = tap * a.C + kc * Cfg::BKE;
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * (Cfg::X3 ? 2 : 1));
+                        tma_load_3d(st + DT_A_BYTES, &tmB, &full_bar[s], kcoord, nb * BN, 0);
+                        if (Cfg::X3) tma_load_3d(st + 2 * DT_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], kcoord, nb * BN, 0);
+                    }
             }
         }
     } else if (warp == 1) {
@@ -183,9 +182,14 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         }
     } else {
         // ===================== samplers: produce the A operand =====================
-        const int sw = warp - 6;                       // 0..3: rows [32 sw, 32 sw + 32) of the tile
-        const int sub = lane >> 3, j = lane & 7;       // 4 pixels per step, 8 lanes x 16 bytes per operand row
-        constexpr int CPL = Cfg::TF32 ? 4 : 8;         // channels per lane per stage
+        // 8 warps in two groups; group gsel fills the stages with (k-iteration & 1) == gsel, so two stages are being
+        // sampled while a third is being multiplied.  Within a stage a warp owns 32 tile rows: 8 lanes x 16 bytes per
+        // operand row, 4 rows per step, 8 steps issued as two batches of 16 independent 128-bit corner loads.
+        const int sw = (warp - 6) & 3;                 // rows [32 sw, 32 sw + 32) of the tile
+        const int gsel = (warp - 6) >> 2;
+        const int sub = lane >> 3, j = lane & 7;
+        constexpr int CPL = Cfg::TF32 ? 4 : 8;         // channels per lane per stage (16 bytes of operand)
+        constexpr int V4 = CPL / 4;
         const int om_c = 27 * a.dg;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -194,23 +198,27 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             r -= n * tiles_xy;
             const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
             const float* xn = a.x + (long long)n * a.H * a.W * a.C;
-            for (int g = 0; g < a.dg; ++g)
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int ti = tap / 3, tj = tap - ti * 3;
-                    for (int kc = 0; kc < a.kchunks_per_tap; ++kc, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait_bounded(&empty_bar[s], ph ^ 1);
-                        uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                        const int cbase = g * a.cpg + kc * Cfg::BKE + j * CPL;
-#pragma unroll 2
-                        for (int step = 0; step < 8; ++step) {
-                            const int m = sw * 32 + step * 4 + sub;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ti = tap / 3, tj = tap - ti * 3;
+                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                    if ((int)(it & 1) != gsel) continue;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const int cbase = kc * Cfg::BKE + j * CPL;             // first channel of this lane
+                    const int g = cbase / a.cpg;                           // its deformable group (cpg % CPL == 0)
+                    mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float cw[4][4];
+                        int co[4][4];
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const int m = sw * 32 + (half * 4 + q4) * 4 + sub;
                             const int py = m / a.TW, px = m - py * a.TW;
                             const int gy = ty * a.TH + py, gx = tx * a.TW + px;
-                            float acc[CPL];
 #pragma unroll
-                            for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+                            for (int k = 0; k < 4; ++k) { cw[q4][k] = 0.f; co[q4][k] = 0; }
                             if (gy < a.H && gx < a.W) {
                                 const float* omp = a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c;
                                 const float oh = __ldg(omp + g * 18 + 2 * tap), ow = __ldg(omp + g * 18 + 2 * tap + 1);
@@ -220,24 +228,39 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                                     const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
                                     const int hh = hl + 1, wh = wl + 1;
                                     const float lh = h_im - hl, lw = w_im - wl, uh = 1.f - lh, uw = 1.f - lw;
-                                    const float cw[4] = {uh * uw * mk, uh * lw * mk, lh * uw * mk, lh * lw * mk};
-                                    const bool ok[4] = {hl >= 0 && wl >= 0, hl >= 0 && wh <= a.W - 1, hh <= a.H - 1 && wl >= 0,
-                                                        hh <= a.H - 1 && wh <= a.W - 1};
-                                    const int cy[4] = {hl, hl, hh, hh}, cx[4] = {wl, wh, wl, wh};
+                                    if (hl >= 0 && wl >= 0) { cw[q4][0] = uh * uw * mk; co[q4][0] = hl * a.W + wl; }
+                                    if (hl >= 0 && wh <= a.W - 1) { cw[q4][1] = uh * lw * mk; co[q4][1] = hl * a.W + wh; }
+                                    if (hh <= a.H - 1 && wl >= 0) { cw[q4][2] = lh * uw * mk; co[q4][2] = hh * a.W + wl; }
+                                    if (hh <= a.H - 1 && wh <= a.W - 1) { cw[q4][3] = lh * lw * mk; co[q4][3] = hh * a.W + wh; }
+                                }
+                            }
+                        }
+                        // corners with zero weight read pixel 0 of the image (valid memory) and contribute nothing
+                        float4 xv[4][4][V4];
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        if (ok[k]) {
-                                            const float4* p = reinterpret_cast<const float4*>(xn + ((long long)cy[k] * a.W + cx[k]) * a.C + cbase);
+                        for (int q4 = 0; q4 < 4; ++q4)
 #pragma unroll
-                                            for (int v4 = 0; v4 < CPL / 4; ++v4) {
-                                                const float4 xv = __ldg(p + v4);
-                                                acc[4 * v4 + 0] = fmaf(cw[k], xv.x, acc[4 * v4 + 0]);
-                                                acc[4 * v4 + 1] = fmaf(cw[k], xv.y, acc[4 * v4 + 1]);
-                                                acc[4 * v4 + 2] = fmaf(cw[k], xv.z, acc[4 * v4 + 2]);
-                                                acc[4 * v4 + 3] = fmaf(cw[k], xv.w, acc[4 * v4 + 3]);
-                                            }
-                                        }
-                                    }
+                            for (int k = 0; k < 4; ++k) {
+                                const float4* p = reinterpret_cast<const float4*>(xn + (long long)co[q4][k] * a.C + cbase);
+#pragma unroll
+                                for (int v4 = 0; v4 < V4; ++v4) xv[q4][k][v4] = __ldg(p + v4);
+                            }
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const int m = sw * 32 + (half * 4 + q4) * 4 + sub;
+                            float acc[CPL];
+#pragma unroll
+                            for (int v4 = 0; v4 < V4; ++v4) {
+                                acc[4 * v4 + 0] = cw[q4][0] * xv[q4][0][v4].x;
+                                acc[4 * v4 + 1] = cw[q4][0] * xv[q4][0][v4].y;
+                                acc[4 * v4 + 2] = cw[q4][0] * xv[q4][0][v4].z;
+                                acc[4 * v4 + 3] = cw[q4][0] * xv[q4][0][v4].w;
+#pragma unroll
+                                for (int k = 1; k < 4; ++k) {
+                                    acc[4 * v4 + 0] = fmaf(cw[q4][k], xv[q4][k][v4].x, acc[4 * v4 + 0]);
+                                    acc[4 * v4 + 1] = fmaf(cw[q4][k], xv[q4][k][v4].y, acc[4 * v4 + 1]);
+                                    acc[4 * v4 + 2] = fmaf(cw[q4][k], xv[q4][k][v4].z, acc[4 * v4 + 2]);
+                                    acc[4 * v4 + 3] = fmaf(cw[q4][k], xv[q4][k][v4].w, acc[4 * v4 + 3]);
                                 }
                             }
                             const uint32_t off = (uint32_t)m * 128u + (uint32_t)((j ^ (m & 7)) << 4);     // SWIZZLE_128B
@@ -258,10 +281,11 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                                     make_float4(acc[0] - h.x, acc[1] - h.y, acc[2] - h.z, acc[3] - h.w);
                             }
                         }
-                        fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-                        mbar_arrive(&full_bar[s]);
                     }
+                    fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                    mbar_arrive(&full_bar[s]);
                 }
+            }
         }
     }
     tc_fence_before();
@@ -320,13 +344,13 @@ GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float
     if (B == 0) return GLARE_OK;
     if (!x || !offmask || !w || !y || (mode == 2 && !w_lo)) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
-    if (C % deformable_groups != 0 || (C / deformable_groups) % bke != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
+    if (C % deformable_groups != 0 || C % bke != 0 || (C / deformable_groups) % 8 != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
     DcnTcArgs a{};
     a.x = x; a.om = offmask; a.bias = bias_or_null; a.y = y;
     a.B = B; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.dg = deformable_groups; a.cpg = C / deformable_groups;
     a.TH = 8; a.TW = 16;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
-    a.kchunks_per_tap = a.cpg / bke;
+    a.kchunks = C / bke;
     int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
     const long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;

@@ -183,7 +183,7 @@ class TcDense:
         """DCNv2Pack.forward after conv_offset (deformableDecoder_arch.py:141-152): x [B,C,H,W], raw conv_offset output
         [B,27*dg,H,W] -> y [B,Cout,H,W].  None when the shape is outside the tensor-core kernel's coverage."""
         C, Cout = x.shape[1], weight.shape[0]
-        if tuple(weight.shape[2:]) != (3, 3) or C % dg or (C // dg) % self.bke or Cout % 4 or not self.dcn_tc:
+        if tuple(weight.shape[2:]) != (3, 3) or C % dg or C % self.bke or (C // dg) % 8 or Cout % 4 or not self.dcn_tc:
             return None
         with self._t("dcn_tc", 2.0 * x.shape[0] * x.shape[2] * x.shape[3] * C * Cout * 9):
             xn, on = _nhwc(x), _nhwc(offmask_raw)

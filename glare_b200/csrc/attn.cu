@@ -11,7 +11,7 @@
 
 namespace glare {
 
-__device__ __forceinline__ float tf32_hi_a(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_hi_a(float x) { return tf32_round(x); }
 
 template <int OUT>
 __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(const float* __restrict__ S, long long lds, int n_keys,

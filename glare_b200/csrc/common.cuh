@@ -72,6 +72,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// fp32 -> nearest tf32 value (round to nearest, low 13 mantissa bits zero).  hi of the 3xTF32 split; lo = x - hi is exact
+// in fp32 and |lo| <= 2^-12 |x|, so the dropped lo*lo term is below fp32 resolution.
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u & 0xFFFFE000u);
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace glare

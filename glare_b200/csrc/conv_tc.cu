@@ -211,6 +211,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + co + j));
                             o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
                         }
+                    } else {                                             // ragged tail of a Cout % 4 != 0 head (3-channel outputs)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (co + j + e < a.Cout) {
+                                if (a.bias) o[j + e] += __ldg(a.bias + co + j + e);
+                                if (rrow) o[j + e] += __ldg(rrow + co + j + e);
+                            }
+                        }
                     }
                 }
                 if (a.tma_store) {
@@ -252,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- weight / activation packing ---------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_hi(float x) { return tf32_round(x); }
 
 // OIHW fp32 -> [Cout][kh*kw][Cin]; mode 0: bf16; mode 1: fp32 (tensor core truncates to tf32); mode 2: hi (low 13
 // mantissa bits cleared) + lo = w - hi (exact in fp32)

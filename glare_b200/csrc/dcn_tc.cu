@@ -49,7 +49,7 @@ struct DcnCfg {
     static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;
 };
 
-__device__ __forceinline__ float tf32_hi_d(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_hi_d(float x) { return tf32_round(x); }
 
 template <int MODE, int BN>
 __global__ void __launch_bounds__(DT_THREADS, 1)

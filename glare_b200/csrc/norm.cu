@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
     }
 }
 
-__device__ __forceinline__ float tf32_hi_n(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_hi_n(float x) { return tf32_round(x); }
 
 // OUT: 0 = bf16, 1 = fp32, 2 = tf32 hi + lo
 template <int OUT>

@@ -1,0 +1,45 @@
+"""GPU: the public entry (GlareEnhancer.enhance: host uint8 in -> host uint8 out) against the oracle run through the
+reference's own pre/post-processing steps (infer_dataset_lol.py:124-135 'lol' padding, infer_unpaired.py:81-88,130 'auto')."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_u8(sd_g, sd_v, lq_u8, pad):
+    from glare_b200 import synth
+    from oracle import glare_oracle as O
+    x = lq_u8.permute(0, 3, 1, 2).float() / 255.0
+    h, w = x.shape[-2:]
+    if pad == "lol":
+        xp = synth.pad_lol(x)
+        box = (0, h, 20, 20 + w)
+    else:
+        xp, (h1, h2, w1, w2) = synth.auto_padding(x)
+        box = (h1, h1 + h, w1, w1 + w)
+    out = O.glare_infer(sd_g, sd_v, O.preprocess(xp))
+    out = out[:, :, box[0]:box[1], box[2]:box[3]].clamp(0, 1) * 255.0
+    return out.to(torch.uint8).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("pad,hw", [("lol", (44, 60)), ("auto", (40, 56)), ("auto", (32, 48))])
+def test_enhance_matches_oracle(glare_lib, sd_g, sd_v, pad, hw):
+    from glare_b200 import synth
+    from glare_b200.api import GlareEnhancer
+    lq, _ = synth.synth_images(2, hw[0], hw[1], seed=9)
+    lq_u8 = (lq.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous()
+    enh = GlareEnhancer(sd_g, sd_v, device="cuda:0", pad=pad)
+    out = enh.enhance(lq_u8.pin_memory())
+    ref = _oracle_u8(sd_g, sd_v, lq_u8, pad)
+    assert out.shape == ref.shape == lq_u8.shape and out.dtype == torch.uint8
+    diff = (out.int() - ref.int()).abs()
+    # uint8 truncation: a 1e-3 float difference can move a value across an integer boundary, never by more than 1
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 0.02
+
+
+def test_enhance_rejects_wrong_input(glare_lib, sd_g, sd_v):
+    from glare_b200.api import GlareEnhancer
+    enh = GlareEnhancer(sd_g, sd_v, device="cuda:0")
+    with pytest.raises(ValueError):
+        enh.enhance(torch.zeros((1, 3, 8, 8)))

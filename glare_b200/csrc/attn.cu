@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(const float* __r
         } else {
             const float4 h = make_float4(tf32_hi_a(p[0]), tf32_hi_a(p[1]), tf32_hi_a(p[2]), tf32_hi_a(p[3]));
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = h;
-            *reinterpret_cast<float4*>(out_lo + o) = make_float4(p[0] - h.x, p[1] - h.y, p[2] - h.z, p[3] - h.w);
+            if (OUT == 2) *reinterpret_cast<float4*>(out_lo + o) = make_float4(p[0] - h.x, p[1] - h.y, p[2] - h.z, p[3] - h.w);
+            else store_x4(reinterpret_cast<__nv_bfloat16*>(out_lo), o, p[0], p[1], p[2], p[3], h.x, h.y, h.z, h.w);
         }
     }
 }
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_reg_kernel(const float*
         } else {
             const float4 h = make_float4(tf32_hi_a(p0), tf32_hi_a(p1), tf32_hi_a(p2), tf32_hi_a(p3));
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = h;
-            *reinterpret_cast<float4*>(out_lo + o) = make_float4(p0 - h.x, p1 - h.y, p2 - h.z, p3 - h.w);
+            if (OUT == 2) *reinterpret_cast<float4*>(out_lo + o) = make_float4(p0 - h.x, p1 - h.y, p2 - h.z, p3 - h.w);
+            else store_x4(reinterpret_cast<__nv_bfloat16*>(out_lo), o, p0, p1, p2, p3, h.x, h.y, h.z, h.w);
         }
     }
 }
@@ -194,7 +196,13 @@ __global__ void __launch_bounds__(256) attn_transpose_v_kernel(const float* __re
             else {
                 const float h = tf32_hi_a(x);
                 reinterpret_cast<float*>(out_hi)[o] = h;
-                out_lo[o] = x - h;
+                if (OUT == 2) out_lo[o] = x - h;
+                else {
+                    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(out_lo);
+                    const long long xi = (o >> 5) * 64 + (o & 31);
+                    xb[xi] = __float2bfloat16_rn(x);
+                    xb[xi + 32] = __float2bfloat16_rn(x - h);
+                }
             }
         }
     }
@@ -208,22 +216,24 @@ using namespace glare;
 // P = softmax(scale * S) over the keys, zero in columns [n_keys, n_pad).
 GLARE_API int glare_attn_softmax_rows(int out_mode, const float* S, long long rows, long long lds, int n_keys, int n_pad, float scale,
                                       void* out_hi, void* out_lo, long long ldp, cudaStream_t stream) {
-    if (out_mode < 0 || out_mode > 2 || rows < 0 || n_keys <= 0 || n_pad < n_keys || (n_pad & 3) || (lds & 3) || (ldp & 3) || lds < n_keys ||
-        ldp < n_pad || scale <= 0.f)
+    if (out_mode < 0 || out_mode > 3 || rows < 0 || n_keys <= 0 || n_pad < n_keys || (n_pad & 3) || (lds & 3) || (ldp & 3) || lds < n_keys ||
+        ldp < n_pad || scale <= 0.f || (out_mode == 3 && ((ldp & 31) || (n_pad & 31))))
         return GLARE_ERR_BAD_ARG;
     if (rows == 0) return GLARE_OK;
-    if (!S || !out_hi || (out_mode == 2 && !out_lo) || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
+    if (!S || !out_hi || (out_mode >= 2 && !out_lo) || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
     float* lo = reinterpret_cast<float*>(out_lo);
     if (n_pad <= 256 * 64) {                         // whole row in registers: one pass over S (N = 16 275 at 600x400)
         if (out_mode == 0) attn_softmax_rows_reg_kernel<0><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
         else if (out_mode == 1) attn_softmax_rows_reg_kernel<1><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
-        else attn_softmax_rows_reg_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+        else if (out_mode == 2) attn_softmax_rows_reg_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+        else attn_softmax_rows_reg_kernel<3><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
         GLARE_CHECK_LAUNCH();
         return GLARE_OK;
     }
     if (out_mode == 0) attn_softmax_rows_kernel<0><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
     else if (out_mode == 1) attn_softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
-    else attn_softmax_rows_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+    else if (out_mode == 2) attn_softmax_rows_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+    else attn_softmax_rows_kernel<3><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -231,14 +241,15 @@ GLARE_API int glare_attn_softmax_rows(int out_mode, const float* S, long long ro
 // v NHWC [B][N][C] fp32 -> V^T [B][C][Np] operand(s) (zero for keys >= N)
 GLARE_API int glare_attn_transpose_v(int out_mode, const float* v, int B, int N, int C, int Np, void* out_hi, void* out_lo,
                                      cudaStream_t stream) {
-    if (out_mode < 0 || out_mode > 2 || B < 0 || N <= 0 || C <= 0 || Np < N) return GLARE_ERR_BAD_ARG;
+    if (out_mode < 0 || out_mode > 3 || B < 0 || N <= 0 || C <= 0 || Np < N || (out_mode == 3 && (Np & 31))) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
-    if (!v || !out_hi || (out_mode == 2 && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
+    if (!v || !out_hi || (out_mode >= 2 && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
     dim3 grid((Np + 31) / 32, (C + 31) / 32, B);
     float* lo = reinterpret_cast<float*>(out_lo);
     if (out_mode == 0) attn_transpose_v_kernel<0><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
     else if (out_mode == 1) attn_transpose_v_kernel<1><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
-    else attn_transpose_v_kernel<2><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
+    else if (out_mode == 2) attn_transpose_v_kernel<2><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
+    else attn_transpose_v_kernel<3><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }

@@ -80,6 +80,23 @@ __device__ __forceinline__ float tf32_round(float x) {
     return __uint_as_float(u & 0xFFFFE000u);
 }
 
+// Mode 3 ("tf32 + 2 x bf16"): D += tf32(A_hi) tf32(B_hi) + bf16(A_lo) bf16(B) + bf16(A) bf16(B_lo).  The two small cross terms
+// tolerate bf16 (|lo| <= 2^-12 |x|, bf16 adds 2^-9 relative to them: ~1e-6 of the product), and bf16 MMAs run at twice the
+// tf32 rate, so the fp32-grade product costs 2 instead of 3 tf32-equivalents.  Cross-term operands live in ONE bf16 "x"
+// tensor, interleaved per 32-element K chunk: [32 x bf16(x) | 32 x bf16(x - hi)] = one 128-byte swizzle row per chunk.
+// For flat element index e (row lengths are multiples of 32): bf16(x) at (e/32)*64 + e%32, bf16(lo) 32 further.
+__device__ __forceinline__ void store_x4(__nv_bfloat16* xbase, long long e, float v0, float v1, float v2, float v3, float h0, float h1,
+                                         float h2, float h3) {
+    const long long xi = (e >> 5) * 64 + (e & 31);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v0, v1), b = __floats2bfloat162_rn(v2, v3);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v0 - h0, v1 - h1), d = __floats2bfloat162_rn(v2 - h2, v3 - h3);
+    uint2 u, w;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    w.x = *reinterpret_cast<uint32_t*>(&c); w.y = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint2*>(xbase + xi) = u;
+    *reinterpret_cast<uint2*>(xbase + xi + 32) = w;
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace glare

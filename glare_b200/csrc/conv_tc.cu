@@ -45,7 +45,8 @@ struct ConvTcArgs {
 
 template <int MODE, int BN>
 struct ConvCfg {
-    static constexpr bool X3 = MODE == 2;
+    static constexpr bool XB = MODE == 3;                      // tf32 main term + two bf16 cross terms
+    static constexpr bool X3 = MODE == 2 || XB;                // second operand pair (lo / interleaved bf16 x) per stage
     static constexpr bool TF32 = MODE >= 1;
     static constexpr int BKE = TF32 ? 32 : 64;                 // elements per 128-byte K chunk
     static constexpr int B_BYTES = BN * 128;
@@ -124,8 +125,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_3d(st + CT_A_BYTES, &tmB, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN, wn);
                         if (Cfg::X3) {
                             uint8_t* lo = st + CT_A_BYTES + Cfg::B_BYTES;
-                            tma_load_4d(lo, &tmAlo, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
-                            tma_load_3d(lo + CT_A_BYTES, &tmBlo, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN, wn);
+                            const int km = Cfg::XB ? 2 : 1;               // the bf16 x tensors hold 64 elements per 32-element K chunk
+                            tma_load_4d(lo, &tmAlo, &full_bar[s], km * kc * Cfg::BKE, x0 + dx, y0 + dy, n);
+                            tma_load_3d(lo + CT_A_BYTES, &tmBlo, &full_bar[s], km * (tap * a.Cin + kc * Cfg::BKE), nb * BN, wn);
                         }
                     }
                 }
@@ -154,9 +156,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 4; ++j) {                       // 4 x 32-byte K steps inside the 128-byte swizzle row
                         const uint64_t adv = (uint64_t)(j * 2);        // +32 bytes in 16-byte units
                         umma_ss<Cfg::TF32>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
-                        if (Cfg::X3) {
+                        if (Cfg::X3 && !Cfg::XB) {
                             umma_ss<true>(d_tmem, dal + adv, db + adv, idesc, 1u);
                             umma_ss<true>(d_tmem, da + adv, dbl + adv, idesc, 1u);
+                        }
+                    }
+                    if (Cfg::XB) {
+                        // x tiles: bytes [0,64) of a row = bf16(x) for the chunk's 32 k, bytes [64,128) = bf16(lo); K = 16 per MMA
+                        constexpr uint32_t idesc_bf = umma_idesc(1, 128, BN);
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const uint64_t adv = (uint64_t)(jj * 2);
+                            umma_ss<false>(d_tmem, dal + 4 + adv, dbl + adv, idesc_bf, 1u);      // A_lo * B
+                            umma_ss<false>(d_tmem, dal + adv, dbl + 4 + adv, idesc_bf, 1u);      // A * B_lo
                         }
                     }
                     umma_commit(&empty_bar[s]);                         // stage reusable once these MMAs retire
@@ -276,10 +288,17 @@ __global__ void conv_pack_weight_kernel(const float* __restrict__ w, int Cout, i
             reinterpret_cast<__nv_bfloat16*>(out_hi)[i] = __float2bfloat16_rn(v);
         } else if (mode == 1) {
             reinterpret_cast<float*>(out_hi)[i] = v;
-        } else {
+        } else if (mode == 2) {
             const float h = tf32_hi(v);
             reinterpret_cast<float*>(out_hi)[i] = h;
             out_lo[i] = v - h;
+        } else {
+            const float h = tf32_hi(v);
+            reinterpret_cast<float*>(out_hi)[i] = h;
+            __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(out_lo);
+            const long long xi = (i >> 5) * 64 + (i & 31);
+            xb[xi] = __float2bfloat16_rn(v);
+            xb[xi + 32] = __float2bfloat16_rn(v - h);
         }
     }
 }
@@ -295,10 +314,14 @@ __global__ void conv_prep_act_kernel(const float4* __restrict__ x, long long n4,
             o.x = *reinterpret_cast<uint32_t*>(&a);
             o.y = *reinterpret_cast<uint32_t*>(&b);
             reinterpret_cast<uint2*>(out_hi)[i] = o;
-        } else {
+        } else if (mode == 2) {
             const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
             reinterpret_cast<float4*>(out_hi)[i] = h;
             out_lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        } else {
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            reinterpret_cast<float4*>(out_hi)[i] = h;
+            store_x4(reinterpret_cast<__nv_bfloat16*>(out_lo), i * 4, v.x, v.y, v.z, v.w, h.x, h.y, h.z, h.w);
         }
     }
 }
@@ -379,12 +402,13 @@ static int launch_conv(const CUtensorMap& tA, const CUtensorMap& tAl, const CUte
 using namespace glare;
 
 // bytes per element of the packed operand for a precision mode (0 bf16, 1 tf32, 2 3xtf32)
-GLARE_API int glare_conv_tc_elem_bytes(int mode) { return mode == 0 ? 2 : 4; }
+GLARE_API int glare_conv_tc_elem_bytes(int mode) { return mode == 0 ? 2 : 4; }   // hi operand; the mode-3 x tensor is bf16 x 2
 
 GLARE_API int glare_conv_pack_weight(int mode, const float* w_oihw, int Cout, int Cin, int ksize, void* out_hi, void* out_lo,
                                      cudaStream_t stream) {
-    if (!w_oihw || !out_hi || (mode == 2 && !out_lo) || mode < 0 || mode > 2 || Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3))
+    if (!w_oihw || !out_hi || (mode >= 2 && !out_lo) || mode < 0 || mode > 3 || Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3))
         return GLARE_ERR_BAD_ARG;
+    if (mode == 3 && Cin % 32 != 0) return GLARE_ERR_UNSUPPORTED;
     const long long n = (long long)Cout * Cin * ksize * ksize;
     const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
     conv_pack_weight_kernel<<<grid, 256, 0, stream>>>(w_oihw, Cout, Cin, ksize * ksize, mode, out_hi, reinterpret_cast<float*>(out_lo));
@@ -394,9 +418,9 @@ GLARE_API int glare_conv_pack_weight(int mode, const float* w_oihw, int Cout, in
 
 // fp32 activations -> tensor-core operand(s): mode 0 bf16 copy, mode 2 tf32 hi/lo split (mode 1 needs no preparation)
 GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* out_hi, void* out_lo, cudaStream_t stream) {
-    if (n < 0 || (mode != 0 && mode != 2) || (n & 3)) return GLARE_ERR_BAD_ARG;
+    if (n < 0 || (mode != 0 && mode != 2 && mode != 3) || (n & 3) || (mode == 3 && (n & 31))) return GLARE_ERR_BAD_ARG;
     if (n == 0) return GLARE_OK;
-    if (!x || !out_hi || (mode == 2 && !out_lo)) return GLARE_ERR_BAD_ARG;
+    if (!x || !out_hi || (mode >= 2 && !out_lo)) return GLARE_ERR_BAD_ARG;
     const long long n4 = n / 4;
     const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
     conv_prep_act_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), n4, mode, out_hi, reinterpret_cast<float4*>(out_lo));
@@ -441,9 +465,9 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, int ksize,
                           int stride, int pad, long long ldy, long long w_batch_stride, cudaStream_t stream) {
     if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
-    if (mode < 0 || mode > 2 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return GLARE_ERR_BAD_ARG;
+    if (mode < 0 || mode > 3 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
-    if (!x || !w || !y || (mode == 2 && (!x_lo || !w_lo))) return GLARE_ERR_BAD_ARG;
+    if (!x || !w || !y || (mode >= 2 && (!x_lo || !w_lo))) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
     if (Cin % bke != 0 || (Cout % 4 != 0 && ldy == Cout)) return GLARE_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return GLARE_ERR_BAD_ARG;
@@ -478,6 +502,9 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if (mode == 2) {
         if ((rc = make_act_map(&tAl, x_lo, false, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
         if ((rc = make_w_map(&tBl, w_lo, false, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
+    } else if (mode == 3) {                        // interleaved bf16 x tensors: 2 bf16 per element, same bytes per row as fp32
+        if ((rc = make_act_map(&tAl, x_lo, true, B, Hin, Win, 2 * Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
+        if ((rc = make_w_map(&tBl, w_lo, true, Cout, 2 * ksize * ksize * Cin, BN, n_w, 2 * w_batch_stride)) != GLARE_OK) return rc;
     }
 #define GLARE_CONV_DISPATCH(M)                                                            \
     do {                                                                                  \
@@ -487,6 +514,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     } while (0)
     if (mode == 0) GLARE_CONV_DISPATCH(0);
     if (mode == 1) GLARE_CONV_DISPATCH(1);
-    GLARE_CONV_DISPATCH(2);
+    if (mode == 2) GLARE_CONV_DISPATCH(2);
+    GLARE_CONV_DISPATCH(3);
 #undef GLARE_CONV_DISPATCH
 }

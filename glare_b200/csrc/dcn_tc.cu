@@ -37,7 +37,8 @@ struct DcnTcArgs {
 
 template <int MODE, int BN>
 struct DcnCfg {
-    static constexpr bool X3 = MODE == 2;
+    static constexpr bool XB = MODE == 3;                      // tf32 main term + two bf16 cross terms (common.cuh store_x4)
+    static constexpr bool X3 = MODE == 2 || XB;
     static constexpr bool TF32 = MODE >= 1;
     static constexpr int BKE = TF32 ? 32 : 64;
     static constexpr int B_BYTES = BN * 128;
@@ -101,7 +102,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                         const int kcoord = tap * a.C + kc * Cfg::BKE;
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * (Cfg::X3 ? 2 : 1));
                         tma_load_3d(st + DT_A_BYTES, &tmB, &full_bar[s], kcoord, nb * BN, 0);
-                        if (Cfg::X3) tma_load_3d(st + 2 * DT_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], kcoord, nb * BN, 0);
+                        if (Cfg::X3)
+                            tma_load_3d(st + 2 * DT_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], (Cfg::XB ? 2 : 1) * kcoord, nb * BN, 0);
                     }
             }
         }
@@ -128,9 +130,18 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t adv = (uint64_t)(j * 2);
                         umma_ss<Cfg::TF32>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
-                        if (Cfg::X3) {
+                        if (Cfg::X3 && !Cfg::XB) {
                             umma_ss<true>(d_tmem, dal + adv, db + adv, idesc, 1u);
                             umma_ss<true>(d_tmem, da + adv, dbl + adv, idesc, 1u);
+                        }
+                    }
+                    if (Cfg::XB) {
+                        constexpr uint32_t idesc_bf = umma_idesc(1, 128, BN);
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const uint64_t adv = (uint64_t)(jj * 2);
+                            umma_ss<false>(d_tmem, dal + 4 + adv, dbl + adv, idesc_bf, 1u);      // A_lo * B
+                            umma_ss<false>(d_tmem, dal + adv, dbl + 4 + adv, idesc_bf, 1u);      // A * B_lo
                         }
                     }
                     umma_commit(&empty_bar[s]);
@@ -274,11 +285,25 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                                 *reinterpret_cast<uint4*>(st + off) = u;
                             } else if (!Cfg::X3) {
                                 *reinterpret_cast<float4*>(st + off) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                            } else {
+                            } else if (!Cfg::XB) {
                                 const float4 h = make_float4(tf32_hi_d(acc[0]), tf32_hi_d(acc[1]), tf32_hi_d(acc[2]), tf32_hi_d(acc[3]));
                                 *reinterpret_cast<float4*>(st + off) = h;
                                 *reinterpret_cast<float4*>(st + DT_A_BYTES + Cfg::B_BYTES + off) =
                                     make_float4(acc[0] - h.x, acc[1] - h.y, acc[2] - h.z, acc[3] - h.w);
+                            } else {
+                                // x tile row: bytes [0,64) bf16(sample) of the 32 channels, [64,128) bf16(sample - hi); this lane owns
+                                // channels 4j..4j+3 = 8 bytes at 8j in each half; swizzle acts on 16-byte chunks
+                                const float4 h = make_float4(tf32_hi_d(acc[0]), tf32_hi_d(acc[1]), tf32_hi_d(acc[2]), tf32_hi_d(acc[3]));
+                                *reinterpret_cast<float4*>(st + off) = h;
+                                uint8_t* xt = st + DT_A_BYTES + Cfg::B_BYTES + (uint32_t)m * 128u + (uint32_t)((j & 1) * 8);
+                                __nv_bfloat162 a0 = __floats2bfloat162_rn(acc[0], acc[1]), a1 = __floats2bfloat162_rn(acc[2], acc[3]);
+                                __nv_bfloat162 l0 = __floats2bfloat162_rn(acc[0] - h.x, acc[1] - h.y),
+                                               l1 = __floats2bfloat162_rn(acc[2] - h.z, acc[3] - h.w);
+                                uint2 u, w2;
+                                u.x = *reinterpret_cast<uint32_t*>(&a0); u.y = *reinterpret_cast<uint32_t*>(&a1);
+                                w2.x = *reinterpret_cast<uint32_t*>(&l0); w2.y = *reinterpret_cast<uint32_t*>(&l1);
+                                *reinterpret_cast<uint2*>(xt + ((((j >> 1)) ^ (m & 7)) << 4)) = u;
+                                *reinterpret_cast<uint2*>(xt + (((4 + (j >> 1)) ^ (m & 7)) << 4)) = w2;
                             }
                         }
                     }
@@ -340,9 +365,9 @@ using namespace glare;
 GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float* offmask, const void* w, const void* w_lo,
                                            const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout,
                                            int deformable_groups, cudaStream_t stream) {
-    if (mode < 0 || mode > 2 || B < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || deformable_groups <= 0) return GLARE_ERR_BAD_ARG;
+    if (mode < 0 || mode > 3 || B < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || deformable_groups <= 0) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
-    if (!x || !offmask || !w || !y || (mode == 2 && !w_lo)) return GLARE_ERR_BAD_ARG;
+    if (!x || !offmask || !w || !y || (mode >= 2 && !w_lo)) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
     if (C % deformable_groups != 0 || C % bke != 0 || (C / deformable_groups) % 8 != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
     DcnTcArgs a{};
@@ -363,6 +388,7 @@ GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float
     if ((rc = make_w_map_d(&tB, w, mode == 0, Cout, 9 * C, BN)) != GLARE_OK) return rc;
     tBl = tB;
     if (mode == 2 && (rc = make_w_map_d(&tBl, w_lo, false, Cout, 9 * C, BN)) != GLARE_OK) return rc;
+    if (mode == 3 && (rc = make_w_map_d(&tBl, w_lo, true, Cout, 2 * 9 * C, BN)) != GLARE_OK) return rc;
 #define GLARE_DCN_DISPATCH(M)                                                 \
     do {                                                                      \
         if (BN == 256) return launch_dcn_tc<M, 256>(tB, tBl, a, stream);      \
@@ -371,6 +397,7 @@ GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float
     } while (0)
     if (mode == 0) GLARE_DCN_DISPATCH(0);
     if (mode == 1) GLARE_DCN_DISPATCH(1);
-    GLARE_DCN_DISPATCH(2);
+    if (mode == 2) GLARE_DCN_DISPATCH(2);
+    GLARE_DCN_DISPATCH(3);
 #undef GLARE_DCN_DISPATCH
 }

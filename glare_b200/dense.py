@@ -67,7 +67,12 @@ class Operand:
 
     def dense(self):
         """fp32 logical-NCHW (channels_last) value of the operand: hi + lo is exact for the tf32 split"""
-        v = self.hi.float() if self.lo is None else self.hi + self.lo
+        if self.lo is None:
+            v = self.hi.float()
+        elif self.lo.dtype == torch.float32:
+            v = self.hi + self.lo
+        else:                                    # mode 3: interleaved bf16 x tensor, second half of every 64 = bf16(x - hi)
+            v = self.hi + self.lo.view(-1, 2, 32)[:, 1].float().reshape(self.hi.shape)
         return v.view(self.B, self.H, self.W, self.C).permute(0, 3, 1, 2)
 
 
@@ -91,9 +96,10 @@ class TcDense:
         from . import ops
         self.ops = ops
         self.mode = mode
-        self.name = {0: "tcgen05-bf16", 1: "tcgen05-tf32", 2: "tcgen05-3xtf32"}[mode]
-        self.dtype_name = {0: "bf16", 1: "tf32", 2: "fp32 (3xTF32 tensor-core emulation, fp32 accumulate)"}[mode]
-        self.lib = TorchDense(torch.float32, allow_tf32=(mode != 2))
+        self.name = {0: "tcgen05-bf16", 1: "tcgen05-tf32", 2: "tcgen05-3xtf32", 3: "tcgen05-tf32+2xbf16"}[mode]
+        self.dtype_name = {0: "bf16", 1: "tf32", 2: "fp32 (3xTF32 tensor-core emulation, fp32 accumulate)",
+                           3: "fp32 (tf32 x tf32 + two bf16 cross terms on tensor cores, fp32 accumulate)"}[mode]
+        self.lib = TorchDense(torch.float32, allow_tf32=(mode in (0, 1)))
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
@@ -216,7 +222,7 @@ class TcDense:
             rows_max = min(band, h) * w
             S = torch.empty((rows_max, Np), device=q.device, dtype=torch.float32)
             p_hi = torch.empty((rows_max, Np), device=q.device, dtype=q_hi.dtype)
-            p_lo = torch.empty_like(p_hi) if self.mode == 2 else None
+            p_lo = ops._lo_like(self.mode, p_hi)
             scale = float(int(C) ** (-0.5))
             for b in range(B):
                 for r0 in range(0, h, band):
@@ -266,6 +272,8 @@ def make_dense(name="auto"):
         return TcDense(2)
     if name == "tc-tf32":
         return TcDense(1)
+    if name == "tc-tf32bf16x2":
+        return TcDense(3)
     if name == "tc-bf16":
         return TcDense(0)
     if name == "torch-fp32":

@@ -101,7 +101,16 @@ def flow_step(direction, coupling, z_in, z_out, pA, pA_strides, hF, hF_batch_str
 
 
 # ------------------------------------------------------------------------------------------- dense convs / GroupNorm
-MODE_BF16, MODE_TF32, MODE_TF32X3 = 0, 1, 2
+MODE_BF16, MODE_TF32, MODE_TF32X3, MODE_TF32_BF16X2 = 0, 1, 2, 3
+
+
+def _lo_like(mode, hi):
+    """second operand tensor of the fp32-grade modes: fp32 lo (mode 2) or the interleaved bf16 x tensor, 2 per element (mode 3)"""
+    if mode == MODE_TF32X3:
+        return torch.empty_like(hi)
+    if mode == MODE_TF32_BF16X2:
+        return torch.empty(tuple(hi.shape[:-1]) + (2 * hi.shape[-1],), device=hi.device, dtype=torch.bfloat16)
+    return None
 
 
 def conv_pack_weight(mode, w_oihw):
@@ -111,7 +120,7 @@ def conv_pack_weight(mode, w_oihw):
     Co, Ci, kh, kw = w.shape
     dt = torch.bfloat16 if mode == MODE_BF16 else torch.float32
     hi = torch.empty((Co, kh * kw, Ci), device=w.device, dtype=dt)
-    lo = torch.empty_like(hi) if mode == MODE_TF32X3 else None
+    lo = _lo_like(mode, hi)
     check(lib().glare_conv_pack_weight(mode, ptr(w), Co, Ci, kh, ptr(hi), ptr(lo), stream()), "glare_conv_pack_weight")
     return hi, lo
 
@@ -122,7 +131,7 @@ def conv_prep_act(mode, x_nhwc):
     if mode == MODE_TF32:
         return x_nhwc, None
     hi = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=torch.bfloat16 if mode == MODE_BF16 else torch.float32)
-    lo = torch.empty_like(hi) if mode == MODE_TF32X3 else None
+    lo = _lo_like(mode, hi)
     check(lib().glare_conv_prep_act(mode, ptr(x_nhwc), x_nhwc.numel(), ptr(hi), ptr(lo), stream()), "glare_conv_prep_act")
     return hi, lo
 
@@ -173,7 +182,7 @@ def attn_transpose_v(mode, v_nhwc, B, N, C, Np):
     require_cuda(v_nhwc)
     dt = torch.bfloat16 if mode == MODE_BF16 else torch.float32
     hi = torch.empty((B, C, Np), device=v_nhwc.device, dtype=dt)
-    lo = torch.empty_like(hi) if mode == MODE_TF32X3 else None
+    lo = _lo_like(mode, hi)
     check(lib().glare_attn_transpose_v(mode, ptr(v_nhwc), B, N, C, Np, ptr(hi), ptr(lo), stream()), "glare_attn_transpose_v")
     return hi, lo
 
@@ -189,7 +198,7 @@ def gn_apply(out_mode, x_nhwc, stats, gamma, beta, swish, B, HW, C, G=32, eps=1e
     """-> (hi, lo|None) with hi bf16 (mode 0) / fp32 (mode 1) / tf32-hi (mode 2), same NHWC shape as x"""
     require_cuda(x_nhwc, stats, gamma, beta)
     hi = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=torch.bfloat16 if out_mode == 0 else torch.float32)
-    lo = torch.empty_like(hi) if out_mode == 2 else None
+    lo = _lo_like(out_mode, hi)
     check(lib().glare_gn_apply_nhwc(out_mode, ptr(x_nhwc), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if swish else 0, B, HW, C, G,
                                     ptr(hi), ptr(lo), stream()), "glare_gn_apply_nhwc")
     return hi, lo

@@ -232,6 +232,8 @@ def main():
     if rank == 0:
         pk = peaks()
         roof = dense.roofline(timers, eng, B, lr_dev.shape, pk)
+        if roof is not None and "share_of_step" in roof:
+            roof["share_of_step"] = roof["ms_per_step"] / (ms / args.steps)
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

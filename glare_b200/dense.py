@@ -207,7 +207,7 @@ class TcDense:
             with self._t("attention"):
                 return self.lib.attention(q, k, v)
         ops = self.ops
-        with self._t("attention"):
+        with self._t("attention_total(incl. its conv_tc GEMMs)"):
             qn, kn, vn = _nhwc(q), _nhwc(k), _nhwc(v)
             B, h, w, _ = qn.shape
             N = h * w
@@ -228,13 +228,15 @@ class TcDense:
                 for r0 in range(0, h, band):
                     r1 = min(h, r0 + band)
                     bh = r1 - r0
-                    ops.conv2d_nhwc_tc_ex(self.mode, q_hi[b, r0:r1], None if q_lo is None else q_lo[b, r0:r1], k_hi[b],
-                                          None if k_lo is None else k_lo[b], S, 1, bh, w, C, N, Np, 0)
-                    ops.attn_softmax_rows(self.mode, S, bh * w, Np, N, Np, scale, p_hi, p_lo, Np)
-                    ops.conv2d_nhwc_tc_ex(self.mode, p_hi, p_lo, vt_hi[b], None if vt_lo is None else vt_lo[b], out[b, r0:r1],
-                                          1, bh, w, Np, C, C, 0)
-            if self.timers is not None:
-                self.timers.setdefault("attention_flops", []).append((None, None, 4.0 * B * N * N * C))
+                    gemm_flops = 2.0 * bh * w * N * C
+                    with self._t("conv_tc", gemm_flops):          # the same tcgen05 kernel: counted with the convolutions
+                        ops.conv2d_nhwc_tc_ex(self.mode, q_hi[b, r0:r1], None if q_lo is None else q_lo[b, r0:r1], k_hi[b],
+                                              None if k_lo is None else k_lo[b], S, 1, bh, w, C, N, Np, 0)
+                    with self._t("attn_softmax"):
+                        ops.attn_softmax_rows(self.mode, S, bh * w, Np, N, Np, scale, p_hi, p_lo, Np)
+                    with self._t("conv_tc", gemm_flops):
+                        ops.conv2d_nhwc_tc_ex(self.mode, p_hi, p_lo, vt_hi[b], None if vt_lo is None else vt_lo[b], out[b, r0:r1],
+                                              1, bh, w, Np, C, C, 0)
         return out.permute(0, 3, 1, 2)
 
     def breakdown(self, eng_timers, steps):
@@ -256,10 +258,31 @@ class TcDense:
         fl = sum(f for _, _, f in ev)
         steps = max(1, self.last_steps)
         ach = fl / (ms / 1e3) / 1e12
-        return {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step, mode %s)" % (len(ev) // steps, self.name),
+        issued = {0: 1.0, 1: 1.0, 2: 3.0, 3: 2.0}[self.mode]          # tf32-equivalent MMA passes per algorithmic MAC
+        return {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM: convolutions + attention GEMMs, %d launches/step, mode %s)"
+                          % (len(ev) // steps, self.name),
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                "traffic": None, "ms_per_step": ms / steps, "algorithmic_tflop_per_step": fl / steps / 1e12,
+                "traffic": self._traffic(B), "ms_per_step": ms / steps, "share_of_step": None,
+                "algorithmic_tflop_per_step": fl / steps / 1e12, "launches_per_step": len(ev) // steps,
+                "mma_passes_per_algorithmic_mac": issued,
+                "note": "achieved counts algorithmic FLOPs (2*Cin*Cout*k*k per pixel, 4*N*N*C per attention block); fp32-grade modes "
+                        "issue %g tensor-core passes per MAC at the tf32 rate (half the bf16 rate the peak is measured in)" % issued,
                 "peak_source": pk["src"] + " (cuBLAS bf16 sustained)"}
+
+    def _traffic(self, B):
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch of conv_tc_kernel, from the committed ncu capture of this
+        exact configuration (profiles/conv_tc_traffic.json); None when no capture matches."""
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "conv_tc_traffic.json")
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            if t.get("mode") != self.name or t.get("batch") != B:
+                return None
+            return t["dram_bytes_per_launch"]
+        except Exception:
+            return None
 
 
 def make_dense(name="auto"):

@@ -118,7 +118,7 @@ def test_attention_gemm_path(glare_lib, shape, mode, tol):
     assert err < tol * max(1.0, float(ref.abs().max())), (shape, mode, err)
 
 
-@pytest.mark.parametrize("mode,tol", [(3, 2e-5), (2, 2e-5), (1, 3e-3), (0, 2e-2)])
+@pytest.mark.parametrize("mode,tol", [(3, 2e-5), (2, 2e-5), (1, 3e-3), (0, 2e-4)])
 def test_dense_backend_covers_small_channel_and_stride2_convs(glare_lib, mode, tol):
     """TcDense: 3-channel convs (channels zero-padded to the K chunk, 3-channel heads through a padded pixel stride) and
     Downsample (encoder_decoder.py:68-72: pad (0,1,0,1) + stride 2) on the tcgen05 kernel, vs cuDNN fp32"""
@@ -131,14 +131,18 @@ def test_dense_backend_covers_small_channel_and_stride2_convs(glare_lib, mode, t
         w = (torch.randn((Co, Ci, ks, ks), generator=g) / (ks * Ci ** 0.5)).cuda()
         b = torch.randn((Co,), generator=g).cuda()
         y = d.conv2d(x, w, b, stride=1, padding=ks // 2)
-        ref = F.conv2d(x, w, b, padding=ks // 2)
+        if mode == 0:
+            x, w = x.bfloat16().float(), w.bfloat16().float()
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=ks // 2)       # fp64: cuDNN's fp32 pick for tiny Cout is ~1e-4
         assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max())), (Ci, Co, ks)
     for (C, Co, H, W) in [(128, 128, 20, 31), (256, 256, 21, 30), (128, 128, 420, 620)]:
         x = torch.randn((1, C, H, W), generator=g).cuda()
         w = (torch.randn((Co, C, 3, 3), generator=g) / (3 * C ** 0.5)).cuda()
         b = torch.randn((Co,), generator=g).cuda()
         y = d.downsample_conv(x, w, b)
-        ref = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+        if mode == 0:
+            x, w = x.bfloat16().float(), w.bfloat16().float()
+        ref = F.conv2d(F.pad(x, (0, 1, 0, 1)).double(), w.double(), b.double(), stride=2)
         assert y.shape == ref.shape
         assert float((y - ref).abs().max()) < tol * max(1.0, float(ref.abs().max())), (C, H, W)
     assert not d.fallbacks

@@ -37,7 +37,10 @@ struct ConvTcArgs {
     float* y;                // NHWC [B,H,W,Cout]
     int B, H, W, Cin, Cout, ksize, pad, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;   // H, W: OUTPUT size
     int stride;              // 1, or 2 (Downsample: zero pad right/bottom, pad = 0; the TMA box walks the input with stride 2)
-    int total_tiles;
+    int ntaps, tap_w, tap_dy0, tap_dx0;   // filter taps: tap t reads input offset (t / tap_w + tap_dy0, t % tap_w + tap_dx0)
+    int oscale, oa, ob;      // output pixel of tile pixel (y, x) = (y * oscale + oa, x * oscale + ob): 2 for the sub-pixel phases of Upsample+conv
+    int total_tiles;         // cluster work items: ceil(m_tiles / CL) * n_blocks
+    int m_tiles;             // B * tiles_y * tiles_x
     int w_batched;           // weights differ per sample (3rd tensor-map coordinate = n): attention S = Q K^T, O = P V
     long long ldy;           // output row (pixel) stride in elements, >= Cout
     int tma_store;           // epilogue: registers -> swizzled smem staging -> TMA tiled store (else per-thread float4 stores)
@@ -59,7 +62,11 @@ struct ConvCfg {
     static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
 };
 
-template <int MODE, int BN>
+// CL = 2: thread-block cluster of two CTAs working on two pixel tiles of the SAME output-channel block; each CTA loads half of
+// the weight tile and TMA-multicasts it into both shared memories, halving the L2 -> SM weight traffic (the fp32-grade modes are
+// L2-bandwidth bound otherwise: 96 KB of operands per 1 M MACs).  A stage is released to the producers of both CTAs by a
+// multicast tcgen05.commit.
+template <int MODE, int BN, int CL>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -85,7 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);                            // one tcgen05.commit per CTA of the cluster
         }
         mbar_init(&tmem_full_bar[0], 1);
         mbar_init(&tmem_full_bar[1], 1);
@@ -96,24 +103,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) tmem_alloc(&s_tmem_base, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                  // peer barriers are initialised before any multicast targets them
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
-    const int k_iters = a.ksize * a.ksize * a.kchunks;
+    const int k_iters = a.ntaps * a.kchunks;
+    const int cl_rank = CL > 1 ? (int)cluster_cta_rank() : 0;
+    const int cl_id = blockIdx.x / CL, n_cl = gridDim.x / CL;
+    const int tiles_xy = a.tiles_y * a.tiles_x;
+    // work item w -> (output-channel block, pixel tile of this CTA); a pixel tile past the end (odd tile count) has n == B:
+    // its loads are out of bounds (zero fill), its stores are clipped
+#define GLARE_DECODE_WORK(w)                                   \
+    const int nb = (w) % a.n_blocks;                           \
+    const int mt = ((w) / a.n_blocks) * CL + cl_rank;          \
+    const int n = mt / tiles_xy;                               \
+    const int r_ = mt - n * tiles_xy;                          \
+    const int ty = r_ / a.tiles_x, tx = r_ - ty * a.tiles_x;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int nb = tile % a.n_blocks;                       // N blocks fastest: CTAs running together share the A tile in L2
-                int r = tile / a.n_blocks;
-                const int n = r / (a.tiles_y * a.tiles_x);
-                r -= n * a.tiles_y * a.tiles_x;
-                const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-                const int y0 = ty * a.TH * a.stride - a.pad, x0 = tx * a.TW * a.stride - a.pad;
-                for (int tap = 0; tap < a.ksize * a.ksize; ++tap) {
-                    const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
+            for (int w = cl_id; w < a.total_tiles; w += n_cl) {
+                GLARE_DECODE_WORK(w)
+                const int y0 = ty * a.TH * a.stride + a.tap_dy0, x0 = tx * a.TW * a.stride + a.tap_dx0;
+                for (int tap = 0; tap < a.ntaps; ++tap) {
+                    const int dy = tap / a.tap_w, dx = tap - dy * a.tap_w;
                     for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
@@ -121,13 +136,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                         tma_load_4d(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
-                        const int wn = a.w_batched ? n : 0;
-                        tma_load_3d(st + CT_A_BYTES, &tmB, &full_bar[s], tap * a.Cin + kc * Cfg::BKE, nb * BN, wn);
+                        const int wn = a.w_batched ? (n < a.B ? n : a.B - 1) : 0;   // a dummy tile still feeds the peer real weights
+                        const int kw = tap * a.Cin + kc * Cfg::BKE;
+                        const int km = Cfg::XB ? 2 : 1;                   // the bf16 x tensors hold 64 elements per 32-element K chunk
+                        uint8_t* lo = st + CT_A_BYTES + Cfg::B_BYTES;
+                        if (CL == 1) {
+                            tma_load_3d(st + CT_A_BYTES, &tmB, &full_bar[s], kw, nb * BN, wn);
+                        } else {                                          // my half of the weight rows, delivered to both CTAs
+                            const int half = cl_rank * (BN / 2);
+                            tma_load_3d_mc(st + CT_A_BYTES + half * 128, &tmB, &full_bar[s], kw, nb * BN + half, wn, (uint16_t)0x3);
+                            if (Cfg::X3)
+                                tma_load_3d_mc(lo + CT_A_BYTES + half * 128, &tmBlo, &full_bar[s], km * kw, nb * BN + half, wn, (uint16_t)0x3);
+                        }
                         if (Cfg::X3) {
-                            uint8_t* lo = st + CT_A_BYTES + Cfg::B_BYTES;
-                            const int km = Cfg::XB ? 2 : 1;               // the bf16 x tensors hold 64 elements per 32-element K chunk
                             tma_load_4d(lo, &tmAlo, &full_bar[s], km * kc * Cfg::BKE, x0 + dx, y0 + dy, n);
-                            tma_load_3d(lo + CT_A_BYTES, &tmBlo, &full_bar[s], km * (tap * a.Cin + kc * Cfg::BKE), nb * BN, wn);
+                            if (CL == 1) tma_load_3d(lo + CT_A_BYTES, &tmBlo, &full_bar[s], km * kw, nb * BN, wn);
                         }
                     }
                 }
@@ -138,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(Cfg::TF32 ? 2 : 1, 128, BN);
             uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+            for (int w = cl_id; w < a.total_tiles; w += n_cl, ++tcount) {
                 const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait_bounded(&tmem_empty_bar[as], aph ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
@@ -171,7 +194,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             umma_ss<false>(d_tmem, dal + adv, dbl + 4 + adv, idesc_bf, 1u);      // A * B_lo
                         }
                     }
-                    umma_commit(&empty_bar[s]);                         // stage reusable once these MMAs retire
+                    if (CL == 1) umma_commit(&empty_bar[s]);            // stage reusable once these MMAs retire
+                    else umma_commit_mc(&empty_bar[s], (uint16_t)0x3);  // ... in both CTAs: the peer multicasts into this stage too
                 }
                 umma_commit(&tmem_full_bar[as]);                        // accumulator complete -> epilogue
             }
@@ -184,18 +208,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool issuer = threadIdx.x == 64;                           // first epilogue thread issues the TMA stores
         uint8_t* const staging = smem_al + (size_t)STAGES * Cfg::STAGE_BYTES;
         uint32_t tcount = 0, chunk_id = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
-            const int nb = tile % a.n_blocks;
-            int r = tile / a.n_blocks;
-            const int n = r / (a.tiles_y * a.tiles_x);
-            r -= n * a.tiles_y * a.tiles_x;
-            const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+        for (int w = cl_id; w < a.total_tiles; w += n_cl, ++tcount) {
+            GLARE_DECODE_WORK(w)
             const int gy = ty * a.TH + py, gx = tx * a.TW + px;
-            const bool valid = gy < a.H && gx < a.W;
+            const bool valid = gy < a.H && gx < a.W && n < a.B;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait_bounded(&tmem_full_bar[as], aph);
             tc_fence_after();
-            const long long pix = ((long long)n * a.H + gy) * a.W + gx;
+            const long long pix = ((long long)n * a.H * a.oscale + (gy * a.oscale + a.oa)) * (a.W * a.oscale) + (gx * a.oscale + a.ob);
             float* yrow = a.y + pix * a.ldy;
             const float* rrow = (a.residual && valid) ? a.residual + pix * a.Cout : nullptr;
 #pragma unroll 1
@@ -243,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async();
                     named_bar_sync(2, 128);
                     if (issuer) {
-                        tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH, n);   // clips pixels / channels outside the tensor
+                        if (n < a.B) tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH, n);   // clips pixels / channels outside the tensor
                         tma_store_commit();
                         tma_store_wait_read<1>();                        // the other staging buffer is free again
                     }
@@ -263,8 +283,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (issuer) tma_store_wait_all<0>();
     }
+#undef GLARE_DECODE_WORK
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                  // no CTA leaves while its peer can still signal its barriers
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -385,16 +407,36 @@ static int make_out_map(CUtensorMap* m, const float* ptr, int B, int H, int W, i
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-template <int MODE, int BN>
-static int launch_conv(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
-                       const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
+template <int MODE, int BN, int CL>
+static int launch_conv_cl(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
+                          const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
     using Cfg = ConvCfg<MODE, BN>;
     static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
-    GLARE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
-    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    conv_tc_kernel<MODE, BN><<<grid, CT_THREADS, Cfg::SMEM_DYN, stream>>>(tA, tAl, tB, tBl, tY, a);
+    auto kern = conv_tc_kernel<MODE, BN, CL>;
+    GLARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
+    const int n_cl = kNumSMs / CL;
+    const int clusters = a.total_tiles < n_cl ? a.total_tiles : n_cl;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    cfg.blockDim = dim3(CT_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_DYN;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GLARE_CUDA(cudaLaunchKernelEx(&cfg, kern, tA, tAl, tB, tBl, tY, a));
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
+}
+
+template <int MODE, int BN>
+static int launch_conv(int cl, const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
+                       const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
+    return cl == 2 ? launch_conv_cl<MODE, BN, 2>(tA, tAl, tB, tBl, tY, a, stream) : launch_conv_cl<MODE, BN, 1>(tA, tAl, tB, tBl, tY, a, stream);
 }
 
 }  // namespace glare
@@ -406,7 +448,7 @@ GLARE_API int glare_conv_tc_elem_bytes(int mode) { return mode == 0 ? 2 : 4; }  
 
 GLARE_API int glare_conv_pack_weight(int mode, const float* w_oihw, int Cout, int Cin, int ksize, void* out_hi, void* out_lo,
                                      cudaStream_t stream) {
-    if (!w_oihw || !out_hi || (mode >= 2 && !out_lo) || mode < 0 || mode > 3 || Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3))
+    if (!w_oihw || !out_hi || (mode >= 2 && !out_lo) || mode < 0 || mode > 3 || Cout <= 0 || Cin <= 0 || ksize < 1 || ksize > 3)
         return GLARE_ERR_BAD_ARG;
     if (mode == 3 && Cin % 32 != 0) return GLARE_ERR_UNSUPPORTED;
     const long long n = (long long)Cout * Cin * ksize * ksize;
@@ -430,15 +472,17 @@ GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* o
 
 // x / x_lo: NHWC [B,H,W,Cin] (bf16 for mode 0, fp32 otherwise; x_lo only for mode 2); w / w_lo: packed by
 // glare_conv_pack_weight; bias [Cout] / residual NHWC [B,H,W,Cout] fp32 or NULL; y NHWC fp32.
+struct TapSpec { int ntaps, tap_w, dy0, dx0, oscale, oa, ob; };
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
-                          const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, int ksize,
-                          int stride, int pad, long long ldy, long long w_batch_stride, cudaStream_t stream);
+                          const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
+                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream);
+static inline TapSpec std_taps(int ksize) { return TapSpec{ksize * ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0}; }
 
 GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                                    const float* residual, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                                    cudaStream_t stream) {
     if (ksize != 1 && ksize != 3) return GLARE_ERR_BAD_ARG;
-    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, H, W, Cin, Cout, ksize, 1, ksize / 2, Cout, 0, stream);
+    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, H, W, Cin, Cout, std_taps(ksize), 1, Cout, 0, stream);
 }
 
 // Downsample.forward (encoder_decoder.py:68-72): zero pad (0,1,0,1) then 3x3 stride-2 conv, pad 0.  x NHWC [B,Hin,Win,Cin];
@@ -447,7 +491,21 @@ GLARE_API int glare_conv2d_nhwc_tc_down2(int mode, const void* x, const void* x_
                                          const float* bias, float* y, int B, int Hin, int Win, int Cin, int Cout, cudaStream_t stream) {
     if (Hin < 2 || Win < 2) return GLARE_ERR_BAD_ARG;
     const int Ho = (Hin + 1 - 3) / 2 + 1, Wo = (Win + 1 - 3) / 2 + 1;
-    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, Hin, Win, Ho, Wo, Cin, Cout, 3, 2, 0, Cout, 0, stream);
+    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, Hin, Win, Ho, Wo, Cin, Cout, TapSpec{9, 3, 0, 0, 1, 0, 0}, 2, Cout, 0,
+                          stream);
+}
+
+// One sub-pixel phase (a, b) in {0,1}^2 of Upsample.forward (encoder_decoder.py:49-53: nearest x2, then 3x3 conv, pad 1):
+// output pixel (2i + a, 2j + b) only sees a 2x2 neighbourhood of the LOW-resolution input, rows {i + a - 1, i + a}, columns
+// {j + b - 1, j + b}, with the 3x3 taps that land on the same source pixel pre-summed into a 2x2 filter (host side, once per
+// weight).  Four launches (one per phase) replace the upsample copy + 3x3 conv at 4/9 of the FLOPs.  x NHWC [B,H,W,Cin] (low
+// resolution), w packed [Cout][4][Cin] for this phase, y NHWC [B,2H,2W,Cout] (full tensor; this call writes one phase).
+GLARE_API int glare_conv2d_nhwc_tc_up2_phase(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo,
+                                             const float* bias, float* y, int B, int H, int W, int Cin, int Cout, int a, int b,
+                                             cudaStream_t stream) {
+    if ((a | b) & ~1) return GLARE_ERR_BAD_ARG;
+    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, H, W, H, W, Cin, Cout, TapSpec{4, 2, a - 1, b - 1, 2, a, b}, 1, Cout, 0,
+                          stream);
 }
 
 // Extended form: ldy = output pixel stride in elements (>= Cout, multiple of 4); w_batch_stride != 0 selects per-sample
@@ -457,15 +515,16 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
                                       const float* bias, const float* residual, float* y, int B, int H, int W, int Cin, int Cout,
                                       int ksize, long long ldy, long long w_batch_stride, cudaStream_t stream) {
     if (ksize != 1 && ksize != 3) return GLARE_ERR_BAD_ARG;
-    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, H, W, Cin, Cout, ksize, 1, ksize / 2, ldy, w_batch_stride,
+    return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, H, W, H, W, Cin, Cout, std_taps(ksize), 1, ldy, w_batch_stride,
                           stream);
 }
 
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
-                          const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, int ksize,
-                          int stride, int pad, long long ldy, long long w_batch_stride, cudaStream_t stream) {
+                          const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
+                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream) {
+    const int ksize = ts.tap_w;
     if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
-    if (mode < 0 || mode > 3 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return GLARE_ERR_BAD_ARG;
+    if (mode < 0 || mode > 3 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize < 1 || ksize > 3)) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
     if (!x || !w || !y || (mode >= 2 && (!x_lo || !w_lo))) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
@@ -473,7 +532,10 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return GLARE_ERR_BAD_ARG;
     ConvTcArgs a{};
     a.bias = bias; a.residual = residual; a.y = y;
-    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.pad = pad; a.stride = stride;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.pad = -ts.dy0; a.stride = stride;
+    a.ntaps = ts.ntaps; a.tap_w = ts.tap_w; a.tap_dy0 = ts.dy0; a.tap_dx0 = ts.dx0;
+    a.oscale = ts.oscale; a.oa = ts.oa; a.ob = ts.ob;
+    if (residual && ts.oscale != 1) return GLARE_ERR_BAD_ARG;
     a.TH = 8; a.TW = 16;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
     a.kchunks = Cin / bke;
@@ -482,9 +544,13 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     const long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
     a.n_blocks = (Cout + BN - 1) / BN;
-    const long long total = (long long)a.n_blocks * m_tiles;
-    if (total > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
+    // clusters of two CTAs share the weight tile by multicast; per-sample weights over a batch cannot be shared across samples
+    static const bool no_cluster = getenv("GLARE_CONV_NO_CLUSTER") != nullptr;    // A/B switch for profiling only
+    const int cl = (no_cluster || (w_batch_stride != 0 && B > 1) || m_tiles < 2) ? 1 : 2;
+    const long long total = (long long)a.n_blocks * ((m_tiles + cl - 1) / cl);
+    if (total > 0x7fffffff || m_tiles > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
     a.total_tiles = (int)total;
+    a.m_tiles = (int)m_tiles;
     a.ldy = ldy;
     a.w_batched = w_batch_stride != 0 ? 1 : 0;
     const int n_w = a.w_batched ? B : 1;
@@ -492,25 +558,25 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     int rc;
     {
         static const bool direct = getenv("GLARE_CONV_DIRECT_STORE") != nullptr;   // A/B switch for profiling only
-        a.tma_store = (!direct && Cout >= 32) ? 1 : 0;
+        a.tma_store = (!direct && Cout >= 32 && ts.oscale == 1) ? 1 : 0;
     }
     if ((rc = make_out_map(&tY, y, B, H, W, Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0;
     if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
-    if ((rc = make_w_map(&tB, w, bf, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
+    if ((rc = make_w_map(&tB, w, bf, Cout, ts.ntaps * Cin, BN / cl, n_w, w_batch_stride)) != GLARE_OK) return rc;
     tAl = tA; tBl = tB;
     if (mode == 2) {
         if ((rc = make_act_map(&tAl, x_lo, false, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
-        if ((rc = make_w_map(&tBl, w_lo, false, Cout, ksize * ksize * Cin, BN, n_w, w_batch_stride)) != GLARE_OK) return rc;
+        if ((rc = make_w_map(&tBl, w_lo, false, Cout, ts.ntaps * Cin, BN / cl, n_w, w_batch_stride)) != GLARE_OK) return rc;
     } else if (mode == 3) {                        // interleaved bf16 x tensors: 2 bf16 per element, same bytes per row as fp32
         if ((rc = make_act_map(&tAl, x_lo, true, B, Hin, Win, 2 * Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
-        if ((rc = make_w_map(&tBl, w_lo, true, Cout, 2 * ksize * ksize * Cin, BN, n_w, 2 * w_batch_stride)) != GLARE_OK) return rc;
+        if ((rc = make_w_map(&tBl, w_lo, true, Cout, 2 * ts.ntaps * Cin, BN / cl, n_w, 2 * w_batch_stride)) != GLARE_OK) return rc;
     }
 #define GLARE_CONV_DISPATCH(M)                                                            \
     do {                                                                                  \
-        if (BN == 256) return launch_conv<M, 256>(tA, tAl, tB, tBl, tY, a, stream);       \
-        if (BN == 128) return launch_conv<M, 128>(tA, tAl, tB, tBl, tY, a, stream);       \
-        return launch_conv<M, 64>(tA, tAl, tB, tBl, tY, a, stream);                       \
+        if (BN == 256) return launch_conv<M, 256>(cl, tA, tAl, tB, tBl, tY, a, stream);   \
+        if (BN == 128) return launch_conv<M, 128>(cl, tA, tAl, tB, tBl, tY, a, stream);   \
+        return launch_conv<M, 64>(cl, tA, tAl, tB, tBl, tY, a, stream);                   \
     } while (0)
     if (mode == 0) GLARE_CONV_DISPATCH(0);
     if (mode == 1) GLARE_CONV_DISPATCH(1);

@@ -114,11 +114,12 @@ class TcDense:
         return _Bracket(self.timers, name, flops)
 
     def _weights(self, w, pad_c=0):
-        key = (w.data_ptr(), tuple(w.shape), pad_c)
+        # keyed by storage address + in-place version; the entry keeps `w` alive so the address cannot be recycled under the cache
+        key = (w.data_ptr(), tuple(w.shape), pad_c, w._version)
         if key not in self._w:
             wp = F.pad(w, (0, 0, 0, 0, 0, pad_c)) if pad_c else w            # zero input channels up to the K chunk
-            self._w[key] = self.ops.conv_pack_weight(self.mode, wp)
-        return self._w[key]
+            self._w[key] = (w, self.ops.conv_pack_weight(self.mode, wp))
+        return self._w[key][1]
 
     def _operand(self, x):
         """logical [B,C,H,W] fp32 tensor -> Operand, input channels zero-padded to a multiple of the 128-byte K chunk"""
@@ -160,6 +161,26 @@ class TcDense:
         res = _nhwc(residual) if residual is not None else None
         with self._t("conv_tc", flops):
             y = self.ops.conv2d_nhwc_tc(self.mode, op.hi, op.lo, w_hi, w_lo, b, res, op.B, op.H, op.W, op.C, Cout, ks)
+        return y.permute(0, 3, 1, 2)
+
+    def upsample_conv(self, x, w, b=None):
+        """Upsample.forward (encoder_decoder.py:49-53): nearest x2 + 3x3 conv, evaluated on the LOW-resolution input as four
+        sub-pixel phases with pre-summed 2x2 filters (no upsampled copy, 4/9 of the FLOPs)"""
+        if not self.cover_all or tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4 or x.shape[1] % self.bke:
+            return None
+        key = ("up2", w.data_ptr(), tuple(w.shape), w._version)
+        if key not in self._w:
+            rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}          # phase -> which 3x3 taps land on source row/col 0 and 1
+            ph = {}
+            for a in (0, 1):
+                for c in (0, 1):
+                    w2 = torch.stack([torch.stack([w[:, :, list(rows[a][r])][:, :, :, list(rows[c][q])].sum(dim=(2, 3))
+                                                   for q in (0, 1)], dim=-1) for r in (0, 1)], dim=-2)      # [Co,Ci,2,2]
+                    ph[(a, c)] = self.ops.conv_pack_weight(self.mode, w2.contiguous())
+            self._w[key] = (w, ph)
+        op, _ = self._operand(x)
+        with self._t("conv_tc", 2.0 * op.B * op.H * op.W * op.C * w.shape[0] * 16):
+            y = self.ops.conv2d_nhwc_tc_up2(self.mode, op.hi, op.lo, self._w[key][1], b, op.B, op.H, op.W, op.C, w.shape[0])
         return y.permute(0, 3, 1, 2)
 
     def downsample_conv(self, x, w, b=None):

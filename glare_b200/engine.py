@@ -132,6 +132,10 @@ class GlareEngine:
 
     def upsample(self, sd, p, x):
         """encoder_decoder.py:49-53"""
+        if hasattr(self.dense, "upsample_conv"):
+            y = self.dense.upsample_conv(x, sd[p + ".conv.weight"], sd.get(p + ".conv.bias"))
+            if y is not None:
+                return y
         return self._conv(sd, p + ".conv", F.interpolate(x, scale_factor=2.0, mode="nearest"))
 
     def vqgan_encode(self, x):

@@ -164,6 +164,17 @@ def conv2d_nhwc_tc_down2(mode, x_hi, x_lo, w_hi, w_lo, bias, B, Hin, Win, Cin, C
     return y
 
 
+def conv2d_nhwc_tc_up2(mode, x_hi, x_lo, phase_weights, bias, B, H, W, Cin, Cout):
+    """Upsample.forward (encoder_decoder.py:49-53) as four sub-pixel phase convolutions -> y NHWC [B,2H,2W,Cout] fp32.
+    phase_weights[(a, b)] = (w_hi, w_lo) packed 2x2 filters"""
+    require_cuda(x_hi, x_lo, bias)
+    y = torch.empty((B, 2 * H, 2 * W, Cout), device=x_hi.device, dtype=torch.float32)
+    for (a, b), (w_hi, w_lo) in phase_weights.items():
+        check(lib().glare_conv2d_nhwc_tc_up2_phase(mode, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(y), B, H, W, Cin, Cout,
+                                                   a, b, stream()), "glare_conv2d_nhwc_tc_up2_phase")
+    return y
+
+
 def conv2d_nhwc_tc_ex(mode, x_hi, x_lo, w_hi, w_lo, y, B, H, W, Cin, Cout, ldy, w_batch_stride, bias=None, ksize=1):
     """form with an output pixel stride and per-sample weights (attention GEMMs, Cout % 4 != 0 heads); writes into ``y``"""
     require_cuda(x_hi, x_lo, w_hi, w_lo, y, bias)

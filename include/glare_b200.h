@@ -128,6 +128,10 @@ int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* 
 /* Downsample.forward (encoder_decoder.py:68-72): zero pad right/bottom by 1 + 3x3 stride-2 conv; y NHWC [B,(Hin-2)/2+1,(Win-2)/2+1,Cout] */
 int glare_conv2d_nhwc_tc_down2(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                                float* y, int B, int Hin, int Win, int Cin, int Cout, cudaStream_t stream);
+/* one sub-pixel phase (a, b) of Upsample.forward (encoder_decoder.py:49-53, nearest x2 + 3x3 conv): 2x2 filter of pre-summed taps on the
+ * low-resolution x NHWC [B,H,W,Cin], writes pixels (2i+a, 2j+b) of y NHWC [B,2H,2W,Cout]; w packed [Cout][4][Cin] for this phase */
+int glare_conv2d_nhwc_tc_up2_phase(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                                   float* y, int B, int H, int W, int Cin, int Cout, int a, int b, cudaStream_t stream);
 /* extended form: ldy = output pixel stride (elements, >= Cout, % 4 == 0); w_batch_stride != 0 -> per-sample weights
  * w + n * w_batch_stride (the attention GEMMs S = Q K^T and O = P V, encoder_decoder.py:176-187) */
 int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,

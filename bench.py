@@ -235,7 +235,7 @@ def main():
         if roof is not None and "share_of_step" in roof:
             roof["share_of_step"] = roof["ms_per_step"] / (ms / args.steps)
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             one = lr_dev[:1].cpu()

@@ -2,7 +2,8 @@
 
 ``make_dense("torch-fp32")``  cuDNN/cuBLAS fp32 (TF32 off) -- library baseline, bring-up backend
 ``make_dense("torch-bf16")``  cuDNN/cuBLAS bf16            -- library baseline
-``make_dense("auto")``        the best hand-written backend available in the built library, else torch-fp32
+``make_dense("auto")``        = "tc-tf32bf16x2": tcgen05 dense path, fp32-grade (tf32 main term + two bf16 cross terms)
+``make_dense("tc-3xtf32" | "tc-tf32" | "tc-bf16")``  the same kernels in the other operand modes
 """
 import torch
 import torch.nn.functional as F
@@ -312,12 +313,12 @@ def make_dense(name="auto"):
         d.attn_impl = "library"
         d.name += "+library-attention"
         return d
-    if name in ("auto", "tc-3xtf32"):
+    if name in ("auto", "tc-tf32bf16x2"):
+        return TcDense(3)
+    if name == "tc-3xtf32":
         return TcDense(2)
     if name == "tc-tf32":
         return TcDense(1)
-    if name == "tc-tf32bf16x2":
-        return TcDense(3)
     if name == "tc-bf16":
         return TcDense(0)
     if name == "torch-fp32":

@@ -46,13 +46,13 @@ struct ConvTcArgs {
     int tma_store;           // epilogue: registers -> swizzled smem staging -> TMA tiled store (else per-thread float4 stores)
 };
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool PAIR = false>
 struct ConvCfg {
     static constexpr bool XB = MODE == 3;                      // tf32 main term + two bf16 cross terms
     static constexpr bool X3 = MODE == 2 || XB;                // second operand pair (lo / interleaved bf16 x) per stage
     static constexpr bool TF32 = MODE >= 1;
     static constexpr int BKE = TF32 ? 32 : 64;                 // elements per 128-byte K chunk
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;  // CTA pair: each CTA stages half of the weight rows
     static constexpr int STAGE_BYTES = (CT_A_BYTES + B_BYTES) * (X3 ? 2 : 1);
     static constexpr int STAGING_BYTES = 2 * 128 * 128;        // epilogue staging: two 128-pixel x 32-fp32 chunks
     static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*align slack*/ - 1024 /*static*/ - STAGING_BYTES;
@@ -62,16 +62,28 @@ struct ConvCfg {
     static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
 };
 
-// CL = 2: thread-block cluster of two CTAs working on two pixel tiles of the SAME output-channel block; each CTA loads half of
+template <bool TF32, bool PAIR>
+__device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma_ss_2sm<TF32>(d, da, db, idesc, acc);
+    else umma_ss<TF32>(d, da, db, idesc, acc);
+}
+
+// CM = 1: thread-block cluster of two CTAs working on two pixel tiles of the SAME output-channel block; each CTA loads half of
 // the weight tile and TMA-multicasts it into both shared memories, halving the L2 -> SM weight traffic (the fp32-grade modes are
 // L2-bandwidth bound otherwise: 96 KB of operands per 1 M MACs).  A stage is released to the producers of both CTAs by a
 // multicast tcgen05.commit.
-template <int MODE, int BN, int CL>
+// CM = 2: CTA pair (cta_group::2).  The two CTAs of a cluster form ONE 256-pixel x BN tile: each stages its own 128 pixel rows
+// and HALF of the weight rows, all TMA loads signal the leader's barrier, the leader's MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both halves and accumulates each CTA's 128 rows into that CTA's TMEM.
+// Weight staging traffic and weight shared-memory reads per CTA are halved -- the binding resources of the fp32-grade modes.
+template <int MODE, int BN, int CM>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmY, const ConvTcArgs a) {
-    using Cfg = ConvCfg<MODE, BN>;
+    constexpr int CL = CM == 0 ? 1 : 2;
+    constexpr bool PAIR = CM == 2, MCAST = CM == 1;
+    using Cfg = ConvCfg<MODE, BN, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
@@ -91,16 +103,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CL);                            // one tcgen05.commit per CTA of the cluster
+            mbar_init(&full_bar[s], PAIR ? 2 : 1);                   // pair: one arrival per CTA's producer, on the leader's barrier
+            mbar_init(&empty_bar[s], MCAST ? 2 : 1);                 // multicast: one tcgen05.commit per CTA of the cluster
         }
         mbar_init(&tmem_full_bar[0], 1);
         mbar_init(&tmem_full_bar[1], 1);
-        mbar_init(&tmem_empty_bar[0], 128);
-        mbar_init(&tmem_empty_bar[1], 128);
+        mbar_init(&tmem_empty_bar[0], PAIR ? 256 : 128);             // pair: the epilogue threads of both CTAs release the leader
+        mbar_init(&tmem_empty_bar[1], PAIR ? 256 : 128);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&s_tmem_base, Cfg::TMEM_COLS);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_2sm(&s_tmem_base, Cfg::TMEM_COLS);
+        else tmem_alloc(&s_tmem_base, Cfg::TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                                  // peer barriers are initialised before any multicast targets them
@@ -134,12 +149,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t ph = (it / STAGES) & 1;
                         mbar_wait_bounded(&empty_bar[s], ph ^ 1);
                         uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                        tma_load_4d(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
                         const int wn = a.w_batched ? (n < a.B ? n : a.B - 1) : 0;   // a dummy tile still feeds the peer real weights
                         const int kw = tap * a.Cin + kc * Cfg::BKE;
                         const int km = Cfg::XB ? 2 : 1;                   // the bf16 x tensors hold 64 elements per 32-element K chunk
                         uint8_t* lo = st + CT_A_BYTES + Cfg::B_BYTES;
+                        if (PAIR) {
+                            // every byte of both CTAs lands on the leader's barrier; my weight slice = rows [rank * BN/2, +BN/2)
+                            if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+                            else mbar_arrive_cluster(&full_bar[s], 0);
+                            const int half = cl_rank * (BN / 2);
+                            tma_load_4d_2sm(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
+                            tma_load_3d_2sm(st + CT_A_BYTES, &tmB, &full_bar[s], kw, nb * BN + half, wn);
+                            if (Cfg::X3) {
+                                tma_load_4d_2sm(lo, &tmAlo, &full_bar[s], km * kc * Cfg::BKE, x0 + dx, y0 + dy, n);
+                                tma_load_3d_2sm(lo + CT_A_BYTES, &tmBlo, &full_bar[s], km * kw, nb * BN + half, wn);
+                            }
+                            continue;
+                        }
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                        tma_load_4d(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
                         if (CL == 1) {
                             tma_load_3d(st + CT_A_BYTES, &tmB, &full_bar[s], kw, nb * BN, wn);
                         } else {                                          // my half of the weight rows, delivered to both CTAs
@@ -158,8 +186,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(Cfg::TF32 ? 2 : 1, 128, BN);
+        if (lane == 0 && (!PAIR || cl_rank == 0)) {                     // pair: only the leader CTA issues
+            constexpr uint32_t idesc = umma_idesc(Cfg::TF32 ? 2 : 1, PAIR ? 256 : 128, BN);
             uint32_t it = 0, tcount = 0;
             for (int w = cl_id; w < a.total_tiles; w += n_cl, ++tcount) {
                 const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -178,26 +206,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {                       // 4 x 32-byte K steps inside the 128-byte swizzle row
                         const uint64_t adv = (uint64_t)(j * 2);        // +32 bytes in 16-byte units
-                        umma_ss<Cfg::TF32>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
+                        mma<Cfg::TF32, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
                         if (Cfg::X3 && !Cfg::XB) {
-                            umma_ss<true>(d_tmem, dal + adv, db + adv, idesc, 1u);
-                            umma_ss<true>(d_tmem, da + adv, dbl + adv, idesc, 1u);
+                            mma<true, PAIR>(d_tmem, dal + adv, db + adv, idesc, 1u);
+                            mma<true, PAIR>(d_tmem, da + adv, dbl + adv, idesc, 1u);
                         }
                     }
                     if (Cfg::XB) {
                         // x tiles: bytes [0,64) of a row = bf16(x) for the chunk's 32 k, bytes [64,128) = bf16(lo); K = 16 per MMA
-                        constexpr uint32_t idesc_bf = umma_idesc(1, 128, BN);
+                        constexpr uint32_t idesc_bf = umma_idesc(1, PAIR ? 256 : 128, BN);
 #pragma unroll
                         for (int jj = 0; jj < 2; ++jj) {
                             const uint64_t adv = (uint64_t)(jj * 2);
-                            umma_ss<false>(d_tmem, dal + 4 + adv, dbl + adv, idesc_bf, 1u);      // A_lo * B
-                            umma_ss<false>(d_tmem, dal + adv, dbl + 4 + adv, idesc_bf, 1u);      // A * B_lo
+                            mma<false, PAIR>(d_tmem, dal + 4 + adv, dbl + adv, idesc_bf, 1u);      // A_lo * B
+                            mma<false, PAIR>(d_tmem, dal + adv, dbl + 4 + adv, idesc_bf, 1u);      // A * B_lo
                         }
                     }
-                    if (CL == 1) umma_commit(&empty_bar[s]);            // stage reusable once these MMAs retire
-                    else umma_commit_mc(&empty_bar[s], (uint16_t)0x3);  // ... in both CTAs: the peer multicasts into this stage too
+                    if (PAIR) umma_commit_2sm_mc(&empty_bar[s], (uint16_t)0x3);   // frees the stage in both CTAs
+                    else if (MCAST) umma_commit_mc(&empty_bar[s], (uint16_t)0x3); // the peer multicasts into this stage too
+                    else umma_commit(&empty_bar[s]);                    // stage reusable once these MMAs retire
                 }
-                umma_commit(&tmem_full_bar[as]);                        // accumulator complete -> epilogue
+                if (PAIR) umma_commit_2sm_mc(&tmem_full_bar[as], (uint16_t)0x3);   // accumulator halves complete in both CTAs
+                else umma_commit(&tmem_full_bar[as]);                   // accumulator complete -> epilogue
             }
         }
     } else {
@@ -225,7 +255,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_wait();
                 if (c0 + 32 >= BN) {                                     // accumulator fully read: hand it back to the MMA thread
                     tc_fence_before();
-                    mbar_arrive(&tmem_empty_bar[as]);
+                    if (PAIR) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // ... which lives in the leader CTA
+                    else mbar_arrive(&tmem_empty_bar[as]);
                 }
                 const int co = nb * BN + c0;
                 if (co >= a.Cout) continue;                              // uniform over the CTA
@@ -289,7 +320,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CL > 1) cluster_sync_all();                                  // no CTA leaves while its peer can still signal its barriers
     if (warp == 1) {
         __syncwarp();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -407,12 +439,13 @@ static int make_out_map(CUtensorMap* m, const float* ptr, int B, int H, int W, i
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-template <int MODE, int BN, int CL>
+template <int MODE, int BN, int CM>
 static int launch_conv_cl(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
                           const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
-    using Cfg = ConvCfg<MODE, BN>;
+    constexpr int CL = CM == 0 ? 1 : 2;
+    using Cfg = ConvCfg<MODE, BN, CM == 2>;
     static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
-    auto kern = conv_tc_kernel<MODE, BN, CL>;
+    auto kern = conv_tc_kernel<MODE, BN, CM>;
     GLARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
     const int n_cl = kNumSMs / CL;
     const int clusters = a.total_tiles < n_cl ? a.total_tiles : n_cl;
@@ -436,7 +469,9 @@ static int launch_conv_cl(const CUtensorMap& tA, const CUtensorMap& tAl, const C
 template <int MODE, int BN>
 static int launch_conv(int cl, const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
                        const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
-    return cl == 2 ? launch_conv_cl<MODE, BN, 2>(tA, tAl, tB, tBl, tY, a, stream) : launch_conv_cl<MODE, BN, 1>(tA, tAl, tB, tBl, tY, a, stream);
+    // cl: 1 = single CTA, 2 = multicast cluster, 3 = CTA pair (cta_group::2)
+    if (cl == 3) return launch_conv_cl<MODE, BN, 2>(tA, tAl, tB, tBl, tY, a, stream);
+    return cl == 2 ? launch_conv_cl<MODE, BN, 1>(tA, tAl, tB, tBl, tY, a, stream) : launch_conv_cl<MODE, BN, 0>(tA, tAl, tB, tBl, tY, a, stream);
 }
 
 }  // namespace glare
@@ -545,9 +580,12 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
     a.n_blocks = (Cout + BN - 1) / BN;
     // clusters of two CTAs share the weight tile by multicast; per-sample weights over a batch cannot be shared across samples
-    static const bool no_cluster = getenv("GLARE_CONV_NO_CLUSTER") != nullptr;    // A/B switch for profiling only
-    const int cl = (no_cluster || (w_batch_stride != 0 && B > 1) || m_tiles < 2) ? 1 : 2;
-    const long long total = (long long)a.n_blocks * ((m_tiles + cl - 1) / cl);
+    static const bool no_cluster = getenv("GLARE_CONV_NO_CLUSTER") != nullptr;    // A/B switches for profiling only
+    static const bool use_pair = getenv("GLARE_CONV_PAIR") != nullptr;
+    int cl = (no_cluster || (w_batch_stride != 0 && B > 1) || m_tiles < 2) ? 1 : 2;
+    if (cl == 2 && use_pair) cl = 3;
+    const int csz = cl == 1 ? 1 : 2;              // CTAs per cluster (box rows of the weight maps = BN / csz in both cluster modes)
+    const long long total = (long long)a.n_blocks * ((m_tiles + csz - 1) / csz);
     if (total > 0x7fffffff || m_tiles > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
     a.total_tiles = (int)total;
     a.m_tiles = (int)m_tiles;
@@ -563,14 +601,14 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if ((rc = make_out_map(&tY, y, B, H, W, Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0;
     if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
-    if ((rc = make_w_map(&tB, w, bf, Cout, ts.ntaps * Cin, BN / cl, n_w, w_batch_stride)) != GLARE_OK) return rc;
+    if ((rc = make_w_map(&tB, w, bf, Cout, ts.ntaps * Cin, BN / csz, n_w, w_batch_stride)) != GLARE_OK) return rc;
     tAl = tA; tBl = tB;
     if (mode == 2) {
         if ((rc = make_act_map(&tAl, x_lo, false, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
-        if ((rc = make_w_map(&tBl, w_lo, false, Cout, ts.ntaps * Cin, BN / cl, n_w, w_batch_stride)) != GLARE_OK) return rc;
+        if ((rc = make_w_map(&tBl, w_lo, false, Cout, ts.ntaps * Cin, BN / csz, n_w, w_batch_stride)) != GLARE_OK) return rc;
     } else if (mode == 3) {                        // interleaved bf16 x tensors: 2 bf16 per element, same bytes per row as fp32
         if ((rc = make_act_map(&tAl, x_lo, true, B, Hin, Win, 2 * Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
-        if ((rc = make_w_map(&tBl, w_lo, true, Cout, 2 * ts.ntaps * Cin, BN / cl, n_w, 2 * w_batch_stride)) != GLARE_OK) return rc;
+        if ((rc = make_w_map(&tBl, w_lo, true, Cout, 2 * ts.ntaps * Cin, BN / csz, n_w, 2 * w_batch_stride)) != GLARE_OK) return rc;
     }
 #define GLARE_CONV_DISPATCH(M)                                                            \
     do {                                                                                  \

@@ -580,10 +580,11 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
     a.n_blocks = (Cout + BN - 1) / BN;
     // clusters of two CTAs share the weight tile by multicast; per-sample weights over a batch cannot be shared across samples
-    static const bool no_cluster = getenv("GLARE_CONV_NO_CLUSTER") != nullptr;    // A/B switches for profiling only
-    static const bool use_pair = getenv("GLARE_CONV_PAIR") != nullptr;
-    int cl = (no_cluster || (w_batch_stride != 0 && B > 1) || m_tiles < 2) ? 1 : 2;
-    if (cl == 2 && use_pair) cl = 3;
+    // default: CTA pair (cta_group::2).  A/B switches for profiling only: GLARE_CONV_MCAST -> two independent CTAs sharing the weight
+    // tile by TMA multicast, GLARE_CONV_NO_CLUSTER -> single CTAs
+    static const bool no_cluster = getenv("GLARE_CONV_NO_CLUSTER") != nullptr;
+    static const bool use_mcast = getenv("GLARE_CONV_MCAST") != nullptr;
+    int cl = (no_cluster || (w_batch_stride != 0 && B > 1) || m_tiles < 2) ? 1 : (use_mcast ? 2 : 3);
     const int csz = cl == 1 ? 1 : 2;              // CTAs per cluster (box rows of the weight maps = BN / csz in both cluster modes)
     const long long total = (long long)a.n_blocks * ((m_tiles + csz - 1) / csz);
     if (total > 0x7fffffff || m_tiles > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;

@@ -28,6 +28,7 @@ SIGNATURES = {
     "glare_conv2d_nhwc_tc": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "glare_conv2d_nhwc_tc_down2": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "glare_conv2d_nhwc_tc_up2_phase": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "glare_conv2d_nhwc_tc_g": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "glare_conv2d_nhwc_tc_ex": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp],
     "glare_attn_softmax_rows": [_i, _vp, _ll, _ll, _i, _i, ctypes.c_float, _vp, _vp, _ll, _vp],
     "glare_attn_transpose_v": [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp],

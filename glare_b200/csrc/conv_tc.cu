@@ -43,6 +43,8 @@ struct ConvTcArgs {
     int m_tiles;             // B * tiles_y * tiles_x
     int w_batched;           // weights differ per sample (3rd tensor-map coordinate = n): attention S = Q K^T, O = P V
     long long ldy;           // output row (pixel) stride in elements, >= Cout
+    double* gn_stats;        // optional [B][32][2] (sum, sum of squares) of the OUTPUT per GroupNorm group, accumulated in the epilogue
+    int gn_cpg;              // channels per group (Cout / 32), a multiple of 4
     int tma_store;           // epilogue: registers -> swizzled smem staging -> TMA tiled store (else per-thread float4 stores)
 };
 
@@ -284,6 +286,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+                if (a.gn_stats != nullptr) {
+                    // GroupNorm statistics of what this conv produces (the next layer's Normalize, encoder_decoder.py:34-35):
+                    // per group fp32 partial sums over this thread's channels, warp-reduced over 32 pixels, one fp64 atomic per
+                    // (warp, group) -- saves the separate statistics pass over the activation
+                    const int qpg = a.gn_cpg >> 2;                          // quads of channels per group: 1, 2, 4 or 8
+                    float s4[8], q4[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float v0 = valid ? o[4 * i] : 0.f, v1 = valid ? o[4 * i + 1] : 0.f;
+                        const float v2 = valid ? o[4 * i + 2] : 0.f, v3 = valid ? o[4 * i + 3] : 0.f;
+                        s4[i] = (v0 + v1) + (v2 + v3);
+                        q4[i] = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, v3 * v3)));
+                    }
+                    if (qpg >= 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2) { s4[i] += s4[i + 1]; q4[i] += q4[i + 1]; }
+                    }
+                    if (qpg >= 4) {
+#pragma unroll
+                        for (int i = 0; i < 8; i += 4) { s4[i] += s4[i + 2]; q4[i] += q4[i + 2]; }
+                    }
+                    if (qpg >= 8) { s4[0] += s4[4]; q4[0] += q4[4]; }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if ((i & (qpg - 1)) != 0) continue;                   // uniform: first quad of each group
+                        float sm = s4[i], sq = q4[i];
+#pragma unroll
+                        for (int sh = 16; sh > 0; sh >>= 1) {
+                            sm += __shfl_xor_sync(0xffffffffu, sm, sh);
+                            sq += __shfl_xor_sync(0xffffffffu, sq, sh);
+                        }
+                        if (lane == 0 && n < a.B && co + 4 * i < a.Cout) {
+                            double* st = a.gn_stats + ((long long)n * 32 + (co + 4 * i) / a.gn_cpg) * 2;
+                            atomicAdd(st, (double)sm);
+                            atomicAdd(st + 1, (double)sq);
+                        }
+                    }
+                }
                 if (a.tma_store) {
                     uint8_t* buf = staging + (chunk_id & 1) * (128 * 128);
                     named_bar_sync(1, 128);                              // issuer has seen the previous store of this buffer drain
@@ -510,7 +550,8 @@ GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* o
 struct TapSpec { int ntaps, tap_w, dy0, dx0, oscale, oa, ob; };
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
-                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream);
+                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats = nullptr,
+                          int gn_zero = 0);
 static inline TapSpec std_taps(int ksize) { return TapSpec{ksize * ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0}; }
 
 GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
@@ -543,6 +584,31 @@ GLARE_API int glare_conv2d_nhwc_tc_up2_phase(int mode, const void* x, const void
                           stream);
 }
 
+// General form used by the Python host: kind 0 = 3x3 / 1x1 stride-1 conv, 1 = Downsample conv (stride 2), 2 = one sub-pixel phase
+// (pa, pb) of Upsample+conv.  gn_stats (optional, [B][32][2] fp64): GroupNorm(32) sum / sum-of-squares of the OUTPUT accumulated in
+// the epilogue; gn_zero != 0 clears it first (phases 2..4 of an upsample conv accumulate into the same buffer).
+GLARE_API int glare_conv2d_nhwc_tc_g(int mode, int kind, const void* x, const void* x_lo, const void* w, const void* w_lo,
+                                     const float* bias, const float* residual, float* y, int B, int Hin, int Win, int Cin, int Cout,
+                                     int ksize, int pa, int pb, double* gn_stats, int gn_zero, cudaStream_t stream) {
+    if (kind == 0) {
+        if (ksize != 1 && ksize != 3) return GLARE_ERR_BAD_ARG;
+        return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, Hin, Win, Hin, Win, Cin, Cout, std_taps(ksize), 1, Cout, 0, stream,
+                              gn_stats, gn_zero);
+    }
+    if (kind == 1) {
+        if (Hin < 2 || Win < 2 || residual) return GLARE_ERR_BAD_ARG;
+        const int Ho = (Hin + 1 - 3) / 2 + 1, Wo = (Win + 1 - 3) / 2 + 1;
+        return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, Hin, Win, Ho, Wo, Cin, Cout, TapSpec{9, 3, 0, 0, 1, 0, 0}, 2, Cout, 0,
+                              stream, gn_stats, gn_zero);
+    }
+    if (kind == 2) {
+        if (((pa | pb) & ~1) || residual) return GLARE_ERR_BAD_ARG;
+        return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, Hin, Win, Hin, Win, Cin, Cout,
+                              TapSpec{4, 2, pa - 1, pb - 1, 2, pa, pb}, 1, Cout, 0, stream, gn_stats, gn_zero);
+    }
+    return GLARE_ERR_BAD_ARG;
+}
+
 // Extended form: ldy = output pixel stride in elements (>= Cout, multiple of 4); w_batch_stride != 0 selects per-sample
 // weights w[n] = w + n * w_batch_stride elements (the two attention GEMMs: S = Q K^T with W = K[n], O = P V with
 // W = V[n]^T -- encoder_decoder.py:176-187).  residual must be null when ldy != Cout.
@@ -556,8 +622,10 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
 
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
-                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream) {
+                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats, int gn_zero) {
     const int ksize = ts.tap_w;
+    if (gn_stats && (Cout % 128 != 0 || B <= 0)) return GLARE_ERR_UNSUPPORTED;       // 32 groups of a multiple of 4 channels
+    if (gn_stats && gn_zero) GLARE_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 64 * (size_t)B, stream));
     if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
     if (mode < 0 || mode > 3 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize < 1 || ksize > 3)) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
@@ -568,6 +636,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     ConvTcArgs a{};
     a.bias = bias; a.residual = residual; a.y = y;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.pad = -ts.dy0; a.stride = stride;
+    a.gn_stats = gn_stats; a.gn_cpg = Cout / 32;
     a.ntaps = ts.ntaps; a.tap_w = ts.tap_w; a.tap_dy0 = ts.dy0; a.tap_dx0 = ts.dx0;
     a.oscale = ts.oscale; a.oa = ts.oa; a.ob = ts.ob;
     if (residual && ts.oscale != 1) return GLARE_ERR_BAD_ARG;

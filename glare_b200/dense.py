@@ -104,6 +104,7 @@ class TcDense:
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
+        self.fuse_gn_stats = True      # GroupNorm sum / sum-of-squares of a conv's output accumulated in its epilogue
         self.cover_all = True          # 3-channel convs (channel-padded) and stride-2 Downsample convs on the tcgen05 kernel too
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
@@ -160,9 +161,24 @@ class TcDense:
             y = y[..., :Cout].permute(0, 3, 1, 2)
             return y if residual is None else y + residual
         res = _nhwc(residual) if residual is not None else None
+        y = torch.empty((op.B, op.H, op.W, Cout), device=op.hi.device, dtype=torch.float32)
+        stats = self._new_stats(op.B, Cout)
         with self._t("conv_tc", flops):
-            y = self.ops.conv2d_nhwc_tc(self.mode, op.hi, op.lo, w_hi, w_lo, b, res, op.B, op.H, op.W, op.C, Cout, ks)
-        return y.permute(0, 3, 1, 2)
+            self.ops.conv2d_nhwc_tc_g(self.mode, 0, op.hi, op.lo, w_hi, w_lo, b, res, y, op.B, op.H, op.W, op.C, Cout, ksize=ks,
+                                      gn_stats=stats)
+        return self._tag(y.permute(0, 3, 1, 2), stats)
+
+    def _new_stats(self, B, Cout):
+        """fp64 [B,32,2] buffer for GroupNorm statistics fused into the conv epilogue (None when the output cannot feed Normalize)"""
+        if not self.fuse_gn_stats or Cout % 128:
+            return None
+        return torch.empty((B, 32, 2), device="cuda", dtype=torch.float64)
+
+    @staticmethod
+    def _tag(y, stats):
+        if stats is not None:
+            y._glare_gn_stats = stats          # consumed by gn_swish if this very tensor is normalised next
+        return y
 
     def upsample_conv(self, x, w, b=None):
         """Upsample.forward (encoder_decoder.py:49-53): nearest x2 + 3x3 conv, evaluated on the LOW-resolution input as four
@@ -180,9 +196,16 @@ class TcDense:
                     ph[(a, c)] = self.ops.conv_pack_weight(self.mode, w2.contiguous())
             self._w[key] = (w, ph)
         op, _ = self._operand(x)
-        with self._t("conv_tc", 2.0 * op.B * op.H * op.W * op.C * w.shape[0] * 16):
-            y = self.ops.conv2d_nhwc_tc_up2(self.mode, op.hi, op.lo, self._w[key][1], b, op.B, op.H, op.W, op.C, w.shape[0])
-        return y.permute(0, 3, 1, 2)
+        Cout = w.shape[0]
+        y = torch.empty((op.B, 2 * op.H, 2 * op.W, Cout), device=op.hi.device, dtype=torch.float32)
+        stats = self._new_stats(op.B, Cout)
+        with self._t("conv_tc", 2.0 * op.B * op.H * op.W * op.C * Cout * 16):
+            first = True
+            for (pa, pb), (w_hi, w_lo) in self._w[key][1].items():
+                self.ops.conv2d_nhwc_tc_g(self.mode, 2, op.hi, op.lo, w_hi, w_lo, b, None, y, op.B, op.H, op.W, op.C, Cout, ksize=2, pa=pa,
+                                          pb=pb, gn_stats=stats, gn_zero=first)
+                first = False
+        return self._tag(y.permute(0, 3, 1, 2), stats)
 
     def downsample_conv(self, x, w, b=None):
         """Downsample.forward (encoder_decoder.py:68-72): pad (0,1,0,1) + 3x3 stride-2 conv, padding by TMA zero fill"""
@@ -191,9 +214,12 @@ class TcDense:
         op, pad_c = self._operand(x)
         w_hi, w_lo = self._weights(w, pad_c)
         Ho, Wo = (op.H - 2) // 2 + 1, (op.W - 2) // 2 + 1
-        with self._t("conv_tc", 2.0 * op.B * Ho * Wo * x.shape[1] * w.shape[0] * 9):
-            y = self.ops.conv2d_nhwc_tc_down2(self.mode, op.hi, op.lo, w_hi, w_lo, b, op.B, op.H, op.W, op.C, w.shape[0])
-        return y.permute(0, 3, 1, 2)
+        Cout = w.shape[0]
+        y = torch.empty((op.B, Ho, Wo, Cout), device=op.hi.device, dtype=torch.float32)
+        stats = self._new_stats(op.B, Cout)
+        with self._t("conv_tc", 2.0 * op.B * Ho * Wo * x.shape[1] * Cout * 9):
+            self.ops.conv2d_nhwc_tc_g(self.mode, 1, op.hi, op.lo, w_hi, w_lo, b, None, y, op.B, op.H, op.W, op.C, Cout, gn_stats=stats)
+        return self._tag(y.permute(0, 3, 1, 2), stats)
 
     def gn_swish(self, x, gamma, beta, swish=True):
         C = x.shape[1]
@@ -201,9 +227,11 @@ class TcDense:
             self.fallbacks["groupnorm C=%d" % C] = self.fallbacks.get("groupnorm C=%d" % C, 0) + 1
             return self.lib.gn_swish(x, gamma, beta, swish)
         with self._t("groupnorm"):
+            stats = getattr(x, "_glare_gn_stats", None)            # produced by the conv epilogue that wrote x
             xn = _nhwc(x)
             B, H, W, _ = xn.shape
-            stats = self.ops.gn_stats(xn, B, H * W, C)
+            if stats is None:
+                stats = self.ops.gn_stats(xn, B, H * W, C)
             hi, lo = self.ops.gn_apply(self.mode, xn, stats, gamma, beta, swish, B, H * W, C)
         return Operand(self.mode, hi, lo, B, C, H, W)
 

@@ -154,6 +154,15 @@ def dcnv2_pack_fwd_nhwc_tc(mode, x_nhwc, offmask_nhwc, w_hi, w_lo, bias, B, H, W
     return y
 
 
+def conv2d_nhwc_tc_g(mode, kind, x_hi, x_lo, w_hi, w_lo, bias, residual, y, B, Hin, Win, Cin, Cout, ksize=3, pa=0, pb=0, gn_stats=None,
+                     gn_zero=True):
+    """general conv entry (kind 0 stride-1, 1 Downsample, 2 Upsample phase) with optional fused GroupNorm statistics of the output"""
+    require_cuda(x_hi, x_lo, w_hi, w_lo, bias, residual, y, gn_stats)
+    check(lib().glare_conv2d_nhwc_tc_g(mode, kind, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(residual), ptr(y), B, Hin, Win,
+                                       Cin, Cout, ksize, pa, pb, ptr(gn_stats), 1 if gn_zero else 0, stream()), "glare_conv2d_nhwc_tc_g")
+    return y
+
+
 def conv2d_nhwc_tc_down2(mode, x_hi, x_lo, w_hi, w_lo, bias, B, Hin, Win, Cin, Cout):
     """Downsample.forward (encoder_decoder.py:68-72) -> y NHWC [B,Ho,Wo,Cout] fp32"""
     require_cuda(x_hi, x_lo, w_hi, w_lo, bias)

@@ -132,6 +132,11 @@ int glare_conv2d_nhwc_tc_down2(int mode, const void* x, const void* x_lo, const 
  * low-resolution x NHWC [B,H,W,Cin], writes pixels (2i+a, 2j+b) of y NHWC [B,2H,2W,Cout]; w packed [Cout][4][Cin] for this phase */
 int glare_conv2d_nhwc_tc_up2_phase(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                                    float* y, int B, int H, int W, int Cin, int Cout, int a, int b, cudaStream_t stream);
+/* general form: kind 0 = stride-1 conv, 1 = Downsample conv, 2 = sub-pixel phase (pa, pb) of Upsample+conv; gn_stats (optional,
+ * [B][32][2] fp64) receives the GroupNorm(32) sum / sum of squares of the OUTPUT from the epilogue (gn_zero != 0 clears it first) */
+int glare_conv2d_nhwc_tc_g(int mode, int kind, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
+                           const float* residual, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize, int pa, int pb,
+                           double* gn_stats, int gn_zero, cudaStream_t stream);
 /* extended form: ldy = output pixel stride (elements, >= Cout, % 4 == 0); w_batch_stride != 0 -> per-sample weights
  * w + n * w_batch_stride (the attention GEMMs S = Q K^T and O = P V, encoder_decoder.py:176-187) */
 int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,

@@ -104,7 +104,10 @@ class TcDense:
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
-        self.fuse_gn_stats = True      # GroupNorm sum / sum-of-squares of a conv's output accumulated in its epilogue
+        # GroupNorm sum / sum-of-squares of a conv's output accumulated in its epilogue.  Measured on B200 (profiles/r01k_*): saves 19 ms of
+        # statistics passes per step but lengthens the short-K conv epilogues by 46 ms (warp reductions + fp64 atomics on the critical
+        # path of the TMEM drain), so it is OFF by default; the separate gn_stats kernel is HBM-bound and cheaper.
+        self.fuse_gn_stats = False
         self.cover_all = True          # 3-channel convs (channel-padded) and stride-2 Downsample convs on the tcgen05 kernel too
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax

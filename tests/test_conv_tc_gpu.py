@@ -180,7 +180,7 @@ def test_groupnorm_statistics_fused_into_conv_epilogue(glare_lib, mode):
     gamma = (1 + 0.1 * torch.randn((C,), generator=g)).cuda()
     beta = (0.1 * torch.randn((C,), generator=g)).cuda()
     d1, d2 = TcDense(mode), TcDense(mode)
-    d2.fuse_gn_stats = False
+    d1.fuse_gn_stats, d2.fuse_gn_stats = True, False
     for fn in (lambda d: d.conv2d(x, w, b, residual=res), lambda d: d.downsample_conv(x, w, b), lambda d: d.upsample_conv(x, w, b)):
         y1, y2 = fn(d1), fn(d2)
         assert hasattr(y1, "_glare_gn_stats") and not hasattr(y2, "_glare_gn_stats")

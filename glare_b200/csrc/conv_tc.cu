@@ -237,8 +237,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                                          // TMEM lane quadrant this warp may access
         const int m = q * 32 + lane;                                     // accumulator row = pixel inside the tile
         const int py = m / a.TW, px = m - py * a.TW;
-        const bool issuer = threadIdx.x == 64;                           // first epilogue thread issues the TMA stores
-        uint8_t* const staging = smem_al + (size_t)STAGES * Cfg::STAGE_BYTES;
+        // each epilogue warp owns its 32 accumulator rows (= 2 image rows x 16 pixels of the tile) end to end: its own two 4 KB
+        // staging buffers and its own TMA stores -- no barrier between the four warps
+        uint8_t* const staging = smem_al + (size_t)STAGES * Cfg::STAGE_BYTES + (size_t)q * (2 * 32 * 128);
         uint32_t tcount = 0, chunk_id = 0;
         for (int w = cl_id; w < a.total_tiles; w += n_cl, ++tcount) {
             GLARE_DECODE_WORK(w)
@@ -325,18 +326,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if (a.tma_store) {
-                    uint8_t* buf = staging + (chunk_id & 1) * (128 * 128);
-                    named_bar_sync(1, 128);                              // issuer has seen the previous store of this buffer drain
+                    uint8_t* buf = staging + (chunk_id & 1) * (32 * 128);
+                    __syncwarp();                                        // lane 0 has seen the previous store of this buffer drain
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)                          // SWIZZLE_128B: 16-byte chunk j of row m at chunk j ^ (m & 7)
-                        *reinterpret_cast<float4*>(buf + m * 128 + ((j ^ (m & 7)) << 4)) =
+                    for (int j = 0; j < 8; ++j)                          // SWIZZLE_128B: 16-byte chunk j of row r at chunk j ^ (r & 7)
+                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                             make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     fence_proxy_async();
-                    named_bar_sync(2, 128);
-                    if (issuer) {
-                        if (n < a.B) tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH, n);   // clips pixels / channels outside the tensor
+                    __syncwarp();
+                    if (lane == 0) {
+                        // box = 32 channels x 16 pixels x 2 rows; clips pixels / channels outside the tensor
+                        if (n < a.B) tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH + 2 * q, n);
                         tma_store_commit();
-                        tma_store_wait_read<1>();                        // the other staging buffer is free again
+                        tma_store_wait_read<1>();                        // this warp's other staging buffer is free again
                     }
                     ++chunk_id;
                 } else if (valid) {
@@ -352,7 +354,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-        if (issuer) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();
     }
 #undef GLARE_DECODE_WORK
     tc_fence_before();
@@ -471,7 +473,7 @@ static int make_out_map(CUtensorMap* m, const float* ptr, int B, int H, int W, i
     if (!enc) return GLARE_ERR_UNSUPPORTED;
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)W * ldy * 4, (cuuint64_t)H * W * ldy * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)(TH / 4), 1};       // one epilogue warp: 32 tile rows = TH/4 image rows x TW pixels
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,

@@ -21,6 +21,8 @@ SIGNATURES = {
     "glare_flow_step_f32": [_i, _i, _vp, _vp, _vp, _ll, _ll, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp],
     "glare_dcn_pack_weight_f32": [_vp, _i, _i, _i, _i, _vp, _vp],
     "glare_dcnv2_fwd_f32": [_vp, _vp, _vp, _vp, _vp] + [_i] * 11 + [_vp, _vp],
+    "glare_dcnv2_bwd_data_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "glare_dcnv2_bwd_weight_f32": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "glare_dcnv2_pack_fwd_nhwc_tc": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "glare_conv_tc_elem_bytes": [_i],
     "glare_conv_pack_weight": [_i, _vp, _i, _i, _i, _vp, _vp, _vp],

@@ -93,8 +93,9 @@ class VectorQuantizer2(nn.Module):
 # ----------------------------------------------------------------------------------------------- DCN
 def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
                           deformable_groups=1):
-    """ops/dcn/deform_conv.py:188 ``modulated_deform_conv = ModulatedDeformConvFunction.apply`` (forward)."""
-    return ops.modulated_deform_conv(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups)
+    """ops/dcn/deform_conv.py:188 ``modulated_deform_conv = ModulatedDeformConvFunction.apply`` (forward and backward)."""
+    from .dcn_backward import ModulatedDeformConvFunction
+    return ModulatedDeformConvFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups)
 
 
 class ModulatedDeformConvPack(nn.Module):

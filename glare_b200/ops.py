@@ -83,6 +83,22 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
     return y
 
 
+def dcnv2_bwd_data(x_nhwc, offset, mask, dcol_nhwc, dg, grad_x_nhwc, grad_offset, grad_mask, col_nhwc):
+    """deform_conv_cuda.cpp:571-685 data half: grad input (accumulated), grad offset, grad mask, im2col operand"""
+    require_cuda(x_nhwc, offset, mask, dcol_nhwc, grad_x_nhwc, grad_offset, grad_mask, col_nhwc)
+    B, H, W, C = x_nhwc.shape
+    check(lib().glare_dcnv2_bwd_data_f32(ptr(x_nhwc), ptr(offset), ptr(mask), ptr(dcol_nhwc), B, C, H, W, dg, ptr(grad_x_nhwc), ptr(grad_offset),
+                                         ptr(grad_mask), ptr(col_nhwc), stream()), "glare_dcnv2_bwd_data_f32")
+
+
+def dcnv2_bwd_weight(col_nhwc, gout_nhwc, grad_w_packed):
+    """grad_w_packed [9C][Cout] += col^T gout over all pixels of the batch"""
+    require_cuda(col_nhwc, gout_nhwc, grad_w_packed)
+    P = col_nhwc.shape[0] * col_nhwc.shape[1] * col_nhwc.shape[2]
+    check(lib().glare_dcnv2_bwd_weight_f32(ptr(col_nhwc), ptr(gout_nhwc), P, col_nhwc.shape[3], gout_nhwc.shape[3], ptr(grad_w_packed),
+                                           stream()), "glare_dcnv2_bwd_weight_f32")
+
+
 # ------------------------------------------------------------------------------------------- flow
 def flow_cond_tail(p, p_strides, nets, n_steps, nout, B, h, w, out, out_batch_stride, out_step_stride):
     """p_strides = (batch, step, channel, pixel) element strides of the pre-activation planes"""

@@ -100,6 +100,17 @@ int glare_dcnv2_fwd_f32(const float* x, const float* offset, const float* mask, 
                         const float* bias_or_null, int B, int C, int H, int W, int Cout, int kh, int kw, int stride,
                         int pad, int dil, int deformable_groups, float* y, cudaStream_t stream);
 
+/* modulated_deform_conv_backward -- ops/dcn/src/deform_conv_ext.cpp:109-147 (pybind signature), deform_conv_cuda.cpp:571-685,
+ * kernels deform_conv_cuda_kernel.cu:499-567, 636-767.  3x3, stride 1, pad 1, dilation 1, groups 1.  x / grad_x / dcol / col NHWC,
+ * offset / mask and their gradients NCHW as in the reference op.  dcol [B,H,W,9C] (channel t*C + c) is W^T applied to grad_output
+ * (a 1x1 glare_conv2d_nhwc_tc with the transposed filter).  grad_x is accumulated into (caller zero-fills); outputs may be NULL. */
+int glare_dcnv2_bwd_data_f32(const float* x, const float* offset, const float* mask, const float* dcol, int B, int C, int H, int W,
+                             int deformable_groups, float* grad_x, float* grad_offset, float* grad_mask, float* col,
+                             cudaStream_t stream);
+/* grad_w_packed [9C][Cout] += col^T gout over P = B*H*W pixels; grad_weight[co,c,i,j] = grad_w_packed[(3i+j)*C + c][co] */
+int glare_dcnv2_bwd_weight_f32(const float* col, const float* gout, long long P, int KC, int Cout, float* grad_w_packed,
+                               cudaStream_t stream);
+
 /* DCNv2Pack.forward tail on tensor cores (deformableDecoder_arch.py:141-152): consumes the RAW conv_offset output
  * (chunk / cat / sigmoid fused), x and offmask NHWC fp32, weights packed by glare_conv_pack_weight, y NHWC fp32.
  * 3x3, stride 1, pad 1, dilation 1, groups 1; (C / deformable_groups) % 64 == 0 (mode 0) or % 32 == 0 (modes 1, 2). */

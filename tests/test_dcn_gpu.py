@@ -122,3 +122,31 @@ def test_tensor_core_dcn_pack_against_fp32_kernel(glare_lib, cfg, mode, tol):
     assert y is not None
     err = float((y - ref).abs().max())
     assert err < tol * max(1.0, float(ref.abs().max())), (cfg, mode, err)
+
+
+@pytest.mark.parametrize("cfg", [(1, 32, 32, 7, 9, 4), (2, 64, 64, 13, 17, 4), (1, 128, 128, 24, 31, 4), (1, 64, 32, 5, 6, 2)])
+def test_backward_against_cpu_autograd(glare_lib, cfg):
+    """grad input / offset / mask / weight / bias of the DCN op (deform_conv.py:155-184) against torchvision's CPU autograd of the
+    same operator (== the reference kernels' semantics, PIN_REPORT).  fp32 path; tolerance 2e-4 of each gradient's scale."""
+    import torchvision.ops
+    from glare_b200.dcn_backward import modulated_deform_conv
+    B, C, Co, H, W, dg = cfg
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn((B, C, H, W), generator=g)
+    off = torch.randn((B, dg * 18, H, W), generator=g) * 2.0
+    off[0, :, 0, 0] = 50.0
+    off[0, 0::2, H - 1, 0] = -0.6
+    msk = torch.sigmoid(torch.randn((B, dg * 9, H, W), generator=g))
+    w = torch.randn((Co, C, 3, 3), generator=g) / (3.0 * C ** 0.5)
+    b = torch.randn((Co,), generator=g)
+    gout = torch.randn((B, Co, H, W), generator=g)
+    ref_in = [t.clone().requires_grad_(True) for t in (x, off, msk, w, b)]
+    torchvision.ops.deform_conv2d(ref_in[0], ref_in[1], ref_in[3], ref_in[4], stride=1, padding=1, dilation=1, mask=ref_in[2]).backward(gout)
+    dev_in = [t.clone().cuda().requires_grad_(True) for t in (x, off, msk, w, b)]
+    y = modulated_deform_conv(dev_in[0], dev_in[1], dev_in[2], dev_in[3], dev_in[4], 1, 1, 1, 1, dg)
+    y.backward(gout.cuda())
+    torch.cuda.synchronize()
+    for name, r, d in zip(("input", "offset", "mask", "weight", "bias"), ref_in, dev_in):
+        err = float((d.grad.cpu() - r.grad).abs().max())
+        scale = max(1.0, float(r.grad.abs().max()))
+        assert err < 2e-4 * scale, (name, cfg, err, scale)

@@ -9,9 +9,8 @@ pad="auto": reflect-pad (edge-repeating, cv2.BORDER_REFLECT) to the next multipl
             (infer_unpaired.py:81-88,130)
 """
 import torch
-import torch.nn.functional as F
 
-from . import synth
+from . import ops
 from .engine import GlareEngine
 
 
@@ -28,27 +27,22 @@ class GlareEnhancer:
         self._pin_in = self._pin_out = None
 
     def preprocess(self, img_u8_dev):
-        """uint8 [B,H,W,3] on device -> (lr [B,3,Hp,Wp] fp32, crop box)"""
-        x = img_u8_dev.permute(0, 3, 1, 2).float() / 255.0                       # t(): infer_unpaired.py:37
-        B, _, h, w = x.shape
+        """uint8 [B,H,W,3] on device -> (lr [B,3,Hp,Wp] fp32, crop box); one kernel (glare_preprocess_u8)"""
+        B, h, w, _ = img_u8_dev.shape
         if self.pad == "lol":
-            x = F.pad(x, (20, 0, 0, 20), mode="reflect")                         # impad(bottom=20, left=20)
+            pad, mode = (0, 20, 20, 0), 0                                        # impad(bottom=20, left=20), np.pad 'reflect'
             box = (0, h, 20, 20 + w)
         else:
             times = 16
             h1, w1 = (times - h % times) // 2, (times - w % times) // 2
             h2, w2 = (times - h % times) - h1, (times - w % times) - w1
-            iy = synth._symmetric_index(h, h1, h2).to(x.device)
-            ix = synth._symmetric_index(w, w1, w2).to(x.device)
-            x = x.index_select(-2, iy).index_select(-1, ix)
+            pad, mode = (h1, h2, w1, w2), 1                                      # cv2.BORDER_REFLECT
             box = (h1, h1 + h, w1, w1 + w)
-        return torch.log(torch.clamp(x + 1e-3, min=1e-3)), box                   # infer_dataset_lol.py:127-128
+        return ops.preprocess_u8(img_u8_dev.contiguous(), pad, mode), box
 
     def postprocess(self, out, box):
-        """rgb(): clip to [0,1], *255, truncate to uint8 (infer_unpaired.py:40-42), NHWC"""
-        y0, y1, x0, x1 = box
-        o = out[:, :, y0:y1, x0:x1].clamp(0, 1) * 255.0
-        return o.to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        """rgb(): clip to [0,1], *255, truncate to uint8 (infer_unpaired.py:40-42), NHWC; one kernel (glare_postprocess_u8)"""
+        return ops.postprocess_u8(out.float(), box)
 
     @torch.no_grad()
     def enhance(self, images_u8, out=None):

@@ -238,3 +238,25 @@ def gn_apply(out_mode, x_nhwc, stats, gamma, beta, swish, B, HW, C, G=32, eps=1e
     check(lib().glare_gn_apply_nhwc(out_mode, ptr(x_nhwc), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if swish else 0, B, HW, C, G,
                                     ptr(hi), ptr(lo), stream()), "glare_gn_apply_nhwc")
     return hi, lo
+
+
+# ------------------------------------------------------------------------------------------- pre / post-processing
+def preprocess_u8(img_u8_nhwc, pad, mode):
+    """uint8 [B,H,W,3] (device) -> log(clamp(x/255 + 1e-3)) fp32 [B,3,Hp,Wp]; pad = (top, bottom, left, right); mode 0 reflect, 1 symmetric"""
+    require_cuda(img_u8_nhwc)
+    B, H, W, _ = img_u8_nhwc.shape
+    t, b, l, r = pad
+    out = torch.empty((B, 3, H + t + b, W + l + r), device=img_u8_nhwc.device, dtype=torch.float32)
+    check(lib().glare_preprocess_u8(ptr(img_u8_nhwc), B, H, W, t, b, l, r, mode, ptr(out), stream()), "glare_preprocess_u8")
+    return out
+
+
+def postprocess_u8(y, box):
+    """fp32 logical [B,3,Hp,Wp] (any strides) -> uint8 [B,H,W,3] of box = (y0, y1, x0, x1): clip to [0,1], * 255, truncate"""
+    require_cuda(y)
+    y0, y1, x0, x1 = box
+    B = y.shape[0]
+    out = torch.empty((B, y1 - y0, x1 - x0, 3), device=y.device, dtype=torch.uint8)
+    sb, sc, sh, sw = y.stride()
+    check(lib().glare_postprocess_u8(ptr(y), sb, sc, sh, sw, B, y0, x0, y1 - y0, x1 - x0, ptr(out), stream()), "glare_postprocess_u8")
+    return out

@@ -174,6 +174,15 @@ int glare_gn_stats_nhwc_f32(const float* x, int B, long long HW, int C, int G, d
 int glare_gn_apply_nhwc(int out_mode, const float* x, const double* stats, const float* gamma, const float* beta, float eps,
                         int swish, int B, long long HW, int C, int G, void* out_hi, void* out_lo, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * (6) Pre/post-processing of the entry points, batched on the device -- infer_dataset_lol.py:124-128,135 and
+ *     infer_unpaired.py:40-42,81-88,121-122,130.  mode 0 = np.pad 'reflect' (LOL eval), 1 = cv2.BORDER_REFLECT (unpaired).
+ * ---------------------------------------------------------------------------------------------------- */
+int glare_preprocess_u8(const uint8_t* img_nhwc, int B, int H, int W, int pad_top, int pad_bottom, int pad_left, int pad_right, int mode,
+                        float* out_nchw, cudaStream_t stream);
+int glare_postprocess_u8(const float* y, long long sb, long long sc, long long sh, long long sw, int B, int y0, int x0, int H, int W,
+                         uint8_t* out_nhwc, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,3 +43,25 @@ def test_enhance_rejects_wrong_input(glare_lib, sd_g, sd_v):
     enh = GlareEnhancer(sd_g, sd_v, device="cuda:0")
     with pytest.raises(ValueError):
         enh.enhance(torch.zeros((1, 3, 8, 8)))
+
+
+@pytest.mark.parametrize("pad,hw", [("lol", (37, 53)), ("auto", (33, 47)), ("auto", (32, 48)), ("lol", (400, 600))])
+def test_pre_and_postprocess_kernels(glare_lib, pad, hw):
+    """glare_preprocess_u8 / glare_postprocess_u8 against the reference steps restated in glare_b200.synth (np.pad 'reflect',
+    cv2.BORDER_REFLECT, /255, log(clamp), clip*255 -> uint8 truncation)"""
+    from glare_b200 import ops, synth
+    g = torch.Generator().manual_seed(hw[0])
+    u8 = torch.randint(0, 256, (2, hw[0], hw[1], 3), generator=g, dtype=torch.uint8)
+    x = u8.permute(0, 3, 1, 2).float() / 255.0
+    h, w = hw
+    if pad == "lol":
+        ref, p, mode, box = synth.preprocess(synth.pad_lol(x)), (0, 20, 20, 0), 0, (0, h, 20, 20 + w)
+    else:
+        xp, (h1, h2, w1, w2) = synth.auto_padding(x)
+        ref, p, mode, box = synth.preprocess(xp), (h1, h2, w1, w2), 1, (h1, h1 + h, w1, w1 + w)
+    lr = ops.preprocess_u8(u8.cuda(), p, mode)
+    assert lr.shape == ref.shape and float((lr.cpu() - ref).abs().max()) < 2e-6
+    y = torch.randn(ref.shape, generator=g) * 0.6 + 0.5
+    want = (y[:, :, box[0]:box[1], box[2]:box[3]].clamp(0, 1) * 255.0).to(torch.uint8).permute(0, 2, 3, 1)
+    got = ops.postprocess_u8(y.cuda().contiguous(memory_format=torch.channels_last), box).cpu()
+    assert torch.equal(got, want)

@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_kernel(const float* __r
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + o) = u;
         } else if (OUT == 1) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = make_float4(p[0], p[1], p[2], p[3]);
+        } else if (OUT == 4) {
+            store_b3_4(reinterpret_cast<__nv_bfloat16*>(out_hi), o, p[0], p[1], p[2], p[3]);
         } else {
             const float4 h = make_float4(tf32_hi_a(p[0]), tf32_hi_a(p[1]), tf32_hi_a(p[2]), tf32_hi_a(p[3]));
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = h;
@@ -161,6 +163,8 @@ __global__ void __launch_bounds__(256) attn_softmax_rows_reg_kernel(const float*
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + o) = u;
         } else if (OUT == 1) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = make_float4(p0, p1, p2, p3);
+        } else if (OUT == 4) {
+            store_b3_4(reinterpret_cast<__nv_bfloat16*>(out_hi), o, p0, p1, p2, p3);
         } else {
             const float4 h = make_float4(tf32_hi_a(p0), tf32_hi_a(p1), tf32_hi_a(p2), tf32_hi_a(p3));
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o) = h;
@@ -193,7 +197,11 @@ __global__ void __launch_bounds__(256) attn_transpose_v_kernel(const float* __re
             const long long o = ((long long)b * C + c) * Np + n;
             if (OUT == 0) reinterpret_cast<__nv_bfloat16*>(out_hi)[o] = __float2bfloat16_rn(x);
             else if (OUT == 1) reinterpret_cast<float*>(out_hi)[o] = x;
-            else {
+            else if (OUT == 4) {
+                __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(out_hi);
+                const long long xi = (o >> 5) * 64 + (o & 31);
+                split_b3(x, xb[xi], xb[xi + 32]);
+            } else {
                 const float h = tf32_hi_a(x);
                 reinterpret_cast<float*>(out_hi)[o] = h;
                 if (OUT == 2) out_lo[o] = x - h;
@@ -216,24 +224,26 @@ using namespace glare;
 // P = softmax(scale * S) over the keys, zero in columns [n_keys, n_pad).
 GLARE_API int glare_attn_softmax_rows(int out_mode, const float* S, long long rows, long long lds, int n_keys, int n_pad, float scale,
                                       void* out_hi, void* out_lo, long long ldp, cudaStream_t stream) {
-    if (out_mode < 0 || out_mode > 3 || rows < 0 || n_keys <= 0 || n_pad < n_keys || (n_pad & 3) || (lds & 3) || (ldp & 3) || lds < n_keys ||
-        ldp < n_pad || scale <= 0.f || (out_mode == 3 && ((ldp & 31) || (n_pad & 31))))
+    if (out_mode < 0 || out_mode > 4 || rows < 0 || n_keys <= 0 || n_pad < n_keys || (n_pad & 3) || (lds & 3) || (ldp & 3) || lds < n_keys ||
+        ldp < n_pad || scale <= 0.f || (out_mode >= 3 && ((ldp & 31) || (n_pad & 31))))
         return GLARE_ERR_BAD_ARG;
     if (rows == 0) return GLARE_OK;
-    if (!S || !out_hi || (out_mode >= 2 && !out_lo) || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
+    if (!S || !out_hi || ((out_mode == 2 || out_mode == 3) && !out_lo) || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
     float* lo = reinterpret_cast<float*>(out_lo);
     if (n_pad <= 256 * 64) {                         // whole row in registers: one pass over S (N = 16 275 at 600x400)
         if (out_mode == 0) attn_softmax_rows_reg_kernel<0><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
         else if (out_mode == 1) attn_softmax_rows_reg_kernel<1><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
         else if (out_mode == 2) attn_softmax_rows_reg_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
-        else attn_softmax_rows_reg_kernel<3><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+        else if (out_mode == 3) attn_softmax_rows_reg_kernel<3><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+        else attn_softmax_rows_reg_kernel<4><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
         GLARE_CHECK_LAUNCH();
         return GLARE_OK;
     }
     if (out_mode == 0) attn_softmax_rows_kernel<0><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
     else if (out_mode == 1) attn_softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
     else if (out_mode == 2) attn_softmax_rows_kernel<2><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
-    else attn_softmax_rows_kernel<3><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+    else if (out_mode == 3) attn_softmax_rows_kernel<3><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
+    else attn_softmax_rows_kernel<4><<<(unsigned)rows, 256, 0, stream>>>(S, lds, n_keys, n_pad, scale, out_hi, lo, ldp);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -241,15 +251,16 @@ GLARE_API int glare_attn_softmax_rows(int out_mode, const float* S, long long ro
 // v NHWC [B][N][C] fp32 -> V^T [B][C][Np] operand(s) (zero for keys >= N)
 GLARE_API int glare_attn_transpose_v(int out_mode, const float* v, int B, int N, int C, int Np, void* out_hi, void* out_lo,
                                      cudaStream_t stream) {
-    if (out_mode < 0 || out_mode > 3 || B < 0 || N <= 0 || C <= 0 || Np < N || (out_mode == 3 && (Np & 31))) return GLARE_ERR_BAD_ARG;
+    if (out_mode < 0 || out_mode > 4 || B < 0 || N <= 0 || C <= 0 || Np < N || (out_mode >= 3 && (Np & 31))) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
-    if (!v || !out_hi || (out_mode >= 2 && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
+    if (!v || !out_hi || ((out_mode == 2 || out_mode == 3) && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
     dim3 grid((Np + 31) / 32, (C + 31) / 32, B);
     float* lo = reinterpret_cast<float*>(out_lo);
     if (out_mode == 0) attn_transpose_v_kernel<0><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
     else if (out_mode == 1) attn_transpose_v_kernel<1><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
     else if (out_mode == 2) attn_transpose_v_kernel<2><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
-    else attn_transpose_v_kernel<3><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
+    else if (out_mode == 3) attn_transpose_v_kernel<3><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
+    else attn_transpose_v_kernel<4><<<grid, 256, 0, stream>>>(v, N, C, Np, out_hi, lo);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }

@@ -97,6 +97,26 @@ __device__ __forceinline__ void store_x4(__nv_bfloat16* xbase, long long e, floa
     *reinterpret_cast<uint2*>(xbase + xi + 32) = w;
 }
 
+// Mode 4 ("bf16x3"): x = a1 + a2 + O(2^-17 x) with a1 = bf16(x), a2 = bf16(x - a1); D += A1 B1 + A1 B2 + A2 B1 (three bf16 passes =
+// 1.5 tf32-equivalents, 16-bit-significand products).  ONE operand tensor per side, interleaved like the mode-3 x tensor:
+// [32 x a1 | 32 x a2] per 32-element K chunk, i.e. 4 bytes per element instead of 8.
+__device__ __forceinline__ void split_b3(float v, __nv_bfloat16& a1, __nv_bfloat16& a2) {
+    a1 = __float2bfloat16_rn(v);
+    a2 = __float2bfloat16_rn(v - __bfloat162float(a1));
+}
+__device__ __forceinline__ void store_b3_4(__nv_bfloat16* xbase, long long e, float v0, float v1, float v2, float v3) {
+    const long long xi = (e >> 5) * 64 + (e & 31);
+    __nv_bfloat16 h[4], l[4];
+    split_b3(v0, h[0], l[0]); split_b3(v1, h[1], l[1]); split_b3(v2, h[2], l[2]); split_b3(v3, h[3], l[3]);
+    uint2 u, w;
+    u.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    u.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    w.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    w.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(xbase + xi) = u;
+    *reinterpret_cast<uint2*>(xbase + xi + 32) = w;
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace glare

@@ -51,9 +51,10 @@ struct ConvTcArgs {
 template <int MODE, int BN, bool PAIR = false>
 struct ConvCfg {
     static constexpr bool XB = MODE == 3;                      // tf32 main term + two bf16 cross terms
+    static constexpr bool B3 = MODE == 4;                      // bf16x3: one interleaved bf16 tile per operand, three bf16 passes
     static constexpr bool X3 = MODE == 2 || XB;                // second operand pair (lo / interleaved bf16 x) per stage
-    static constexpr bool TF32 = MODE >= 1;
-    static constexpr int BKE = TF32 ? 32 : 64;                 // elements per 128-byte K chunk
+    static constexpr bool TF32 = MODE >= 1 && MODE <= 3;
+    static constexpr int BKE = (TF32 || B3) ? 32 : 64;         // K elements per 128-byte chunk (mode 4: 32 elements x 2 bf16 pieces)
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;  // CTA pair: each CTA stages half of the weight rows
     static constexpr int STAGE_BYTES = (CT_A_BYTES + B_BYTES) * (X3 ? 2 : 1);
     static constexpr int STAGING_BYTES = 2 * 128 * 128;        // epilogue staging: two 128-pixel x 32-fp32 chunks
@@ -154,14 +155,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int wn = a.w_batched ? (n < a.B ? n : a.B - 1) : 0;   // a dummy tile still feeds the peer real weights
                         const int kw = tap * a.Cin + kc * Cfg::BKE;
                         const int km = Cfg::XB ? 2 : 1;                   // the bf16 x tensors hold 64 elements per 32-element K chunk
+                        const int k1 = Cfg::B3 ? 2 : 1;                   // ... and in mode 4 the (only) operand tensor is such an x tensor
                         uint8_t* lo = st + CT_A_BYTES + Cfg::B_BYTES;
                         if (PAIR) {
                             // every byte of both CTAs lands on the leader's barrier; my weight slice = rows [rank * BN/2, +BN/2)
                             if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
                             else mbar_arrive_cluster(&full_bar[s], 0);
                             const int half = cl_rank * (BN / 2);
-                            tma_load_4d_2sm(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
-                            tma_load_3d_2sm(st + CT_A_BYTES, &tmB, &full_bar[s], kw, nb * BN + half, wn);
+                            tma_load_4d_2sm(st, &tmA, &full_bar[s], k1 * kc * Cfg::BKE, x0 + dx, y0 + dy, n);
+                            tma_load_3d_2sm(st + CT_A_BYTES, &tmB, &full_bar[s], k1 * kw, nb * BN + half, wn);
                             if (Cfg::X3) {
                                 tma_load_4d_2sm(lo, &tmAlo, &full_bar[s], km * kc * Cfg::BKE, x0 + dx, y0 + dy, n);
                                 tma_load_3d_2sm(lo + CT_A_BYTES, &tmBlo, &full_bar[s], km * kw, nb * BN + half, wn);
@@ -169,12 +171,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             continue;
                         }
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                        tma_load_4d(st, &tmA, &full_bar[s], kc * Cfg::BKE, x0 + dx, y0 + dy, n);
+                        tma_load_4d(st, &tmA, &full_bar[s], k1 * kc * Cfg::BKE, x0 + dx, y0 + dy, n);
                         if (CL == 1) {
-                            tma_load_3d(st + CT_A_BYTES, &tmB, &full_bar[s], kw, nb * BN, wn);
+                            tma_load_3d(st + CT_A_BYTES, &tmB, &full_bar[s], k1 * kw, nb * BN, wn);
                         } else {                                          // my half of the weight rows, delivered to both CTAs
                             const int half = cl_rank * (BN / 2);
-                            tma_load_3d_mc(st + CT_A_BYTES + half * 128, &tmB, &full_bar[s], kw, nb * BN + half, wn, (uint16_t)0x3);
+                            tma_load_3d_mc(st + CT_A_BYTES + half * 128, &tmB, &full_bar[s], k1 * kw, nb * BN + half, wn, (uint16_t)0x3);
                             if (Cfg::X3)
                                 tma_load_3d_mc(lo + CT_A_BYTES + half * 128, &tmBlo, &full_bar[s], km * kw, nb * BN + half, wn, (uint16_t)0x3);
                         }
@@ -205,8 +207,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + CT_A_BYTES);
                     const uint64_t dal = umma_desc_sw128(sa + CT_A_BYTES + Cfg::B_BYTES);
                     const uint64_t dbl = umma_desc_sw128(sa + 2 * CT_A_BYTES + Cfg::B_BYTES);
+                    if (Cfg::B3) {
+                        // rows = [32 x a1 | 32 x a2]: A1 B1 + A1 B2 + A2 B1, K = 16 per MMA, two K steps per half row
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {                       // 4 x 32-byte K steps inside the 128-byte swizzle row
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const uint64_t adv = (uint64_t)(jj * 2);
+                            mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | jj) != 0 ? 1u : 0u);
+                            mma<false, PAIR>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);
+                            mma<false, PAIR>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < (Cfg::B3 ? 0 : 4); ++j) {       // 4 x 32-byte K steps inside the 128-byte swizzle row
                         const uint64_t adv = (uint64_t)(j * 2);        // +32 bytes in 16-byte units
                         mma<Cfg::TF32, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
                         if (Cfg::X3 && !Cfg::XB) {
@@ -388,13 +400,17 @@ __global__ void conv_pack_weight_kernel(const float* __restrict__ w, int Cout, i
             const float h = tf32_hi(v);
             reinterpret_cast<float*>(out_hi)[i] = h;
             out_lo[i] = v - h;
-        } else {
+        } else if (mode == 3) {
             const float h = tf32_hi(v);
             reinterpret_cast<float*>(out_hi)[i] = h;
             __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(out_lo);
             const long long xi = (i >> 5) * 64 + (i & 31);
             xb[xi] = __float2bfloat16_rn(v);
             xb[xi + 32] = __float2bfloat16_rn(v - h);
+        } else {
+            __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(out_hi);
+            const long long xi = (i >> 5) * 64 + (i & 31);
+            split_b3(v, xb[xi], xb[xi + 32]);
         }
     }
 }
@@ -414,10 +430,12 @@ __global__ void conv_prep_act_kernel(const float4* __restrict__ x, long long n4,
             const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
             reinterpret_cast<float4*>(out_hi)[i] = h;
             out_lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        } else {
+        } else if (mode == 3) {
             const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
             reinterpret_cast<float4*>(out_hi)[i] = h;
             store_x4(reinterpret_cast<__nv_bfloat16*>(out_lo), i * 4, v.x, v.y, v.z, v.w, h.x, h.y, h.z, h.w);
+        } else {
+            store_b3_4(reinterpret_cast<__nv_bfloat16*>(out_hi), i * 4, v.x, v.y, v.z, v.w);
         }
     }
 }
@@ -525,9 +543,9 @@ GLARE_API int glare_conv_tc_elem_bytes(int mode) { return mode == 0 ? 2 : 4; }  
 
 GLARE_API int glare_conv_pack_weight(int mode, const float* w_oihw, int Cout, int Cin, int ksize, void* out_hi, void* out_lo,
                                      cudaStream_t stream) {
-    if (!w_oihw || !out_hi || (mode >= 2 && !out_lo) || mode < 0 || mode > 3 || Cout <= 0 || Cin <= 0 || ksize < 1 || ksize > 3)
+    if (!w_oihw || !out_hi || ((mode == 2 || mode == 3) && !out_lo) || mode < 0 || mode > 4 || Cout <= 0 || Cin <= 0 || ksize < 1 || ksize > 3)
         return GLARE_ERR_BAD_ARG;
-    if (mode == 3 && Cin % 32 != 0) return GLARE_ERR_UNSUPPORTED;
+    if (mode >= 3 && Cin % 32 != 0) return GLARE_ERR_UNSUPPORTED;
     const long long n = (long long)Cout * Cin * ksize * ksize;
     const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
     conv_pack_weight_kernel<<<grid, 256, 0, stream>>>(w_oihw, Cout, Cin, ksize * ksize, mode, out_hi, reinterpret_cast<float*>(out_lo));
@@ -537,9 +555,9 @@ GLARE_API int glare_conv_pack_weight(int mode, const float* w_oihw, int Cout, in
 
 // fp32 activations -> tensor-core operand(s): mode 0 bf16 copy, mode 2 tf32 hi/lo split (mode 1 needs no preparation)
 GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* out_hi, void* out_lo, cudaStream_t stream) {
-    if (n < 0 || (mode != 0 && mode != 2 && mode != 3) || (n & 3) || (mode == 3 && (n & 31))) return GLARE_ERR_BAD_ARG;
+    if (n < 0 || (mode != 0 && mode != 2 && mode != 3 && mode != 4) || (n & 3) || (mode >= 3 && (n & 31))) return GLARE_ERR_BAD_ARG;
     if (n == 0) return GLARE_OK;
-    if (!x || !out_hi || (mode >= 2 && !out_lo)) return GLARE_ERR_BAD_ARG;
+    if (!x || !out_hi || ((mode == 2 || mode == 3) && !out_lo)) return GLARE_ERR_BAD_ARG;
     const long long n4 = n / 4;
     const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
     conv_prep_act_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), n4, mode, out_hi, reinterpret_cast<float4*>(out_lo));
@@ -629,9 +647,9 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if (gn_stats && (Cout % 128 != 0 || B <= 0)) return GLARE_ERR_UNSUPPORTED;       // 32 groups of a multiple of 4 channels
     if (gn_stats && gn_zero) GLARE_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 64 * (size_t)B, stream));
     if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
-    if (mode < 0 || mode > 3 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize < 1 || ksize > 3)) return GLARE_ERR_BAD_ARG;
+    if (mode < 0 || mode > 4 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize < 1 || ksize > 3)) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
-    if (!x || !w || !y || (mode >= 2 && (!x_lo || !w_lo))) return GLARE_ERR_BAD_ARG;
+    if (!x || !w || !y || ((mode == 2 || mode == 3) && (!x_lo || !w_lo))) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
     if (Cin % bke != 0 || (Cout % 4 != 0 && ldy == Cout)) return GLARE_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15) return GLARE_ERR_BAD_ARG;
@@ -671,9 +689,10 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
         a.tma_store = (!direct && Cout >= 32 && ts.oscale == 1) ? 1 : 0;
     }
     if ((rc = make_out_map(&tY, y, B, H, W, Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
-    const bool bf = mode == 0;
-    if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
-    if ((rc = make_w_map(&tB, w, bf, Cout, ts.ntaps * Cin, BN / csz, n_w, w_batch_stride)) != GLARE_OK) return rc;
+    const bool bf = mode == 0 || mode == 4;
+    const int e2 = mode == 4 ? 2 : 1;              // mode 4: the operand tensors are interleaved bf16 pairs, 2 per element
+    if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, e2 * Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
+    if ((rc = make_w_map(&tB, w, bf, Cout, e2 * ts.ntaps * Cin, BN / csz, n_w, e2 * w_batch_stride)) != GLARE_OK) return rc;
     tAl = tA; tBl = tB;
     if (mode == 2) {
         if ((rc = make_act_map(&tAl, x_lo, false, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
@@ -691,6 +710,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if (mode == 0) GLARE_CONV_DISPATCH(0);
     if (mode == 1) GLARE_CONV_DISPATCH(1);
     if (mode == 2) GLARE_CONV_DISPATCH(2);
-    GLARE_CONV_DISPATCH(3);
+    if (mode == 3) GLARE_CONV_DISPATCH(3);
+    GLARE_CONV_DISPATCH(4);
 #undef GLARE_CONV_DISPATCH
 }

@@ -38,9 +38,10 @@ struct DcnTcArgs {
 template <int MODE, int BN>
 struct DcnCfg {
     static constexpr bool XB = MODE == 3;                      // tf32 main term + two bf16 cross terms (common.cuh store_x4)
+    static constexpr bool B3 = MODE == 4;                      // bf16x3: one interleaved bf16 tile per operand (common.cuh split_b3)
     static constexpr bool X3 = MODE == 2 || XB;
-    static constexpr bool TF32 = MODE >= 1;
-    static constexpr int BKE = TF32 ? 32 : 64;
+    static constexpr bool TF32 = MODE >= 1 && MODE <= 3;
+    static constexpr int BKE = (TF32 || B3) ? 32 : 64;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = (DT_A_BYTES + B_BYTES) * (X3 ? 2 : 1);
     static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
@@ -101,7 +102,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                         uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                         const int kcoord = tap * a.C + kc * Cfg::BKE;
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * (Cfg::X3 ? 2 : 1));
-                        tma_load_3d(st + DT_A_BYTES, &tmB, &full_bar[s], kcoord, nb * BN, 0);
+                        tma_load_3d(st + DT_A_BYTES, &tmB, &full_bar[s], (Cfg::B3 ? 2 : 1) * kcoord, nb * BN, 0);
                         if (Cfg::X3)
                             tma_load_3d(st + 2 * DT_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], (Cfg::XB ? 2 : 1) * kcoord, nb * BN, 0);
                     }
@@ -126,8 +127,17 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + DT_A_BYTES);
                     const uint64_t dal = umma_desc_sw128(sa + DT_A_BYTES + Cfg::B_BYTES);
                     const uint64_t dbl = umma_desc_sw128(sa + 2 * DT_A_BYTES + Cfg::B_BYTES);
+                    if (Cfg::B3) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const uint64_t adv = (uint64_t)(jj * 2);
+                            umma_ss<false>(d_tmem, da + adv, db + adv, idesc, (ki | jj) != 0 ? 1u : 0u);   // A1 B1
+                            umma_ss<false>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);                     // A1 B2
+                            umma_ss<false>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);                     // A2 B1
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < (Cfg::B3 ? 0 : 4); ++j) {
                         const uint64_t adv = (uint64_t)(j * 2);
                         umma_ss<Cfg::TF32>(d_tmem, da + adv, db + adv, idesc, (ki | j) != 0 ? 1u : 0u);
                         if (Cfg::X3 && !Cfg::XB) {
@@ -199,7 +209,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         const int sw = (warp - 6) & 3;                 // rows [32 sw, 32 sw + 32) of the tile
         const int gsel = (warp - 6) >> 2;
         const int sub = lane >> 3, j = lane & 7;
-        constexpr int CPL = Cfg::TF32 ? 4 : 8;         // channels per lane per stage (16 bytes of operand)
+        constexpr int CPL = (Cfg::TF32 || Cfg::B3) ? 4 : 8;   // channels per lane per stage
         constexpr int V4 = CPL / 4;
         const int om_c = 27 * a.dg;
         uint32_t it = 0;
@@ -275,7 +285,20 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                                 }
                             }
                             const uint32_t off = (uint32_t)m * 128u + (uint32_t)((j ^ (m & 7)) << 4);     // SWIZZLE_128B
-                            if (!Cfg::TF32) {
+                            if (Cfg::B3) {
+                                // single x tile: bytes [0,64) = a1 of the 32 channels, [64,128) = a2; this lane owns 8 bytes at 8j in each half
+                                __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) split_b3(acc[k], h4[k], l4[k]);
+                                uint2 u, w2;
+                                u.x = (uint32_t)__bfloat16_as_ushort(h4[0]) | ((uint32_t)__bfloat16_as_ushort(h4[1]) << 16);
+                                u.y = (uint32_t)__bfloat16_as_ushort(h4[2]) | ((uint32_t)__bfloat16_as_ushort(h4[3]) << 16);
+                                w2.x = (uint32_t)__bfloat16_as_ushort(l4[0]) | ((uint32_t)__bfloat16_as_ushort(l4[1]) << 16);
+                                w2.y = (uint32_t)__bfloat16_as_ushort(l4[2]) | ((uint32_t)__bfloat16_as_ushort(l4[3]) << 16);
+                                uint8_t* xt = st + (uint32_t)m * 128u + (uint32_t)((j & 1) * 8);
+                                *reinterpret_cast<uint2*>(xt + (((j >> 1) ^ (m & 7)) << 4)) = u;
+                                *reinterpret_cast<uint2*>(xt + (((4 + (j >> 1)) ^ (m & 7)) << 4)) = w2;
+                            } else if (!Cfg::TF32) {
                                 __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[0], acc[1]), b1 = __floats2bfloat162_rn(acc[2], acc[3]);
                                 __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[CPL - 4], acc[CPL - 3]),
                                                b3 = __floats2bfloat162_rn(acc[CPL - 2], acc[CPL - 1]);
@@ -365,9 +388,9 @@ using namespace glare;
 GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float* offmask, const void* w, const void* w_lo,
                                            const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout,
                                            int deformable_groups, cudaStream_t stream) {
-    if (mode < 0 || mode > 3 || B < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || deformable_groups <= 0) return GLARE_ERR_BAD_ARG;
+    if (mode < 0 || mode > 4 || B < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || deformable_groups <= 0) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
-    if (!x || !offmask || !w || !y || (mode >= 2 && !w_lo)) return GLARE_ERR_BAD_ARG;
+    if (!x || !offmask || !w || !y || ((mode == 2 || mode == 3) && !w_lo)) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
     if (C % deformable_groups != 0 || C % bke != 0 || (C / deformable_groups) % 8 != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
     DcnTcArgs a{};
@@ -385,7 +408,7 @@ GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float
     a.total_tiles = (int)total;
     CUtensorMap tB, tBl;
     int rc;
-    if ((rc = make_w_map_d(&tB, w, mode == 0, Cout, 9 * C, BN)) != GLARE_OK) return rc;
+    if ((rc = make_w_map_d(&tB, w, mode == 0 || mode == 4, Cout, (mode == 4 ? 2 : 1) * 9 * C, BN)) != GLARE_OK) return rc;
     tBl = tB;
     if (mode == 2 && (rc = make_w_map_d(&tBl, w_lo, false, Cout, 9 * C, BN)) != GLARE_OK) return rc;
     if (mode == 3 && (rc = make_w_map_d(&tBl, w_lo, true, Cout, 2 * 9 * C, BN)) != GLARE_OK) return rc;
@@ -398,6 +421,7 @@ GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float
     if (mode == 0) GLARE_DCN_DISPATCH(0);
     if (mode == 1) GLARE_DCN_DISPATCH(1);
     if (mode == 2) GLARE_DCN_DISPATCH(2);
-    GLARE_DCN_DISPATCH(3);
+    if (mode == 3) GLARE_DCN_DISPATCH(3);
+    GLARE_DCN_DISPATCH(4);
 #undef GLARE_DCN_DISPATCH
 }

@@ -92,10 +92,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
             const float4 h = make_float4(tf32_hi_n(y[0]), tf32_hi_n(y[1]), tf32_hi_n(y[2]), tf32_hi_n(y[3]));
             reinterpret_cast<float4*>(out_hi)[base4 + i] = h;
             reinterpret_cast<float4*>(out_lo)[base4 + i] = make_float4(y[0] - h.x, y[1] - h.y, y[2] - h.z, y[3] - h.w);
-        } else {
+        } else if (OUT == 3) {
             const float4 h = make_float4(tf32_hi_n(y[0]), tf32_hi_n(y[1]), tf32_hi_n(y[2]), tf32_hi_n(y[3]));
             reinterpret_cast<float4*>(out_hi)[base4 + i] = h;
             store_x4(reinterpret_cast<__nv_bfloat16*>(out_lo), (base4 + i) * 4, y[0], y[1], y[2], y[3], h.x, h.y, h.z, h.w);
+        } else {
+            store_b3_4(reinterpret_cast<__nv_bfloat16*>(out_hi), (base4 + i) * 4, y[0], y[1], y[2], y[3]);
         }
     }
 }
@@ -125,10 +127,10 @@ GLARE_API int glare_gn_stats_nhwc_f32(const float* x, int B, long long HW, int C
 GLARE_API int glare_gn_apply_nhwc(int out_mode, const float* x, const double* stats, const float* gamma, const float* beta,
                                   float eps, int swish, int B, long long HW, int C, int G, void* out_hi, void* out_lo,
                                   cudaStream_t stream) {
-    if (out_mode < 0 || out_mode > 3 || B < 0 || HW < 0 || C <= 0 || G <= 0 || C % G != 0 || (C & 3) || C > 1024) return GLARE_ERR_BAD_ARG;
-    if (out_mode == 3 && (C & 31)) return GLARE_ERR_UNSUPPORTED;
+    if (out_mode < 0 || out_mode > 4 || B < 0 || HW < 0 || C <= 0 || G <= 0 || C % G != 0 || (C & 3) || C > 1024) return GLARE_ERR_BAD_ARG;
+    if (out_mode >= 3 && (C & 31)) return GLARE_ERR_UNSUPPORTED;
     if (B == 0 || HW == 0) return GLARE_OK;
-    if (!x || !stats || !gamma || !beta || !out_hi || (out_mode >= 2 && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
+    if (!x || !stats || !gamma || !beta || !out_hi || ((out_mode == 2 || out_mode == 3) && !out_lo) || B > 65535) return GLARE_ERR_BAD_ARG;
     const long long n4 = HW * (C / 4);
     long long blocks = (n4 + GN_THREADS * 4 - 1) / (GN_THREADS * 4);
     const long long cap = (148 * 16 + B - 1) / B;
@@ -140,7 +142,8 @@ GLARE_API int glare_gn_apply_nhwc(int out_mode, const float* x, const double* st
     if (out_mode == 0) gn_apply_kernel<0><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
     else if (out_mode == 1) gn_apply_kernel<1><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
     else if (out_mode == 2) gn_apply_kernel<2><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
-    else gn_apply_kernel<3><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
+    else if (out_mode == 3) gn_apply_kernel<3><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
+    else gn_apply_kernel<4><<<grid, GN_THREADS, smem, stream>>>(x, stats, gamma, beta, eps, swish, HW, C, G, out_hi, lo);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }

@@ -68,7 +68,10 @@ class Operand:
 
     def dense(self):
         """fp32 logical-NCHW (channels_last) value of the operand: hi + lo is exact for the tf32 split"""
-        if self.lo is None:
+        if self.mode == 4:                       # interleaved bf16 pair: x = a1 + a2
+            pair = self.hi.view(-1, 2, 32).float()
+            v = (pair[:, 0] + pair[:, 1]).reshape(self.B, self.H, self.W, self.C)
+        elif self.lo is None:
             v = self.hi.float()
         elif self.lo.dtype == torch.float32:
             v = self.hi + self.lo
@@ -97,9 +100,10 @@ class TcDense:
         from . import ops
         self.ops = ops
         self.mode = mode
-        self.name = {0: "tcgen05-bf16", 1: "tcgen05-tf32", 2: "tcgen05-3xtf32", 3: "tcgen05-tf32+2xbf16"}[mode]
+        self.name = {0: "tcgen05-bf16", 1: "tcgen05-tf32", 2: "tcgen05-3xtf32", 3: "tcgen05-tf32+2xbf16", 4: "tcgen05-bf16x3"}[mode]
         self.dtype_name = {0: "bf16", 1: "tf32", 2: "fp32 (3xTF32 tensor-core emulation, fp32 accumulate)",
-                           3: "fp32 (tf32 x tf32 + two bf16 cross terms on tensor cores, fp32 accumulate)"}[mode]
+                           3: "fp32 (tf32 x tf32 + two bf16 cross terms on tensor cores, fp32 accumulate)",
+                           4: "fp32 split into two bf16 pieces per operand, three bf16 tensor-core passes (16-bit significand), fp32 accumulate"}[mode]
         self.lib = TorchDense(torch.float32, allow_tf32=(mode in (0, 1)))
         self.bke = 64 if mode == 0 else 32
         self._w = {}
@@ -274,7 +278,7 @@ class TcDense:
             band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
             rows_max = min(band, h) * w
             S = torch.empty((rows_max, Np), device=q.device, dtype=torch.float32)
-            p_hi = torch.empty((rows_max, Np), device=q.device, dtype=q_hi.dtype)
+            p_hi = ops._hi_alloc(self.mode, (rows_max, Np), q.device)
             p_lo = ops._lo_like(self.mode, p_hi)
             scale = float(int(C) ** (-0.5))
             for b in range(B):
@@ -311,7 +315,7 @@ class TcDense:
         fl = sum(f for _, _, f in ev)
         steps = max(1, self.last_steps)
         ach = fl / (ms / 1e3) / 1e12
-        issued = {0: 1.0, 1: 1.0, 2: 3.0, 3: 2.0}[self.mode]          # tf32-equivalent MMA passes per algorithmic MAC
+        issued = {0: 0.5, 1: 1.0, 2: 3.0, 3: 2.0, 4: 1.5}[self.mode]  # tf32-equivalent MMA passes per algorithmic MAC
         return {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM: convolutions + attention GEMMs, %d launches/step, mode %s)"
                           % (len(ev) // steps, self.name),
                 "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
@@ -348,6 +352,8 @@ def make_dense(name="auto"):
         return TcDense(3)
     if name == "tc-3xtf32":
         return TcDense(2)
+    if name == "tc-bf16x3":
+        return TcDense(4)
     if name == "tc-tf32":
         return TcDense(1)
     if name == "tc-bf16":

@@ -117,7 +117,16 @@ def flow_step(direction, coupling, z_in, z_out, pA, pA_strides, hF, hF_batch_str
 
 
 # ------------------------------------------------------------------------------------------- dense convs / GroupNorm
-MODE_BF16, MODE_TF32, MODE_TF32X3, MODE_TF32_BF16X2 = 0, 1, 2, 3
+MODE_BF16, MODE_TF32, MODE_TF32X3, MODE_TF32_BF16X2, MODE_BF16X3 = 0, 1, 2, 3, 4
+
+
+def _hi_alloc(mode, shape, device):
+    """primary operand tensor: bf16 (mode 0), fp32 (modes 1-3), interleaved bf16 pair with 2 entries per element (mode 4)"""
+    if mode == MODE_BF16:
+        return torch.empty(shape, device=device, dtype=torch.bfloat16)
+    if mode == MODE_BF16X3:
+        return torch.empty(tuple(shape[:-1]) + (2 * shape[-1],), device=device, dtype=torch.bfloat16)
+    return torch.empty(shape, device=device, dtype=torch.float32)
 
 
 def _lo_like(mode, hi):
@@ -134,8 +143,7 @@ def conv_pack_weight(mode, w_oihw):
     require_cuda(w_oihw)
     w = f32c(w_oihw)
     Co, Ci, kh, kw = w.shape
-    dt = torch.bfloat16 if mode == MODE_BF16 else torch.float32
-    hi = torch.empty((Co, kh * kw, Ci), device=w.device, dtype=dt)
+    hi = _hi_alloc(mode, (Co, kh * kw, Ci), w.device)
     lo = _lo_like(mode, hi)
     check(lib().glare_conv_pack_weight(mode, ptr(w), Co, Ci, kh, ptr(hi), ptr(lo), stream()), "glare_conv_pack_weight")
     return hi, lo
@@ -146,7 +154,7 @@ def conv_prep_act(mode, x_nhwc):
     require_cuda(x_nhwc)
     if mode == MODE_TF32:
         return x_nhwc, None
-    hi = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=torch.bfloat16 if mode == MODE_BF16 else torch.float32)
+    hi = _hi_alloc(mode, tuple(x_nhwc.shape), x_nhwc.device)
     lo = _lo_like(mode, hi)
     check(lib().glare_conv_prep_act(mode, ptr(x_nhwc), x_nhwc.numel(), ptr(hi), ptr(lo), stream()), "glare_conv_prep_act")
     return hi, lo
@@ -216,8 +224,7 @@ def attn_softmax_rows(mode, S, rows, lds, n_keys, n_pad, scale, out_hi, out_lo, 
 
 def attn_transpose_v(mode, v_nhwc, B, N, C, Np):
     require_cuda(v_nhwc)
-    dt = torch.bfloat16 if mode == MODE_BF16 else torch.float32
-    hi = torch.empty((B, C, Np), device=v_nhwc.device, dtype=dt)
+    hi = _hi_alloc(mode, (B, C, Np), v_nhwc.device)
     lo = _lo_like(mode, hi)
     check(lib().glare_attn_transpose_v(mode, ptr(v_nhwc), B, N, C, Np, ptr(hi), ptr(lo), stream()), "glare_attn_transpose_v")
     return hi, lo
@@ -233,7 +240,7 @@ def gn_stats(x_nhwc, B, HW, C, G=32):
 def gn_apply(out_mode, x_nhwc, stats, gamma, beta, swish, B, HW, C, G=32, eps=1e-6):
     """-> (hi, lo|None) with hi bf16 (mode 0) / fp32 (mode 1) / tf32-hi (mode 2), same NHWC shape as x"""
     require_cuda(x_nhwc, stats, gamma, beta)
-    hi = torch.empty(x_nhwc.shape, device=x_nhwc.device, dtype=torch.bfloat16 if out_mode == 0 else torch.float32)
+    hi = _hi_alloc(out_mode, tuple(x_nhwc.shape), x_nhwc.device)
     lo = _lo_like(out_mode, hi)
     check(lib().glare_gn_apply_nhwc(out_mode, ptr(x_nhwc), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if swish else 0, B, HW, C, G,
                                     ptr(hi), ptr(lo), stream()), "glare_gn_apply_nhwc")

@@ -97,7 +97,7 @@ def test_bad_shapes_raise(glare_lib):
                                   torch.zeros((8, 8, 3, 3), device="cuda"), None, 1, 1, 1, 1, 4)
 
 
-@pytest.mark.parametrize("mode,tol", [(3, 5e-5), (2, 5e-5), (1, 5e-3), (0, 3e-2)])
+@pytest.mark.parametrize("mode,tol", [(4, 1e-4), (3, 5e-5), (2, 5e-5), (1, 5e-3), (0, 3e-2)])
 @pytest.mark.parametrize("cfg", [(1, 128, 128, 8, 16), (2, 128, 128, 19, 27), (1, 256, 256, 33, 41), (1, 128, 128, 105, 155)])
 def test_tensor_core_dcn_pack_against_fp32_kernel(glare_lib, cfg, mode, tol):
     """dcn_tc.cu (sampled A operand + tcgen05) vs the fp32 FMA kernel (itself checked against the oracle above),

@@ -10,7 +10,7 @@ from conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["tc-3xtf32", "tc-tf32bf16x2", "torch-fp32"])
+@pytest.fixture(scope="module", params=["tc-3xtf32", "tc-tf32bf16x2", "tc-bf16x3", "torch-fp32"])
 def engine(request, glare_lib, sd_g, sd_v):
     """fp32-grade configurations: the tensor-core dense path in 3xTF32 mode, and the cuDNN fp32 library baseline"""
     from glare_b200.dense import make_dense

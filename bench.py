@@ -29,7 +29,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "600x400 images/sec (LOL eval15 shape, batch 15 per GPU)"
+METRIC = "600x400 images/sec"          # BASELINE.json metric; the workload (LOL eval15 shape, batch 15 per GPU) is in config
 H, W, BATCH = 400, 600, 15
 
 

@@ -18,7 +18,7 @@ class GlareEnhancer:
     def __init__(self, sd_g, sd_vq, device="cuda:0", pad="lol", dense=None):
         if dense is None:
             from .dense import make_dense
-            dense = make_dense("auto")          # tcgen05 dense path, fp32-grade (tf32 + 2 x bf16 cross terms)
+            dense = make_dense("auto")          # tcgen05 dense path, fp32-grade (bf16x3 split operands)
         self.engine = GlareEngine(sd_g, sd_vq, device=device, dense=dense)
         self.device = self.engine.device
         if pad not in ("lol", "auto"):

@@ -2,8 +2,9 @@
 
 ``make_dense("torch-fp32")``  cuDNN/cuBLAS fp32 (TF32 off) -- library baseline, bring-up backend
 ``make_dense("torch-bf16")``  cuDNN/cuBLAS bf16            -- library baseline
-``make_dense("auto")``        = "tc-tf32bf16x2": tcgen05 dense path, fp32-grade (tf32 main term + two bf16 cross terms)
-``make_dense("tc-3xtf32" | "tc-tf32" | "tc-bf16")``  the same kernels in the other operand modes
+``make_dense("auto")``        = "tc-bf16x3": tcgen05 dense path, fp32-grade (each fp32 operand split into two bf16 pieces, three
+                              bf16 passes; measured as accurate as 3xTF32 on this network, profiles/r01n_fullsize_parity_420x620.txt)
+``make_dense("tc-tf32bf16x2" | "tc-3xtf32" | "tc-tf32" | "tc-bf16")``  the same kernels in the other operand modes
 """
 import torch
 import torch.nn.functional as F
@@ -322,8 +323,9 @@ class TcDense:
                 "traffic": self._traffic(B), "ms_per_step": ms / steps, "share_of_step": None,
                 "algorithmic_tflop_per_step": fl / steps / 1e12, "launches_per_step": len(ev) // steps,
                 "mma_passes_per_algorithmic_mac": issued,
-                "note": "achieved counts algorithmic FLOPs (2*Cin*Cout*k*k per pixel, 4*N*N*C per attention block); fp32-grade modes "
-                        "issue %g tensor-core passes per MAC at the tf32 rate (half the bf16 rate the peak is measured in)" % issued,
+                "issued_bf16_equivalent_tflops": ach * issued * 2.0, "issued_frac_of_peak": ach * issued * 2.0 / pk["tensor"],
+                "note": "achieved counts algorithmic FLOPs (2*Cin*Cout*k*k per pixel, 4*N*N*C per attention block); this mode issues %g "
+                        "tf32-equivalent (= %g bf16) tensor-core passes per algorithmic MAC, the peak is the bf16 one" % (issued, 2 * issued),
                 "peak_source": pk["src"] + " (cuBLAS bf16 sustained)"}
 
     def _traffic(self, B):
@@ -348,12 +350,12 @@ def make_dense(name="auto"):
         d.attn_impl = "library"
         d.name += "+library-attention"
         return d
-    if name in ("auto", "tc-tf32bf16x2"):
+    if name in ("auto", "tc-bf16x3"):
+        return TcDense(4)
+    if name == "tc-tf32bf16x2":
         return TcDense(3)
     if name == "tc-3xtf32":
         return TcDense(2)
-    if name == "tc-bf16x3":
-        return TcDense(4)
     if name == "tc-tf32":
         return TcDense(1)
     if name == "tc-bf16":

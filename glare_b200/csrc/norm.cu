@@ -27,7 +27,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
         const long long per = (HW + gridDim.x - 1) / gridDim.x;
         const long long p0 = (long long)blockIdx.x * per, p1 = (p0 + per < HW) ? p0 + per : HW;
         const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * HW * C);
-        for (long long p = p0 + my_row; p < p1; p += rows) {
+        // four independent 128-bit loads in flight per thread (a single one leaves HBM latency exposed)
+        long long p = p0 + my_row;
+        for (; p + 3LL * rows < p1; p += 4LL * rows) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + (p + (long long)u * rows) * c4n + my_c4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
+                q += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
+            }
+        }
+        for (; p < p1; p += rows) {
             const float4 v = __ldg(xb + p * c4n + my_c4);
             s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
             q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
@@ -70,34 +82,45 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
     const long long n4 = HW * c4n;
     const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * HW * C);
     const long long base4 = (long long)b * n4;
-    for (long long i = (long long)blockIdx.x * GN_THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * GN_THREADS) {
-        const int c = (int)(i % c4n) * 4;
-        const float4 v = __ldg(xb + i);
-        float y[4] = {fmaf(v.x - s_ab[2 * C + c], s_ab[c], s_ab[C + c]), fmaf(v.y - s_ab[2 * C + c + 1], s_ab[c + 1], s_ab[C + c + 1]),
-                      fmaf(v.z - s_ab[2 * C + c + 2], s_ab[c + 2], s_ab[C + c + 2]),
-                      fmaf(v.w - s_ab[2 * C + c + 3], s_ab[c + 3], s_ab[C + c + 3])};
-        if (swish) {
+    const long long stride = (long long)gridDim.x * GN_THREADS;
+    for (long long i0 = (long long)blockIdx.x * GN_THREADS + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+        // two independent 128-bit loads in flight per thread
+        const long long i1 = i0 + stride;
+        const bool has1 = i1 < n4;
+        const float4 va = __ldg(xb + i0);
+        const float4 vb = has1 ? __ldg(xb + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.0f + expf(-y[k]));
-        }
-        if (OUT == 0) {
-            __nv_bfloat162 a0 = __floats2bfloat162_rn(y[0], y[1]), a1 = __floats2bfloat162_rn(y[2], y[3]);
-            uint2 o;
-            o.x = *reinterpret_cast<uint32_t*>(&a0);
-            o.y = *reinterpret_cast<uint32_t*>(&a1);
-            reinterpret_cast<uint2*>(out_hi)[base4 + i] = o;
-        } else if (OUT == 1) {
-            reinterpret_cast<float4*>(out_hi)[base4 + i] = make_float4(y[0], y[1], y[2], y[3]);
-        } else if (OUT == 2) {
-            const float4 h = make_float4(tf32_hi_n(y[0]), tf32_hi_n(y[1]), tf32_hi_n(y[2]), tf32_hi_n(y[3]));
-            reinterpret_cast<float4*>(out_hi)[base4 + i] = h;
-            reinterpret_cast<float4*>(out_lo)[base4 + i] = make_float4(y[0] - h.x, y[1] - h.y, y[2] - h.z, y[3] - h.w);
-        } else if (OUT == 3) {
-            const float4 h = make_float4(tf32_hi_n(y[0]), tf32_hi_n(y[1]), tf32_hi_n(y[2]), tf32_hi_n(y[3]));
-            reinterpret_cast<float4*>(out_hi)[base4 + i] = h;
-            store_x4(reinterpret_cast<__nv_bfloat16*>(out_lo), (base4 + i) * 4, y[0], y[1], y[2], y[3], h.x, h.y, h.z, h.w);
-        } else {
-            store_b3_4(reinterpret_cast<__nv_bfloat16*>(out_hi), (base4 + i) * 4, y[0], y[1], y[2], y[3]);
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has1) break;
+            const long long i = u == 0 ? i0 : i1;
+            const float4 v = u == 0 ? va : vb;
+            const int c = (int)(i % c4n) * 4;
+            float y[4] = {fmaf(v.x - s_ab[2 * C + c], s_ab[c], s_ab[C + c]), fmaf(v.y - s_ab[2 * C + c + 1], s_ab[c + 1], s_ab[C + c + 1]),
+                          fmaf(v.z - s_ab[2 * C + c + 2], s_ab[c + 2], s_ab[C + c + 2]),
+                          fmaf(v.w - s_ab[2 * C + c + 3], s_ab[c + 3], s_ab[C + c + 3])};
+            if (swish) {
+    #pragma unroll
+                for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.0f + expf(-y[k]));
+            }
+            if (OUT == 0) {
+                __nv_bfloat162 a0 = __floats2bfloat162_rn(y[0], y[1]), a1 = __floats2bfloat162_rn(y[2], y[3]);
+                uint2 o;
+                o.x = *reinterpret_cast<uint32_t*>(&a0);
+                o.y = *reinterpret_cast<uint32_t*>(&a1);
+                reinterpret_cast<uint2*>(out_hi)[base4 + i] = o;
+            } else if (OUT == 1) {
+                reinterpret_cast<float4*>(out_hi)[base4 + i] = make_float4(y[0], y[1], y[2], y[3]);
+            } else if (OUT == 2) {
+                const float4 h = make_float4(tf32_hi_n(y[0]), tf32_hi_n(y[1]), tf32_hi_n(y[2]), tf32_hi_n(y[3]));
+                reinterpret_cast<float4*>(out_hi)[base4 + i] = h;
+                reinterpret_cast<float4*>(out_lo)[base4 + i] = make_float4(y[0] - h.x, y[1] - h.y, y[2] - h.z, y[3] - h.w);
+            } else if (OUT == 3) {
+                const float4 h = make_float4(tf32_hi_n(y[0]), tf32_hi_n(y[1]), tf32_hi_n(y[2]), tf32_hi_n(y[3]));
+                reinterpret_cast<float4*>(out_hi)[base4 + i] = h;
+                store_x4(reinterpret_cast<__nv_bfloat16*>(out_lo), (base4 + i) * 4, y[0], y[1], y[2], y[3], h.x, h.y, h.z, h.w);
+            } else {
+                store_b3_4(reinterpret_cast<__nv_bfloat16*>(out_hi), (base4 + i) * 4, y[0], y[1], y[2], y[3]);
+            }
         }
     }
 }

@@ -247,6 +247,10 @@ class GlareEngine:
     @torch.no_grad()
     def infer(self, lr, stages=None):
         """lr [B,3,H,W] = log(clamp(x + 1e-3)) (infer_unpaired.py:121-122), H and W multiples of 4... returns RGB [B,3,H,W] fp32."""
+        if lr.dim() != 4 or lr.shape[1] != 3 or lr.shape[2] % 4 or lr.shape[3] % 4:
+            # the encoder halves the resolution twice and the decoders double it back onto the encoder's skip features
+            # (deformableDecoder_arch.py:553-566); the reference entry points pad to multiples of 16 / by 20 for this reason
+            raise ValueError("expected lr [B,3,H,W] with H and W multiples of 4 (pad first, see api.GlareEnhancer); got %s" % (tuple(lr.shape),))
         with torch.cuda.device(self.device):
             lr = lr.to(self.device, torch.float32)
             enc = self.cond_encoder(lr)

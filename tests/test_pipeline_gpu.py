@@ -101,3 +101,10 @@ def test_stage2_forward_nll_against_reference(glare_lib):
     nll = flow.gaussian_nll(z, enc["color_map"], logdet)
     assert torch.allclose(z.cpu(), torch.from_numpy(g["z"]), atol=2e-4, rtol=2e-5)
     assert torch.allclose(nll.cpu(), torch.from_numpy(g["nll"]), atol=1e-4, rtol=1e-5)
+
+
+def test_infer_rejects_unpadded_sizes(engine):
+    with pytest.raises(ValueError):
+        engine.infer(torch.zeros((1, 3, 30, 48)))
+    with pytest.raises(ValueError):
+        engine.infer(torch.zeros((1, 4, 32, 48)))

@@ -18,6 +18,7 @@
 // Layouts: x NHWC fp32 [B,H,W,C]; om = raw conv_offset output NHWC fp32 [B,H,W,3*dg*9] (channels [0,18dg) offsets in the
 // reference's (g, tap, {dh,dw}) order, [18dg,27dg) mask logits); weights packed [Cout][9][C] (glare_conv_pack_weight).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc.cuh"
 
@@ -35,7 +36,9 @@ struct DcnTcArgs {
     int total_tiles;
 };
 
-template <int MODE, int BN>
+constexpr int DT_OM_MAX = 108;            // 27 * deformable_groups floats of conv_offset output per pixel staged in smem (dg <= 4)
+
+template <int MODE, int BN, bool OMS = false>
 struct DcnCfg {
     static constexpr bool XB = MODE == 3;                      // tf32 main term + two bf16 cross terms (common.cuh store_x4)
     static constexpr bool B3 = MODE == 4;                      // bf16x3: one interleaved bf16 tile per operand (common.cuh split_b3)
@@ -44,19 +47,20 @@ struct DcnCfg {
     static constexpr int BKE = (TF32 || B3) ? 32 : 64;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = (DT_A_BYTES + B_BYTES) * (X3 ? 2 : 1);
-    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
+    static constexpr int OM_BYTES = OMS ? 128 * DT_OM_MAX * 4 : 0;        // the tile's offsets + sigmoid(mask), loaded once per tile
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048 - OM_BYTES;
     static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 1 ? 1 : STAGES_RAW);
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + 1024;
+    static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + OM_BYTES + 1024;
 };
 
 __device__ __forceinline__ float tf32_hi_d(float x) { return tf32_round(x); }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool OMS>
 __global__ void __launch_bounds__(DT_THREADS, 1)
 dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const DcnTcArgs a) {
-    using Cfg = DcnCfg<MODE, BN>;
+    using Cfg = DcnCfg<MODE, BN, OMS>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
@@ -212,6 +216,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         constexpr int CPL = (Cfg::TF32 || Cfg::B3) ? 4 : 8;   // channels per lane per stage
         constexpr int V4 = CPL / 4;
         const int om_c = 27 * a.dg;
+        float* const s_om = reinterpret_cast<float*>(smem_al + (size_t)STAGES * Cfg::STAGE_BYTES);   // [128][om_c] when OMS
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             int r = tile / a.n_blocks;
@@ -219,6 +224,24 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             r -= n * tiles_xy;
             const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
             const float* xn = a.x + (long long)n * a.H * a.W * a.C;
+            if (OMS) {
+                // stage the tile's conv_offset output once (offsets raw, mask through the sigmoid): the geometry of every
+                // (pixel, group, tap) then starts from shared memory instead of a dependent global load per use
+                named_bar_sync(3, 256);                        // all sampler warps are done with the previous tile's values
+                const int st_id = threadIdx.x - 192;           // sampler threads are 192..447
+                for (int i = st_id; i < 128 * om_c; i += 256) {
+                    const int m = i / om_c, ch = i - m * om_c;
+                    const int py = m / a.TW, px = m - py * a.TW;
+                    const int gy = ty * a.TH + py, gx = tx * a.TW + px;
+                    float v = 0.f;
+                    if (gy < a.H && gx < a.W) {
+                        v = __ldg(a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c + ch);
+                        if (ch >= 18 * a.dg) v = 1.0f / (1.0f + expf(-v));
+                    }
+                    s_om[i] = v;
+                }
+                named_bar_sync(3, 256);
+            }
             for (int tap = 0; tap < 9; ++tap) {
                 const int ti = tap / 3, tj = tap - ti * 3;
                 for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
@@ -241,9 +264,15 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
 #pragma unroll
                             for (int k = 0; k < 4; ++k) { cw[q4][k] = 0.f; co[q4][k] = 0; }
                             if (gy < a.H && gx < a.W) {
-                                const float* omp = a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c;
-                                const float oh = __ldg(omp + g * 18 + 2 * tap), ow = __ldg(omp + g * 18 + 2 * tap + 1);
-                                const float mk = 1.0f / (1.0f + expf(-__ldg(omp + 18 * a.dg + g * 9 + tap)));
+                                float oh, ow, mk;
+                                if (OMS) {
+                                    const float* omp = s_om + m * om_c;
+                                    oh = omp[g * 18 + 2 * tap]; ow = omp[g * 18 + 2 * tap + 1]; mk = omp[18 * a.dg + g * 9 + tap];
+                                } else {
+                                    const float* omp = a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c;
+                                    oh = __ldg(omp + g * 18 + 2 * tap); ow = __ldg(omp + g * 18 + 2 * tap + 1);
+                                    mk = 1.0f / (1.0f + expf(-__ldg(omp + 18 * a.dg + g * 9 + tap)));
+                                }
                                 const float h_im = (float)(gy - 1 + ti) + oh, w_im = (float)(gx - 1 + tj) + ow;   // .cu:607-612
                                 if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {            // .cu:618
                                     const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
@@ -368,15 +397,25 @@ static int make_w_map_d(CUtensorMap* m, const void* ptr, bool bf16, int Cout, in
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-template <int MODE, int BN>
-static int launch_dcn_tc(const CUtensorMap& tB, const CUtensorMap& tBl, const DcnTcArgs& a, cudaStream_t stream) {
-    using Cfg = DcnCfg<MODE, BN>;
-    static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
-    GLARE_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
+template <int MODE, int BN, bool OMS>
+static int launch_dcn_tc_v(const CUtensorMap& tB, const CUtensorMap& tBl, const DcnTcArgs& a, cudaStream_t stream) {
+    using Cfg = DcnCfg<MODE, BN, OMS>;
+    GLARE_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<MODE, BN, OMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
     const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    dcn_tc_kernel<MODE, BN><<<grid, DT_THREADS, Cfg::SMEM_DYN, stream>>>(tB, tBl, a);
+    dcn_tc_kernel<MODE, BN, OMS><<<grid, DT_THREADS, Cfg::SMEM_DYN, stream>>>(tB, tBl, a);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
+}
+
+template <int MODE, int BN>
+static int launch_dcn_tc(const CUtensorMap& tB, const CUtensorMap& tBl, const DcnTcArgs& a, cudaStream_t stream) {
+    static_assert(DcnCfg<MODE, BN, false>::STAGES >= 2, "pipeline needs at least two stages");
+    // offsets/mask staged in shared memory when that still leaves a two-stage ring (not for the 96 KB stages of modes 2/3 at BN = 256)
+    if constexpr (DcnCfg<MODE, BN, true>::STAGES_RAW >= 2) {
+        static const bool no_oms = getenv("GLARE_DCN_NO_OM_SMEM") != nullptr;      // A/B switch for profiling only
+        if (27 * a.dg <= DT_OM_MAX && !no_oms) return launch_dcn_tc_v<MODE, BN, true>(tB, tBl, a, stream);
+    }
+    return launch_dcn_tc_v<MODE, BN, false>(tB, tBl, a, stream);
 }
 
 }  // namespace glare

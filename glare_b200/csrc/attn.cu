@@ -216,9 +216,74 @@ __global__ void __launch_bounds__(256) attn_transpose_v_kernel(const float* __re
     }
 }
 
+// ---- softmax fused into the two GEMM epilogues (mode 4) ---------------------------------------------------------------
+// softmax is invariant to the per-row reference that is subtracted before exp, and fp32 keeps full relative precision over
+// ~76 decades, so the scores GEMM does not need the exact row maximum: any ref(row) with  max_j l_ij - ref(row)  in about
+// [-115, +60] (l = scale * s) gives the same P up to rounding.  ref(row) = scale |q_row| max_j |k_j| - margin is a Cauchy-Schwarz
+// upper bound of every logit of the row minus `margin`, known BEFORE the GEMM, so its epilogue can emit
+//     p~_ij = exp(l_ij - ref_i)     (<= e^margin, the bf16x3 operand of the P V GEMM)   and partial row sums,
+// and the P V GEMM's epilogue multiplies row i by 1 / sum_j p~_ij.  The N x N matrix is written once and read once (the
+// separate softmax pass read it and wrote it again).  The bound is loose when the row maximum sits far below |q||k|: rows whose sum
+// falls under 1e-24 (more than ~115 below the bound) or is not finite set a device flag, and the host re-runs the block with the exact
+// three-kernel path (dense.py).
+//   attn_row_norm_kernel : |x_row| of q (per row) and max_j |k_j| (per sample, atomicMax on the bits of a non-negative float)
+//   attn_row_sum_finish  : row_scale = 1 / sum of the partial row sums, fixed summation order; raises the flag
+__global__ void __launch_bounds__(256) attn_row_norm_kernel(const float* __restrict__ x, long long rows, int C, long long rows_per_sample,
+                                                            float* __restrict__ norm_out, unsigned* __restrict__ max_bits) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    float s = 0.f;
+    for (int i = lane; i < C / 4; i += 32) {
+        const float4 v = __ldg(xr + i);
+        s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const float nrm = sqrtf(s) * 1.00001f;                       // covers the rounding of the sum and of the GEMM's operands
+        if (norm_out) norm_out[row] = nrm;
+        if (max_bits) atomicMax(max_bits + row / rows_per_sample, __float_as_uint(nrm));
+    }
+}
+
+__global__ void __launch_bounds__(256) attn_row_sum_finish_kernel(const float* __restrict__ part, long long part_stride, int n_blocks,
+                                                                  long long rows, float* __restrict__ row_scale, int* __restrict__ flag) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) s += __ldg(part + (long long)b * part_stride + r);
+    if (!(s >= 1e-24f && s <= 3e38f)) atomicOr(flag, 1);              // also catches NaN
+    row_scale[r] = 1.0f / s;
+}
+
 }  // namespace glare
 
 using namespace glare;
+
+// x [rows][C] fp32 (C % 4 == 0): norm_out[row] = |x_row| (may be null); max_bits[row / rows_per_sample] = max over the sample's rows
+// (may be null; the caller zeroes it first)
+GLARE_API int glare_attn_row_norm(const float* x, long long rows, int C, long long rows_per_sample, float* norm_out, unsigned* max_bits,
+                                  cudaStream_t stream) {
+    if (rows < 0 || C <= 0 || (C & 3) || rows_per_sample <= 0 || (!norm_out && !max_bits)) return GLARE_ERR_BAD_ARG;
+    if (rows == 0) return GLARE_OK;
+    if (!x || (rows + 7) / 8 > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
+    attn_row_norm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, rows, C, rows_per_sample, norm_out, max_bits);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// row_scale[r] = 1 / sum_{b < n_blocks} part[b * part_stride + r]; *flag |= 1 when a sum is < 1e-24, infinite or NaN
+GLARE_API int glare_attn_row_sum_finish(const float* part, long long part_stride, int n_blocks, long long rows, float* row_scale, int* flag,
+                                        cudaStream_t stream) {
+    if (rows < 0 || n_blocks <= 0 || part_stride < rows) return GLARE_ERR_BAD_ARG;
+    if (rows == 0) return GLARE_OK;
+    if (!part || !row_scale || !flag) return GLARE_ERR_BAD_ARG;
+    attn_row_sum_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(part, part_stride, n_blocks, rows, row_scale, flag);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
 
 // S [rows][lds] fp32 logits (first n_keys columns valid) -> P [rows][ldp] operand (out_mode 0 bf16, 1 fp32, 2 tf32 hi+lo),
 // P = softmax(scale * S) over the keys, zero in columns [n_keys, n_pad).

@@ -46,6 +46,15 @@ struct ConvTcArgs {
     double* gn_stats;        // optional [B][32][2] (sum, sum of squares) of the OUTPUT per GroupNorm group, accumulated in the epilogue
     int gn_cpg;              // channels per group (Cout / 32), a multiple of 4
     int tma_store;           // epilogue: registers -> swizzled smem staging -> TMA tiled store (else per-thread float4 stores)
+    // attention epilogues (mode 4 only; attn.cu documents the scheme).  Scores GEMM: the accumulator s becomes
+    // p = exp(exp_scale * s - ref(row)), ref(row) = row_norm[row] * exp_scale * max|k| - exp_margin >= every logit of the row - margin,
+    // written as the bf16x3 operand of the P V GEMM; per-(row, output block) partial row sums go to row_sum_part.
+    const float* row_norm;        // [rows] |q_row|, or null
+    const unsigned* key_norm_max; // bits of max_j |k_j| (non-negative float)
+    float* row_sum_part;          // [n_blocks][part_stride]
+    long long part_stride;
+    float exp_scale, exp_margin;
+    const float* row_scale;       // P V GEMM: y[row] *= row_scale[row] (1 / row sum), or null
 };
 
 template <int MODE, int BN, bool PAIR = false>
@@ -64,6 +73,12 @@ struct ConvCfg {
     static constexpr int TMEM_COLS = 2 * BN;                   // 128 / 256 / 512: powers of two >= 32
     static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <bool TF32, bool PAIR>
 __device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -263,40 +278,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long pix = ((long long)n * a.H * a.oscale + (gy * a.oscale + a.oa)) * (a.W * a.oscale) + (gx * a.oscale + a.ob);
             float* yrow = a.y + pix * a.ldy;
             const float* rrow = (a.residual && valid) ? a.residual + pix * a.Cout : nullptr;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c0, v);
-                tmem_ld_wait();
-                if (c0 + 32 >= BN) {                                     // accumulator fully read: hand it back to the MMA thread
-                    tc_fence_before();
-                    if (PAIR) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // ... which lives in the leader CTA
-                    else mbar_arrive(&tmem_empty_bar[as]);
-                }
+            const bool epi_exp = MODE == 4 && a.row_norm != nullptr;
+            float e_ref = 0.f, e_sum = 0.f, r_scale = 1.f;
+            if (epi_exp && valid) e_ref = fmaf(__ldg(a.row_norm + pix), a.exp_scale * __uint_as_float(__ldg(a.key_norm_max)), -a.exp_margin);
+            if (a.row_scale != nullptr) r_scale = valid ? __ldg(a.row_scale + pix) : 0.f;
+            // one 32-column chunk of this thread's accumulator row: registers -> bias / residual / attention epilogues -> store
+            auto process = [&](const uint32_t (&v)[32], const int c0) {
                 const int co = nb * BN + c0;
-                if (co >= a.Cout) continue;                              // uniform over the CTA
+                if (co >= a.Cout) return;                                // uniform over the CTA
+                const bool full = co + 32 <= a.Cout;                     // uniform: no ragged tail inside this chunk
                 float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    o[j] = __uint_as_float(v[j]); o[j + 1] = __uint_as_float(v[j + 1]);
-                    o[j + 2] = __uint_as_float(v[j + 2]); o[j + 3] = __uint_as_float(v[j + 3]);
-                    if (co + j + 4 <= a.Cout) {
-                        if (a.bias) {
+                for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+                if (full) {
+                    if (a.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
                             const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
                             o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
                         }
-                        if (rrow) {
+                    }
+                    if (rrow) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
                             const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + co + j));
                             o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
                         }
-                    } else {                                             // ragged tail of a Cout % 4 != 0 head (3-channel outputs)
+                    }
+                } else {                                                 // last chunk of a Cout % 32 != 0 output (3-channel heads, attention keys)
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (co + j + e < a.Cout) {
-                                if (a.bias) o[j + e] += __ldg(a.bias + co + j + e);
-                                if (rrow) o[j + e] += __ldg(rrow + co + j + e);
-                            }
+                    for (int j = 0; j < 32; ++j) {
+                        if (co + j < a.Cout) {
+                            if (a.bias) o[j] += __ldg(a.bias + co + j);
+                            if (rrow) o[j] += __ldg(rrow + co + j);
                         }
+                    }
+                }
+                if (a.row_scale != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] *= r_scale;
+                }
+                if (epi_exp) {
+                    // keys [co, co + 32) of this query row = one 128-byte operand chunk [16 words of a1 pairs | 16 words of a2 pairs]
+                    // p = 2^(s * scale*log2(e) - ref*log2(e)): one FFMA + one MUFU.EX2 per element, branch-free (a single epilogue warp per
+                    // scheduler has no other latency hiding).  The exponent's rounding (2^-24 |t|, |t| <~ 90) and ex2.approx (2^-22) stay
+                    // below the 2^-17 resolution of the two-piece bf16 operand p is stored as.
+                    float p[32];
+                    const float c1 = a.exp_scale * 1.4426950408889634f, r1 = e_ref * 1.4426950408889634f;
+                    if (co + 32 <= a.Cout) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) p[j] = ex2_approx(fmaf(o[j], c1, -r1));
+                    } else {                                            // ragged last chunk: keys past the end get exp2(-inf) = 0
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) p[j] = ex2_approx((co + j < a.Cout) ? fmaf(o[j], c1, -r1) : -INFINITY);
+                    }
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // fixed order: repeatable row sums
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) { s0 += p[j]; s1 += p[j + 1]; s2 += p[j + 2]; s3 += p[j + 3]; }
+                    e_sum += (s0 + s1) + (s2 + s3);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(p[j], p[j + 1]);               // a1 pair (one F2FP)
+                        const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h);
+                        const float r0 = p[j] - __uint_as_float(hw << 16), r1 = p[j + 1] - __uint_as_float(hw & 0xffff0000u);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);                      // a2 pair
+                        o[j >> 1] = __uint_as_float(hw);
+                        o[16 + (j >> 1)] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
                     }
                 }
                 if (a.gn_stats != nullptr) {
@@ -353,7 +400,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_store_wait_read<1>();                        // this warp's other staging buffer is free again
                     }
                     ++chunk_id;
-                } else if (valid) {
+                } else if (valid && !epi_exp) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         if (co + j + 4 <= a.Cout) *reinterpret_cast<float4*>(yrow + co + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -364,7 +411,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+            };
+            // TMEM -> registers, double buffered: the load of chunk c + 1 is in flight while chunk c is processed
+            uint32_t va[32], vb[32];
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+            tmem_ld_32x32(tacc, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 64) {
+                tmem_ld_wait();
+                tmem_ld_32x32(tacc + c0 + 32, vb);
+                process(va, c0);
+                tmem_ld_wait();
+                if (c0 + 64 < BN) {
+                    tmem_ld_32x32(tacc + c0 + 64, va);
+                } else {                                                 // accumulator fully read: hand it back to the MMA thread
+                    tc_fence_before();
+                    if (PAIR) mbar_arrive_cluster(&tmem_empty_bar[as], 0);   // ... which lives in the leader CTA
+                    else mbar_arrive(&tmem_empty_bar[as]);
+                }
+                process(vb, c0 + 32);
             }
+            if (epi_exp && valid) a.row_sum_part[(long long)nb * a.part_stride + pix] = e_sum;
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -568,10 +635,14 @@ GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* o
 // x / x_lo: NHWC [B,H,W,Cin] (bf16 for mode 0, fp32 otherwise; x_lo only for mode 2); w / w_lo: packed by
 // glare_conv_pack_weight; bias [Cout] / residual NHWC [B,H,W,Cout] fp32 or NULL; y NHWC fp32.
 struct TapSpec { int ntaps, tap_w, dy0, dx0, oscale, oa, ob; };
+struct AttnEpi {                       // attention epilogues of the two GEMMs (ConvTcArgs documents the fields)
+    const float* row_norm; const unsigned* key_norm_max; float* row_sum_part; long long part_stride; float exp_scale, exp_margin;
+    const float* row_scale; int* n_blocks_out;
+};
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
                           int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats = nullptr,
-                          int gn_zero = 0);
+                          int gn_zero = 0, const AttnEpi* ae = nullptr);
 static inline TapSpec std_taps(int ksize) { return TapSpec{ksize * ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0}; }
 
 GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
@@ -640,10 +711,40 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
                           stream);
 }
 
+// Attention scores with the softmax numerator fused into the epilogue (mode 4 operands; attn.cu has the scheme and the kernels around it).
+// q: operand [rows_h * rows_w][C] of the query rows, k: operand [n_keys][C] of this sample's keys; writes the bf16x3 operand
+// P~ [rows][n_pad] = exp(scale * q k^T - ref(row)) (zero for keys in [n_keys, roundup32(n_keys)); chunks past that are not touched) and
+// row_sum_part[nb][row], nb < *n_blocks_host, the partial row sums per output block (part_stride >= rows elements apart).
+GLARE_API int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, int rows_h, int rows_w, int C, int n_keys, int n_pad,
+                                       float scale, float margin, const float* q_row_norm, const unsigned* key_norm_max, void* p_out,
+                                       float* row_sum_part, long long part_stride, int* n_blocks_host, cudaStream_t stream) {
+    if (mode != 4) return GLARE_ERR_UNSUPPORTED;
+    if (!q_row_norm || !key_norm_max || !row_sum_part || !n_blocks_host || n_pad < n_keys || (n_pad & 31) || !(scale > 0.f) || !(margin >= 0.f))
+        return GLARE_ERR_BAD_ARG;
+    AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host};
+    return conv_tc_launch(mode, q, nullptr, k, nullptr, nullptr, nullptr, reinterpret_cast<float*>(p_out), 1, rows_h, rows_w, rows_h, rows_w, C,
+                          n_keys, std_taps(1), 1, n_pad, 0, stream, nullptr, 0, &ae);
+}
+
+// O = diag(row_scale) P~ V: p operand [rows][n_pad], vt operand [C][n_pad] (V^T of the sample), y [rows][ldy] fp32
+GLARE_API int glare_attn_pv_tc(int mode, const void* p, const void* vt, const float* row_scale, float* y, int rows_h, int rows_w, int n_pad,
+                               int C, long long ldy, cudaStream_t stream) {
+    if (mode != 4) return GLARE_ERR_UNSUPPORTED;
+    if (!row_scale) return GLARE_ERR_BAD_ARG;
+    AttnEpi ae{nullptr, nullptr, nullptr, 0, 0.f, 0.f, row_scale, nullptr};
+    return conv_tc_launch(mode, p, nullptr, vt, nullptr, nullptr, nullptr, y, 1, rows_h, rows_w, rows_h, rows_w, n_pad, C, std_taps(1), 1, ldy, 0,
+                          stream, nullptr, 0, &ae);
+}
+
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
-                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats, int gn_zero) {
+                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats, int gn_zero,
+                          const AttnEpi* ae) {
     const int ksize = ts.tap_w;
+    const bool epi_exp = ae && ae->row_norm;
+    if (ae && (mode != 4 || bias || residual || gn_stats)) return GLARE_ERR_UNSUPPORTED;
+    if (epi_exp && (!ae->key_norm_max || !ae->row_sum_part || ae->part_stride < (long long)B * H * W || (ldy & 31) || Cout < 32))
+        return GLARE_ERR_BAD_ARG;
     if (gn_stats && (Cout % 128 != 0 || B <= 0)) return GLARE_ERR_UNSUPPORTED;       // 32 groups of a multiple of 4 channels
     if (gn_stats && gn_zero) GLARE_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 64 * (size_t)B, stream));
     if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
@@ -668,6 +769,11 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     const long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
     a.n_blocks = (Cout + BN - 1) / BN;
+    if (ae) {
+        a.row_norm = ae->row_norm; a.key_norm_max = ae->key_norm_max; a.row_sum_part = ae->row_sum_part; a.part_stride = ae->part_stride;
+        a.exp_scale = ae->exp_scale; a.exp_margin = ae->exp_margin; a.row_scale = ae->row_scale;
+        if (ae->n_blocks_out) *ae->n_blocks_out = a.n_blocks;
+    }
     // clusters of two CTAs share the weight tile by multicast; per-sample weights over a batch cannot be shared across samples
     // default: CTA pair (cta_group::2).  A/B switches for profiling only: GLARE_CONV_MCAST -> two independent CTAs sharing the weight
     // tile by TMA multicast, GLARE_CONV_NO_CLUSTER -> single CTAs
@@ -686,9 +792,10 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     int rc;
     {
         static const bool direct = getenv("GLARE_CONV_DIRECT_STORE") != nullptr;   // A/B switch for profiling only
-        a.tma_store = (!direct && Cout >= 32 && ts.oscale == 1) ? 1 : 0;
+        a.tma_store = ((!direct || epi_exp) && Cout >= 32 && ts.oscale == 1) ? 1 : 0;
     }
-    if ((rc = make_out_map(&tY, y, B, H, W, Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
+    // exp epilogue: the output is an operand tensor of 128-byte chunks (32 keys each), written whole up to the padded row length ldy
+    if ((rc = make_out_map(&tY, y, B, H, W, epi_exp ? (int)ldy : Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0 || mode == 4;
     const int e2 = mode == 4 ? 2 : 1;              // mode 4: the operand tensors are interleaved bf16 pairs, 2 per element
     if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, e2 * Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;

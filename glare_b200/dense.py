@@ -117,6 +117,13 @@ class TcDense:
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
         self.attn_s_budget = 3 << 29   # bytes of fp32 score matrix materialised per pass (1.5 GiB)
+        # mode 4: softmax fused into the epilogues of the two GEMMs (csrc/attn.cu): exp against a Cauchy-Schwarz row reference in the scores
+        # GEMM, 1 / row sum in the P V GEMM; rows that fall outside the safe window raise `attn_flag` and `attention_verified()` tells
+        # the caller (engine.infer) to re-run with the exact three-kernel path
+        import os
+        self.attn_fused = mode == 4 and not os.environ.get("GLARE_ATTN_UNFUSED")
+        self.attn_margin = 60.0
+        self.attn_flag = None
         self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
         self.last_timers, self.last_steps = None, 1
 
@@ -274,6 +281,9 @@ class TcDense:
             k_hi, k_lo = ops.conv_prep_act(self.mode, kn)                 # K[n] as GEMM weights [N][C]
             vt_hi, vt_lo = ops.attn_transpose_v(self.mode, vn, B, N, C, Np)
             out = torch.empty((B, h, w, C), device=q.device, dtype=torch.float32)
+            if self.attn_fused and N >= 32:
+                self._attention_fused(qn, kn, q_hi, k_hi, vt_hi, out, B, h, w, N, Np, C)
+                return out.permute(0, 3, 1, 2)
             # query rows per pass: the whole sample when its score matrix fits the budget (tile-filling GEMMs matter more
             # than L2 residency of S: the P V GEMM needs >= 74 M-tiles to give every SM a 128x256 tile), else 8-row multiples
             band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
@@ -296,6 +306,51 @@ class TcDense:
                         ops.conv2d_nhwc_tc_ex(self.mode, p_hi, p_lo, vt_hi[b], None if vt_lo is None else vt_lo[b], out[b, r0:r1],
                                               1, bh, w, Np, C, C, 0)
         return out.permute(0, 3, 1, 2)
+
+    def _attention_fused(self, qn, kn, q_op, k_op, vt_op, out, B, h, w, N, Np, C):
+        """mode 4: scores GEMM with the exp epilogue -> row-sum finish -> P V GEMM with the 1 / row-sum epilogue (csrc/attn.cu)"""
+        ops, dev = self.ops, qn.device
+        if self.attn_flag is None or self.attn_flag.device != dev:
+            self.attn_flag = torch.zeros((1,), device=dev, dtype=torch.int32)
+        scale = float(int(C) ** (-0.5))
+        q_norm = torch.empty((B, N), device=dev, dtype=torch.float32)
+        k_max = torch.zeros((B,), device=dev, dtype=torch.int32)
+        with self._t("attn_softmax"):
+            ops.attn_row_norm(qn, B * N, C, N, norm_out=q_norm)
+            ops.attn_row_norm(kn, B * N, C, N, max_bits=k_max)
+        # whole-sample passes while the operand matrix fits the budget, else bands of 8-row multiples
+        band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
+        rows_max = min(band, h) * w
+        p_op = ops._hi_alloc(self.mode, (rows_max, Np), dev)
+        n32 = (N + 31) // 32 * 32
+        if n32 < Np:
+            p_op[:, 2 * n32:].zero_()                                    # operand chunks past the last key chunk are never written
+        part = torch.empty(((N + 63) // 64, rows_max), device=dev, dtype=torch.float32)
+        row_scale = torch.empty((rows_max,), device=dev, dtype=torch.float32)
+        for b in range(B):
+            for r0 in range(0, h, band):
+                r1 = min(h, r0 + band)
+                bh = r1 - r0
+                gemm_flops = 2.0 * bh * w * N * C
+                with self._t("conv_tc", gemm_flops):
+                    nb = ops.attn_scores_exp_tc(self.mode, q_op[b, r0:r1], k_op[b], bh, w, C, N, Np, scale, self.attn_margin,
+                                                q_norm[b, r0 * w:], k_max[b:], p_op, part, rows_max)
+                with self._t("attn_softmax"):
+                    ops.attn_row_sum_finish(part, rows_max, nb, bh * w, row_scale, self.attn_flag)
+                with self._t("conv_tc", gemm_flops):
+                    ops.attn_pv_tc(self.mode, p_op, vt_op[b], row_scale, out[b, r0:r1], bh, w, Np, C, C)
+
+    def attention_verified(self):
+        """True when every fused-softmax row so far stayed inside the safe window (one 4-byte device read).  On False the fused path is
+        switched off for this backend and the caller must recompute with the exact path."""
+        if self.attn_flag is None or not self.attn_fused:
+            return True
+        if int(self.attn_flag.item()) == 0:
+            return True
+        self.attn_fused = False
+        self.attn_flag.zero_()
+        self.fallbacks["attention: fused softmax window exceeded -> exact softmax path"] = 1
+        return False
 
     def breakdown(self, eng_timers, steps):
         out = {}

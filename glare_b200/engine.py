@@ -253,11 +253,17 @@ class GlareEngine:
             raise ValueError("expected lr [B,3,H,W] with H and W multiples of 4 (pad first, see api.GlareEnhancer); got %s" % (tuple(lr.shape),))
         with torch.cuda.device(self.device):
             lr = lr.to(self.device, torch.float32)
-            enc = self.cond_encoder(lr)
-            z = self.flow_decode(enc["color_map"], enc["cond_feat"])
-            zq, idx = self.vector_quantize(z)
-            vq_feats = self.vq_decoder_features(zq)
-            out = self.aft_decoder(z, vq_feats, enc["mid_feat"])
+            for _ in range(2):
+                enc = self.cond_encoder(lr)
+                z = self.flow_decode(enc["color_map"], enc["cond_feat"])
+                zq, idx = self.vector_quantize(z)
+                vq_feats = self.vq_decoder_features(zq)
+                out = self.aft_decoder(z, vq_feats, enc["mid_feat"])
+                # the fused-softmax attention (dense.py) verifies its row sums on the device; a tripped flag switches the backend to the
+                # exact softmax path and the batch is recomputed (4-byte read, once per call)
+                verified = getattr(self.dense, "attention_verified", None)
+                if verified is None or verified():
+                    break
         if stages is not None:
             stages.update(cond_feat=enc["cond_feat"], color_map=enc["color_map"], mid0=enc["mid_feat"][0], mid1=enc["mid_feat"][1],
                           z_flow=z, z_q=zq, idx=idx, vq_feat1=vq_feats[0], vq_feat0=vq_feats[1], out=out)

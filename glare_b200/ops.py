@@ -230,6 +230,33 @@ def attn_transpose_v(mode, v_nhwc, B, N, C, Np):
     return hi, lo
 
 
+def attn_row_norm(x_rows, rows, C, rows_per_sample, norm_out=None, max_bits=None):
+    """|x_row| per row and / or the per-sample maximum (bits of a non-negative float, zeroed by the caller)"""
+    require_cuda(x_rows, norm_out, max_bits)
+    check(lib().glare_attn_row_norm(ptr(x_rows), rows, C, rows_per_sample, ptr(norm_out), ptr(max_bits), stream()), "glare_attn_row_norm")
+
+
+def attn_scores_exp_tc(mode, q_op, k_op, rows_h, rows_w, C, n_keys, n_pad, scale, margin, q_norm, key_max, p_out, row_sum_part, part_stride):
+    """scores GEMM with exp(scale * s - ref(row)) in the epilogue; returns the number of output blocks (valid planes of row_sum_part)"""
+    import ctypes
+    require_cuda(q_op, k_op, q_norm, key_max, p_out, row_sum_part)
+    nb = ctypes.c_int(0)
+    check(lib().glare_attn_scores_exp_tc(mode, ptr(q_op), ptr(k_op), rows_h, rows_w, C, n_keys, n_pad, scale, margin, ptr(q_norm), ptr(key_max),
+                                         ptr(p_out), ptr(row_sum_part), part_stride, ctypes.cast(ctypes.byref(nb), ctypes.c_void_p), stream()),
+          "glare_attn_scores_exp_tc")
+    return nb.value
+
+
+def attn_row_sum_finish(part, part_stride, n_blocks, rows, row_scale, flag):
+    require_cuda(part, row_scale, flag)
+    check(lib().glare_attn_row_sum_finish(ptr(part), part_stride, n_blocks, rows, ptr(row_scale), ptr(flag), stream()), "glare_attn_row_sum_finish")
+
+
+def attn_pv_tc(mode, p_op, vt_op, row_scale, y, rows_h, rows_w, n_pad, C, ldy):
+    require_cuda(p_op, vt_op, row_scale, y)
+    check(lib().glare_attn_pv_tc(mode, ptr(p_op), ptr(vt_op), ptr(row_scale), ptr(y), rows_h, rows_w, n_pad, C, ldy, stream()), "glare_attn_pv_tc")
+
+
 def gn_stats(x_nhwc, B, HW, C, G=32):
     require_cuda(x_nhwc)
     stats = torch.empty((B, G, 2), device=x_nhwc.device, dtype=torch.float64)

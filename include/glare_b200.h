@@ -164,6 +164,19 @@ int glare_attn_softmax_rows(int out_mode, const float* S, long long rows, long l
 /* v NHWC [B][N][C] fp32 -> V^T [B][C][Np] operand(s) */
 int glare_attn_transpose_v(int out_mode, const float* v, int B, int N, int C, int Np, void* out_hi, void* out_lo,
                            cudaStream_t stream);
+/* Softmax fused into the epilogues of the two GEMMs (mode 4 = bf16x3 operands; same reference lines).  The scores GEMM emits
+ * p~ = exp(scale * q.k - ref(row)) with ref(row) = scale * |q_row| * max_j |k_j| - margin (an upper bound of the row's logits minus
+ * margin, so no row maximum is needed before the GEMM) directly as the operand of the second GEMM, plus partial row sums; the second
+ * GEMM scales row i by 1 / sum_j p~_ij.  A row whose sum leaves [1e-24, 3e38] sets *flag (the caller re-runs with the exact path). */
+int glare_attn_row_norm(const float* x, long long rows, int C, long long rows_per_sample, float* norm_out, unsigned* max_bits,
+                        cudaStream_t stream);
+int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, int rows_h, int rows_w, int C, int n_keys, int n_pad, float scale,
+                             float margin, const float* q_row_norm, const unsigned* key_norm_max, void* p_out, float* row_sum_part,
+                             long long part_stride, int* n_blocks_host, cudaStream_t stream);
+int glare_attn_row_sum_finish(const float* part, long long part_stride, int n_blocks, long long rows, float* row_scale, int* flag,
+                              cudaStream_t stream);
+int glare_attn_pv_tc(int mode, const void* p, const void* vt, const float* row_scale, float* y, int rows_h, int rows_w, int n_pad, int C,
+                     long long ldy, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (5) Normalize = GroupNorm(32, eps 1e-6) (+ swish) -- encoder_decoder.py:29-35 as used by ResnetBlock.forward

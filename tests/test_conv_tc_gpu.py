@@ -110,6 +110,14 @@ def test_attention_gemm_path(glare_lib, shape, mode, tol):
     d = TcDense(mode)
     out = d.attention(q, k, v)
     torch.cuda.synchronize()
+    assert d.attention_verified()
+    ref = _attention_fp64(q, k, v)
+    err = float((out.reshape(B, C, h * w).double() - ref).abs().max())
+    assert err < tol * max(1.0, float(ref.abs().max())), (shape, mode, err)
+
+
+def _attention_fp64(q, k, v):
+    B, C, h, w = q.shape
     N = h * w
     ref = torch.empty((B, C, N), dtype=torch.float64, device="cuda")
     for b in range(B):
@@ -117,8 +125,59 @@ def test_attention_gemm_path(glare_lib, shape, mode, tol):
         for i0 in range(0, N, 4096):                         # query chunks: keep the fp64 score matrix small
             s = torch.softmax(qq[:, i0:i0 + 4096].t() @ kk * (int(C) ** -0.5), dim=1)
             ref[b, :, i0:i0 + 4096] = vv @ s.t()
-    err = float((out.reshape(B, C, N).double() - ref).abs().max())
-    assert err < tol * max(1.0, float(ref.abs().max())), (shape, mode, err)
+    return ref
+
+
+@pytest.mark.parametrize("shape", [(1, 512, 9, 14), (2, 512, 24, 21), (1, 512, 105, 155), (1, 128, 40, 33)])
+def test_attention_fused_softmax_matches_exact_path(glare_lib, shape):
+    """mode 4: exp in the scores-GEMM epilogue + 1/rowsum in the P V epilogue vs the three-kernel path (S, softmax, P V) and fp64;
+    large logits (|q||k| C^-0.5 up to ~60 with peaked rows) stay inside the safe window"""
+    from glare_b200.dense import TcDense
+    B, C, h, w = shape
+    g = torch.Generator().manual_seed(7 + h)
+    q = (torch.randn((B, C, h, w), generator=g) * 2.0).cuda()
+    k = (torch.randn((B, C, h, w), generator=g) * 1.5).cuda()
+    v = torch.randn((B, C, h, w), generator=g).cuda()
+    fused, exact = TcDense(4), TcDense(4)
+    exact.attn_fused = False
+    assert fused.attn_fused
+    o1 = fused.attention(q, k, v)
+    o2 = exact.attention(q, k, v)
+    torch.cuda.synchronize()
+    assert fused.attention_verified() and fused.attn_fused
+    ref = _attention_fp64(q, k, v)
+    sc = max(1.0, float(ref.abs().max()))
+    e1 = float((o1.reshape(B, C, h * w).double() - ref).abs().max())
+    e2 = float((o2.reshape(B, C, h * w).double() - ref).abs().max())
+    assert e1 < 6e-5 * sc and e2 < 6e-5 * sc, (shape, e1, e2)
+    # bitwise repeatable (fixed summation order of the partial row sums)
+    o3 = fused.attention(q, k, v)
+    assert torch.equal(o1, o3)
+
+
+def test_attention_fused_softmax_window_flag_and_fallback(glare_lib):
+    """rows whose maximum logit sits > ~115 below the Cauchy-Schwarz bound raise the device flag; attention_verified() then switches the
+    backend to the exact path, which is what the engine re-runs with"""
+    from glare_b200.dense import TcDense
+    B, C, h, w = 1, 512, 12, 16
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn((B, C, h, w), generator=g) * 0.05
+    k = torch.randn((B, C, h, w), generator=g) * 0.05
+    q[:, 0] = 400.0                                   # huge norms along orthogonal directions: bound ~ 400 * 400 / 22.6, logits ~ 0
+    k[:, 0] = 0.0
+    k[:, 1] = 400.0
+    q[:, 1] = 0.0
+    v = torch.randn((B, C, h, w), generator=g)
+    q, k, v = q.cuda(), k.cuda(), v.cuda()
+    d = TcDense(4)
+    d.attention(q, k, v)
+    assert not d.attention_verified()
+    assert not d.attn_fused and d.fallbacks
+    out = d.attention(q, k, v)
+    assert d.attention_verified()
+    ref = _attention_fp64(q, k, v)
+    err = float((out.reshape(B, C, h * w).double() - ref).abs().max())
+    assert err < 6e-5 * max(1.0, float(ref.abs().max())), err
 
 
 @pytest.mark.parametrize("mode,tol", [(4, 1e-4), (3, 5e-5), (2, 5e-5), (1, 3e-3), (0, 2e-4)])   # K = 4608 with a truncating fp32 accumulator

@@ -105,16 +105,24 @@ __device__ __forceinline__ void split_b3(float v, __nv_bfloat16& a1, __nv_bfloat
     a2 = __float2bfloat16_rn(v - __bfloat162float(a1));
 }
 __device__ __forceinline__ void store_b3_4(__nv_bfloat16* xbase, long long e, float v0, float v1, float v2, float v3) {
+    // same values as split_b3 per element; pairs are rounded and packed by one F2FP each
     const long long xi = (e >> 5) * 64 + (e & 31);
-    __nv_bfloat16 h[4], l[4];
-    split_b3(v0, h[0], l[0]); split_b3(v1, h[1], l[1]); split_b3(v2, h[2], l[2]); split_b3(v3, h[3], l[3]);
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
     uint2 u, w;
-    u.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-    u.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-    w.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-    w.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    u.x = *reinterpret_cast<const uint32_t*>(&h01);
+    u.y = *reinterpret_cast<const uint32_t*>(&h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v0 - __uint_as_float(u.x << 16), v1 - __uint_as_float(u.x & 0xffff0000u));
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v2 - __uint_as_float(u.y << 16), v3 - __uint_as_float(u.y & 0xffff0000u));
+    w.x = *reinterpret_cast<const uint32_t*>(&l01);
+    w.y = *reinterpret_cast<const uint32_t*>(&l23);
     *reinterpret_cast<uint2*>(xbase + xi) = u;
     *reinterpret_cast<uint2*>(xbase + xi + 32) = w;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }

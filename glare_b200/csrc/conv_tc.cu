@@ -72,13 +72,18 @@ struct ConvCfg {
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BN;                   // 128 / 256 / 512: powers of two >= 32
     static constexpr int SMEM_DYN = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
+    // HALO variant (3x3 stride-1 convs, mode 4, CTA pair, BN <= 128): a stage holds the activation patch of one filter ROW -- an
+    // (8 + 2) x 16 pixel box, 160 rows of 128 bytes -- and the weight slabs of its three taps.  Tap dx reads the same patch shifted by
+    // dx rows (the descriptor's start address moves by dx * 128 bytes, 8-row groups stay 1280 bytes apart), so the patch is fetched
+    // once instead of three times: 44 KB instead of 72 KB per three taps at BN = 128, where the L2 -> SM path (not the tensor pipe)
+    // was the limit (profiles/r01o: 57 % tensor-pipe activity).
+    static constexpr int HALO_TW = 8, HALO_TH = 16;
+    static constexpr int HALO_A_BYTES = (HALO_TW + 2) * HALO_TH * 128;
+    static constexpr int HALO_STAGE_BYTES = HALO_A_BYTES + 3 * B_BYTES;
+    static constexpr int HALO_STAGES_RAW = SMEM_BUDGET / HALO_STAGE_BYTES;
+    static constexpr int HALO_STAGES = HALO_STAGES_RAW > 8 ? 8 : HALO_STAGES_RAW;
+    static constexpr int HALO_SMEM_DYN = HALO_STAGES * HALO_STAGE_BYTES + STAGING_BYTES + 1024;
 };
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 template <bool TF32, bool PAIR>
 __device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -94,7 +99,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32
 // and HALF of the weight rows, all TMA loads signal the leader's barrier, the leader's MMA thread issues
 // tcgen05.mma.cta_group::2 (M = 256) which reads both halves and accumulates each CTA's 128 rows into that CTA's TMEM.
 // Weight staging traffic and weight shared-memory reads per CTA are halved -- the binding resources of the fp32-grade modes.
-template <int MODE, int BN, int CM>
+template <int MODE, int BN, int CM, bool HALO = false>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -102,7 +107,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CL = CM == 0 ? 1 : 2;
     constexpr bool PAIR = CM == 2, MCAST = CM == 1;
     using Cfg = ConvCfg<MODE, BN, PAIR>;
-    constexpr int STAGES = Cfg::STAGES;
+    static_assert(!HALO || (MODE == 4 && CM == 2 && BN <= 128), "halo staging: mode 4, CTA pair, BN <= 128");
+    constexpr int STAGES = HALO ? Cfg::HALO_STAGES : Cfg::STAGES;
+    constexpr int STAGE_BYTES = HALO ? Cfg::HALO_STAGE_BYTES : Cfg::STAGE_BYTES;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t s_tmem_base;
@@ -160,13 +167,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int w = cl_id; w < a.total_tiles; w += n_cl) {
                 GLARE_DECODE_WORK(w)
                 const int y0 = ty * a.TH * a.stride + a.tap_dy0, x0 = tx * a.TW * a.stride + a.tap_dx0;
+                if (HALO) {
+                    const int wn = a.w_batched ? (n < a.B ? n : a.B - 1) : 0;
+                    const int half = cl_rank * (BN / 2);
+                    for (int dy = 0; dy < 3; ++dy) {
+                        for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                            const int s = it % STAGES;
+                            const uint32_t ph = (it / STAGES) & 1;
+                            mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                            uint8_t* st = smem_al + (size_t)s * STAGE_BYTES;
+                            if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                            else mbar_arrive_cluster(&full_bar[s], 0);
+                            tma_load_4d_2sm(st, &tmA, &full_bar[s], 2 * kc * Cfg::BKE, x0, y0 + dy, n);      // (TW + 2) x TH patch of this filter row
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+                                tma_load_3d_2sm(st + Cfg::HALO_A_BYTES + dx * Cfg::B_BYTES, &tmB, &full_bar[s],
+                                                2 * ((dy * 3 + dx) * a.Cin + kc * Cfg::BKE), nb * BN + half, wn);
+                        }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < a.ntaps; ++tap) {
                     const int dy = tap / a.tap_w, dx = tap - dy * a.tap_w;
                     for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
                         mbar_wait_bounded(&empty_bar[s], ph ^ 1);
-                        uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
+                        uint8_t* st = smem_al + (size_t)s * STAGE_BYTES;
                         const int wn = a.w_batched ? (n < a.B ? n : a.B - 1) : 0;   // a dummy tile still feeds the peer real weights
                         const int kw = tap * a.Cin + kc * Cfg::BKE;
                         const int km = Cfg::XB ? 2 : 1;                   // the bf16 x tensors hold 64 elements per 32-element K chunk
@@ -213,12 +240,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait_bounded(&tmem_empty_bar[as], aph ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
+                if (HALO) {
+                    for (int ki = 0; ki < 3 * a.kchunks; ++ki, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait_bounded(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)s * STAGE_BYTES;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            // pixel (y, x + dx) of the patch is row y * (TW + 2) + x + dx: start dx rows in, 8-row groups one patch row apart
+                            const uint64_t da = umma_desc_sw128_sbo(sa + dx * 128, (Cfg::HALO_TW + 2) * 128);
+                            const uint64_t db = umma_desc_sw128(sa + Cfg::HALO_A_BYTES + dx * Cfg::B_BYTES);
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj) {
+                                const uint64_t adv = (uint64_t)(jj * 2);
+                                mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | jj) != 0 ? 1u : 0u);
+                                mma<false, PAIR>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);
+                                mma<false, PAIR>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);
+                            }
+                        }
+                        umma_commit_2sm_mc(&empty_bar[s], (uint16_t)0x3);
+                    }
+                    umma_commit_2sm_mc(&tmem_full_bar[as], (uint16_t)0x3);
+                    continue;
+                }
                 for (int ki = 0; ki < k_iters; ++ki, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait_bounded(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + (uint32_t)s * Cfg::STAGE_BYTES;
+                    const uint32_t sa = smem_base + (uint32_t)s * STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + CT_A_BYTES);
                     const uint64_t dal = umma_desc_sw128(sa + CT_A_BYTES + Cfg::B_BYTES);
                     const uint64_t dbl = umma_desc_sw128(sa + 2 * CT_A_BYTES + Cfg::B_BYTES);
@@ -266,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int py = m / a.TW, px = m - py * a.TW;
         // each epilogue warp owns its 32 accumulator rows (= 2 image rows x 16 pixels of the tile) end to end: its own two 4 KB
         // staging buffers and its own TMA stores -- no barrier between the four warps
-        uint8_t* const staging = smem_al + (size_t)STAGES * Cfg::STAGE_BYTES + (size_t)q * (2 * 32 * 128);
+        uint8_t* const staging = smem_al + (size_t)STAGES * STAGE_BYTES + (size_t)q * (2 * 32 * 128);
         uint32_t tcount = 0, chunk_id = 0;
         for (int w = cl_id; w < a.total_tiles; w += n_cl, ++tcount) {
             GLARE_DECODE_WORK(w)
@@ -394,8 +446,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        // box = 32 channels x 16 pixels x 2 rows; clips pixels / channels outside the tensor
-                        if (n < a.B) tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH + 2 * q, n);
+                        // box = 32 channels x TW pixels x TH / 4 rows; clips pixels / channels outside the tensor
+                        if (n < a.B) tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH + (a.TH >> 2) * q, n);
                         tma_store_commit();
                         tma_store_wait_read<1>();                        // this warp's other staging buffer is free again
                     }
@@ -566,20 +618,22 @@ static int make_out_map(CUtensorMap* m, const float* ptr, int B, int H, int W, i
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-template <int MODE, int BN, int CM>
+template <int MODE, int BN, int CM, bool HALO = false>
 static int launch_conv_cl(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
                           const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
     constexpr int CL = CM == 0 ? 1 : 2;
     using Cfg = ConvCfg<MODE, BN, CM == 2>;
     static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
-    auto kern = conv_tc_kernel<MODE, BN, CM>;
-    GLARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
+    static_assert(!HALO || Cfg::HALO_STAGES >= 3, "halo pipeline needs at least three stages");
+    constexpr int SMEM = HALO ? Cfg::HALO_SMEM_DYN : Cfg::SMEM_DYN;
+    auto kern = conv_tc_kernel<MODE, BN, CM, HALO>;
+    GLARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int n_cl = kNumSMs / CL;
     const int clusters = a.total_tiles < n_cl ? a.total_tiles : n_cl;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * CL));
     cfg.blockDim = dim3(CT_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_DYN;
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -596,7 +650,11 @@ static int launch_conv_cl(const CUtensorMap& tA, const CUtensorMap& tAl, const C
 template <int MODE, int BN>
 static int launch_conv(int cl, const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
                        const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
-    // cl: 1 = single CTA, 2 = multicast cluster, 3 = CTA pair (cta_group::2)
+    // cl: 1 = single CTA, 2 = multicast cluster, 3 = CTA pair (cta_group::2), 4 = CTA pair with filter-row halo staging
+    if (cl == 4) {
+        if constexpr (MODE == 4 && BN <= 128) return launch_conv_cl<MODE, BN, 2, true>(tA, tAl, tB, tBl, tY, a, stream);
+        else return GLARE_ERR_UNSUPPORTED;
+    }
     if (cl == 3) return launch_conv_cl<MODE, BN, 2>(tA, tAl, tB, tBl, tY, a, stream);
     return cl == 2 ? launch_conv_cl<MODE, BN, 1>(tA, tAl, tB, tBl, tY, a, stream) : launch_conv_cl<MODE, BN, 0>(tA, tAl, tB, tBl, tY, a, stream);
 }
@@ -766,8 +824,17 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     a.kchunks = Cin / bke;
     // N tile: as wide as Cout allows, narrowed while the launch would leave SMs without a tile (short-M GEMMs: O = P V)
     int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
-    const long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
+    long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
+    // filter-row halo staging (ConvCfg): 3x3 stride-1 convs with narrow N tiles, 8 x 16 pixel tiles
+    static const bool no_halo = getenv("GLARE_CONV_NO_HALO") != nullptr;            // A/B switch for profiling only
+    const bool halo = !no_halo && mode == 4 && BN <= 128 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
+                      w_batch_stride == 0 && getenv("GLARE_CONV_NO_CLUSTER") == nullptr && getenv("GLARE_CONV_MCAST") == nullptr;
+    if (halo) {
+        a.TH = 16; a.TW = 8;
+        a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
+        m_tiles = (long long)B * a.tiles_y * a.tiles_x;
+    }
     a.n_blocks = (Cout + BN - 1) / BN;
     if (ae) {
         a.row_norm = ae->row_norm; a.key_norm_max = ae->key_norm_max; a.row_sum_part = ae->row_sum_part; a.part_stride = ae->part_stride;
@@ -780,6 +847,13 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     static const bool no_cluster = getenv("GLARE_CONV_NO_CLUSTER") != nullptr;
     static const bool use_mcast = getenv("GLARE_CONV_MCAST") != nullptr;
     int cl = (no_cluster || (w_batch_stride != 0 && B > 1) || m_tiles < 2) ? 1 : (use_mcast ? 2 : 3);
+    const bool use_halo = halo && cl == 3;
+    if (halo && !use_halo) {                      // single tile: back to the standard geometry
+        a.TH = 8; a.TW = 16;
+        a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
+        m_tiles = (long long)B * a.tiles_y * a.tiles_x;
+    }
+    if (use_halo) cl = 4;
     const int csz = cl == 1 ? 1 : 2;              // CTAs per cluster (box rows of the weight maps = BN / csz in both cluster modes)
     const long long total = (long long)a.n_blocks * ((m_tiles + csz - 1) / csz);
     if (total > 0x7fffffff || m_tiles > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;
@@ -798,7 +872,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if ((rc = make_out_map(&tY, y, B, H, W, epi_exp ? (int)ldy : Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0 || mode == 4;
     const int e2 = mode == 4 ? 2 : 1;              // mode 4: the operand tensors are interleaved bf16 pairs, 2 per element
-    if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, e2 * Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
+    if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, e2 * Cin, a.TH, use_halo ? a.TW + 2 : a.TW, stride)) != GLARE_OK) return rc;
     if ((rc = make_w_map(&tB, w, bf, Cout, e2 * ts.ntaps * Cin, BN / csz, n_w, e2 * w_batch_stride)) != GLARE_OK) return rc;
     tAl = tA; tBl = tB;
     if (mode == 2) {

@@ -33,11 +33,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
             float4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + (p + (long long)u * rows) * c4n + my_c4);
+            // 16 values in fp32 (relative error 1e-7 of a 16-term sum), then into the fp64 running sums
+            float s32 = 0.f, q32 = 0.f;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
-                q += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
+                s32 += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+                q32 = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, fmaf(v[u].w, v[u].w, q32))));
             }
+            s += (double)s32;
+            q += (double)q32;
         }
         for (; p < p1; p += rows) {
             const float4 v = __ldg(xb + p * c4n + my_c4);
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               float eps, int swish, long long HW, int C, int G,
                                                               void* __restrict__ out_hi, float* __restrict__ out_lo) {
-    extern __shared__ float s_ab[];                  // [C] rstd*gamma, [C] beta, [C] mean for this sample
+    extern __shared__ __align__(16) float s_ab[];    // [C] rstd*gamma, [C] beta, [C] mean for this sample
     const int b = blockIdx.y;
     const int cpg = C / G;
     const double cnt = (double)HW * cpg;
@@ -79,6 +83,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
     }
     __syncthreads();
     const int c4n = C >> 2;
+    const int cmask = (c4n & (c4n - 1)) == 0 ? c4n - 1 : 0;
     const long long n4 = HW * c4n;
     const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * HW * C);
     const long long base4 = (long long)b * n4;
@@ -94,13 +99,20 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const float* __res
             if (u == 1 && !has1) break;
             const long long i = u == 0 ? i0 : i1;
             const float4 v = u == 0 ? va : vb;
-            const int c = (int)(i % c4n) * 4;
-            float y[4] = {fmaf(v.x - s_ab[2 * C + c], s_ab[c], s_ab[C + c]), fmaf(v.y - s_ab[2 * C + c + 1], s_ab[c + 1], s_ab[C + c + 1]),
-                          fmaf(v.z - s_ab[2 * C + c + 2], s_ab[c + 2], s_ab[C + c + 2]),
-                          fmaf(v.w - s_ab[2 * C + c + 3], s_ab[c + 3], s_ab[C + c + 3])};
+            const int c = (cmask ? ((int)i & cmask) : (int)(i % c4n)) * 4;       // C / 4 is a power of two for every GLARE layer
+            const float4 ga = *reinterpret_cast<const float4*>(s_ab + c), be = *reinterpret_cast<const float4*>(s_ab + C + c);
+            const float4 mu = *reinterpret_cast<const float4*>(s_ab + 2 * C + c);
+            float y[4] = {fmaf(v.x - mu.x, ga.x, be.x), fmaf(v.y - mu.y, ga.y, be.y), fmaf(v.z - mu.z, ga.z, be.z), fmaf(v.w - mu.w, ga.w, be.w)};
             if (swish) {
-    #pragma unroll
-                for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.0f + expf(-y[k]));
+                if (OUT == 0 || OUT == 4) {
+                    // operands of 8 / 16 significant bits: ex2.approx + fast divide (~1e-6 relative) is below their resolution and keeps
+                    // this pass HBM-bound instead of ALU-bound
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) y[k] = __fdividef(y[k], 1.0f + ex2_approx(-1.4426950408889634f * y[k]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.0f + expf(-y[k]));
+                }
             }
             if (OUT == 0) {
                 __nv_bfloat162 a0 = __floats2bfloat162_rn(y[0], y[1]), a1 = __floats2bfloat162_rn(y[2], y[3]);

@@ -155,6 +155,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
 }
+// same with an explicit stride between 8-row groups; the start address may sit any whole number of 128-byte rows into a region that
+// TMA filled from a 1024-byte aligned base (the swizzle XOR acts on absolute shared-memory address bits)
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor (InstrDescriptor): c_format F32, K-major A and B, dense.
 // fmt: 1 = BF16, 2 = TF32 (F16F32Format)
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {

@@ -6,6 +6,8 @@
                               bf16 passes; measured as accurate as 3xTF32 on this network, profiles/r01n_fullsize_parity_420x620.txt)
 ``make_dense("tc-tf32bf16x2" | "tc-3xtf32" | "tc-tf32" | "tc-bf16")``  the same kernels in the other operand modes
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -112,7 +114,7 @@ class TcDense:
         # GroupNorm sum / sum-of-squares of a conv's output accumulated in its epilogue.  Measured on B200 (profiles/r01k_*): saves 19 ms of
         # statistics passes per step but lengthens the short-K conv epilogues by 46 ms (warp reductions + fp64 atomics on the critical
         # path of the TMEM drain), so it is OFF by default; the separate gn_stats kernel is HBM-bound and cheaper.
-        self.fuse_gn_stats = False
+        self.fuse_gn_stats = bool(os.environ.get("GLARE_FUSE_GN_STATS"))      # A/B switch
         self.cover_all = True          # 3-channel convs (channel-padded) and stride-2 Downsample convs on the tcgen05 kernel too
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
@@ -120,7 +122,6 @@ class TcDense:
         # mode 4: softmax fused into the epilogues of the two GEMMs (csrc/attn.cu): exp against a Cauchy-Schwarz row reference in the scores
         # GEMM, 1 / row sum in the P V GEMM; rows that fall outside the safe window raise `attn_flag` and `attention_verified()` tells
         # the caller (engine.infer) to re-run with the exact three-kernel path
-        import os
         self.attn_fused = mode == 4 and not os.environ.get("GLARE_ATTN_UNFUSED")
         self.attn_margin = 60.0
         self.attn_flag = None

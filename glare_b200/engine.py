@@ -93,6 +93,7 @@ class GlareEngine:
             self.flow_plan = flowmod.FlowPlan(sd_g, self.device) if flow and "flowUpsamplerNet.layers.0.actnorm.bias" in sd_g else None
             self.codebook_packed = (ops.vq_pack_codebook(self.v["quantize.embedding.weight"])
                                     if "quantize.embedding.weight" in self.v else None)
+            self._one = torch.ones((1,), device=self.device, dtype=torch.float32)
             self.dcn_w = {i: ops.dcn_pack_weight(self.g["deformable_decoder.warp.%d.dcn.weight" % i]) for i in (0, 1)
                           if decoders and ("deformable_decoder.warp.%d.dcn.weight" % i) in self.g}
 
@@ -189,6 +190,11 @@ class GlareEngine:
                 h = self.upsample(sd, "%s.up.%d.upsample" % (p, lvl), h)
         return feats
 
+    @staticmethod
+    def _can_fuse_axpby(a, b):
+        return (a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape and a.stride() == b.stride() and a[0].numel() % 4 == 0
+                and (a.is_contiguous() or a.is_contiguous(memory_format=torch.channels_last)))
+
     # ------------------------------------------------------------------ AFT / DCN (deformableDecoder_arch.py)
     def warp_block(self, i, x_vq, h):
         """WarpBlock.forward (:285-290) + DCNv2Pack.forward (:141-152)"""
@@ -218,7 +224,11 @@ class GlareEngine:
                     h = self.attn_block(sd, "%s.up.%d.attn.%d" % (p, lvl, blk), h)
             if lvl != 2:
                 mixf = torch.sigmoid(sd["%s.mix.%d.w" % (p, 1 - lvl)])
-                h = enc_feats[lvl] * mixf + h * (1 - mixf)                       # Mix.forward :587-590
+                fused = self._can_fuse_axpby(enc_feats[lvl], h) and mixf.numel() == 1
+                if fused:
+                    h = ops.aft_axpby(enc_feats[lvl], h, mixf, 1 - mixf)         # Mix.forward :587-590 in one pass
+                else:
+                    h = enc_feats[lvl] * mixf + h * (1 - mixf)
                 x_vq = self.warp_block(1 - lvl, vq_feats[1 - lvl], h).to(h.dtype)
                 if self.per_sample_ratio:
                     # :567 reduces over the whole batch but the reference only ever runs batch 1; per-sample
@@ -226,7 +236,10 @@ class GlareEngine:
                     ratio = h.float().mean(dim=(1, 2, 3), keepdim=True) / x_vq.float().mean(dim=(1, 2, 3), keepdim=True)
                 else:
                     ratio = h.float().mean() / x_vq.float().mean()
-                h = h + x_vq * ratio.to(h.dtype)
+                if self.per_sample_ratio and self._can_fuse_axpby(h, x_vq):
+                    h = ops.aft_axpby(h, x_vq, self._one, ratio)                 # h * 1 is exact: h + x_vq * ratio, one pass
+                else:
+                    h = h + x_vq * ratio.to(h.dtype)
             if lvl != 0:
                 h = self.upsample(sd, "%s.up.%d.upsample" % (p, lvl), h)
         return self._conv(sd, p + ".residual_conv", self._gn(sd, p + ".norm_out", h)).float()

@@ -274,6 +274,27 @@ def gn_apply(out_mode, x_nhwc, stats, gamma, beta, swish, B, HW, C, G=32, eps=1e
     return hi, lo
 
 
+# ------------------------------------------------------------------------------------------- AFT decoder glue
+def aft_axpby(a, b, alpha, beta):
+    """out = a * alpha + b * beta with alpha / beta device tensors of 1 or B elements (Mix.forward, deformableDecoder_arch.py:587-590, and
+    the mean-ratio residual :567); a, b logical [B,C,H,W] fp32 sharing one dense storage order (NHWC or NCHW); rounding as the reference's
+    separate mul / mul / add kernels"""
+    require_cuda(a, b, alpha, beta)
+    if a.shape != b.shape or a.dtype != torch.float32 or b.dtype != torch.float32 or a.stride() != b.stride():
+        raise ValueError("aft_axpby needs two fp32 tensors of one shape and storage order")
+    if not (a.is_contiguous() or a.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("aft_axpby needs dense NCHW or NHWC storage")
+    B = a.shape[0]
+    n = a[0].numel()
+    alpha, beta = f32c(alpha).reshape(-1), f32c(beta).reshape(-1)
+    if alpha.numel() not in (1, B) or beta.numel() not in (1, B) or n % 4:
+        raise ValueError("alpha / beta must hold 1 or B values and the sample size must be a multiple of 4")
+    out = torch.empty_like(a)
+    check(lib().glare_aft_axpby_f32(ptr(a), ptr(b), ptr(alpha), ptr(beta), int(alpha.numel() == B and B > 1), int(beta.numel() == B and B > 1),
+                                    B, n, ptr(out), stream()), "glare_aft_axpby_f32")
+    return out
+
+
 # ------------------------------------------------------------------------------------------- pre / post-processing
 def preprocess_u8(img_u8_nhwc, pad, mode):
     """uint8 [B,H,W,3] (device) -> log(clamp(x/255 + 1e-3)) fp32 [B,3,Hp,Wp]; pad = (top, bottom, left, right); mode 0 reflect, 1 symmetric"""

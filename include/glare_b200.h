@@ -196,6 +196,14 @@ int glare_preprocess_u8(const uint8_t* img_nhwc, int B, int H, int W, int pad_to
 int glare_postprocess_u8(const float* y, long long sb, long long sc, long long sh, long long sw, int B, int y0, int x0, int H, int W,
                          uint8_t* out_nhwc, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * (7) Elementwise glue of the AFT decoder -- deformableDecoder_arch.py:587-590 (Mix: enc * m + h * (1 - m)) and :567
+ *     (h + x_vq * mean(h) / mean(x_vq)): out[n][i] = a[n][i] * alpha[n * alpha_stride] + b[n][i] * beta[n * beta_stride], each product
+ *     rounded before the sum like the reference's separate ATen kernels.  Strides 0 (one scalar) or 1 (per sample).
+ * ---------------------------------------------------------------------------------------------------- */
+int glare_aft_axpby_f32(const float* a, const float* b, const float* alpha, const float* beta, int alpha_stride, int beta_stride, int B,
+                        long long n_per_sample, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

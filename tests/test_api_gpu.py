@@ -65,3 +65,23 @@ def test_pre_and_postprocess_kernels(glare_lib, pad, hw):
     want = (y[:, :, box[0]:box[1], box[2]:box[3]].clamp(0, 1) * 255.0).to(torch.uint8).permute(0, 2, 3, 1)
     got = ops.postprocess_u8(y.cuda().contiguous(memory_format=torch.channels_last), box).cpu()
     assert torch.equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["nhwc", "nchw"])
+def test_aft_axpby_matches_reference_rounding(glare_lib, layout):
+    """Mix.forward (deformableDecoder_arch.py:587-590) and the mean-ratio residual (:567) in one pass each: bitwise what the
+    reference's separate mul / mul / add kernels produce"""
+    from glare_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    a = torch.randn((3, 128, 17, 22), generator=g).cuda()
+    b = torch.randn((3, 128, 17, 22), generator=g).cuda()
+    if layout == "nhwc":
+        a, b = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+    m = torch.sigmoid(torch.tensor([0.3])).cuda()
+    assert torch.equal(ops.aft_axpby(a, b, m, 1 - m), a * m + b * (1 - m))
+    ratio = (a.mean(dim=(1, 2, 3), keepdim=True) / b.mean(dim=(1, 2, 3), keepdim=True))
+    one = torch.ones((1,), device="cuda")
+    assert torch.equal(ops.aft_axpby(a, b, one, ratio), a + b * ratio)
+    with pytest.raises(ValueError):
+        ops.aft_axpby(a, b[:, :64], m, m)

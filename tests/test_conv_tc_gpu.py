@@ -155,6 +155,25 @@ def test_attention_fused_softmax_matches_exact_path(glare_lib, shape):
     assert torch.equal(o1, o3)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_attention_query_bands(glare_lib, fused):
+    """score matrices larger than the budget (1080p: 131 648 tokens) are processed in bands of query rows; forced here on a small shape"""
+    from glare_b200.dense import TcDense
+    B, C, h, w = 2, 512, 24, 21
+    g = torch.Generator().manual_seed(5)
+    q, k, v = (torch.randn((B, C, h, w), generator=g).cuda() for _ in range(3))
+    d = TcDense(4)
+    d.attn_fused = fused
+    whole = d.attention(q, k, v).clone()
+    d.attn_s_budget = 8 * w * 512 * 4                  # 8 image rows of queries per pass -> 3 bands
+    banded = d.attention(q, k, v)
+    assert d.attention_verified()
+    ref = _attention_fp64(q, k, v)
+    err = float((banded.reshape(B, C, h * w).double() - ref).abs().max())
+    assert err < 6e-5 * max(1.0, float(ref.abs().max())), err
+    assert float((banded - whole).abs().max()) < 1e-5
+
+
 def test_attention_fused_softmax_window_flag_and_fallback(glare_lib):
     """rows whose maximum logit sits > ~115 below the Cauchy-Schwarz bound raise the device flag; attention_verified() then switches the
     backend to the exact path, which is what the engine re-runs with"""

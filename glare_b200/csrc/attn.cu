@@ -235,7 +235,15 @@ __global__ void __launch_bounds__(256) attn_row_norm_kernel(const float* __restr
     if (row >= rows) return;
     const float4* xr = reinterpret_cast<const float4*>(x + row * C);
     float s = 0.f;
-    for (int i = lane; i < C / 4; i += 32) {
+    int i = lane;
+    for (; i + 96 < C / 4; i += 128) {                                   // four independent 128-bit loads in flight per lane
+        const float4 v0 = __ldg(xr + i), v1 = __ldg(xr + i + 32), v2 = __ldg(xr + i + 64), v3 = __ldg(xr + i + 96);
+        s = fmaf(v0.x, v0.x, fmaf(v0.y, v0.y, fmaf(v0.z, v0.z, fmaf(v0.w, v0.w, s))));
+        s = fmaf(v1.x, v1.x, fmaf(v1.y, v1.y, fmaf(v1.z, v1.z, fmaf(v1.w, v1.w, s))));
+        s = fmaf(v2.x, v2.x, fmaf(v2.y, v2.y, fmaf(v2.z, v2.z, fmaf(v2.w, v2.w, s))));
+        s = fmaf(v3.x, v3.x, fmaf(v3.y, v3.y, fmaf(v3.z, v3.z, fmaf(v3.w, v3.w, s))));
+    }
+    for (; i < C / 4; i += 32) {
         const float4 v = __ldg(xr + i);
         s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
     }

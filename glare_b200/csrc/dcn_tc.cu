@@ -24,7 +24,7 @@
 
 namespace glare {
 
-constexpr int DT_THREADS = 448;           // warp 0 TMA(weights), 1 MMA, 2-5 epilogue, 6-13 samplers (two groups of four)
+constexpr int DT_FIXED_THREADS = 192;     // warp 0 TMA(weights), 1 MMA, 2-5 epilogue; then two groups of SW sampler warps (SW = 4 or 8)
 constexpr int DT_A_BYTES = 128 * 128;
 
 struct DcnTcArgs {
@@ -34,6 +34,8 @@ struct DcnTcArgs {
     float* y;
     int B, H, W, C, Cout, dg, cpg, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;   // kchunks = C / BKE channel chunks per tap
     int total_tiles;
+    int stages;              // ring depth actually used (<= DcnCfg::STAGES): fewer stages leave more of the SM's 256 KB to the L1 cache,
+                             // which is what serves the bilinear corner gathers (each 128-byte channel line is touched ~36 times per tile)
 };
 
 constexpr int DT_OM_MAX = 108;            // 27 * deformable_groups floats of conv_offset output per pixel staged in smem (dg <= 4)
@@ -57,11 +59,11 @@ struct DcnCfg {
 
 __device__ __forceinline__ float tf32_hi_d(float x) { return tf32_round(x); }
 
-template <int MODE, int BN, bool OMS>
-__global__ void __launch_bounds__(DT_THREADS, 1)
+template <int MODE, int BN, bool OMS, int SW>
+__global__ void __launch_bounds__(DT_FIXED_THREADS + 64 * SW, 1)
 dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const DcnTcArgs a) {
     using Cfg = DcnCfg<MODE, BN, OMS>;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = a.stages;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t s_tmem_base;
@@ -73,9 +75,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmB);
         if (Cfg::X3) tma_prefetch_desc(&tmBlo);
-#pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1 + 128);          // weight TMA (expect_tx) + 128 sampler threads
+            mbar_init(&full_bar[s], 1 + 32 * SW);      // weight TMA (expect_tx) + the sampler threads of one group
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&tmem_full_bar[0], 1);
@@ -210,8 +211,10 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         // 8 warps in two groups; group gsel fills the stages with (k-iteration & 1) == gsel, so two stages are being
         // sampled while a third is being multiplied.  Within a stage a warp owns 32 tile rows: 8 lanes x 16 bytes per
         // operand row, 4 rows per step, 8 steps issued as two batches of 16 independent 128-bit corner loads.
-        const int sw = (warp - 6) & 3;                 // rows [32 sw, 32 sw + 32) of the tile
-        const int gsel = (warp - 6) >> 2;
+        constexpr int RW = 128 / SW;                   // tile rows per sampler warp: 32 (two 16-row passes) or 16
+        constexpr int QB = SW == 8 ? 2 : 4;            // pixel rows per lane whose corner loads are in flight together (x 4 corners)
+        const int sw = (warp - 6) % SW;                // rows [RW sw, RW sw + RW) of the tile
+        const int gsel = (warp - 6) / SW;
         const int sub = lane >> 3, j = lane & 7;
         constexpr int CPL = (Cfg::TF32 || Cfg::B3) ? 4 : 8;   // channels per lane per stage
         constexpr int V4 = CPL / 4;
@@ -227,9 +230,9 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             if (OMS) {
                 // stage the tile's conv_offset output once (offsets raw, mask through the sigmoid): the geometry of every
                 // (pixel, group, tap) then starts from shared memory instead of a dependent global load per use
-                named_bar_sync(3, 256);                        // all sampler warps are done with the previous tile's values
-                const int st_id = threadIdx.x - 192;           // sampler threads are 192..447
-                for (int i = st_id; i < 128 * om_c; i += 256) {
+                named_bar_sync(3, 64 * SW);                    // all sampler warps are done with the previous tile's values
+                const int st_id = threadIdx.x - DT_FIXED_THREADS;
+                for (int i = st_id; i < 128 * om_c; i += 64 * SW) {
                     const int m = i / om_c, ch = i - m * om_c;
                     const int py = m / a.TW, px = m - py * a.TW;
                     const int gy = ty * a.TH + py, gx = tx * a.TW + px;
@@ -240,7 +243,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                     }
                     s_om[i] = v;
                 }
-                named_bar_sync(3, 256);
+                named_bar_sync(3, 64 * SW);
             }
             for (int tap = 0; tap < 9; ++tap) {
                 const int ti = tap / 3, tj = tap - ti * 3;
@@ -253,12 +256,15 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                     mbar_wait_bounded(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float cw[4][4];
-                        int co[4][4];
+                    for (int hq = 0; hq < (RW / 16) * (4 / QB); ++hq) {
+                        // 16-row pass `half`, pixel rows q4 = qb .. qb + QB - 1 of it; row = 16 half + q4 + 4 sub, so the four rows one warp
+                        // instruction stores differ in bit 2 of the row index pairwise (two shared-memory wavefronts instead of four)
+                        const int half = hq / (4 / QB), qb = (hq % (4 / QB)) * QB;
+                        float cw[QB][4];
+                        int co[QB][4];
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const int m = sw * 32 + (half * 4 + q4) * 4 + sub;
+                        for (int q4 = 0; q4 < QB; ++q4) {
+                            const int m = sw * RW + half * 16 + (qb + q4) + 4 * sub;
                             const int py = m / a.TW, px = m - py * a.TW;
                             const int gy = ty * a.TH + py, gx = tx * a.TW + px;
 #pragma unroll
@@ -286,9 +292,9 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                             }
                         }
                         // corners with zero weight read pixel 0 of the image (valid memory) and contribute nothing
-                        float4 xv[4][4][V4];
+                        float4 xv[QB][4][V4];
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4)
+                        for (int q4 = 0; q4 < QB; ++q4)
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float4* p = reinterpret_cast<const float4*>(xn + (long long)co[q4][k] * a.C + cbase);
@@ -296,8 +302,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                                 for (int v4 = 0; v4 < V4; ++v4) xv[q4][k][v4] = __ldg(p + v4);
                             }
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const int m = sw * 32 + (half * 4 + q4) * 4 + sub;
+                        for (int q4 = 0; q4 < QB; ++q4) {
+                            const int m = sw * RW + half * 16 + (qb + q4) + 4 * sub;
                             float acc[CPL];
 #pragma unroll
                             for (int v4 = 0; v4 < V4; ++v4) {
@@ -316,14 +322,16 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                             const uint32_t off = (uint32_t)m * 128u + (uint32_t)((j ^ (m & 7)) << 4);     // SWIZZLE_128B
                             if (Cfg::B3) {
                                 // single x tile: bytes [0,64) = a1 of the 32 channels, [64,128) = a2; this lane owns 8 bytes at 8j in each half
-                                __nv_bfloat16 h4[4], l4[4];
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) split_b3(acc[k], h4[k], l4[k]);
+                                const __nv_bfloat162 h01 = __floats2bfloat162_rn(acc[0], acc[1]), h23 = __floats2bfloat162_rn(acc[2], acc[3]);
                                 uint2 u, w2;
-                                u.x = (uint32_t)__bfloat16_as_ushort(h4[0]) | ((uint32_t)__bfloat16_as_ushort(h4[1]) << 16);
-                                u.y = (uint32_t)__bfloat16_as_ushort(h4[2]) | ((uint32_t)__bfloat16_as_ushort(h4[3]) << 16);
-                                w2.x = (uint32_t)__bfloat16_as_ushort(l4[0]) | ((uint32_t)__bfloat16_as_ushort(l4[1]) << 16);
-                                w2.y = (uint32_t)__bfloat16_as_ushort(l4[2]) | ((uint32_t)__bfloat16_as_ushort(l4[3]) << 16);
+                                u.x = *reinterpret_cast<const uint32_t*>(&h01);
+                                u.y = *reinterpret_cast<const uint32_t*>(&h23);
+                                const __nv_bfloat162 l01 = __floats2bfloat162_rn(acc[0] - __uint_as_float(u.x << 16),
+                                                                                 acc[1] - __uint_as_float(u.x & 0xffff0000u));
+                                const __nv_bfloat162 l23 = __floats2bfloat162_rn(acc[2] - __uint_as_float(u.y << 16),
+                                                                                 acc[3] - __uint_as_float(u.y & 0xffff0000u));
+                                w2.x = *reinterpret_cast<const uint32_t*>(&l01);
+                                w2.y = *reinterpret_cast<const uint32_t*>(&l23);
                                 uint8_t* xt = st + (uint32_t)m * 128u + (uint32_t)((j & 1) * 8);
                                 *reinterpret_cast<uint2*>(xt + (((j >> 1) ^ (m & 7)) << 4)) = u;
                                 *reinterpret_cast<uint2*>(xt + (((4 + (j >> 1)) ^ (m & 7)) << 4)) = w2;
@@ -397,14 +405,31 @@ static int make_w_map_d(CUtensorMap* m, const void* ptr, bool bf16, int Cout, in
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-template <int MODE, int BN, bool OMS>
-static int launch_dcn_tc_v(const CUtensorMap& tB, const CUtensorMap& tBl, const DcnTcArgs& a, cudaStream_t stream) {
+template <int MODE, int BN, bool OMS, int SW>
+static int launch_dcn_tc_w(const CUtensorMap& tB, const CUtensorMap& tBl, const DcnTcArgs& a, int smem, cudaStream_t stream) {
     using Cfg = DcnCfg<MODE, BN, OMS>;
-    GLARE_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<MODE, BN, OMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
+    GLARE_CUDA(cudaFuncSetAttribute(dcn_tc_kernel<MODE, BN, OMS, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_DYN));
     const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    dcn_tc_kernel<MODE, BN, OMS><<<grid, DT_THREADS, Cfg::SMEM_DYN, stream>>>(tB, tBl, a);
+    dcn_tc_kernel<MODE, BN, OMS, SW><<<grid, DT_FIXED_THREADS + 64 * SW, smem, stream>>>(tB, tBl, a);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
+}
+
+template <int MODE, int BN, bool OMS>
+static int launch_dcn_tc_v(const CUtensorMap& tB, const CUtensorMap& tBl, DcnTcArgs a, cudaStream_t stream) {
+    using Cfg = DcnCfg<MODE, BN, OMS>;
+    // ring depth: GLARE_DCN_STAGES overrides (A/B switch for profiling; measured flat between 2 and 6 stages, profiles/r30)
+    static const int want = getenv("GLARE_DCN_STAGES") ? atoi(getenv("GLARE_DCN_STAGES")) : Cfg::STAGES;
+    a.stages = want < 2 ? 2 : want;
+    if (a.stages > Cfg::STAGES) a.stages = Cfg::STAGES;
+    const int smem = a.stages * Cfg::STAGE_BYTES + Cfg::OM_BYTES + 1024;
+    // sampler warps per stage group: 8 (16 warps in flight, 2 x 4 corner loads per lane per batch) for the default mode, the profile of the
+    // 4-warp version showed 3.5 warps per scheduler half of whose cycles waited on the corner loads (profiles/r31); GLARE_DCN_SW=4 selects it
+    if constexpr (MODE == 4) {
+        static const bool sw4 = getenv("GLARE_DCN_SW") != nullptr && atoi(getenv("GLARE_DCN_SW")) == 4;
+        if (!sw4) return launch_dcn_tc_w<MODE, BN, OMS, 8>(tB, tBl, a, smem, stream);
+    }
+    return launch_dcn_tc_w<MODE, BN, OMS, 4>(tB, tBl, a, smem, stream);
 }
 
 template <int MODE, int BN>

@@ -266,9 +266,46 @@ __global__ void __launch_bounds__(256) attn_row_sum_finish_kernel(const float* _
     row_scale[r] = 1.0f / s;
 }
 
+// |row| from the partial sums of squares a conv epilogue left per (output block, row) (glare_conv2d_nhwc_tc_pack)
+__global__ void __launch_bounds__(256) attn_row_norm_finish_kernel(const float* __restrict__ part, long long part_stride, int n_blocks, long long rows,
+                                                                   long long rows_per_sample, float* __restrict__ norm_out,
+                                                                   unsigned* __restrict__ max_bits) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float nrm = 0.f;
+    if (r < rows) {
+        float s = 0.f;
+        for (int b = 0; b < n_blocks; ++b) s += __ldg(part + (long long)b * part_stride + r);
+        nrm = sqrtf(s) * 1.00001f;
+        if (norm_out) norm_out[r] = nrm;
+    }
+    if (max_bits) {                                                  // one atomic per warp and sample it touches (warps rarely straddle two)
+        const long long smp = r < rows ? r / rows_per_sample : -1;
+        const long long smp0 = __shfl_sync(0xffffffffu, smp, 0);
+        if (__all_sync(0xffffffffu, smp == smp0)) {
+            float m = nrm;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((threadIdx.x & 31) == 0 && smp0 >= 0) atomicMax(max_bits + smp0, __float_as_uint(m));
+        } else if (smp >= 0) {
+            atomicMax(max_bits + smp, __float_as_uint(nrm));
+        }
+    }
+}
+
 }  // namespace glare
 
 using namespace glare;
+
+// norm_out[r] = sqrt(sum_{b < n_blocks} part[b * part_stride + r]) (may be null); max_bits[r / rows_per_sample] = max over the sample (may be null)
+GLARE_API int glare_attn_row_norm_finish(const float* part, long long part_stride, int n_blocks, long long rows, long long rows_per_sample,
+                                         float* norm_out, unsigned* max_bits, cudaStream_t stream) {
+    if (rows < 0 || n_blocks <= 0 || part_stride < rows || rows_per_sample <= 0 || (!norm_out && !max_bits)) return GLARE_ERR_BAD_ARG;
+    if (rows == 0) return GLARE_OK;
+    if (!part) return GLARE_ERR_BAD_ARG;
+    attn_row_norm_finish_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(part, part_stride, n_blocks, rows, rows_per_sample, norm_out, max_bits);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
 
 // x [rows][C] fp32 (C % 4 == 0): norm_out[row] = |x_row| (may be null); max_bits[row / rows_per_sample] = max over the sample's rows
 // (may be null; the caller zeroes it first)

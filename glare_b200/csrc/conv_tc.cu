@@ -55,6 +55,8 @@ struct ConvTcArgs {
     long long part_stride;
     float exp_scale, exp_margin;
     const float* row_scale;       // P V GEMM: y[row] *= row_scale[row] (1 / row sum), or null
+    int pack_out;                 // y is the bf16x3 operand of the next GEMM (same geometry as the fp32 output: 4 bytes per element), not fp32
+    float* row_sq_part;           // [n_blocks][part_stride] partial sums of squares of the output rows (|q_i|, |k_j| of the attention reference), or null
 };
 
 template <int MODE, int BN, bool PAIR = false>
@@ -331,7 +333,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* yrow = a.y + pix * a.ldy;
             const float* rrow = (a.residual && valid) ? a.residual + pix * a.Cout : nullptr;
             const bool epi_exp = MODE == 4 && a.row_norm != nullptr;
-            float e_ref = 0.f, e_sum = 0.f, r_scale = 1.f;
+            const bool epi_pack = MODE == 4 && (epi_exp || a.pack_out != 0);
+            const bool epi_sq = MODE == 4 && a.row_sq_part != nullptr;
+            float e_ref = 0.f, e_sum = 0.f, r_scale = 1.f, e_sq = 0.f;
             if (epi_exp && valid) e_ref = fmaf(__ldg(a.row_norm + pix), a.exp_scale * __uint_as_float(__ldg(a.key_norm_max)), -a.exp_margin);
             if (a.row_scale != nullptr) r_scale = valid ? __ldg(a.row_scale + pix) : 0.f;
             // one 32-column chunk of this thread's accumulator row: registers -> bias / residual / attention epilogues -> store
@@ -370,24 +374,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) o[j] *= r_scale;
                 }
-                if (epi_exp) {
-                    // keys [co, co + 32) of this query row = one 128-byte operand chunk [16 words of a1 pairs | 16 words of a2 pairs]
-                    // p = 2^(s * scale*log2(e) - ref*log2(e)): one FFMA + one MUFU.EX2 per element, branch-free (a single epilogue warp per
-                    // scheduler has no other latency hiding).  The exponent's rounding (2^-24 |t|, |t| <~ 90) and ex2.approx (2^-22) stay
-                    // below the 2^-17 resolution of the two-piece bf16 operand p is stored as.
+                if (epi_sq) {
+                    float q0 = 0.f, q1 = 0.f;                           // columns past Cout hold exact zeros (zero-filled weight rows, no bias)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) { q0 = fmaf(o[j], o[j], q0); q1 = fmaf(o[j + 1], o[j + 1], q1); }
+                    e_sq += q0 + q1;
+                }
+                if (epi_pack) {
+                    // columns [co, co + 32) of this row = one 128-byte operand chunk [16 words of a1 pairs | 16 words of a2 pairs]
                     float p[32];
-                    const float c1 = a.exp_scale * 1.4426950408889634f, r1 = e_ref * 1.4426950408889634f;
-                    if (co + 32 <= a.Cout) {
+                    if (epi_exp) {
+                        // p = 2^(s * scale*log2(e) - ref*log2(e)): one FFMA + one MUFU.EX2 per element, branch-free (a single epilogue warp per
+                        // scheduler has no other latency hiding).  The exponent's rounding (2^-24 |t|, |t| <~ 90) and ex2.approx (2^-22) stay
+                        // below the 2^-17 resolution of the two-piece bf16 operand p is stored as.
+                        const float c1 = a.exp_scale * 1.4426950408889634f, r1 = e_ref * 1.4426950408889634f;
+                        if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) p[j] = ex2_approx(fmaf(o[j], c1, -r1));
-                    } else {                                            // ragged last chunk: keys past the end get exp2(-inf) = 0
+                            for (int j = 0; j < 32; ++j) p[j] = ex2_approx(fmaf(o[j], c1, -r1));
+                        } else {                                        // ragged last chunk: keys past the end get exp2(-inf) = 0
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) p[j] = ex2_approx((co + j < a.Cout) ? fmaf(o[j], c1, -r1) : -INFINITY);
+                            for (int j = 0; j < 32; ++j) p[j] = ex2_approx((co + j < a.Cout) ? fmaf(o[j], c1, -r1) : -INFINITY);
+                        }
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // fixed order: repeatable row sums
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) { s0 += p[j]; s1 += p[j + 1]; s2 += p[j + 2]; s3 += p[j + 3]; }
+                        e_sum += (s0 + s1) + (s2 + s3);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) p[j] = o[j];
                     }
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // fixed order: repeatable row sums
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) { s0 += p[j]; s1 += p[j + 1]; s2 += p[j + 2]; s3 += p[j + 3]; }
-                    e_sum += (s0 + s1) + (s2 + s3);
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         const __nv_bfloat162 h = __floats2bfloat162_rn(p[j], p[j + 1]);               // a1 pair (one F2FP)
@@ -452,7 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_store_wait_read<1>();                        // this warp's other staging buffer is free again
                     }
                     ++chunk_id;
-                } else if (valid && !epi_exp) {
+                } else if (valid && !epi_pack) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         if (co + j + 4 <= a.Cout) *reinterpret_cast<float4*>(yrow + co + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -484,6 +499,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 process(vb, c0 + 32);
             }
             if (epi_exp && valid) a.row_sum_part[(long long)nb * a.part_stride + pix] = e_sum;
+            if (epi_sq && valid) a.row_sq_part[(long long)nb * a.part_stride + pix] = e_sq;
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -695,7 +711,7 @@ GLARE_API int glare_conv_prep_act(int mode, const float* x, long long n, void* o
 struct TapSpec { int ntaps, tap_w, dy0, dx0, oscale, oa, ob; };
 struct AttnEpi {                       // attention epilogues of the two GEMMs (ConvTcArgs documents the fields)
     const float* row_norm; const unsigned* key_norm_max; float* row_sum_part; long long part_stride; float exp_scale, exp_margin;
-    const float* row_scale; int* n_blocks_out;
+    const float* row_scale; int* n_blocks_out; int pack_out; float* row_sq_part;
 };
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
@@ -779,19 +795,33 @@ GLARE_API int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, i
     if (mode != 4) return GLARE_ERR_UNSUPPORTED;
     if (!q_row_norm || !key_norm_max || !row_sum_part || !n_blocks_host || n_pad < n_keys || (n_pad & 31) || !(scale > 0.f) || !(margin >= 0.f))
         return GLARE_ERR_BAD_ARG;
-    AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host};
+    AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host, 0, nullptr};
     return conv_tc_launch(mode, q, nullptr, k, nullptr, nullptr, nullptr, reinterpret_cast<float*>(p_out), 1, rows_h, rows_w, rows_h, rows_w, C,
                           n_keys, std_taps(1), 1, n_pad, 0, stream, nullptr, 0, &ae);
 }
 
-// O = diag(row_scale) P~ V: p operand [rows][n_pad], vt operand [C][n_pad] (V^T of the sample), y [rows][ldy] fp32
-GLARE_API int glare_attn_pv_tc(int mode, const void* p, const void* vt, const float* row_scale, float* y, int rows_h, int rows_w, int n_pad,
-                               int C, long long ldy, cudaStream_t stream) {
+// O = diag(row_scale) P~ V: p operand [rows][n_pad], vt operand [C][n_pad] (V^T of the sample); y [rows][ldy] fp32, or with pack_out != 0
+// (ldy == C, C % 32 == 0) the bf16x3 operand of the following proj_out conv
+GLARE_API int glare_attn_pv_tc(int mode, const void* p, const void* vt, const float* row_scale, void* y, int rows_h, int rows_w, int n_pad,
+                               int C, long long ldy, int pack_out, cudaStream_t stream) {
     if (mode != 4) return GLARE_ERR_UNSUPPORTED;
     if (!row_scale) return GLARE_ERR_BAD_ARG;
-    AttnEpi ae{nullptr, nullptr, nullptr, 0, 0.f, 0.f, row_scale, nullptr};
-    return conv_tc_launch(mode, p, nullptr, vt, nullptr, nullptr, nullptr, y, 1, rows_h, rows_w, rows_h, rows_w, n_pad, C, std_taps(1), 1, ldy, 0,
-                          stream, nullptr, 0, &ae);
+    AttnEpi ae{nullptr, nullptr, nullptr, 0, 0.f, 0.f, row_scale, nullptr, pack_out ? 1 : 0, nullptr};
+    return conv_tc_launch(mode, p, nullptr, vt, nullptr, nullptr, nullptr, reinterpret_cast<float*>(y), 1, rows_h, rows_w, rows_h, rows_w, n_pad, C,
+                          std_taps(1), 1, ldy, 0, stream, nullptr, 0, &ae);
+}
+
+// Stride-1 conv (ksize 1 or 3) whose output goes straight to another tensor-core GEMM: y is written as that GEMM's bf16x3 operand (NHWC
+// [B,H,W,Cout], 4 bytes per element, Cout % 32 == 0) instead of fp32 -- the q / k projections of AttnBlock (encoder_decoder.py:172-174), the
+// WarpBlock offset conv feeding conv_offset (deformableDecoder_arch.py:285-287).  row_sq_part (optional, [n_blocks][part_stride], part_stride >=
+// B*H*W): per output row the partial sums of squares of the fp32 values per output block, *n_blocks_host planes (the attention row reference).
+GLARE_API int glare_conv2d_nhwc_tc_pack(int mode, const void* x, const void* w, const float* bias, void* y_operand, int B, int H, int W, int Cin,
+                                        int Cout, int ksize, float* row_sq_part, long long part_stride, int* n_blocks_host, cudaStream_t stream) {
+    if (mode != 4) return GLARE_ERR_UNSUPPORTED;
+    if ((ksize != 1 && ksize != 3) || (row_sq_part && !n_blocks_host)) return GLARE_ERR_BAD_ARG;
+    AttnEpi ae{nullptr, nullptr, nullptr, part_stride, 0.f, 0.f, nullptr, n_blocks_host, 1, row_sq_part};
+    return conv_tc_launch(mode, x, nullptr, w, nullptr, bias, nullptr, reinterpret_cast<float*>(y_operand), B, H, W, H, W, Cin, Cout, std_taps(ksize), 1,
+                          Cout, 0, stream, nullptr, 0, &ae);
 }
 
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
@@ -800,7 +830,11 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
                           const AttnEpi* ae) {
     const int ksize = ts.tap_w;
     const bool epi_exp = ae && ae->row_norm;
-    if (ae && (mode != 4 || bias || residual || gn_stats)) return GLARE_ERR_UNSUPPORTED;
+    const bool epi_pack = ae && (ae->row_norm || ae->pack_out);          // the output is an operand tensor
+    if (ae && mode != 4) return GLARE_ERR_UNSUPPORTED;
+    if (ae && (ae->row_norm || ae->row_scale) && (bias || residual || gn_stats)) return GLARE_ERR_UNSUPPORTED;
+    if (ae && ae->pack_out && !ae->row_norm && ((Cout & 31) || ldy != Cout || residual || gn_stats || ts.oscale != 1)) return GLARE_ERR_UNSUPPORTED;
+    if (ae && ae->row_sq_part && ae->part_stride < (long long)B * H * W) return GLARE_ERR_BAD_ARG;
     if (epi_exp && (!ae->key_norm_max || !ae->row_sum_part || ae->part_stride < (long long)B * H * W || (ldy & 31) || Cout < 32))
         return GLARE_ERR_BAD_ARG;
     if (gn_stats && (Cout % 128 != 0 || B <= 0)) return GLARE_ERR_UNSUPPORTED;       // 32 groups of a multiple of 4 channels
@@ -839,6 +873,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if (ae) {
         a.row_norm = ae->row_norm; a.key_norm_max = ae->key_norm_max; a.row_sum_part = ae->row_sum_part; a.part_stride = ae->part_stride;
         a.exp_scale = ae->exp_scale; a.exp_margin = ae->exp_margin; a.row_scale = ae->row_scale;
+        a.pack_out = ae->pack_out; a.row_sq_part = ae->row_sq_part;
         if (ae->n_blocks_out) *ae->n_blocks_out = a.n_blocks;
     }
     // clusters of two CTAs share the weight tile by multicast; per-sample weights over a batch cannot be shared across samples
@@ -866,7 +901,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     int rc;
     {
         static const bool direct = getenv("GLARE_CONV_DIRECT_STORE") != nullptr;   // A/B switch for profiling only
-        a.tma_store = ((!direct || epi_exp) && Cout >= 32 && ts.oscale == 1) ? 1 : 0;
+        a.tma_store = ((!direct || epi_pack) && Cout >= 32 && ts.oscale == 1) ? 1 : 0;
     }
     // exp epilogue: the output is an operand tensor of 128-byte chunks (32 keys each), written whole up to the padded row length ldy
     if ((rc = make_out_map(&tY, y, B, H, W, epi_exp ? (int)ldy : Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;

@@ -125,6 +125,7 @@ class TcDense:
         self.attn_fused = mode == 4 and not os.environ.get("GLARE_ATTN_UNFUSED")
         self.attn_margin = 60.0
         self.attn_flag = None
+        self.pack_epilogue = mode == 4 and not os.environ.get("GLARE_NO_PACK_EPILOGUE")   # A/B switch: operands written by the producing conv
         self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
         self.last_timers, self.last_steps = None, 1
 
@@ -183,6 +184,22 @@ class TcDense:
             self.ops.conv2d_nhwc_tc_g(self.mode, 0, op.hi, op.lo, w_hi, w_lo, b, res, y, op.B, op.H, op.W, op.C, Cout, ksize=ks,
                                       gn_stats=stats)
         return self._tag(y.permute(0, 3, 1, 2), stats)
+
+    def conv2d_operand(self, x, w, b=None, row_sq=False):
+        """stride-1 'same' conv whose only consumer is another tensor-core GEMM: the epilogue writes the bf16x3 operand directly (no fp32
+        tensor, no conversion pass).  row_sq: also per-row partial sums of squares (AttnBlock q / k -> the fused softmax's row reference).
+        None when this backend / shape has no such epilogue (the caller falls back to conv2d)."""
+        Cout, ks = w.shape[0], w.shape[2]
+        Cin = x.C if isinstance(x, Operand) else x.shape[1]
+        if self.mode != 4 or not self.pack_epilogue or Cout % 32 or Cin % self.bke or w.shape[2] != w.shape[3] or ks not in (1, 3):
+            return None
+        op, pad_c = self._operand(x)
+        w_hi, _ = self._weights(w, pad_c)
+        with self._t("conv_tc", 2.0 * op.B * op.H * op.W * Cin * Cout * ks * ks):
+            y, sq = self.ops.conv2d_nhwc_tc_pack(self.mode, op.hi, w_hi, b, op.B, op.H, op.W, op.C, Cout, ks, row_sq=row_sq)
+        out = Operand(self.mode, y, None, op.B, Cout, op.H, op.W)
+        out.row_sq = sq
+        return out
 
     def _new_stats(self, B, Cout):
         """fp64 [B,32,2] buffer for GroupNorm statistics fused into the conv epilogue (None when the output cannot feed Normalize)"""
@@ -264,33 +281,42 @@ class TcDense:
             y = self.ops.dcnv2_pack_fwd_nhwc_tc(self.mode, xn, on, w_hi, w_lo, bias, B, H, W, C, Cout, dg)
         return y.permute(0, 3, 1, 2)
 
-    def attention(self, q, k, v):
+    def attention(self, q, k, v, as_operand=False):
         """AttnBlock core (encoder_decoder.py:176-187) on the tcgen05 GEMM path: per sample and per band of query rows
         S = Q K^T (W = K[n]) -> fused scale + row softmax emitting the operand P -> O = P V (W = V[n]^T)."""
-        C = q.shape[1]
+        q_is_op, k_is_op = isinstance(q, Operand), isinstance(k, Operand)
+        C = q.C if q_is_op else q.shape[1]
         if self.attn_impl == "library" or C % self.bke != 0:
             self.fallbacks["attention bmm+softmax (library)"] = self.fallbacks.get("attention bmm+softmax (library)", 0) + 1
             with self._t("attention"):
-                return self.lib.attention(q, k, v)
+                return self.lib.attention(q.dense() if q_is_op else q, k.dense() if k_is_op else k, v)
         ops = self.ops
         with self._t("attention_total(incl. its conv_tc GEMMs)"):
-            qn, kn, vn = _nhwc(q), _nhwc(k), _nhwc(v)
-            B, h, w, _ = qn.shape
+            vn = _nhwc(v)
+            B, h, w, _ = vn.shape
             N = h * w
             Np = (N + 63) // 64 * 64
-            q_hi, q_lo = ops.conv_prep_act(self.mode, qn)
-            k_hi, k_lo = ops.conv_prep_act(self.mode, kn)                 # K[n] as GEMM weights [N][C]
+            qn = None if q_is_op else _nhwc(q)
+            kn = None if k_is_op else _nhwc(k)
+            q_hi, q_lo = (q.hi, q.lo) if q_is_op else ops.conv_prep_act(self.mode, qn)
+            k_hi, k_lo = (k.hi, k.lo) if k_is_op else ops.conv_prep_act(self.mode, kn)      # K[n] as GEMM weights [N][C]
             vt_hi, vt_lo = ops.attn_transpose_v(self.mode, vn, B, N, C, Np)
-            out = torch.empty((B, h, w, C), device=q.device, dtype=torch.float32)
             if self.attn_fused and N >= 32:
-                self._attention_fused(qn, kn, q_hi, k_hi, vt_hi, out, B, h, w, N, Np, C)
+                sq = (getattr(q, "row_sq", None), getattr(k, "row_sq", None))
+                if as_operand and self.pack_epilogue and C % 32 == 0:  # the P V epilogue writes proj_out's operand
+                    out_op = ops._hi_alloc(self.mode, (B, h, w, C), vn.device)
+                    self._attention_fused(qn, kn, q_hi, k_hi, vt_hi, out_op, B, h, w, N, Np, C, sq, pack=True)
+                    return Operand(self.mode, out_op, None, B, C, h, w)
+                out = torch.empty((B, h, w, C), device=vn.device, dtype=torch.float32)
+                self._attention_fused(qn, kn, q_hi, k_hi, vt_hi, out, B, h, w, N, Np, C, sq)
                 return out.permute(0, 3, 1, 2)
+            out = torch.empty((B, h, w, C), device=vn.device, dtype=torch.float32)
             # query rows per pass: the whole sample when its score matrix fits the budget (tile-filling GEMMs matter more
             # than L2 residency of S: the P V GEMM needs >= 74 M-tiles to give every SM a 128x256 tile), else 8-row multiples
             band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
             rows_max = min(band, h) * w
-            S = torch.empty((rows_max, Np), device=q.device, dtype=torch.float32)
-            p_hi = ops._hi_alloc(self.mode, (rows_max, Np), q.device)
+            S = torch.empty((rows_max, Np), device=vn.device, dtype=torch.float32)
+            p_hi = ops._hi_alloc(self.mode, (rows_max, Np), vn.device)
             p_lo = ops._lo_like(self.mode, p_hi)
             scale = float(int(C) ** (-0.5))
             for b in range(B):
@@ -308,17 +334,24 @@ class TcDense:
                                               1, bh, w, Np, C, C, 0)
         return out.permute(0, 3, 1, 2)
 
-    def _attention_fused(self, qn, kn, q_op, k_op, vt_op, out, B, h, w, N, Np, C):
-        """mode 4: scores GEMM with the exp epilogue -> row-sum finish -> P V GEMM with the 1 / row-sum epilogue (csrc/attn.cu)"""
-        ops, dev = self.ops, qn.device
+    def _attention_fused(self, qn, kn, q_op, k_op, vt_op, out, B, h, w, N, Np, C, sq=(None, None), pack=False):
+        """mode 4: scores GEMM with the exp epilogue -> row-sum finish -> P V GEMM with the 1 / row-sum epilogue (csrc/attn.cu).
+        qn / kn: fp32 NHWC q / k (row norms by a pass over them) or None when sq carries the partial sums of squares their conv left."""
+        ops, dev = self.ops, q_op.device
         if self.attn_flag is None or self.attn_flag.device != dev:
             self.attn_flag = torch.zeros((1,), device=dev, dtype=torch.int32)
         scale = float(int(C) ** (-0.5))
         q_norm = torch.empty((B, N), device=dev, dtype=torch.float32)
         k_max = torch.zeros((B,), device=dev, dtype=torch.int32)
         with self._t("attn_softmax"):
-            ops.attn_row_norm(qn, B * N, C, N, norm_out=q_norm)
-            ops.attn_row_norm(kn, B * N, C, N, max_bits=k_max)
+            if sq[0] is not None:
+                ops.attn_row_norm_finish(sq[0][0], sq[0][1], B * N, N, norm_out=q_norm)
+            else:
+                ops.attn_row_norm(qn, B * N, C, N, norm_out=q_norm)
+            if sq[1] is not None:
+                ops.attn_row_norm_finish(sq[1][0], sq[1][1], B * N, N, max_bits=k_max)
+            else:
+                ops.attn_row_norm(kn, B * N, C, N, max_bits=k_max)
         # whole-sample passes while the operand matrix fits the budget, else bands of 8-row multiples
         band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
         rows_max = min(band, h) * w
@@ -339,7 +372,7 @@ class TcDense:
                 with self._t("attn_softmax"):
                     ops.attn_row_sum_finish(part, rows_max, nb, bh * w, row_scale, self.attn_flag)
                 with self._t("conv_tc", gemm_flops):
-                    ops.attn_pv_tc(self.mode, p_op, vt_op[b], row_scale, out[b, r0:r1], bh, w, Np, C, C)
+                    ops.attn_pv_tc(self.mode, p_op, vt_op[b], row_scale, out[b, r0:r1], bh, w, Np, C, C, pack_out=pack)
 
     def attention_verified(self):
         """True when every fused-softmax row so far stayed inside the safe window (one 4-byte device read).  On False the fused path is

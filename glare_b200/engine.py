@@ -117,10 +117,19 @@ class GlareEngine:
     def attn_block(self, sd, p, x):
         """AttnBlock.forward   encoder_decoder.py:168-192"""
         hn = self._gn(sd, p + ".norm", x, swish=False)
-        q = self._conv(sd, p + ".q", hn, padding=0)
-        k = self._conv(sd, p + ".k", hn, padding=0)
+        q = k = None
+        if getattr(self.dense, "attn_fused", False) and hasattr(self.dense, "conv2d_operand"):
+            # q / k only feed the scores GEMM: their convs write its operands and the row norms of the softmax reference directly
+            q = self.dense.conv2d_operand(hn, sd[p + ".q.weight"], sd.get(p + ".q.bias"), row_sq=True)
+            k = self.dense.conv2d_operand(hn, sd[p + ".k.weight"], sd.get(p + ".k.bias"), row_sq=True)
+        if q is None or k is None:
+            q = self._conv(sd, p + ".q", hn, padding=0)
+            k = self._conv(sd, p + ".k", hn, padding=0)
         v = self._conv(sd, p + ".v", hn, padding=0)
-        o = self.dense.attention(q, k, v)
+        if hasattr(self.dense, "conv2d_operand"):
+            o = self.dense.attention(q, k, v, as_operand=True)           # proj_out's operand straight from the P V epilogue when fused
+        else:
+            o = self.dense.attention(q, k, v)
         return self._conv(sd, p + ".proj_out", o, padding=0, residual=x)
 
     def downsample(self, sd, p, x):
@@ -199,7 +208,12 @@ class GlareEngine:
     def warp_block(self, i, x_vq, h):
         """WarpBlock.forward (:285-290) + DCNv2Pack.forward (:141-152)"""
         sd, p = self.g, "deformable_decoder.warp.%d" % i
-        feat = self._conv(sd, p + ".offset", torch.cat([x_vq, h], dim=1))
+        cat = torch.cat([x_vq, h], dim=1)
+        feat = None
+        if hasattr(self.dense, "conv2d_operand"):                        # feat only feeds conv_offset: written as its operand
+            feat = self.dense.conv2d_operand(cat, sd[p + ".offset.weight"], sd.get(p + ".offset.bias"))
+        if feat is None:
+            feat = self._conv(sd, p + ".offset", cat)
         out = self._conv(sd, p + ".dcn.conv_offset", feat).float()
         if hasattr(self.dense, "dcn_pack"):
             y = self.dense.dcn_pack(x_vq.float(), out, sd[p + ".dcn.weight"], sd[p + ".dcn.bias"], 4)

@@ -252,9 +252,30 @@ def attn_row_sum_finish(part, part_stride, n_blocks, rows, row_scale, flag):
     check(lib().glare_attn_row_sum_finish(ptr(part), part_stride, n_blocks, rows, ptr(row_scale), ptr(flag), stream()), "glare_attn_row_sum_finish")
 
 
-def attn_pv_tc(mode, p_op, vt_op, row_scale, y, rows_h, rows_w, n_pad, C, ldy):
+def attn_pv_tc(mode, p_op, vt_op, row_scale, y, rows_h, rows_w, n_pad, C, ldy, pack_out=False):
+    """y: fp32 [rows][ldy], or with pack_out the bf16x3 operand [rows][2 * C] of the following conv"""
     require_cuda(p_op, vt_op, row_scale, y)
-    check(lib().glare_attn_pv_tc(mode, ptr(p_op), ptr(vt_op), ptr(row_scale), ptr(y), rows_h, rows_w, n_pad, C, ldy, stream()), "glare_attn_pv_tc")
+    check(lib().glare_attn_pv_tc(mode, ptr(p_op), ptr(vt_op), ptr(row_scale), ptr(y), rows_h, rows_w, n_pad, C, ldy, 1 if pack_out else 0, stream()),
+          "glare_attn_pv_tc")
+
+
+def conv2d_nhwc_tc_pack(mode, x_op, w_op, bias, B, H, W, Cin, Cout, ksize, row_sq=False):
+    """stride-1 conv whose output is written as the operand of the next GEMM; returns (operand [B,H,W,2*Cout] bf16, (part, n_blocks) | None)"""
+    import ctypes
+    require_cuda(x_op, w_op, bias)
+    y = _hi_alloc(mode, (B, H, W, Cout), x_op.device)
+    part, nb = None, ctypes.c_int(0)
+    if row_sq:
+        part = torch.empty(((Cout + 63) // 64, B * H * W), device=x_op.device, dtype=torch.float32)
+    check(lib().glare_conv2d_nhwc_tc_pack(mode, ptr(x_op), ptr(w_op), ptr(bias), ptr(y), B, H, W, Cin, Cout, ksize, ptr(part), B * H * W,
+                                          ctypes.cast(ctypes.byref(nb), ctypes.c_void_p), stream()), "glare_conv2d_nhwc_tc_pack")
+    return y, ((part, nb.value) if row_sq else None)
+
+
+def attn_row_norm_finish(part, n_blocks, rows, rows_per_sample, norm_out=None, max_bits=None):
+    require_cuda(part, norm_out, max_bits)
+    check(lib().glare_attn_row_norm_finish(ptr(part), part.shape[1], n_blocks, rows, rows_per_sample, ptr(norm_out), ptr(max_bits), stream()),
+          "glare_attn_row_norm_finish")
 
 
 def gn_stats(x_nhwc, B, HW, C, G=32):

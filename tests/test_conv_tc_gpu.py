@@ -155,6 +155,58 @@ def test_attention_fused_softmax_matches_exact_path(glare_lib, shape):
     assert torch.equal(o1, o3)
 
 
+@pytest.mark.parametrize("shape", [(2, 13, 21, 128, 128, 3), (1, 24, 40, 512, 512, 1), (1, 105, 155, 256, 128, 3)])
+def test_conv_operand_epilogue(glare_lib, shape):
+    """conv whose epilogue writes the next GEMM's bf16x3 operand (+ per-row sums of squares): bitwise the operand that the conversion pass
+    makes from the fp32 conv output"""
+    from glare_b200 import ops
+    B, H, W, Ci, Co, ks = shape
+    g = torch.Generator().manual_seed(Ci + Co + H)
+    x = torch.randn((B, H, W, Ci), generator=g).cuda()
+    w = (torch.randn((Co, Ci, ks, ks), generator=g) / (ks * Ci ** 0.5)).cuda()
+    b = torch.randn((Co,), generator=g).cuda()
+    w_hi, _ = ops.conv_pack_weight(4, w)
+    x_hi, _ = ops.conv_prep_act(4, x)
+    y = ops.conv2d_nhwc_tc(4, x_hi, None, w_hi, None, b, None, B, H, W, Ci, Co, ks)
+    y_op, _ = ops.conv_prep_act(4, y)
+    packed, (part, nb) = ops.conv2d_nhwc_tc_pack(4, x_hi, w_hi, b, B, H, W, Ci, Co, ks, row_sq=True)
+    torch.cuda.synchronize()
+    assert torch.equal(packed.view(torch.int16), y_op.view(torch.int16))
+    sq = part[:nb].sum(0).double()
+    ref = (y.double() ** 2).sum(-1).reshape(-1)
+    assert float((sq - ref).abs().max()) < 1e-5 * float(ref.max())
+    norm = torch.empty((B * H * W,), device="cuda")
+    mx = torch.zeros((B,), device="cuda", dtype=torch.int32)
+    ops.attn_row_norm_finish(part, nb, B * H * W, H * W, norm_out=norm, max_bits=mx)
+    assert float((norm.double() - ref.sqrt()).abs().max()) < 2e-5 * float(ref.sqrt().max())
+    ref_max = ref.sqrt().reshape(B, -1).max(1).values
+    assert float((mx.view(torch.float32).double() - ref_max).abs().max()) < 2e-5 * float(ref_max.max())
+
+
+def test_attention_block_operand_route(glare_lib):
+    """q / k written as operands by their convs and the attention output written as proj_out's operand (engine.attn_block route) against the
+    route through fp32 tensors"""
+    from glare_b200.dense import TcDense, Operand
+    B, C, h, w = 2, 512, 24, 21
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((B, C, h, w), generator=g).cuda()
+    wq, wk = ((torch.randn((C, C, 1, 1), generator=g) / C ** 0.5).cuda() for _ in range(2))
+    bq, bk = (torch.randn((C,), generator=g).cuda() for _ in range(2))
+    v = torch.randn((B, C, h, w), generator=g).cuda()
+    d = TcDense(4)
+    q_op, k_op = d.conv2d_operand(x, wq, bq, row_sq=True), d.conv2d_operand(x, wk, bk, row_sq=True)
+    assert isinstance(q_op, Operand) and q_op.row_sq is not None
+    o_op = d.attention(q_op, k_op, v, as_operand=True)
+    assert isinstance(o_op, Operand)
+    o_ref = d.attention(d.conv2d(x, wq, bq, padding=0), d.conv2d(x, wk, bk, padding=0), v)
+    assert d.attention_verified()
+    ref = _attention_fp64(torch.nn.functional.conv2d(x.double(), wq.double(), bq.double()).float(),
+                          torch.nn.functional.conv2d(x.double(), wk.double(), bk.double()).float(), v)
+    sc = max(1.0, float(ref.abs().max()))
+    assert float((o_op.dense().reshape(B, C, h * w).double() - ref).abs().max()) < 6e-5 * sc
+    assert float((o_op.dense() - o_ref).abs().max()) < 2e-5 * sc
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_attention_query_bands(glare_lib, fused):
     """score matrices larger than the budget (1080p: 131 648 tokens) are processed in bands of query rows; forced here on a small shape"""

@@ -93,11 +93,13 @@ def _nhwc(x):
 
 
 class TcDense:
-    """tcgen05 implicit-GEMM convolutions + fused GroupNorm/swish operand kernels (libglare_b200.so).
+    """tcgen05 implicit-GEMM convolutions, attention GEMMs, DCNv2 and the GroupNorm/swish operand kernels (libglare_b200.so).
 
-    mode 0 bf16 operands, 1 tf32, 2 3xTF32 (~fp32).  Shapes the kernel does not cover (3-channel heads, the two
-    stride-2 downsample convs; < 2.5 % of the FLOPs) and the attention matmuls go to the cuDNN/cuBLAS library
-    backend ``self.lib`` -- listed in ``self.fallbacks`` so the bench can report them."""
+    mode 0 bf16 operands, 1 tf32, 2 3xTF32, 3 tf32 + 2 x bf16 cross terms, 4 bf16x3 (default; fp32-grade).  Every conv shape of the path
+    runs on the tcgen05 kernel (3-channel layers through channel padding, Downsample through the TMA traversal stride, Upsample as four
+    sub-pixel phases) and so do the attention matmuls.  ``self.lib`` (cuDNN / cuBLAS) is only reached when a caller asks for it
+    (``attn_impl = "library"``, ``cover_all = False``) or a shape falls outside the kernels; every such call is counted in
+    ``self.fallbacks`` and reported by the bench (empty on the GLARE network)."""
 
     def __init__(self, mode):
         from . import ops
@@ -117,7 +119,7 @@ class TcDense:
         self.fuse_gn_stats = bool(os.environ.get("GLARE_FUSE_GN_STATS"))      # A/B switch
         self.cover_all = True          # 3-channel convs (channel-padded) and stride-2 Downsample convs on the tcgen05 kernel too
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
-        self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs + fused softmax kernel; "library": cuBLAS bmm + torch softmax
+        self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs (softmax in their epilogues, or the softmax kernel); "library": cuBLAS bmm + torch softmax
         self.attn_s_budget = 3 << 29   # bytes of fp32 score matrix materialised per pass (1.5 GiB)
         # mode 4: softmax fused into the epilogues of the two GEMMs (csrc/attn.cu): exp against a Cauchy-Schwarz row reference in the scores
         # GEMM, 1 / row sum in the P V GEMM; rows that fall outside the safe window raise `attn_flag` and `attention_verified()` tells

@@ -89,3 +89,60 @@ def test_pipeline_32x48(sd_g, sd_v):
     assert torch.allclose(out, T(g["out"]), atol=1e-4)
     gt = T(g["gt"])
     assert abs(O.psnr(out.clamp(0, 1), gt) - O.psnr(T(g["out"]).clamp(0, 1), gt)) < 0.01
+
+
+def test_stage2_gradients_match_reference_autograd():
+    """BASELINE config 4: the oracle's stage-2 objective and its autograd gradients against the reference's own
+    forward + backward (tests/golden/stage2.npz, written by oracle/gen_golden.py from LLFlowVQGAN2_arch.py:75-122)"""
+    from glare_b200 import synth
+    g = load_golden("stage2")
+    sd2 = {k: v.clone().requires_grad_(True) for k, v in synth.synth_state_dict("netG_stage2", 0).items()}
+    z, nll = O.stage2_nll(sd2, T(g["gt_latent"]), T(g["lr"]))
+    assert torch.allclose(z, T(g["z"]), atol=1e-4, rtol=1e-5)
+    assert torch.allclose(nll, T(g["nll"]), atol=1e-4, rtol=1e-5)
+    nll.mean().backward()
+    for key in list(g):
+        if key.startswith("grad."):
+            ref = T(g[key])
+            got = sd2[key[5:]].grad
+            assert float((got - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), key
+
+
+def test_flow_explicit_backward_matches_autograd(sd_g):
+    """oracle/flow_backward.py (the hand-derived backward the training kernels follow) against autograd of the oracle's flow"""
+    from oracle import flow_backward as FB
+    gen = torch.Generator().manual_seed(4)
+    B, h, w = 2, 6, 7
+    gt = torch.randn((B, 3, h, w), generator=gen)
+    ft = torch.sigmoid(torch.randn((B, 64, h, w), generator=gen))
+    mean = torch.randn((B, 3, h, w), generator=gen) * 0.1
+    keys = [k for k in sd_g if k.startswith("flowUpsamplerNet.layers.")]
+    sd = dict(sd_g)
+    leaf = {k: sd_g[k].clone().requires_grad_(True) for k in keys}
+    sd.update(leaf)
+    gt_a, ft_a, mean_a = (t.clone().requires_grad_(True) for t in (gt, ft, mean))
+    z, logdet = O.flow_encode(sd, gt_a, ft_a)
+    import math
+    pixels = h * w
+    logp = (-0.5 * ((z - mean_a) ** 2 + math.log(2 * math.pi))).sum(dim=(1, 2, 3))
+    nll = -(logdet + logp) / (math.log(2.0) * pixels)
+    nll.mean().backward()
+    with torch.no_grad():
+        nll_e, z_e, g_gt, g_ft, g_mean, grads = FB.nll_forward_backward(sd_g, gt, ft, mean)
+    assert torch.allclose(nll_e, nll.detach(), atol=1e-4, rtol=1e-5) and torch.allclose(z_e, z.detach(), atol=1e-4, rtol=1e-5)
+
+    def close(a, b, what):
+        sc = max(float(b.abs().max()), 1e-6)
+        assert float((a - b).abs().max()) <= 2e-4 * sc + 1e-7, (what, float((a - b).abs().max()), sc)
+
+    close(g_gt, gt_a.grad, "gt")
+    close(g_ft, ft_a.grad, "ft")
+    close(g_mean, mean_a.grad, "mean")
+    checked = 0
+    for k in keys:
+        if leaf[k].grad is None:
+            continue                                  # the unused `f` nets of the noCoupling steps
+        assert k in grads, k
+        close(grads[k], leaf[k].grad, k)
+        checked += 1
+    assert checked >= 24 * 2 * 9 + 28 * 3

@@ -1,0 +1,200 @@
+"""Stage-2 training of the conditional flow on the library's kernels: the objective of LLFlowVQGAN2.normal_flow
+(LLFlowVQGAN2_arch.py:75-122) and its gradients with respect to the latent, the conditioning features, the Gaussian mean and
+every flow parameter (reference: torch autograd through FlowUpsamplerNet.encode, FlowUpsamplerNet.py:228-274).
+
+Formulas: oracle/flow_backward.py (CPU specification, checked against autograd and the reference's own gradients).  Kernels:
+csrc/flow_bwd.cu + the split-K GEMM of csrc/dcn_bwd.cu + the tensor-core conv path for the hoisted 64 -> 3072 conv.  This module is
+the host side: buffer management, the 28-step loops, and the assembly of the packed gradients into state-dict shaped tensors.
+
+STATUS (round 1): the host logic is verified on the CPU against the specification through a torch restatement of every kernel
+contract (tests/flow_train_emu.py, tests/test_flow_train_cpu.py); the CUDA kernels compile for sm_100a and have not run on
+hardware yet (tests/test_zz_flow_train_gpu.py runs them in a child process).
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import flow as flowmod
+from .flow import COUPLING_STEPS, HIDDEN, N_FLOW_STEPS, NO_COUPLING_STEPS
+
+C = HIDDEN
+NPRE = 128 * len(COUPLING_STEPS)            # channels of the hoisted pre-activation tensor: per coupling step 64 (NN_A) + 64 (NN_F)
+
+
+class CudaKernels:
+    """The library's kernels (include/glare_b200.h section 2b).  Pointers are passed as (tensor, element offset) pairs."""
+
+    def __init__(self):
+        from . import ops
+        from ._lib import lib, stream
+        self.ops, self.lib, self.stream = ops, lib, stream
+
+    @staticmethod
+    def _p(t, off=0):
+        return None if t is None else ctypes.c_void_p(t.data_ptr() + 4 * off)
+
+    def _call(self, name, *args):
+        self.ops.check(getattr(self.lib(), name)(*args, self.stream()), name)
+
+    def zeros(self, shape, like):
+        return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+    def empty(self, shape, like):
+        return torch.empty(shape, device=like.device, dtype=torch.float32)
+
+    def encode_chain(self, plan, gt, ft, conv2d):
+        """FlowUpsamplerNet.encode with every step's input kept: -> (zs [29,B,3,h,w], logdet [B], P [B,NPRE,h,w] any dense layout)"""
+        z = gt.float().contiguous()
+        B, _, h, w = z.shape
+        hw, n = h * w, len(COUPLING_STEPS)
+        logdet = torch.zeros(B, device=z.device, dtype=torch.float32)
+        P, hF = flowmod.precompute(plan, ft, conv2d)
+        zs = torch.empty((N_FLOW_STEPS + 1, B, 3, h, w), device=z.device, dtype=torch.float32)
+        zs[0].copy_(z)
+        for s in range(N_FLOW_STEPS):
+            logdet += (plan.ld_const[s, 0] + plan.ld_const[s, 1]) * float(hw)
+            if s not in NO_COUPLING_STEPS:
+                ci = COUPLING_STEPS.index(s)
+                self.ops.flow_step(0, True, zs[s], zs[s + 1], P[:, ci * 128:], flowmod.plane_strides(P, False), hF[:, ci * 6:], n * 6 * hw,
+                                   plan.nets_a[ci], plan.pw_fwd[s], logdet)
+            else:
+                self.ops.flow_step(0, False, zs[s], zs[s + 1], None, (0, 0, 0), None, 0, None, plan.pw_fwd[s], None)
+        return zs, logdet, P
+
+    def net_fwd(self, pre, pre_off, pre_ld, z1, z1_ld, net, B, h, w, h1, h2, hout):
+        self._call("glare_flow_train_net_fwd_f32", self._p(pre, pre_off), pre_ld, self._p(z1), z1_ld, self._p(net), B, h, w, self._p(h1), self._p(h2),
+                   self._p(hout))
+
+    def point_fwd(self, z_in, pw, hF, B, h, w, t, u, v):
+        self._call("glare_flow_train_point_fwd_f32", self._p(z_in), self._p(pw), self._p(hF), B, h, w, self._p(t), self._p(u), self._p(v))
+
+    def coupling_bwd(self, which, g_in, g_z1, x, hraw, g_ld, B, h, w, g_h, g_x):
+        self._call("glare_flow_train_coupling_bwd_f32", which, self._p(g_in), self._p(g_z1), self._p(x), self._p(hraw), ctypes.c_float(g_ld), B, h, w,
+                   self._p(g_h), self._p(g_x))
+
+    def net_bwd(self, g_h, h1, h2, net, B, h, w, g_a3, g_n2, g_a2, g_n1, g_a1, g_pre, pre_off, pre_ld, g_z1):
+        self._call("glare_flow_train_net_bwd_f32", self._p(g_h), self._p(h1), self._p(h2), self._p(net), B, h, w, self._p(g_a3), self._p(g_n2),
+                   self._p(g_a2), self._p(g_n1), self._p(g_a1), self._p(g_pre, pre_off), pre_ld, self._p(g_z1))
+
+    def point_bwd(self, g_u, t, pw, B, h, w, g_z, sums):
+        self._call("glare_flow_train_point_bwd_f32", self._p(g_u), self._p(t), self._p(pw), B, h, w, self._p(g_z), self._p(sums))
+
+    def im2col3x3(self, x, ldx, Cx, B, h, w, col):
+        self._call("glare_flow_train_im2col3x3_f32", self._p(x), ldx, Cx, 0, B, h, w, self._p(col))
+
+    def colsum(self, a, lda, b, ldb, Cx, P, out):
+        self._call("glare_flow_train_colsum_f32", self._p(a), lda, self._p(b), ldb, Cx, P, self._p(out))
+
+    def gemm_tn(self, a, M, b, N, P, out):
+        """out [M][N] += a [P][M]^T b [P][N] (csrc/dcn_bwd.cu split-K fp32 GEMM)"""
+        self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, N, self._p(out))
+
+
+def _net_param_grads(K, key, net_has_z, bufs, v, B, h, w, P, grads, like):
+    """parameter gradients of one coupling net from the buffers its data backward left (oracle/flow_backward.py nn_backward)"""
+    h1, h2, hout, g_h, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9 = bufs
+    nout = 4 if net_has_z else 6
+    # Conv2dZeros: weight [nout][64][3][3], bias, logs (out = (conv + bias) * exp(3 logs))
+    K.im2col3x3(h2, C, C, B, h, w, col576)
+    G3 = K.zeros((9 * C, 8), like)
+    K.gemm_tn(col576, 9 * C, g_a3, 8, P, G3)
+    grads[key + ".4.weight"] = G3.view(9, C, 8).permute(2, 1, 0)[:nout].reshape(nout, C, 3, 3).contiguous()
+    s8 = K.zeros((2, 8), like)
+    K.colsum(g_a3, 8, None, 0, 8, P, s8[0])
+    K.colsum(g_h, 8, hout, 8, 8, P, s8[1])
+    grads[key + ".4.bias"] = s8[0, :nout].clone()
+    grads[key + ".4.logs"] = (3.0 * s8[1, :nout]).view(nout, 1, 1)
+    # 1x1 conv + ActNorm
+    G2 = K.zeros((C, C), like)
+    K.gemm_tn(h1, C, g_a2, C, P, G2)
+    grads[key + ".2.weight"] = G2.t().reshape(C, C, 1, 1).contiguous()
+    s64 = K.zeros((4, C), like)
+    K.colsum(g_a2, C, None, 0, C, P, s64[0])
+    K.colsum(g_n2, C, h2, C, C, P, s64[1])
+    K.colsum(g_a1, C, None, 0, C, P, s64[2])
+    K.colsum(g_n1, C, h1, C, C, P, s64[3])
+    grads[key + ".2.actnorm.bias"] = s64[0].view(1, C, 1, 1).clone()
+    grads[key + ".2.actnorm.logs"] = s64[1].view(1, C, 1, 1).clone()
+    grads[key + ".0.actnorm.bias"] = s64[2].view(1, C, 1, 1).clone()
+    grads[key + ".0.actnorm.logs"] = s64[3].view(1, C, 1, 1).clone()
+    if net_has_z:                               # the z1 input channel of the first 3x3 conv; the ft channels come from the hoisted conv
+        K.im2col3x3(v, 4, 1, B, h, w, col9)
+        G1 = K.zeros((9, C), like)
+        K.gemm_tn(col9, 9, g_a1, C, P, G1)
+        grads[key + ".0.weight.z"] = G1.t().reshape(C, 1, 3, 3).contiguous()
+
+
+def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="flowUpsamplerNet"):
+    """gt [B,3,h,w] latent, ft [B,64,h,w] conditioning features, mean [B,3,h,w] (color_map) -> (nll [B], z, dL/dgt, dL/dft, dL/dmean,
+    {state-dict key: dL/dparam}) for L = nll.mean(); ``conv2d(x, weight)`` is the dense 3x3 'same' conv path (no bias), ``sd`` supplies
+    invconv weights for the log|det| term."""
+    K = kernels if kernels is not None else CudaKernels()
+    B, _, h, w = gt.shape
+    hw = h * w
+    P = B * hw
+    zs, logdet, Ppre = K.encode_chain(plan, gt, ft, conv2d)
+    z = zs[N_FLOW_STEPS]
+    logp = (-0.5 * ((z - mean) ** 2 + math.log(2 * math.pi))).sum(dim=(1, 2, 3))
+    k = 1.0 / (math.log(2.0) * hw)
+    nll = -(logdet + logp) * k
+    g_ld = -k / B                                                       # dL/dlogdet of every sample
+    g_z = ((z - mean) * (k / B)).contiguous()
+    g_mean = -g_z
+
+    pre = Ppre.permute(0, 2, 3, 1).contiguous()                          # NHWC [P][NPRE] (a view when the conv path wrote channels_last)
+    g_pre = K.empty((B, h, w, NPRE), gt)
+    new = lambda c: K.empty((P, c), gt)                                  # noqa: E731
+    h1A, h2A, h1F, h2F, g_n2, g_a2, g_n1, g_a1 = (new(C) for _ in range(8))
+    hA, hF, g_hA, g_hF, g_a3 = (new(8) for _ in range(5))
+    t, u, v, g_v, g_u = (new(4) for _ in range(5))
+    g_z1, col576, col9 = new(1), new(9 * C), new(9)
+    grads = {}
+    for s in range(N_FLOW_STEPS - 1, -1, -1):
+        p = "%s.layers.%d" % (prefix, s)
+        pw = plan.pw_fwd[s]
+        if s not in NO_COUPLING_STEPS:
+            ci = COUPLING_STEPS.index(s)
+            netA, netF = plan.nets_a[ci], plan.nets_f[ci]
+            offA, offF = ci * 128, ci * 128 + 64
+            # forward activations of the step, recomputed from its input
+            K.net_fwd(pre, offF, NPRE, None, 0, netF, B, h, w, h1F, h2F, hF)
+            K.point_fwd(zs[s], pw, hF, B, h, w, t, u, v)
+            K.net_fwd(pre, offA, NPRE, v, 4, netA, B, h, w, h1A, h2A, hA)
+            # self coupling -> NN_A -> feature affine -> NN_F
+            K.coupling_bwd(0, g_z, None, v, hA, g_ld, B, h, w, g_hA, g_v)
+            K.net_bwd(g_hA, h1A, h2A, netA, B, h, w, g_a3, g_n2, g_a2, g_n1, g_a1, g_pre, offA, NPRE, g_z1)
+            _net_param_grads(K, p + ".affine.fAffine", True, (h1A, h2A, hA, g_hA, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9), v, B, h, w, P, grads, gt)
+            K.coupling_bwd(1, g_v, g_z1, u, hF, g_ld, B, h, w, g_hF, g_u)
+            K.net_bwd(g_hF, h1F, h2F, netF, B, h, w, g_a3, g_n2, g_a2, g_n1, g_a1, g_pre, offF, NPRE, None)
+            _net_param_grads(K, p + ".affine.fFeatures", False, (h1F, h2F, hF, g_hF, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9), v, B, h, w, P, grads, gt)
+            gu = g_u
+        else:
+            K.point_fwd(zs[s], pw, None, B, h, w, t, u, v)
+            gu = F.pad(g_z.permute(0, 2, 3, 1), (0, 1)).reshape(P, 4).contiguous()
+        sums = K.zeros((16,), gt)
+        g_z = K.empty((B, 3, h, w), gt)
+        K.point_bwd(gu, t, pw, B, h, w, g_z, sums)
+        wmat = sd[p + ".invconv.weight"].to(gt.device, torch.float32)
+        ld_total = g_ld * B * hw                                        # sum over samples of dL/dlogdet, times the pixel count
+        grads[p + ".invconv.weight"] = sums[0:9].view(3, 3) + ld_total * torch.inverse(wmat.double()).t().float()
+        grads[p + ".actnorm.logs"] = (sums[9:12] + ld_total).view(1, 3, 1, 1)
+        grads[p + ".actnorm.bias"] = sums[12:15].view(1, 3, 1, 1).clone()
+
+    # hoisted conv over ft: data gradient on the tensor-core conv path (transpose of a stride-1 'same' conv = the conv with the flipped,
+    # transposed filter), weight gradient by the split-K GEMM over im2col(ft)
+    if getattr(plan, "_w_pre_t", None) is None:                        # once per plan: the packed-weight cache of the conv path keys on it
+        plan._w_pre_t = plan.w_pre.flip(2, 3).transpose(0, 1).contiguous()
+    w_t = plan._w_pre_t
+    g_ft = conv2d(g_pre.permute(0, 3, 1, 2), w_t).float()
+    ftn = ft.float().permute(0, 2, 3, 1).contiguous()
+    K.im2col3x3(ftn, C, C, B, h, w, col576)
+    Gp = K.zeros((9 * C, NPRE), gt)
+    K.gemm_tn(col576, 9 * C, g_pre, NPRE, P, Gp)
+    g_wpre = Gp.view(9, C, NPRE).permute(2, 1, 0).reshape(NPRE, C, 3, 3)
+    for ci, s in enumerate(COUPLING_STEPS):
+        p = "%s.layers.%d.affine" % (prefix, s)
+        grads[p + ".fAffine.0.weight"] = torch.cat([grads.pop(p + ".fAffine.0.weight.z"), g_wpre[ci * 128:ci * 128 + 64]], dim=1).contiguous()
+        grads[p + ".fFeatures.0.weight"] = g_wpre[ci * 128 + 64:ci * 128 + 128].contiguous()
+    return nll, z, g_z, g_ft, g_mean, grads

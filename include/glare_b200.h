@@ -203,6 +203,27 @@ int glare_postprocess_u8(const float* y, long long sb, long long sc, long long s
                          uint8_t* out_nhwc, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * (2b) Stage-2 training support for the flow (train_stage2.py / LLFlowVQGAN2_arch.py:75-122): forward activations of one coupling
+ *      net and the backward pass of FlowStep.normal_flow (FlowStep.py:75-98) -- the autograd of FlowActNorms.py:48-100,
+ *      Permutations.py:21-59, FlowAffineCouplingsAblation.py:50-151, flow.py:13-70 -- over NHWC-flattened [P][C] fp32 buffers,
+ *      P = B*h*w.  Formulas: oracle/flow_backward.py (checked against autograd on the CPU).  Weight gradients are formed from the
+ *      buffers below with glare_dcnv2_bwd_weight_f32 (grad[M][N] += a[P][M]^T b[P][N]) and glare_flow_train_colsum_f32; the host side is
+ *      glare_b200/flow_train.py.  Not yet run on hardware in round 1 (csrc/flow_bwd.cu header).
+ * ---------------------------------------------------------------------------------------------------- */
+int glare_flow_train_net_fwd_f32(const float* pre, long long pre_ld, const float* z1, long long z1_ld, const float* net, int B, int h, int w,
+                                 float* h1, float* h2, float* hout, cudaStream_t stream);
+int glare_flow_train_point_fwd_f32(const float* z_in, const float* pw_fwd, const float* hF, int B, int h, int w, float* t, float* u, float* v,
+                                   cudaStream_t stream);
+int glare_flow_train_coupling_bwd_f32(int which, const float* g_in, const float* g_z1, const float* x, const float* hraw, float g_ld, int B, int h,
+                                      int w, float* g_h, float* g_x, cudaStream_t stream);
+int glare_flow_train_net_bwd_f32(const float* g_h, const float* h1, const float* h2, const float* net, int B, int h, int w, float* g_a3, float* g_n2,
+                                 float* g_a2, float* g_n1, float* g_a1, float* g_pre, long long pre_ld, float* g_z1, cudaStream_t stream);
+int glare_flow_train_point_bwd_f32(const float* g_u, const float* t, const float* pw_fwd, int B, int h, int w, float* g_z, float* sums,
+                                   cudaStream_t stream);
+int glare_flow_train_im2col3x3_f32(const float* x, long long ldx, int C, int relu, int B, int h, int w, float* col, cudaStream_t stream);
+int glare_flow_train_colsum_f32(const float* a, long long lda, const float* b, long long ldb, int C, long long P, float* out, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * (7) Elementwise glue of the AFT decoder -- deformableDecoder_arch.py:587-590 (Mix: enc * m + h * (1 - m)) and :567
  *     (h + x_vq * mean(h) / mean(x_vq)): out[n][i] = a[n][i] * alpha[n * alpha_stride] + b[n][i] * beta[n * beta_stride], each product
  *     rounded before the sum like the reference's separate ATen kernels.  Strides 0 (one scalar) or 1 (per sample).

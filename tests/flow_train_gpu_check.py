@@ -1,0 +1,133 @@
+"""Child process of tests/test_zz_flow_train_gpu.py: the stage-2 flow training kernels (csrc/flow_bwd.cu) on cuda:0, kernel by kernel against
+the torch restatement of their contracts (tests/flow_train_emu.py) and end to end against the CPU specification (oracle/flow_backward.py).
+Prints one line per check and exits 0 only if every check holds.  Runs in its own process so that a faulting kernel cannot take the
+CUDA context of the main test run with it."""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+from flow_train_emu import TorchEmuKernels  # noqa: E402
+from glare_b200 import flow, flow_train, synth  # noqa: E402
+from glare_b200.flow import COUPLING_STEPS  # noqa: E402
+from oracle import flow_backward as FB  # noqa: E402
+
+OK = True
+
+
+def check(name, a, b, tol=2e-4):
+    global OK
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    sc = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max()) if a.shape == b.shape else float("inf")
+    good = err <= tol * sc + 1e-7 and bool(torch.isfinite(a).all())
+    OK = OK and good
+    print("%-4s %-58s err %.3g (scale %.3g)" % ("ok" if good else "FAIL", name, err, sc), flush=True)
+
+
+def main():
+    dev = torch.device("cuda:0")
+    sd = synth.synth_state_dict("netG", 0)
+    sd_d = {k: v.to(dev) for k, v in sd.items()}
+    plan = flow.FlowPlan(sd, dev)
+    gen = torch.Generator().manual_seed(33)
+    B, h, w = 2, 9, 11
+    P = B * h * w
+    gt = torch.randn((B, 3, h, w), generator=gen)
+    ft = torch.sigmoid(torch.randn((B, 64, h, w), generator=gen))
+    mean = torch.randn((B, 3, h, w), generator=gen) * 0.1
+    K, E = flow_train.CudaKernels(), TorchEmuKernels(sd_d)
+    rnd = lambda *s: torch.randn(s, generator=gen).to(dev)             # noqa: E731
+    new = lambda *s: torch.full(s, float("nan"), device=dev)           # noqa: E731
+
+    # ---- kernel by kernel (same inputs through the CUDA kernel and through the torch restatement of its contract)
+    ci = 3
+    netA, netF, pw = plan.nets_a[ci], plan.nets_f[ci], plan.pw_fwd[COUPLING_STEPS[ci]]
+    pre = rnd(B, h, w, 256)
+    zin = rnd(B, 3, h, w)
+    for tag, net, z1 in (("NN_A", netA, rnd(P, 4)), ("NN_F", netF, None)):
+        outs = [[new(P, 64), new(P, 64), new(P, 8)] for _ in range(2)]
+        for kern, o in ((K, outs[0]), (E, outs[1])):
+            kern.net_fwd(pre, 128, 256, z1, 4, net, B, h, w, *o)
+        for nm, a, b in zip(("h1", "h2", "hout"), *outs):
+            check("net_fwd %s %s" % (tag, nm), a, b)
+        h1, h2, hout = outs[1]
+        g_h = rnd(P, 8)
+        g_h[:, (4 if z1 is not None else 6):] = 0
+        res = []
+        for kern in (K, E):
+            bufs = [new(P, 8), new(P, 64), new(P, 64), new(P, 64), new(P, 64)]
+            g_pre, g_z1 = torch.zeros((B, h, w, 256), device=dev), (new(P, 1) if z1 is not None else None)
+            kern.net_bwd(g_h, h1, h2, net, B, h, w, *bufs, g_pre, 64, 256, g_z1)
+            res.append(bufs + [g_pre] + ([g_z1] if g_z1 is not None else []))
+        for nm, a, b in zip(("g_a3", "g_n2", "g_a2", "g_n1", "g_a1", "g_pre", "g_z1"), *res):
+            check("net_bwd %s %s" % (tag, nm), a, b)
+    hF = rnd(P, 8)
+    for hf, tag in ((hF, "coupling"), (None, "noCoupling")):
+        outs = [[new(P, 4), new(P, 4), new(P, 4)] for _ in range(2)]
+        for kern, o in ((K, outs[0]), (E, outs[1])):
+            kern.point_fwd(zin, pw, hf, B, h, w, *o)
+        for nm, a, b in zip("tuv", *outs):
+            check("point_fwd %s %s" % (tag, nm), a, b)
+    t, u, v = outs[1]
+    hA, g_out, g_z1 = rnd(P, 8), rnd(B, 3, h, w), rnd(P, 1)
+    for which, g_in, gz, x, hr in ((0, g_out, None, v, hA), (1, rnd(P, 4), g_z1, u, hF)):
+        outs = [[new(P, 8), new(P, 4)] for _ in range(2)]
+        for kern, o in ((K, outs[0]), (E, outs[1])):
+            kern.coupling_bwd(which, g_in, gz, x, hr, -0.0123, B, h, w, *o)
+        check("coupling_bwd %d g_h" % which, outs[0][0], outs[1][0])
+        check("coupling_bwd %d g_x" % which, outs[0][1][:, :3], outs[1][0 + 1][:, :3])
+    g_u = rnd(P, 4)
+    outs = [[new(B, 3, h, w), torch.zeros(16, device=dev)] for _ in range(2)]
+    for kern, o in ((K, outs[0]), (E, outs[1])):
+        kern.point_bwd(g_u, t, pw, B, h, w, *o)
+    check("point_bwd g_z", outs[0][0], outs[1][0])
+    check("point_bwd sums", outs[0][1][:15], outs[1][1][:15])
+    for Cx, ldx in ((64, 64), (1, 4)):
+        x = rnd(P, ldx)
+        outs = [new(P, 9 * Cx) for _ in range(2)]
+        for kern, o in ((K, outs[0]), (E, outs[1])):
+            kern.im2col3x3(x, ldx, Cx, B, h, w, o)
+        check("im2col3x3 C=%d" % Cx, *outs)
+    a, b = rnd(P, 64), rnd(P, 64)
+    for Cx, bb in ((64, b), (64, None), (8, None)):
+        outs = [torch.zeros(64, device=dev) for _ in range(2)]
+        for kern, o in ((K, outs[0]), (E, outs[1])):
+            kern.colsum(a, 64 if Cx == 64 else 8, bb, 64, Cx, P if Cx == 64 else P * 8, o)
+        check("colsum C=%d%s" % (Cx, " dot" if bb is not None else ""), *outs)
+    outs = [torch.zeros((9, 64), device=dev) for _ in range(2)]
+    c9 = rnd(P, 9)
+    for kern, o in ((K, outs[0]), (E, outs[1])):
+        kern.gemm_tn(c9, 9, a, 64, P, o)
+    check("gemm_tn 9 x 64", *outs)
+
+    # ---- the whole training step: CUDA kernels + tensor-core conv path against the CPU specification
+    from glare_b200.dense import make_dense
+    dense = make_dense("auto")
+    conv = lambda x, wgt: dense.conv2d(x, wgt).float()                  # noqa: E731
+    with torch.no_grad():
+        nll, z, g_gt, g_ft, g_mean, grads = flow_train.nll_forward_backward(plan, sd, gt.to(dev), ft.to(dev), mean.to(dev), conv)
+        torch.cuda.synchronize()
+        nll_s, z_s, g_gt_s, g_ft_s, g_mean_s, grads_s = FB.nll_forward_backward(sd, gt, ft, mean)
+    check("step nll", nll, nll_s, 1e-4)
+    check("step z", z, z_s, 1e-3)
+    check("step dL/dgt", g_gt, g_gt_s, 2e-3)
+    check("step dL/dft", g_ft, g_ft_s, 2e-3)
+    check("step dL/dmean", g_mean, g_mean_s, 2e-3)
+    # a pre-activation within rounding of zero can land on the other side of the ReLU in a different evaluation order (the hoisted conv splits
+    # the first layer's sum): such a flip changes one output channel of one net's gradients by ~1e-3 of their scale.  Allow a few such tensors.
+    rel = sorted(((float((grads[k].cpu() - grads_s[k]).abs().max()) / max(float(grads_s[k].abs().max()), 1e-6), k) for k in grads_s), reverse=True)
+    outliers = [r for r in rel if r[0] >= 5e-4]
+    good = sorted(grads) == sorted(grads_s) and len(outliers) <= 6 and rel[0][0] < 5e-2
+    print("%-4s step parameter gradients: %d tensors, %d above 5e-4 of their scale, worst %.3g at %s" %
+          ("ok" if good else "FAIL", len(grads_s), len(outliers), rel[0][0], rel[0][1]))
+    sys.exit(0 if (OK and good) else 1)
+
+
+if __name__ == "__main__":
+    main()

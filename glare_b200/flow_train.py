@@ -198,3 +198,44 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
         grads[p + ".fAffine.0.weight"] = torch.cat([grads.pop(p + ".fAffine.0.weight.z"), g_wpre[ci * 128:ci * 128 + 64]], dim=1).contiguous()
         grads[p + ".fFeatures.0.weight"] = g_wpre[ci * 128 + 64:ci * 128 + 128].contiguous()
     return nll, z, g_z, g_ft, g_mean, grads
+
+
+class FlowNLL(torch.autograd.Function):
+    """``nll = FlowNLL.apply(plan, sd, conv2d, kernels, keys, gt, ft, mean, *params)`` -- the objective of LLFlowVQGAN2.normal_flow as an
+    autograd node: the forward runs the library's forward AND backward once (the gradients are linear in the incoming gradient only through
+    a per-sample factor, so they are formed for L = nll.mean() and rescaled), the backward hands them out.  ``params`` are the flow
+    parameters in the order of ``keys`` (they only mark the graph edges; values are read from ``sd`` / ``plan``).  Gradients of
+    ``ft`` / ``mean`` continue into whatever produced them (the reference's ConEncoder1 under torch autograd).
+
+    Restriction: the incoming gradient must be the same for every sample (any mean / sum reduction of the per-sample nll), which is what
+    LLFlow_model.optimize_parameters does (LLFlow_model.py:215-232: ``nll.mean()``)."""
+
+    @staticmethod
+    def forward(ctx, plan, sd, conv2d, kernels, keys, gt, ft, mean, *params):
+        with torch.no_grad():
+            nll, z, g_gt, g_ft, g_mean, grads = nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=kernels)
+        ctx.batch = gt.shape[0]
+        ctx.save_for_backward(g_gt, g_ft, g_mean, *[grads[k] for k in keys])
+        return nll
+
+    @staticmethod
+    def backward(ctx, g_nll):
+        g_gt, g_ft, g_mean, *g_params = ctx.saved_tensors
+        if not bool((g_nll == g_nll[0]).all()):
+            raise RuntimeError("FlowNLL supports reductions that weigh every sample equally (nll.mean(), nll.sum())")
+        scale = g_nll[0] * ctx.batch                                     # stored gradients are those of nll.mean()
+        return (None, None, None, None, None, g_gt * scale, g_ft * scale, g_mean * scale) + tuple(g * scale for g in g_params)
+
+
+def flow_parameter_keys(sd, prefix="flowUpsamplerNet"):
+    """state-dict keys of the flow parameters that receive a gradient (the unused ``f`` nets of the noCoupling steps do not)"""
+    keys = []
+    for s in range(N_FLOW_STEPS):
+        p = "%s.layers.%d" % (prefix, s)
+        keys += [p + ".actnorm.bias", p + ".actnorm.logs", p + ".invconv.weight"]
+        if s not in NO_COUPLING_STEPS:
+            for net in ("fAffine", "fFeatures"):
+                q = "%s.affine.%s" % (p, net)
+                keys += [q + ".0.weight", q + ".0.actnorm.bias", q + ".0.actnorm.logs", q + ".2.weight", q + ".2.actnorm.bias",
+                         q + ".2.actnorm.logs", q + ".4.weight", q + ".4.bias", q + ".4.logs"]
+    return [k for k in keys if k in sd]

@@ -32,3 +32,29 @@ def test_flow_training_step_host_logic_matches_specification(sd_g):
     for k in grads_s:
         close(grads[k], grads_s[k], k)
         assert tuple(grads[k].shape) == tuple(sd_g[k].shape), k
+
+
+def test_stage2_step_through_autograd_node_matches_reference_gradients():
+    """BASELINE config 4 wiring: cond encoder under torch autograd (the oracle's restatement on the CPU) + the flow objective as the
+    FlowNLL autograd node (host logic of glare_b200/flow_train.py on the emulated kernels) against the REFERENCE's own forward and
+    backward (tests/golden/stage2.npz from LLFlowVQGAN2_arch.py:75-122): objective, and the gradients of flow and encoder parameters"""
+    import numpy as np
+    from conftest import load_golden
+    from glare_b200 import flow, flow_train, synth
+    from oracle import glare_oracle as O
+    g = load_golden("stage2")
+    sd2 = {k: v.clone().requires_grad_(True) for k, v in synth.synth_state_dict("netG_stage2", 0).items()}
+    gt, lr = torch.from_numpy(g["gt_latent"]), torch.from_numpy(g["lr"])
+    enc = O.cond_encoder(sd2, lr, "RRDB")                                   # differentiable torch ops
+    sd_val = {k: v.detach() for k, v in sd2.items()}
+    plan = flow.FlowPlan(sd_val, torch.device("cpu"))
+    keys = flow_train.flow_parameter_keys(sd_val)
+    conv = lambda x, wgt: F.conv2d(x, wgt, None, padding=1)                # noqa: E731
+    nll = flow_train.FlowNLL.apply(plan, sd_val, conv, TorchEmuKernels(sd_val), keys, gt, enc["cond_feat"], enc["color_map"], *[sd2[k] for k in keys])
+    assert np.allclose(nll.detach().numpy(), g["nll"], atol=1e-4, rtol=1e-5)
+    nll.mean().backward()
+    for key in list(g):
+        if key.startswith("grad."):
+            ref, got = torch.from_numpy(g[key]), sd2[key[5:]].grad
+            assert got is not None, key
+            assert float((got - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), key

@@ -6,7 +6,7 @@ Never imported by the package."""
 import torch
 import torch.nn.functional as F
 
-from glare_b200.flow import COUPLING_STEPS, N_FLOW_STEPS, NO_COUPLING_STEPS
+from glare_b200.flow import N_FLOW_STEPS, NO_COUPLING_STEPS
 from oracle import glare_oracle as O
 
 EPS = 0.0001

@@ -11,7 +11,13 @@
 // (flow.cu NET_* layout) read through the read-only cache or staged in shared memory -- plus the split-K fp32 GEMM of dcn_bwd.cu
 // (glare_dcnv2_bwd_weight_f32: grad[M][N] += a[P][M]^T b[P][N]) for every weight gradient.  The hoisted 64 -> 3072 conv over ft
 // (DESIGN.md "flow") gets its data gradient from the tensor-core conv path and its weight gradient from the same GEMM.
+#ifdef GLARE_CUDA_EMU
+#include "cuda_emu.h"        // tests/cuda_emu: the same kernel source executed on the host (CPU check of indexing and arithmetic)
+#define FB_LAUNCH(kern, grid, block, stream, ...) glare_emu::launch(kern, dim3(grid), dim3(block), __VA_ARGS__)
+#else
 #include "common.cuh"
+#define FB_LAUNCH(kern, grid, block, stream, ...) kern<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 
 namespace glare {
 
@@ -357,9 +363,9 @@ GLARE_API int glare_flow_train_net_fwd_f32(const float* pre, long long pre_ld, c
     if (B == 0) return GLARE_OK;
     if (!pre || !net || !n1 || !n2 || !hout) return GLARE_ERR_BAD_ARG;
     const long long P = (long long)B * h * w;
-    flow_tr_net1_kernel<<<FB_GRID(P, 128), 128, 0, stream>>>(pre, pre_ld, z1, z1_ld, net, P, h, w, n1);
-    flow_tr_net2_kernel<<<FB_GRID(P, 128), 128, 0, stream>>>(n1, net, P, n2);
-    flow_tr_net3_kernel<<<FB_GRID(P, 128), 128, 0, stream>>>(n2, net, P, h, w, hout);
+    FB_LAUNCH(flow_tr_net1_kernel, FB_GRID(P, 128), 128, stream, pre, pre_ld, z1, z1_ld, net, P, h, w, n1);
+    FB_LAUNCH(flow_tr_net2_kernel, FB_GRID(P, 128), 128, stream, n1, net, P, n2);
+    FB_LAUNCH(flow_tr_net3_kernel, FB_GRID(P, 128), 128, stream, n2, net, P, h, w, hout);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -371,7 +377,7 @@ GLARE_API int glare_flow_train_point_fwd_f32(const float* z_in, const float* pw_
     if (B == 0) return GLARE_OK;
     if (!z_in || !pw_fwd || !t || !u || !v) return GLARE_ERR_BAD_ARG;
     const long long P = (long long)B * h * w;
-    flow_tr_point_fwd_kernel<<<FB_GRID(P, 256), 256, 0, stream>>>(z_in, pw_fwd, hF, P, (long long)h * w, t, u, v);
+    FB_LAUNCH(flow_tr_point_fwd_kernel, FB_GRID(P, 256), 256, stream, z_in, pw_fwd, hF, P, (long long)h * w, t, u, v);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -384,8 +390,8 @@ GLARE_API int glare_flow_train_coupling_bwd_f32(int which, const float* g_in, co
     if (B == 0) return GLARE_OK;
     if (!g_in || !x || !hraw || !g_h || !g_x || (which == 1 && !g_z1)) return GLARE_ERR_BAD_ARG;
     const long long P = (long long)B * h * w;
-    if (which == 0) flow_tr_coupling_bwd_a_kernel<<<FB_GRID(P, 256), 256, 0, stream>>>(g_in, x, hraw, g_ld, P, (long long)h * w, g_h, g_x);
-    else flow_tr_coupling_bwd_f_kernel<<<FB_GRID(P, 256), 256, 0, stream>>>(g_in, g_z1, x, hraw, g_ld, P, g_h, g_x);
+    if (which == 0) FB_LAUNCH(flow_tr_coupling_bwd_a_kernel, FB_GRID(P, 256), 256, stream, g_in, x, hraw, g_ld, P, (long long)h * w, g_h, g_x);
+    else FB_LAUNCH(flow_tr_coupling_bwd_f_kernel, FB_GRID(P, 256), 256, stream, g_in, g_z1, x, hraw, g_ld, P, g_h, g_x);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -400,10 +406,10 @@ GLARE_API int glare_flow_train_net_bwd_f32(const float* g_h, const float* n1, co
     if (B == 0) return GLARE_OK;
     if (!g_h || !n1 || !n2 || !net || !g_a3 || !g_n2 || !g_a2 || !g_n1 || !g_a1) return GLARE_ERR_BAD_ARG;
     const long long P = (long long)B * h * w;
-    flow_tr_scale8_kernel<<<FB_GRID(P * 8, 256), 256, 0, stream>>>(g_h, net, P, g_a3);
-    flow_tr_net3_dgrad_kernel<<<FB_GRID(P, 128), 128, 0, stream>>>(g_a3, n2, net, P, h, w, g_n2);
-    flow_tr_net2_dgrad_kernel<<<FB_GRID(P, 128), 128, 0, stream>>>(g_n2, n1, net, P, g_a2, g_n1, g_a1, g_pre, pre_ld);
-    if (g_z1) flow_tr_net1_zgrad_kernel<<<FB_GRID(P, 128), 128, 0, stream>>>(g_a1, net, P, h, w, g_z1);
+    FB_LAUNCH(flow_tr_scale8_kernel, FB_GRID(P * 8, 256), 256, stream, g_h, net, P, g_a3);
+    FB_LAUNCH(flow_tr_net3_dgrad_kernel, FB_GRID(P, 128), 128, stream, g_a3, n2, net, P, h, w, g_n2);
+    FB_LAUNCH(flow_tr_net2_dgrad_kernel, FB_GRID(P, 128), 128, stream, g_n2, n1, net, P, g_a2, g_n1, g_a1, g_pre, pre_ld);
+    if (g_z1) FB_LAUNCH(flow_tr_net1_zgrad_kernel, FB_GRID(P, 128), 128, stream, g_a1, net, P, h, w, g_z1);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -415,7 +421,7 @@ GLARE_API int glare_flow_train_point_bwd_f32(const float* g_u, const float* t, c
     if (B == 0) return GLARE_OK;
     if (!g_u || !t || !pw_fwd || !g_z || !sums) return GLARE_ERR_BAD_ARG;
     const long long P = (long long)B * h * w;
-    flow_tr_point_bwd_kernel<<<FB_GRID(P, 256), 256, 0, stream>>>(g_u, t, pw_fwd, P, (long long)h * w, g_z, sums);
+    FB_LAUNCH(flow_tr_point_bwd_kernel, FB_GRID(P, 256), 256, stream, g_u, t, pw_fwd, P, (long long)h * w, g_z, sums);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -427,7 +433,7 @@ GLARE_API int glare_flow_train_im2col3x3_f32(const float* x, long long ldx, int 
     if (!x || !col) return GLARE_ERR_BAD_ARG;
     const long long P = (long long)B * h * w, total = P * 9 * C;
     const long long blocks = (total + 255) / 256;
-    flow_tr_im2col3x3_kernel<<<(unsigned)(blocks < 148LL * 32 ? blocks : 148LL * 32), 256, 0, stream>>>(x, ldx, C, relu, P, h, w, col);
+    FB_LAUNCH(flow_tr_im2col3x3_kernel, (unsigned)(blocks < 148LL * 32 ? blocks : 148LL * 32), 256, stream, x, ldx, C, relu, P, h, w, col);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -442,7 +448,7 @@ GLARE_API int glare_flow_train_colsum_f32(const float* a, long long lda, const f
     if (chunks > 148 * 4) chunks = 148 * 4;
     const long long per = (P + chunks - 1) / chunks;
     chunks = (P + per - 1) / per;
-    flow_tr_colsum_kernel<<<(unsigned)chunks, 256, 0, stream>>>(a, lda, b, ldb, C, P, per, out);
+    FB_LAUNCH(flow_tr_colsum_kernel, (unsigned)chunks, 256, stream, a, lda, b, ldb, C, P, per, out);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }

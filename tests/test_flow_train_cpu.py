@@ -58,3 +58,51 @@ def test_stage2_step_through_autograd_node_matches_reference_gradients():
             ref, got = torch.from_numpy(g[key]), sd2[key[5:]].grad
             assert got is not None, key
             assert float((got - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), key
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# The ACTUAL kernel source of csrc/flow_bwd.cu, compiled for the host through tests/cuda_emu/cuda_emu.h (threads of a block as OS
+# threads, __syncthreads / shuffles / atomics with their CUDA meaning) and driven through the same C ABI.
+def _build_host_kernels():
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+    import pytest
+    from conftest import ROOT
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    emu = os.path.join(ROOT, "tests", "cuda_emu")
+    out = os.path.join(emu, "_build", "libflow_bwd_emu.so")
+    src = os.path.join(ROOT, "glare_b200", "csrc", "flow_bwd.cu")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(emu, "cuda_emu.h"))):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-x", "c++", "-DGLARE_CUDA_EMU", "-I", emu, "-shared", "-fPIC", "-pthread", src, "-o", out])
+    return ctypes.CDLL(out)
+
+
+def test_flow_training_kernel_source_on_the_host(sd_g):
+    """every kernel of csrc/flow_bwd.cu (the very source nvcc compiles) executed on the CPU against the torch restatement of its contract, then the
+    whole training step through them against the specification -- what tests/test_zz_flow_train_gpu.py repeats on the GPU"""
+    import ctypes
+    from glare_b200 import _lib, flow_train
+    import flow_train_gpu_check as chk
+    host = _build_host_kernels()
+    emu = TorchEmuKernels(sd_g)
+
+    class HostCompiledKernels(flow_train.CudaKernels):
+        def __init__(self):
+            pass
+
+        def _call(self, name, *args):
+            fn = getattr(host, name)
+            fn.argtypes, fn.restype = _lib.SIGNATURES[name], ctypes.c_int
+            assert fn(*args, None) == 0, name
+
+        encode_chain = emu.encode_chain          # the forward chain kernels (csrc/flow.cu) are GPU-validated separately
+        gemm_tn = emu.gemm_tn                    # csrc/dcn_bwd.cu GEMM: GPU-validated by tests/test_dcn_gpu.py
+
+    chk.OK = True
+    conv = lambda x, wgt: F.conv2d(x, wgt, None, padding=1)               # noqa: E731
+    # small shape: the host shim spawns one OS thread per CUDA thread
+    assert chk.run_checks(torch.device("cpu"), HostCompiledKernels(), emu, conv, shape=(2, 4, 5))

@@ -1,0 +1,186 @@
+// Backward-pass kernels of the taming-style blocks of the condition encoder (stage-2 training, BASELINE config 4): the reference runs these
+// through torch autograd of encoder_decoder.py:29-35 (Normalize + nonlinearity), :117-137 (ResnetBlock), :168-192 (AttnBlock), :68-72 (Downsample).
+// The dense parts of the backward (data gradients of convolutions, the attention GEMMs) reuse the tensor-core conv path with transposed / flipped
+// operands and the split-K GEMM of dcn_bwd.cu; this file holds the memory-bound pieces in between (glare_b200/encoder_train.py is the host side):
+//   gn_bwd_stats / gn_bwd_apply : GroupNorm(32) (+ swish) backward -- per (sample, group) sums of dxhat and dxhat * xhat, dgamma / dbeta, then dx
+//   im2col_nhwc                 : [B,H,W,C] -> [B*Ho*Wo][k*k*C] (tap-major) for any 1x1 / 3x3, stride 1 / 2, low-side padding 0 / 1 conv: the
+//                                 operand of a weight gradient  dW[tap*C + c][co] = sum_p col[p][tap*C + c] * dY[p][co]
+//   attn_softmax_bwd            : dS = scale * P o (dP - rowsum(dP o P))
+// STATUS: like flow_bwd.cu -- verified on the CPU (the same source through tests/cuda_emu), not yet run on hardware.
+#ifdef GLARE_CUDA_EMU
+#include "cuda_emu.h"
+#define TE_LAUNCH(kern, grid, block, stream, ...) glare_emu::launch(kern, grid, dim3(block), __VA_ARGS__)
+#else
+#include "common.cuh"
+#define TE_LAUNCH(kern, grid, block, stream, ...) kern<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
+
+namespace glare {
+
+__device__ __forceinline__ float te_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// dn = dL/d(normalised, affine value n = xhat * gamma + beta) given dy = dL/d(output), output = swish ? n * sigmoid(n) : n
+__device__ __forceinline__ float te_dn(float n, float dy, int swish) {
+    if (!swish) return dy;
+    const float s = te_sigmoid(n);
+    return dy * (s * (1.0f + n * (1.0f - s)));
+}
+
+// stats [B][G][2] = (sum x, sum x^2) in fp64 as written by glare_gn_stats_nhwc_f32 -> mean, rstd of the group
+__device__ __forceinline__ void te_mean_rstd(const double* stats, int b, int G, int g, double cnt, float eps, float& mean, float& rstd) {
+    const double m = stats[((long long)b * G + g) * 2] / cnt;
+    double var = stats[((long long)b * G + g) * 2 + 1] / cnt - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// grid (chunks, B), 256 threads; x, gy NHWC [B][HW][C], C <= 1024, C % 4 == 0 handled per element (thread = one channel column walker)
+// sums [B][G][2] += (sum dxhat, sum dxhat * xhat) ; dgamma[C] += sum dn * xhat ; dbeta[C] += sum dn
+__global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ gy, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int swish,
+                                                           long long HW, int C, int G, double* __restrict__ sums, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta) {
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    const double cnt = (double)HW * cpg;
+    const long long per = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per, p1 = (p0 + per < HW) ? p0 + per : HW;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float mean, rstd;
+        te_mean_rstd(stats, b, G, g, cnt, eps, mean, rstd);
+        const float ga = __ldg(gamma + c), be = __ldg(beta + c);
+        float s1 = 0.f, s2 = 0.f, sg = 0.f, sb = 0.f;
+        for (long long p = p0; p < p1; ++p) {
+            const long long i = ((long long)b * HW + p) * C + c;
+            const float xh = (__ldg(x + i) - mean) * rstd;
+            const float dn = te_dn(fmaf(xh, ga, be), __ldg(gy + i), swish);
+            const float dxh = dn * ga;
+            s1 += dxh;
+            s2 = fmaf(dxh, xh, s2);
+            sg = fmaf(dn, xh, sg);
+            sb += dn;
+        }
+        atomicAdd(sums + ((long long)b * G + g) * 2, (double)s1);
+        atomicAdd(sums + ((long long)b * G + g) * 2 + 1, (double)s2);
+        atomicAdd(dgamma + c, sg);
+        atomicAdd(dbeta + c, sb);
+    }
+}
+
+// gx = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat * xhat))
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gy, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int swish,
+                                                           long long HW, int C, int G, const double* __restrict__ sums, float* __restrict__ gx) {
+    const int b = blockIdx.y;
+    const int cpg = C / G;
+    const double cnt = (double)HW * cpg;
+    const long long n = HW * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C), g = c / cpg;
+        float mean, rstd;
+        te_mean_rstd(stats, b, G, g, cnt, eps, mean, rstd);
+        const float m1 = (float)(sums[((long long)b * G + g) * 2] / cnt), m2 = (float)(sums[((long long)b * G + g) * 2 + 1] / cnt);
+        const long long i = (long long)b * n + e;
+        const float ga = __ldg(gamma + c);
+        const float xh = (__ldg(x + i) - mean) * rstd;
+        const float dxh = te_dn(fmaf(xh, ga, __ldg(beta + c)), __ldg(gy + i), swish) * ga;
+        gx[i] = rstd * (dxh - m1 - xh * m2);
+    }
+}
+
+// col[(b, oy, ox)][t * C + c] = x[b][oy * stride + t / k - pad][ox * stride + t % k - pad][c]  (zero outside the H x W image)
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, int k, int stride, int pad, int Ho,
+                                                          int Wo, float* __restrict__ col) {
+    const long long total = (long long)B * Ho * Wo * k * k * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int t = (int)(r % (k * k));
+        r /= (k * k);
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho), b = (int)(r / Ho);
+        const int y = oy * stride + t / k - pad, xx = ox * stride + t % k - pad;
+        col[i] = (y >= 0 && y < H && xx >= 0 && xx < W) ? __ldg(x + (((long long)b * H + y) * W + xx) * C + c) : 0.f;
+    }
+}
+
+// one row per block: dS[r][j] = scale * P[r][j] * (dP[r][j] - sum_j' dP[r][j'] P[r][j']), j < n_keys
+__global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ dP, long long ld, int n_keys,
+                                                               float scale, float* __restrict__ dS) {
+    __shared__ float s_red[8];
+    __shared__ float s_dot;
+    const long long row = blockIdx.x;
+    const float* p = P + row * ld;
+    const float* d = dP + row * ld;
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < n_keys; j += blockDim.x) acc = fmaf(__ldg(p + j), __ldg(d + j), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_red[i];
+        s_dot = t;
+    }
+    __syncthreads();
+    const float dot = s_dot;
+    float* o = dS + row * ld;
+    for (int j = threadIdx.x; j < n_keys; j += blockDim.x) o[j] = scale * __ldg(p + j) * (__ldg(d + j) - dot);
+}
+
+}  // namespace glare
+
+using namespace glare;
+
+// GroupNorm(G, eps) (+ swish) backward on NHWC fp32: stats = (sum x, sum x^2) per (sample, group) from glare_gn_stats_nhwc_f32;
+// sums [B][G][2] fp64 scratch (overwritten); gx NHWC; dgamma / dbeta [C] are ACCUMULATED into (caller zero-fills)
+GLARE_API int glare_gn_bwd_nhwc_f32(const float* x, const float* gy, const double* stats, const float* gamma, const float* beta, float eps, int swish,
+                                    int B, long long HW, int C, int G, double* sums, float* gx, float* dgamma, float* dbeta, cudaStream_t stream) {
+    if (B < 0 || HW < 0 || C <= 0 || G <= 0 || C % G != 0) return GLARE_ERR_BAD_ARG;
+    if (B == 0 || HW == 0) return GLARE_OK;
+    if (!x || !gy || !stats || !gamma || !beta || !sums || !gx || !dgamma || !dbeta || B > 65535) return GLARE_ERR_BAD_ARG;
+#ifndef GLARE_CUDA_EMU
+    GLARE_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * G, stream));
+#else
+    memset(sums, 0, sizeof(double) * 2 * (size_t)B * G);
+#endif
+    long long chunks = (HW + 63) / 64;
+    const long long cap = (148LL * 8 + B - 1) / B;
+    if (chunks > cap) chunks = cap;
+    TE_LAUNCH(gn_bwd_stats_kernel, dim3((unsigned)chunks, (unsigned)B), 256, stream, x, gy, stats, gamma, beta, eps, swish, HW, C, G, sums, dgamma, dbeta);
+    long long blocks = (HW * C + 1023) / 1024;
+    const long long cap2 = (148LL * 16 + B - 1) / B;
+    if (blocks > cap2) blocks = cap2;
+    TE_LAUNCH(gn_bwd_apply_kernel, dim3((unsigned)blocks, (unsigned)B), 256, stream, x, gy, stats, gamma, beta, eps, swish, HW, C, G, sums, gx);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// x NHWC [B,H,W,C] -> col [B*Ho*Wo][k*k*C]; k in {1, 3}, stride in {1, 2}, pad = low-side padding (high side: zero fill as far as the taps reach)
+GLARE_API int glare_im2col_nhwc_f32(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, float* col,
+                                    cudaStream_t stream) {
+    if (B < 0 || H <= 0 || W <= 0 || C <= 0 || (k != 1 && k != 3) || (stride != 1 && stride != 2) || pad < 0 || pad > 1 || Ho <= 0 || Wo <= 0)
+        return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!x || !col) return GLARE_ERR_BAD_ARG;
+    const long long total = (long long)B * Ho * Wo * k * k * C;
+    const long long blocks = (total + 255) / 256;
+    TE_LAUNCH(im2col_nhwc_kernel, dim3((unsigned)(blocks < 148LL * 32 ? blocks : 148LL * 32)), 256, stream, x, B, H, W, C, k, stride, pad, Ho, Wo, col);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// P, dP, dS [rows][ld] fp32 (first n_keys columns used): softmax backward of AttnBlock (encoder_decoder.py:181-183: w = softmax(scale * q k))
+GLARE_API int glare_attn_softmax_bwd_f32(const float* P, const float* dP, long long rows, long long ld, int n_keys, float scale, float* dS,
+                                         cudaStream_t stream) {
+    if (rows < 0 || n_keys <= 0 || ld < n_keys) return GLARE_ERR_BAD_ARG;
+    if (rows == 0) return GLARE_OK;
+    if (!P || !dP || !dS || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
+    TE_LAUNCH(attn_softmax_bwd_kernel, dim3((unsigned)rows), 256, stream, P, dP, ld, n_keys, scale, dS);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}

@@ -1,0 +1,302 @@
+"""Stage-2 training step on the library's kernels: condition encoder (ConEncoder1, ConditionEncoder.py:46-55 over the taming Encoder,
+encoder_decoder.py:406-442) forward with a tape, the flow objective through glare_b200/flow_train.py, and the backward pass of every block
+-- what the reference gets from torch autograd in LLFlow_model.optimize_parameters (LLFlow_model.py:215-232) around
+LLFlowVQGAN2.normal_flow (LLFlowVQGAN2_arch.py:75-122).
+
+Layering: ``Leaves`` are the kernel-level primitives (tensor-core conv path, split-K GEMM, GroupNorm / softmax forward and backward kernels);
+the block-level backward rules above them (how a conv's data gradient becomes a conv with the flipped, transposed filter, how a stride-2
+Downsample's becomes a conv over the zero-interleaved gradient, the five matmuls of the attention backward ...) are plain Python shared by
+every backend, so the CPU test (tests/test_encoder_train_cpu.py) runs exactly this logic with torch / host-compiled leaves against torch
+autograd of the oracle and the reference's own gradients.
+
+STATUS (round 1): CPU-verified; the new kernels (csrc/train_enc.cu) have not run on hardware yet.  Weight gradients use the fp32 split-K
+GEMM over an explicit im2col (correctness baseline; a tensor-core weight-gradient kernel is the follow-up).
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import flow_train
+
+
+def _nhwc(x):
+    """logical [B,C,H,W] -> contiguous [B,H,W,C] fp32"""
+    return x.float().permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+_WT = {}
+
+
+def _flipped_transposed(w):
+    """[Co,Ci,k,k] -> [Ci,Co,k,k] with the taps reversed; cached per weight version so that the conv path's packed-weight cache (keyed on the
+    tensor it is given) does not grow with every training step"""
+    key = (w.data_ptr(), w._version, tuple(w.shape))
+    if key not in _WT:
+        if len(_WT) > 4096:
+            _WT.clear()
+        _WT[key] = (w, w.flip(2, 3).transpose(0, 1).contiguous())
+    return _WT[key][1]
+
+
+class CudaLeaves:
+    """kernel-level primitives on the GPU (libglare_b200.so through glare_b200.ops / the dense backend)"""
+
+    def __init__(self, dense):
+        from . import ops
+        from ._lib import lib, stream
+        self.dense, self.ops, self.lib, self.stream = dense, ops, lib, stream
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _call(self, name, *args):
+        self.ops.check(getattr(self.lib(), name)(*args, self.stream()), name)
+
+    # dense
+    def conv_same(self, x, w, b=None):
+        return self.dense.conv2d(x, w, b, stride=1, padding=w.shape[2] // 2).float()
+
+    def conv_down(self, x, w, b=None):
+        y = self.dense.downsample_conv(x, w, b)
+        return (y if y is not None else F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)).float()
+
+    def attention(self, q, k, v):
+        return self.dense.attention(q, k, v).float()
+
+    def gemm_tn(self, a, b):
+        """a [P][M], b [P][N] -> a^T b [M][N] (fp32 split-K GEMM, csrc/dcn_bwd.cu)"""
+        P, M = a.shape
+        out = torch.zeros((M, b.shape[1]), device=a.device, dtype=torch.float32)
+        self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, b.shape[1], self._p(out))
+        return out
+
+    def gemm_nt(self, a, b, rows_hw):
+        """a [R][K], b [N][K] -> a b^T [R][N] on the tcgen05 GEMM path (R = rows_hw[0] * rows_hw[1], the tile walk needs the 2-D factorisation)"""
+        R, K = a.shape
+        N = b.shape[0]
+        padk = (-K) % 32
+        if padk:
+            a, b = F.pad(a, (0, padk)), F.pad(b, (0, padk))
+        mode = self.dense.mode
+        a_hi, a_lo = self.ops.conv_prep_act(mode, a.contiguous())
+        b_hi, b_lo = self.ops.conv_prep_act(mode, b.contiguous())
+        ldy = (N + 3) // 4 * 4
+        y = torch.empty((R, ldy), device=a.device, dtype=torch.float32)
+        self.ops.conv2d_nhwc_tc_ex(mode, a_hi, a_lo, b_hi, b_lo, y, 1, rows_hw[0], rows_hw[1], K + padk, N, ldy, 0)
+        return y[:, :N]
+
+    # memory-bound kernels
+    def im2col(self, x_nhwc, k, stride, pad, Ho, Wo):
+        B, H, W, C = x_nhwc.shape
+        col = torch.empty((B * Ho * Wo, k * k * C), device=x_nhwc.device, dtype=torch.float32)
+        self._call("glare_im2col_nhwc_f32", self._p(x_nhwc), B, H, W, C, k, stride, pad, Ho, Wo, self._p(col))
+        return col
+
+    def gn_fwd(self, x_nhwc, gamma, beta, swish):
+        B, H, W, C = x_nhwc.shape
+        stats = self.ops.gn_stats(x_nhwc, B, H * W, C)
+        y, _ = self.ops.gn_apply(1, x_nhwc, stats, gamma, beta, swish, B, H * W, C)
+        return y, stats
+
+    def gn_bwd(self, x_nhwc, gy_nhwc, stats, gamma, beta, swish):
+        B, H, W, C = x_nhwc.shape
+        sums = torch.empty((B, 32, 2), device=x_nhwc.device, dtype=torch.float64)
+        gx = torch.empty_like(x_nhwc)
+        dg, db = torch.zeros_like(gamma), torch.zeros_like(beta)
+        self._call("glare_gn_bwd_nhwc_f32", self._p(x_nhwc), self._p(gy_nhwc), self._p(stats), self._p(gamma), self._p(beta), ctypes.c_float(1e-6),
+                   1 if swish else 0, B, H * W, C, 32, self._p(sums), self._p(gx), self._p(dg), self._p(db))
+        return gx, dg, db
+
+    def softmax_rows(self, S, scale):
+        R, N = S.shape
+        ld = (N + 3) // 4 * 4                                              # the kernel reads / writes rows of a multiple of 4 floats
+        Sp = F.pad(S, (0, ld - N)).contiguous() if ld != N else S.contiguous()
+        P = torch.empty_like(Sp)
+        self.ops.attn_softmax_rows(1, Sp, R, ld, N, ld, scale, P, None, ld)
+        return P[:, :N].contiguous() if ld != N else P
+
+    def softmax_bwd(self, P, dP, scale):
+        dS = torch.empty_like(P)
+        self._call("glare_attn_softmax_bwd_f32", self._p(P), self._p(dP), P.shape[0], P.shape[1], P.shape[1], ctypes.c_float(scale), self._p(dS))
+        return dS
+
+
+# ---------------------------------------------------------------------------------------------------------------- tape
+class Tape:
+    """reverse-mode bookkeeping for the encoder's five block types; gradients of parameters are accumulated under their state-dict keys"""
+
+    def __init__(self, leaves, sd):
+        self.L, self.sd, self.ops, self.grads = leaves, sd, [], {}
+
+    def _acc(self, key, g):
+        self.grads[key] = self.grads[key] + g if key in self.grads else g
+
+    # -- convolution (encoder_decoder.py nn.Conv2d 3x3 / 1x1 stride 1, and Downsample :68-72) -----------------------------------------
+    def conv(self, p, x, down=False, need_gx=True):
+        w, b = self.sd[p + ".weight"], self.sd.get(p + ".bias")
+        y = self.L.conv_down(x, w, b) if down else self.L.conv_same(x, w, b)
+        self.ops.append(("conv", p, x, y, down, need_gx))
+        return y
+
+    def _conv_bwd(self, p, x, y, down, need_gx, gy):
+        w = self.sd[p + ".weight"]
+        Co, Ci, k, _ = w.shape
+        B, _, H, W = x.shape
+        Ho, Wo = y.shape[2], y.shape[3]
+        gyn = _nhwc(gy).reshape(-1, Co)
+        col = self.L.im2col(_nhwc(x), k, 2 if down else 1, 0 if down else k // 2, Ho, Wo)
+        G = self.L.gemm_tn(col, gyn)                                                   # [k*k*Ci][Co], tap-major rows
+        self._acc(p + ".weight", G.view(k * k, Ci, Co).permute(2, 1, 0).reshape(Co, Ci, k, k).contiguous())
+        if (p + ".bias") in self.sd:
+            self._acc(p + ".bias", self.L.gemm_tn(torch.ones((gyn.shape[0], 1), device=gyn.device), gyn)[0])
+        if not need_gx:
+            return None
+        w_t = _flipped_transposed(w)                                                  # transpose of a stride-1 'same' conv
+        if not down:
+            return self.L.conv_same(gy, w_t)
+        # stride 2 over the (0,1,0,1)-padded input: the data gradient is the stride-1 conv of the zero-interleaved output gradient,
+        # placed at odd positions of an (H + 1) x (W + 1) canvas, cropped back to H x W
+        canvas = torch.zeros((B, Co, H + 1, W + 1), device=gy.device, dtype=torch.float32)
+        canvas[:, :, 1:2 * Ho:2, 1:2 * Wo:2] = gy
+        return self.L.conv_same(canvas, w_t)[:, :, :H, :W]
+
+    # -- Normalize (+ swish) (encoder_decoder.py:29-35) -------------------------------------------------------------------------------
+    def gn(self, p, x, swish):
+        xn = _nhwc(x)
+        y, stats = self.L.gn_fwd(xn, self.sd[p + ".weight"], self.sd[p + ".bias"], swish)
+        self.ops.append(("gn", p, xn, stats, swish))
+        return _nchw(y)
+
+    def _gn_bwd(self, p, xn, stats, swish, gy):
+        gx, dg, db = self.L.gn_bwd(xn, _nhwc(gy), stats, self.sd[p + ".weight"], self.sd[p + ".bias"], swish)
+        self._acc(p + ".weight", dg)
+        self._acc(p + ".bias", db)
+        return _nchw(gx)
+
+    # -- AttnBlock core (encoder_decoder.py:176-187) -----------------------------------------------------------------------------------
+    def attention(self, q, k, v):
+        o = self.L.attention(q, k, v)
+        self.ops.append(("attn", q, k, v))
+        return o
+
+    def _attn_bwd(self, q, k, v, go):
+        B, C, h, w = q.shape
+        scale = float(int(C) ** (-0.5))
+        gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        hw = (h, w)
+        for b in range(B):
+            Q, K, V, dO = (_nhwc(t[b:b + 1]).reshape(h * w, C) for t in (q, k, v, go))
+            P = self.L.softmax_rows(self.L.gemm_nt(Q, K, hw).contiguous(), scale)       # w_ = softmax(scale q^T k)          :181-183
+            dP = self.L.gemm_nt(dO, V, hw).contiguous()                                 # h_[n] = sum_j w_[n][j] v[j]        :186-187
+            dS = self.L.softmax_bwd(P, dP, scale)
+            dV = self.L.gemm_nt(P.t().contiguous(), dO.t().contiguous(), hw)
+            dQ = self.L.gemm_nt(dS, K.t().contiguous(), hw)
+            dK = self.L.gemm_nt(dS.t().contiguous(), Q.t().contiguous(), hw)
+            for dst, src in ((gq, dQ), (gk, dK), (gv, dV)):
+                dst[b] = src.reshape(h, w, C).permute(2, 0, 1)
+        return gq, gk, gv
+
+
+class EncoderTrainer:
+    """forward with tape and backward of ConEncoder1; parameter names are the reference's state-dict keys under ``prefix`` ('RRDB')"""
+
+    def __init__(self, leaves, sd, prefix="RRDB"):
+        self.L, self.sd, self.p = leaves, sd, prefix
+
+    # forward graph: a list of nodes (kind, output id, input ids, payload); ids index self.vals
+    def forward(self, x):
+        self.tape = Tape(self.L, self.sd)
+        self.nodes, self.vals = [], [x]
+        sd, e = self.sd, self.p + ".encoder"
+        h = self._conv(e + ".conv_in", 0, need_gx=False)
+        for lvl in range(3):
+            for blk in range(2):
+                h = self._resnet("%s.down.%d.block.%d" % (e, lvl, blk), h)
+                if ("%s.down.%d.attn.%d.q.weight" % (e, lvl, blk)) in sd:
+                    h = self._attn("%s.down.%d.attn.%d" % (e, lvl, blk), h)
+            if lvl != 2:
+                h = self._conv("%s.down.%d.downsample.conv" % (e, lvl), h, down=True)
+        h = self._resnet(e + ".mid.block_1", h)
+        h = self._attn(e + ".mid.attn_1", h)
+        h = self._resnet(e + ".mid.block_2", h)
+        enc = self._conv(e + ".conv_out", self._gn(e + ".norm_out", h, True))
+        cond_pre = self._conv(self.p + ".cond_conv.0", enc)
+        color = self._conv(self.p + ".color_conv", enc)
+        self.out_ids = (cond_pre, color)
+        cond = torch.sigmoid(self.vals[cond_pre])                                       # ConditionEncoder.py:52
+        return {"cond_feat": cond, "color_map": self.vals[color]}
+
+    def _push(self, kind, val, inputs, payload):
+        self.vals.append(val)
+        self.nodes.append((kind, len(self.vals) - 1, inputs, payload))
+        return len(self.vals) - 1
+
+    def _conv(self, p, i, down=False, need_gx=True):
+        y = self.tape.conv(p, self.vals[i], down, need_gx)
+        return self._push("op", y, (i,), self.tape.ops[-1])
+
+    def _gn(self, p, i, swish):
+        y = self.tape.gn(p, self.vals[i], swish)
+        return self._push("op", y, (i,), self.tape.ops[-1])
+
+    def _add(self, i, j):
+        return self._push("add", self.vals[i] + self.vals[j], (i, j), None)
+
+    def _resnet(self, p, i):
+        """ResnetBlock.forward   encoder_decoder.py:117-137"""
+        h = self._conv(p + ".conv1", self._gn(p + ".norm1", i, True))
+        h = self._conv(p + ".conv2", self._gn(p + ".norm2", h, True))
+        s = self._conv(p + ".nin_shortcut", i) if (p + ".nin_shortcut.weight") in self.sd else i
+        return self._add(s, h)
+
+    def _attn(self, p, i):
+        """AttnBlock.forward   encoder_decoder.py:168-192"""
+        hn = self._gn(p + ".norm", i, False)
+        q, k, v = (self._conv(p + "." + n, hn) for n in "qkv")
+        o = self.tape.attention(self.vals[q], self.vals[k], self.vals[v])
+        o = self._push("op", o, (q, k, v), self.tape.ops[-1])
+        return self._add(i, self._conv(p + ".proj_out", o))
+
+    def backward(self, g_cond_feat, g_color_map):
+        """gradients of the two heads -> {state-dict key: gradient} of every encoder parameter"""
+        T = self.tape
+        cond_pre, color = self.out_ids
+        s = torch.sigmoid(self.vals[cond_pre])
+        g = {cond_pre: g_cond_feat * s * (1.0 - s), color: g_color_map}
+
+        def give(i, val):
+            if val is not None:
+                g[i] = g[i] + val if i in g else val
+
+        for kind, out, inputs, op in reversed(self.nodes):
+            gy = g.pop(out, None)
+            if gy is None:
+                continue
+            if kind == "add":
+                give(inputs[0], gy)
+                give(inputs[1], gy)
+            elif op[0] == "conv":
+                give(inputs[0], T._conv_bwd(op[1], op[2], op[3], op[4], op[5], gy))
+            elif op[0] == "gn":
+                give(inputs[0], T._gn_bwd(op[1], op[2], op[3], op[4], gy))
+            else:
+                for i, val in zip(inputs, T._attn_bwd(op[1], op[2], op[3], gy)):
+                    give(i, val)
+        return T.grads
+
+
+def stage2_step(sd, plan, lr, gt_latent, leaves, conv2d, flow_kernels=None):
+    """One stage-2 objective evaluation with all gradients: -> (nll [B], {state-dict key: dL/dparam}) for L = nll.mean().
+    ``lr`` preprocessed low-light input [B,3,H,W], ``gt_latent`` [B,3,H/4,W/4] (the frozen VQGAN's encoding of the ground truth)."""
+    enc = EncoderTrainer(leaves, sd)
+    heads = enc.forward(lr)
+    nll, _, _, g_ft, g_mean, grads = flow_train.nll_forward_backward(plan, sd, gt_latent, heads["cond_feat"], heads["color_map"], conv2d,
+                                                                     kernels=flow_kernels)
+    grads.update(enc.backward(g_ft, g_mean))
+    return nll, grads

@@ -224,6 +224,18 @@ int glare_flow_train_im2col3x3_f32(const float* x, long long ldx, int C, int rel
 int glare_flow_train_colsum_f32(const float* a, long long lda, const float* b, long long ldb, int C, long long P, float* out, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * (5b) Backward of the condition encoder's blocks for stage-2 training (autograd of encoder_decoder.py:29-35, 68-72, 117-137, 168-192):
+ *      GroupNorm (+ swish) backward, the im2col operand of a conv weight gradient (dW = col^T dY through glare_dcnv2_bwd_weight_f32), and the
+ *      softmax backward of AttnBlock.  Data gradients of the convolutions and the attention matmuls reuse the tensor-core conv path with
+ *      flipped / transposed operands (glare_b200/encoder_train.py).  CPU-verified, not yet run on hardware (csrc/train_enc.cu header).
+ * ---------------------------------------------------------------------------------------------------- */
+int glare_gn_bwd_nhwc_f32(const float* x, const float* gy, const double* stats, const float* gamma, const float* beta, float eps, int swish, int B,
+                          long long HW, int C, int G, double* sums, float* gx, float* dgamma, float* dbeta, cudaStream_t stream);
+int glare_im2col_nhwc_f32(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, float* col, cudaStream_t stream);
+int glare_attn_softmax_bwd_f32(const float* P, const float* dP, long long rows, long long ld, int n_keys, float scale, float* dS,
+                               cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * (7) Elementwise glue of the AFT decoder -- deformableDecoder_arch.py:587-590 (Mix: enc * m + h * (1 - m)) and :567
  *     (h + x_vq * mean(h) / mean(x_vq)): out[n][i] = a[n][i] * alpha[n * alpha_stride] + b[n][i] * beta[n * beta_stride], each product
  *     rounded before the sum like the reference's separate ATen kernels.  Strides 0 (one scalar) or 1 (per sample).

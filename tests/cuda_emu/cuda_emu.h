@@ -80,6 +80,12 @@ static inline float atomicAdd(float* p, float v) {
     *p = old + v;
     return old;
 }
+static inline double atomicAdd(double* p, double v) {
+    std::lock_guard<std::mutex> g(glare_emu::atomic_mutex());
+    const double old = *p;
+    *p = old + v;
+    return old;
+}
 
 namespace glare_emu {
 template <class K, class... A>

@@ -1,0 +1,63 @@
+"""Torch restatement of the kernel-level primitives ("leaves") of glare_b200/encoder_train.py.  TEST INFRASTRUCTURE (see flow_train_emu.py)."""
+import torch
+import torch.nn.functional as F
+
+
+class TorchLeaves:
+    def conv_same(self, x, w, b=None):
+        return F.conv2d(x, w, b, padding=w.shape[2] // 2)
+
+    def conv_down(self, x, w, b=None):
+        return F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+
+    def attention(self, q, k, v):
+        B, C, h, w = q.shape
+        s = torch.softmax(torch.bmm(q.reshape(B, C, h * w).permute(0, 2, 1), k.reshape(B, C, h * w)) * (int(C) ** (-0.5)), dim=2)
+        return torch.bmm(v.reshape(B, C, h * w), s.permute(0, 2, 1)).reshape(B, C, h, w)
+
+    def gemm_tn(self, a, b):
+        return a.t() @ b
+
+    def gemm_nt(self, a, b, rows_hw):
+        return a @ b.t()
+
+    def im2col(self, x_nhwc, k, stride, pad, Ho, Wo):
+        B, H, W, C = x_nhwc.shape
+        need_h, need_w = (Ho - 1) * stride + k - pad - H, (Wo - 1) * stride + k - pad - W
+        xp = F.pad(x_nhwc.permute(0, 3, 1, 2), (pad, max(need_w, 0), pad, max(need_h, 0)))
+        unf = F.unfold(xp, k, stride=stride).view(B, C, k * k, Ho * Wo)           # [B][c][t][pixel]
+        return unf.permute(0, 3, 2, 1).reshape(B * Ho * Wo, k * k * C).contiguous()
+
+    def gn_fwd(self, x_nhwc, gamma, beta, swish):
+        B, H, W, C = x_nhwc.shape
+        xg = x_nhwc.double().reshape(B, H * W, 32, C // 32)
+        stats = torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], dim=-1)          # [B][32][2] fp64: sum, sum of squares
+        y = F.group_norm(x_nhwc.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)
+        if swish:
+            y = y * torch.sigmoid(y)
+        return y.permute(0, 2, 3, 1).contiguous(), stats
+
+    def gn_bwd(self, x_nhwc, gy_nhwc, stats, gamma, beta, swish):
+        B, H, W, C = x_nhwc.shape
+        cnt = float(H * W * (C // 32))
+        mean = (stats[..., 0] / cnt)
+        rstd = 1.0 / torch.sqrt((stats[..., 1] / cnt - mean * mean).clamp_min(0) + 1e-6)
+        mean_c = mean.float().repeat_interleave(C // 32, dim=1).view(B, 1, 1, C)
+        rstd_c = rstd.float().repeat_interleave(C // 32, dim=1).view(B, 1, 1, C)
+        xh = (x_nhwc - mean_c) * rstd_c
+        n = xh * gamma + beta
+        if swish:
+            s = torch.sigmoid(n)
+            dn = gy_nhwc * (s * (1 + n * (1 - s)))
+        else:
+            dn = gy_nhwc
+        dxh = dn * gamma
+        g = lambda t: t.reshape(B, H * W, 32, C // 32).mean(dim=(1, 3)).repeat_interleave(C // 32, dim=1).view(B, 1, 1, C)    # noqa: E731
+        gx = rstd_c * (dxh - g(dxh) - xh * g(dxh * xh))
+        return gx, (dn * xh).sum(dim=(0, 1, 2)), dn.sum(dim=(0, 1, 2))
+
+    def softmax_rows(self, S, scale):
+        return torch.softmax(S * scale, dim=1)
+
+    def softmax_bwd(self, P, dP, scale):
+        return scale * P * (dP - (dP * P).sum(dim=1, keepdim=True))

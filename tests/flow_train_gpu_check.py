@@ -129,8 +129,35 @@ def main():
     sd_d = {k: v.to(dev) for k, v in synth.synth_state_dict("netG", 0).items()}
     from glare_b200.dense import make_dense
     dense = make_dense("auto")
-    ok = run_checks(dev, flow_train.CudaKernels(), TorchEmuKernels(sd_d), lambda x, wgt: dense.conv2d(x, wgt).float())
+    conv = lambda x, wgt: dense.conv2d(x, wgt).float()                  # noqa: E731
+    ok = run_checks(dev, flow_train.CudaKernels(), TorchEmuKernels(sd_d), conv)
+    ok = encoder_step_check(dev, dense, conv) and ok
     sys.exit(0 if ok else 1)
+
+
+def encoder_step_check(dev, dense, conv):
+    """the whole stage-2 step (tape over ConEncoder1 + flow objective) on the GPU kernels against the same host logic on torch primitives (CPU),
+    which tests/test_encoder_train_cpu.py ties to autograd and to the reference's gradients"""
+    import torch.nn.functional as F
+    from encoder_train_emu import TorchLeaves
+    from glare_b200 import encoder_train
+    sd = synth.synth_state_dict("netG_stage2", 0)
+    gen = torch.Generator().manual_seed(5)
+    gt = torch.randn((2, 3, 8, 8), generator=gen)
+    lr = synth.preprocess(torch.rand((2, 3, 32, 32), generator=gen))
+    with torch.no_grad():
+        nll_c, grads_c = encoder_train.stage2_step(sd, flow.FlowPlan(sd, torch.device("cpu")), lr, gt, TorchLeaves(),
+                                                   lambda x, wgt: F.conv2d(x, wgt, None, padding=1), flow_kernels=TorchEmuKernels(sd))
+        sd_d = {k: v.to(dev) for k, v in sd.items()}
+        nll_g, grads_g = encoder_train.stage2_step(sd_d, flow.FlowPlan(sd, dev), lr.to(dev), gt.to(dev), encoder_train.CudaLeaves(dense), conv)
+        torch.cuda.synchronize()
+    check("stage-2 step nll", nll_g, nll_c, 1e-4)
+    rel = sorted(((float((grads_g[k].cpu() - grads_c[k]).abs().max()) / max(float(grads_c[k].abs().max()), 1e-6), k) for k in grads_c), reverse=True)
+    outliers = [r for r in rel if r[0] >= 2e-3]
+    good = sorted(grads_g) == sorted(grads_c) and len(outliers) <= 8 and rel[0][0] < 5e-2
+    print("%-4s stage-2 step gradients: %d tensors, %d above 2e-3 of their scale, worst %.3g at %s" %
+          ("ok" if good else "FAIL", len(grads_c), len(outliers), rel[0][0], rel[0][1]))
+    return OK and good
 
 
 if __name__ == "__main__":

@@ -1,0 +1,106 @@
+"""CPU: the stage-2 training step of glare_b200/encoder_train.py (tape over ConEncoder1 + the flow objective of flow_train.py).
+  * block-level backward rules and the whole step, with torch restatements of the kernel-level primitives, against torch autograd of the
+    oracle for EVERY parameter and against the reference's own gradients (tests/golden/stage2.npz);
+  * the new kernels of csrc/train_enc.cu: the very source nvcc compiles, executed on the host (tests/cuda_emu), against those restatements."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT, load_golden
+from encoder_train_emu import TorchLeaves
+from flow_train_emu import TorchEmuKernels
+
+
+def _step(sd, lr, gt, leaves):
+    from glare_b200 import encoder_train, flow
+    plan = flow.FlowPlan(sd, torch.device("cpu"))
+    conv = lambda x, wgt: F.conv2d(x, wgt, None, padding=1)               # noqa: E731
+    with torch.no_grad():
+        return encoder_train.stage2_step(sd, plan, lr, gt, leaves, conv, flow_kernels=TorchEmuKernels(sd))
+
+
+def test_stage2_step_matches_autograd_and_reference():
+    from glare_b200 import synth
+    from oracle import glare_oracle as O
+    g = load_golden("stage2")
+    sd = synth.synth_state_dict("netG_stage2", 0)
+    gt, lr = torch.from_numpy(g["gt_latent"]), torch.from_numpy(g["lr"])
+    nll, grads = _step(sd, lr, gt, TorchLeaves())
+    assert np.allclose(nll.numpy(), g["nll"], atol=1e-4, rtol=1e-5)
+    # the reference's own gradients (flow and encoder parameters)
+    for key in list(g):
+        if key.startswith("grad."):
+            ref = torch.from_numpy(g[key])
+            assert float((grads[key[5:]] - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), key
+    # every parameter against torch autograd of the oracle
+    sda = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    _, nll_a = O.stage2_nll(sda, gt, lr)
+    nll_a.mean().backward()
+    checked = 0
+    for k, v in sda.items():
+        if v.grad is None:
+            assert k not in grads or float(grads[k].abs().max()) == 0.0, k
+            continue
+        assert k in grads, k
+        assert grads[k].shape == v.shape, k
+        sc = max(float(v.grad.abs().max()), 1e-6)
+        assert float((grads[k] - v.grad).abs().max()) <= 1e-3 * sc + 1e-7, (k, float((grads[k] - v.grad).abs().max()), sc)
+        checked += 1
+    assert checked > 600
+
+
+def _host_lib():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    emu = os.path.join(ROOT, "tests", "cuda_emu")
+    out = os.path.join(emu, "_build", "libtrain_enc_emu.so")
+    src = os.path.join(ROOT, "glare_b200", "csrc", "train_enc.cu")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(emu, "cuda_emu.h"))):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-x", "c++", "-DGLARE_CUDA_EMU", "-I", emu, "-shared", "-fPIC", "-pthread", src, "-o", out])
+    return ctypes.CDLL(out)
+
+
+def test_train_enc_kernel_source_on_the_host():
+    from glare_b200 import _lib, encoder_train
+    host = _host_lib()
+
+    class HostLeaves(encoder_train.CudaLeaves):
+        def __init__(self):
+            pass
+
+        def _call(self, name, *args):
+            fn = getattr(host, name)
+            fn.argtypes, fn.restype = _lib.SIGNATURES[name], ctypes.c_int
+            assert fn(*args, None) == 0, name
+
+    H, T = HostLeaves(), TorchLeaves()
+    gen = torch.Generator().manual_seed(8)
+
+    def close(a, b, what, tol=2e-5):
+        sc = max(float(b.abs().max()), 1e-6)
+        assert a.shape == b.shape and float((a - b).abs().max()) <= tol * sc, (what, float((a - b).abs().max()), sc)
+
+    # GroupNorm (+ swish) backward
+    for C, swish in ((64, True), (128, False)):
+        x = torch.randn((2, 3, 4, C), generator=gen) * 1.5 + 0.7
+        gy = torch.randn((2, 3, 4, C), generator=gen)
+        gamma, beta = 1 + 0.2 * torch.randn(C, generator=gen), 0.1 * torch.randn(C, generator=gen)
+        _, stats = T.gn_fwd(x, gamma, beta, swish)
+        for nm, a, b in zip(("gx", "dgamma", "dbeta"), H.gn_bwd(x, gy, stats, gamma, beta, swish), T.gn_bwd(x, gy, stats, gamma, beta, swish)):
+            close(a, b, "gn_bwd %s C=%d" % (nm, C))
+    # im2col for every conv geometry of the encoder
+    for (Hh, Ww, C, k, stride, pad) in ((5, 6, 8, 3, 1, 1), (5, 6, 8, 1, 1, 0), (6, 8, 4, 3, 2, 0), (7, 5, 4, 3, 2, 0)):
+        x = torch.randn((2, Hh, Ww, C), generator=gen)
+        Ho, Wo = (Hh, Ww) if stride == 1 else ((Hh + 1 - 3) // 2 + 1, (Ww + 1 - 3) // 2 + 1)
+        close(H.im2col(x, k, stride, pad, Ho, Wo), T.im2col(x, k, stride, pad, Ho, Wo), "im2col %s" % ((Hh, Ww, C, k, stride, pad),), 0.0)
+    # softmax backward
+    P = torch.softmax(torch.randn((9, 20), generator=gen), dim=1)
+    dP = torch.randn((9, 20), generator=gen)
+    close(H.softmax_bwd(P, dP, 0.3), T.softmax_bwd(P, dP, 0.3), "softmax_bwd")

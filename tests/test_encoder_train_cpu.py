@@ -104,3 +104,43 @@ def test_train_enc_kernel_source_on_the_host():
     P = torch.softmax(torch.randn((9, 20), generator=gen), dim=1)
     dP = torch.randn((9, 20), generator=gen)
     close(H.softmax_bwd(P, dP, 0.3), T.softmax_bwd(P, dP, 0.3), "softmax_bwd")
+
+
+def test_cuda_leaves_glue_with_fake_ops():
+    """the padding / leading-dimension logic of encoder_train.CudaLeaves.gemm_nt and .softmax_rows, driven through stand-ins for the two library
+    calls they wrap that enforce the C entry points' argument checks (csrc/conv_tc.cu conv_tc_launch, csrc/attn.cu glare_attn_softmax_rows)"""
+    from glare_b200 import encoder_train
+
+    class FakeOps:
+        @staticmethod
+        def conv_prep_act(mode, x):
+            assert mode == 1 and x.is_contiguous()
+            return x, None
+
+        @staticmethod
+        def conv2d_nhwc_tc_ex(mode, x_hi, x_lo, w_hi, w_lo, y, B, H, W, Cin, Cout, ldy, w_batch_stride, bias=None, ksize=1):
+            assert Cin % 32 == 0 and ldy >= Cout and ldy % 4 == 0 and not (Cout % 4 != 0 and ldy == Cout) and w_batch_stride == 0
+            assert x_hi.numel() == B * H * W * Cin and w_hi.numel() == Cout * Cin and y.numel() == B * H * W * ldy
+            y.view(-1, ldy)[:, :Cout] = x_hi.reshape(-1, Cin) @ w_hi.reshape(Cout, Cin).t()
+
+        @staticmethod
+        def attn_softmax_rows(mode, S, rows, lds, n_keys, n_pad, scale, out_hi, out_lo, ldp):
+            assert mode == 1 and n_pad >= n_keys and n_pad % 4 == 0 and lds % 4 == 0 and ldp % 4 == 0 and lds >= n_keys and ldp >= n_pad and scale > 0
+            assert S.is_contiguous() and S.numel() == rows * lds and out_hi.numel() == rows * ldp
+            out_hi.view(rows, ldp).zero_()
+            out_hi.view(rows, ldp)[:, :n_keys] = torch.softmax(S.view(rows, lds)[:, :n_keys] * scale, dim=1)
+
+    class FakeDense:
+        mode = 1
+
+    L = encoder_train.CudaLeaves.__new__(encoder_train.CudaLeaves)
+    L.dense, L.ops = FakeDense(), FakeOps()
+    gen = torch.Generator().manual_seed(3)
+    for (h, w, K, N) in ((4, 5, 20, 20), (4, 5, 64, 7), (3, 3, 9, 64), (8, 8, 512, 64)):
+        a, b = torch.randn((h * w, K), generator=gen), torch.randn((N, K), generator=gen)
+        got = L.gemm_nt(a, b, (h, w))
+        assert got.shape == (h * w, N) and torch.allclose(got, a @ b.t(), atol=1e-5)
+    for (R, N) in ((6, 20), (5, 7), (3, 64)):
+        S = torch.randn((R, N), generator=gen)
+        got = L.softmax_rows(S, 0.25)
+        assert got.shape == (R, N) and got.is_contiguous() and torch.allclose(got, torch.softmax(S * 0.25, dim=1), atol=1e-6)

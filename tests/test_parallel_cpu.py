@@ -51,3 +51,29 @@ def test_enhance_sharded_gloo_world2(n):
     [p.join(timeout=60) for p in procs]
     assert all(ok for _, _, ok in res)
     assert res[0][1] + res[1][1] == n and res[0][1] - res[1][1] in (0, 1)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from glare_b200.parallel import allreduce_gradients
+    g = {"b.weight": torch.full((3, 2), float(rank + 1)), "a.bias": torch.arange(4, dtype=torch.float32) * (rank + 1)}
+    out = allreduce_gradients(g)
+    ok = torch.allclose(out["b.weight"], torch.full((3, 2), 1.5)) and torch.allclose(out["a.bias"], torch.arange(4, dtype=torch.float32) * 1.5)
+    q.put((rank, bool(ok), tuple(out["b.weight"].shape)))
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_gloo_world2():
+    """stage-2 data parallelism: one flat all-reduce averages the per-rank gradient dictionaries"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(ok and shape == (3, 2) for _, ok, shape in res)

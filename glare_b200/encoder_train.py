@@ -50,6 +50,8 @@ class CudaLeaves:
         from . import ops
         from ._lib import lib, stream
         self.dense, self.ops, self.lib, self.stream = dense, ops, lib, stream
+        import os
+        self.wgrad_tc = bool(os.environ.get("GLARE_WGRAD_TC")) and getattr(dense, "mode", None) == 4
 
     @staticmethod
     def _p(t):
@@ -72,9 +74,34 @@ class CudaLeaves:
     def gemm_tn(self, a, b):
         """a [P][M], b [P][N] -> a^T b [M][N] (fp32 split-K GEMM, csrc/dcn_bwd.cu)"""
         P, M = a.shape
+        if self.wgrad_tc and M >= 128 and b.shape[1] >= 32:
+            return self.gemm_tn_tc(a, b)
         out = torch.zeros((M, b.shape[1]), device=a.device, dtype=torch.float32)
         self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, b.shape[1], self._p(out))
         return out
+
+    def gemm_tn_tc(self, a, b, chunk=8192):
+        """a [P][M], b [P][N] -> a^T b [M][N] on the tensor cores: the reduction over the P pixels is cut into chunks that become the BATCH of one
+        tcgen05 GEMM launch with per-sample weights (sample c: rows = a_c^T [M][chunk], weights = b_c^T [N][chunk]), the per-chunk products are
+        summed in fp32.  Opt-in (GLARE_WGRAD_TC=1) until the batched-weights path of conv_tc has a recorded hardware run; the fp32 split-K GEMM
+        (gemm_tn) is the default."""
+        P, M = a.shape
+        N = b.shape[1]
+        chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
+        nch = (P + chunk - 1) // chunk
+        pad = nch * chunk - P
+        if pad:
+            a, b = F.pad(a, (0, 0, 0, pad)), F.pad(b, (0, 0, 0, pad))
+        at = a.view(nch, chunk, M).transpose(1, 2).contiguous()             # [nch][M][chunk]
+        bt = b.view(nch, chunk, N).transpose(1, 2).contiguous()             # [nch][N][chunk]
+        mode = self.dense.mode
+        a_hi, a_lo = self.ops.conv_prep_act(mode, at)
+        b_hi, b_lo = self.ops.conv_prep_act(mode, bt)
+        rows_w = 16 if M % 16 == 0 else 1
+        ldy = (N + 3) // 4 * 4
+        y = torch.empty((nch, M, ldy), device=a.device, dtype=torch.float32)
+        self.ops.conv2d_nhwc_tc_ex(mode, a_hi, a_lo, b_hi, b_lo, y, nch, M // rows_w, rows_w, chunk, N, ldy, N * chunk)
+        return y[:, :, :N].sum(dim=0)
 
     def gemm_nt(self, a, b, rows_hw):
         """a [R][K], b [N][K] -> a b^T [R][N] on the tcgen05 GEMM path (R = rows_hw[0] * rows_hw[1], the tile walk needs the 2-D factorisation)"""

@@ -152,6 +152,11 @@ def encoder_step_check(dev, dense, conv):
         nll_g, grads_g = encoder_train.stage2_step(sd_d, flow.FlowPlan(sd, dev), lr.to(dev), gt.to(dev), encoder_train.CudaLeaves(dense), conv)
         torch.cuda.synchronize()
     check("stage-2 step nll", nll_g, nll_c, 1e-4)
+    # opt-in tensor-core weight gradient (chunked reduction as the batch of one GEMM with per-sample weights) against fp64
+    Lg = encoder_train.CudaLeaves(dense)
+    for (Pp, M, N) in ((5000, 1152, 128), (777, 128, 64)):
+        a, b = torch.randn((Pp, M), generator=gen).to(dev), torch.randn((Pp, N), generator=gen).to(dev)
+        check("gemm_tn_tc %dx%dx%d" % (Pp, M, N), Lg.gemm_tn_tc(a, b, chunk=1024), (a.double().t() @ b.double()).float(), 1e-4)
     rel = sorted(((float((grads_g[k].cpu() - grads_c[k]).abs().max()) / max(float(grads_c[k].abs().max()), 1e-6), k) for k in grads_c), reverse=True)
     # first hardware run of a 40-layer backward through fp32-grade (bf16x3) tensor-core convs against fp32 CPU arithmetic: report the error
     # distribution, require it to be small for all but a few tensors (isolated ReLU sign flips of the flow nets, see run_checks)

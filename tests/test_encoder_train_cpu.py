@@ -119,9 +119,14 @@ def test_cuda_leaves_glue_with_fake_ops():
 
         @staticmethod
         def conv2d_nhwc_tc_ex(mode, x_hi, x_lo, w_hi, w_lo, y, B, H, W, Cin, Cout, ldy, w_batch_stride, bias=None, ksize=1):
-            assert Cin % 32 == 0 and ldy >= Cout and ldy % 4 == 0 and not (Cout % 4 != 0 and ldy == Cout) and w_batch_stride == 0
-            assert x_hi.numel() == B * H * W * Cin and w_hi.numel() == Cout * Cin and y.numel() == B * H * W * ldy
-            y.view(-1, ldy)[:, :Cout] = x_hi.reshape(-1, Cin) @ w_hi.reshape(Cout, Cin).t()
+            assert Cin % 32 == 0 and ldy >= Cout and ldy % 4 == 0 and not (Cout % 4 != 0 and ldy == Cout)
+            assert w_batch_stride in (0, Cout * Cin) and x_hi.numel() == B * H * W * Cin and y.numel() == B * H * W * ldy
+            if w_batch_stride == 0:
+                assert w_hi.numel() == Cout * Cin
+                y.view(-1, ldy)[:, :Cout] = x_hi.reshape(-1, Cin) @ w_hi.reshape(Cout, Cin).t()
+            else:                                   # per-sample weights: sample n uses w + n * w_batch_stride
+                assert w_hi.numel() == B * Cout * Cin
+                y.view(B, H * W, ldy)[:, :, :Cout] = torch.bmm(x_hi.reshape(B, H * W, Cin), w_hi.reshape(B, Cout, Cin).transpose(1, 2))
 
         @staticmethod
         def attn_softmax_rows(mode, S, rows, lds, n_keys, n_pad, scale, out_hi, out_lo, ldp):
@@ -140,6 +145,10 @@ def test_cuda_leaves_glue_with_fake_ops():
         a, b = torch.randn((h * w, K), generator=gen), torch.randn((N, K), generator=gen)
         got = L.gemm_nt(a, b, (h, w))
         assert got.shape == (h * w, N) and torch.allclose(got, a @ b.t(), atol=1e-5)
+    for (P, M, N, chunk) in ((200, 128, 32, 64), (97, 144, 40, 8192), (64, 9, 64, 32)):
+        a, b = torch.randn((P, M), generator=gen), torch.randn((P, N), generator=gen)
+        got = L.gemm_tn_tc(a, b, chunk=chunk)
+        assert got.shape == (M, N) and torch.allclose(got, a.t() @ b, atol=1e-4)
     for (R, N) in ((6, 20), (5, 7), (3, 64)):
         S = torch.randn((R, N), generator=gen)
         got = L.softmax_rows(S, 0.25)

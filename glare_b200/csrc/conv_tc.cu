@@ -85,6 +85,14 @@ struct ConvCfg {
     static constexpr int HALO_STAGES_RAW = SMEM_BUDGET / HALO_STAGE_BYTES;
     static constexpr int HALO_STAGES = HALO_STAGES_RAW > 8 ? 8 : HALO_STAGES_RAW;
     static constexpr int HALO_SMEM_DYN = HALO_STAGES * HALO_STAGE_BYTES + STAGING_BYTES + 1024;
+    // RING2 variant (opt-in, GLARE_CONV_RING2=1; not yet run on hardware): the same filter-row patch staging for the 256-wide N tile, where one
+    // stage per filter row (patch + three 16 KB weight slabs = 68 KB) would leave only two stages.  Activation patches and weight slabs get their
+    // own rings instead: R2_A_SLOTS patches (one per filter row and K chunk) and R2_B_SLOTS slabs (one per tap and K chunk).
+    static constexpr int R2_A_SLOTS = 3;
+    static constexpr int R2_B_RAW = (SMEM_BUDGET - R2_A_SLOTS * HALO_A_BYTES - 64) / B_BYTES;
+    static constexpr int R2_B_SLOTS = R2_B_RAW > 8 ? 8 : R2_B_RAW;
+    static constexpr int R2_RING_BYTES = R2_A_SLOTS * HALO_A_BYTES + R2_B_SLOTS * B_BYTES;
+    static constexpr int R2_SMEM_DYN = R2_RING_BYTES + STAGING_BYTES + 64 + 1024;      // + 64: the patch ring's mbarriers live behind the staging tiles
 };
 
 template <bool TF32, bool PAIR>
@@ -101,7 +109,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t da, uint64_t db, uint32
 // and HALF of the weight rows, all TMA loads signal the leader's barrier, the leader's MMA thread issues
 // tcgen05.mma.cta_group::2 (M = 256) which reads both halves and accumulates each CTA's 128 rows into that CTA's TMEM.
 // Weight staging traffic and weight shared-memory reads per CTA are halved -- the binding resources of the fp32-grade modes.
-template <int MODE, int BN, int CM, bool HALO = false>
+template <int MODE, int BN, int CM, bool HALO = false, bool RING2 = false>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -110,8 +118,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool PAIR = CM == 2, MCAST = CM == 1;
     using Cfg = ConvCfg<MODE, BN, PAIR>;
     static_assert(!HALO || (MODE == 4 && CM == 2 && BN <= 128), "halo staging: mode 4, CTA pair, BN <= 128");
+    static_assert(!RING2 || (MODE == 4 && CM == 2 && !HALO && Cfg::R2_B_SLOTS >= 4), "two-ring staging: mode 4, CTA pair");
     constexpr int STAGES = HALO ? Cfg::HALO_STAGES : Cfg::STAGES;
     constexpr int STAGE_BYTES = HALO ? Cfg::HALO_STAGE_BYTES : Cfg::STAGE_BYTES;
+    constexpr int RING_BYTES = RING2 ? Cfg::R2_RING_BYTES : STAGES * STAGE_BYTES;        // operand rings; the epilogue staging tiles follow
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t s_tmem_base;
@@ -129,9 +139,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_prefetch_desc(&tmBlo);
         }
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < (RING2 ? Cfg::R2_B_SLOTS : STAGES); ++s) {
             mbar_init(&full_bar[s], PAIR ? 2 : 1);                   // pair: one arrival per CTA's producer, on the leader's barrier
             mbar_init(&empty_bar[s], MCAST ? 2 : 1);                 // multicast: one tcgen05.commit per CTA of the cluster
+        }
+        if (RING2) {
+            // full_bar / empty_bar above serve the weight-slab ring; the patch ring's barriers sit behind the epilogue staging tiles
+            uint64_t* a_bars = reinterpret_cast<uint64_t*>(smem_al + RING_BYTES + Cfg::STAGING_BYTES);
+#pragma unroll
+            for (int s = 0; s < Cfg::R2_A_SLOTS; ++s) {
+                mbar_init(&a_bars[s], 2);                                // full: one arrival per CTA's producer
+                mbar_init(&a_bars[4 + s], 1);                            // empty
+            }
         }
         mbar_init(&tmem_full_bar[0], 1);
         mbar_init(&tmem_full_bar[1], 1);
@@ -150,6 +169,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = s_tmem_base;
 
     const int k_iters = a.ntaps * a.kchunks;
+    uint64_t* const a_full = reinterpret_cast<uint64_t*>(smem_al + RING_BYTES + Cfg::STAGING_BYTES);   // RING2 only
+    uint64_t* const a_empty = a_full + 4;
     const int cl_rank = CL > 1 ? (int)cluster_cta_rank() : 0;
     const int cl_id = blockIdx.x / CL, n_cl = gridDim.x / CL;
     const int tiles_xy = a.tiles_y * a.tiles_x;
@@ -169,6 +190,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int w = cl_id; w < a.total_tiles; w += n_cl) {
                 GLARE_DECODE_WORK(w)
                 const int y0 = ty * a.TH * a.stride + a.tap_dy0, x0 = tx * a.TW * a.stride + a.tap_dx0;
+                if (RING2) {
+                    const int half = cl_rank * (BN / 2);
+                    uint8_t* const ring_b = smem_al + Cfg::R2_A_SLOTS * Cfg::HALO_A_BYTES;
+                    for (int dy = 0; dy < 3; ++dy) {
+                        for (int kc = 0; kc < a.kchunks; ++kc, ++it) {           // it counts patches; slabs are 3 * it + dx
+                            const int sa = it % Cfg::R2_A_SLOTS;
+                            mbar_wait_bounded(&a_empty[sa], ((it / Cfg::R2_A_SLOTS) & 1) ^ 1);
+                            if (cl_rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * Cfg::HALO_A_BYTES);
+                            else mbar_arrive_cluster(&a_full[sa], 0);
+                            tma_load_4d_2sm(smem_al + (size_t)sa * Cfg::HALO_A_BYTES, &tmA, &a_full[sa], 2 * kc * Cfg::BKE, x0, y0 + dy, n);
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const uint32_t ib = 3u * it + dx;
+                                const int sb = ib % Cfg::R2_B_SLOTS;
+                                mbar_wait_bounded(&empty_bar[sb], ((ib / Cfg::R2_B_SLOTS) & 1) ^ 1);
+                                if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[sb], 2 * Cfg::B_BYTES);
+                                else mbar_arrive_cluster(&full_bar[sb], 0);
+                                tma_load_3d_2sm(ring_b + (size_t)sb * Cfg::B_BYTES, &tmB, &full_bar[sb],
+                                                2 * ((dy * 3 + dx) * a.Cin + kc * Cfg::BKE), nb * BN + half, 0);
+                            }
+                        }
+                    }
+                    continue;
+                }
                 if (HALO) {
                     const int wn = a.w_batched ? (n < a.B ? n : a.B - 1) : 0;
                     const int half = cl_rank * (BN / 2);
@@ -242,6 +287,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait_bounded(&tmem_empty_bar[as], aph ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
+                if (RING2) {
+                    const uint32_t ring_b = smem_base + Cfg::R2_A_SLOTS * Cfg::HALO_A_BYTES;
+                    for (int ki = 0; ki < 3 * a.kchunks; ++ki, ++it) {
+                        const int sa = it % Cfg::R2_A_SLOTS;
+                        mbar_wait_bounded(&a_full[sa], (it / Cfg::R2_A_SLOTS) & 1);
+                        const uint32_t pa = smem_base + (uint32_t)sa * Cfg::HALO_A_BYTES;
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const uint32_t ib = 3u * it + dx;
+                            const int sb = ib % Cfg::R2_B_SLOTS;
+                            mbar_wait_bounded(&full_bar[sb], (ib / Cfg::R2_B_SLOTS) & 1);
+                            tc_fence_after();
+                            const uint64_t da = umma_desc_sw128_sbo(pa + dx * 128, (Cfg::HALO_TW + 2) * 128);
+                            const uint64_t db = umma_desc_sw128(ring_b + (uint32_t)sb * Cfg::B_BYTES);
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj) {
+                                const uint64_t adv = (uint64_t)(jj * 2);
+                                mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | jj) != 0 ? 1u : 0u);
+                                mma<false, PAIR>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);
+                                mma<false, PAIR>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);
+                            }
+                            umma_commit_2sm_mc(&empty_bar[sb], (uint16_t)0x3);       // this tap's weight slab is free in both CTAs
+                        }
+                        umma_commit_2sm_mc(&a_empty[sa], (uint16_t)0x3);             // ... and after the third tap, the patch
+                    }
+                    umma_commit_2sm_mc(&tmem_full_bar[as], (uint16_t)0x3);
+                    continue;
+                }
                 if (HALO) {
                     for (int ki = 0; ki < 3 * a.kchunks; ++ki, ++it) {
                         const int s = it % STAGES;
@@ -320,7 +393,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int py = m / a.TW, px = m - py * a.TW;
         // each epilogue warp owns its 32 accumulator rows (= 2 image rows x 16 pixels of the tile) end to end: its own two 4 KB
         // staging buffers and its own TMA stores -- no barrier between the four warps
-        uint8_t* const staging = smem_al + (size_t)STAGES * STAGE_BYTES + (size_t)q * (2 * 32 * 128);
+        uint8_t* const staging = smem_al + (size_t)RING_BYTES + (size_t)q * (2 * 32 * 128);
         uint32_t tcount = 0, chunk_id = 0;
         for (int w = cl_id; w < a.total_tiles; w += n_cl, ++tcount) {
             GLARE_DECODE_WORK(w)
@@ -634,15 +707,15 @@ static int make_out_map(CUtensorMap* m, const float* ptr, int B, int H, int W, i
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-template <int MODE, int BN, int CM, bool HALO = false>
+template <int MODE, int BN, int CM, bool HALO = false, bool RING2 = false>
 static int launch_conv_cl(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
                           const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
     constexpr int CL = CM == 0 ? 1 : 2;
     using Cfg = ConvCfg<MODE, BN, CM == 2>;
     static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
     static_assert(!HALO || Cfg::HALO_STAGES >= 3, "halo pipeline needs at least three stages");
-    constexpr int SMEM = HALO ? Cfg::HALO_SMEM_DYN : Cfg::SMEM_DYN;
-    auto kern = conv_tc_kernel<MODE, BN, CM, HALO>;
+    constexpr int SMEM = RING2 ? Cfg::R2_SMEM_DYN : (HALO ? Cfg::HALO_SMEM_DYN : Cfg::SMEM_DYN);
+    auto kern = conv_tc_kernel<MODE, BN, CM, HALO, RING2>;
     GLARE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     const int n_cl = kNumSMs / CL;
     const int clusters = a.total_tiles < n_cl ? a.total_tiles : n_cl;
@@ -669,6 +742,10 @@ static int launch_conv(int cl, const CUtensorMap& tA, const CUtensorMap& tAl, co
     // cl: 1 = single CTA, 2 = multicast cluster, 3 = CTA pair (cta_group::2), 4 = CTA pair with filter-row halo staging
     if (cl == 4) {
         if constexpr (MODE == 4 && BN <= 128) return launch_conv_cl<MODE, BN, 2, true>(tA, tAl, tB, tBl, tY, a, stream);
+        else return GLARE_ERR_UNSUPPORTED;
+    }
+    if (cl == 5) {                                                   // opt-in two-ring patch staging for the 256-wide N tile
+        if constexpr (MODE == 4 && BN == 256) return launch_conv_cl<MODE, BN, 2, false, true>(tA, tAl, tB, tBl, tY, a, stream);
         else return GLARE_ERR_UNSUPPORTED;
     }
     if (cl == 3) return launch_conv_cl<MODE, BN, 2>(tA, tAl, tB, tBl, tY, a, stream);
@@ -864,7 +941,10 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     static const bool no_halo = getenv("GLARE_CONV_NO_HALO") != nullptr;            // A/B switch for profiling only
     const bool halo = !no_halo && mode == 4 && BN <= 128 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
                       w_batch_stride == 0 && getenv("GLARE_CONV_NO_CLUSTER") == nullptr && getenv("GLARE_CONV_MCAST") == nullptr;
-    if (halo) {
+    static const bool want_ring2 = getenv("GLARE_CONV_RING2") != nullptr;             // opt-in, not yet run on hardware
+    const bool ring2 = want_ring2 && !no_halo && mode == 4 && BN == 256 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
+                       w_batch_stride == 0 && !ae && getenv("GLARE_CONV_NO_CLUSTER") == nullptr && getenv("GLARE_CONV_MCAST") == nullptr;
+    if (halo || ring2) {
         a.TH = 16; a.TW = 8;
         a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
         m_tiles = (long long)B * a.tiles_y * a.tiles_x;
@@ -882,13 +962,13 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     static const bool no_cluster = getenv("GLARE_CONV_NO_CLUSTER") != nullptr;
     static const bool use_mcast = getenv("GLARE_CONV_MCAST") != nullptr;
     int cl = (no_cluster || (w_batch_stride != 0 && B > 1) || m_tiles < 2) ? 1 : (use_mcast ? 2 : 3);
-    const bool use_halo = halo && cl == 3;
-    if (halo && !use_halo) {                      // single tile: back to the standard geometry
+    const bool use_halo = (halo || ring2) && cl == 3;
+    if ((halo || ring2) && !use_halo) {           // single tile: back to the standard geometry
         a.TH = 8; a.TW = 16;
         a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
         m_tiles = (long long)B * a.tiles_y * a.tiles_x;
     }
-    if (use_halo) cl = 4;
+    if (use_halo) cl = ring2 ? 5 : 4;
     const int csz = cl == 1 ? 1 : 2;              // CTAs per cluster (box rows of the weight maps = BN / csz in both cluster modes)
     const long long total = (long long)a.n_blocks * ((m_tiles + csz - 1) / csz);
     if (total > 0x7fffffff || m_tiles > 0x7fffffff) return GLARE_ERR_UNSUPPORTED;

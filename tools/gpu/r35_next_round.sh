@@ -15,3 +15,5 @@ except Exception as e:
     print("${v:-default} failed", e)
 PY
 done
+timeout 900 python tools/gpu/train_probe.py 3 > gpurun_out/r35_train_probe.txt 2>&1; tail -3 gpurun_out/r35_train_probe.txt
+GLARE_WGRAD_TC=1 timeout 900 python tools/gpu/train_probe.py 3 > gpurun_out/r35_train_probe_wgrad_tc.txt 2>&1; tail -3 gpurun_out/r35_train_probe_wgrad_tc.txt

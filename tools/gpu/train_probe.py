@@ -1,0 +1,45 @@
+"""BASELINE config 4 shape (stage-2 flow training: batch 4, 320x320 crops, latent 80x80) through glare_b200.encoder_train.stage2_step:
+wall-clock per step and the split encoder forward / flow forward+backward / encoder backward.  python tools/gpu/train_probe.py [steps]
+(GLARE_WGRAD_TC=1 selects the tensor-core weight gradient)."""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from glare_b200 import encoder_train, flow, flow_train, synth  # noqa: E402
+from glare_b200.dense import make_dense  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+dev = torch.device("cuda:0")
+sd = {k: v.to(dev) for k, v in synth.synth_state_dict("netG_stage2", 0).items()}
+plan = flow.FlowPlan({k: v.cpu() for k, v in sd.items()}, dev)
+dense = make_dense("auto")
+leaves = encoder_train.CudaLeaves(dense)
+conv = lambda x, w: dense.conv2d(x, w).float()      # noqa: E731
+gen = torch.Generator().manual_seed(10)             # train_stage2_LOL.yml manual_seed
+lr = synth.preprocess(torch.rand((4, 3, 320, 320), generator=gen)).to(dev)
+gt = torch.randn((4, 3, 80, 80), generator=gen).to(dev)
+
+
+def step():
+    t = [time.perf_counter()]
+    enc = encoder_train.EncoderTrainer(leaves, sd)
+    heads = enc.forward(lr)
+    torch.cuda.synchronize(); t.append(time.perf_counter())
+    nll, _, _, g_ft, g_mean, grads = flow_train.nll_forward_backward(plan, sd, gt, heads["cond_feat"], heads["color_map"], conv)
+    torch.cuda.synchronize(); t.append(time.perf_counter())
+    grads.update(enc.backward(g_ft, g_mean))
+    torch.cuda.synchronize(); t.append(time.perf_counter())
+    return nll, [b - a for a, b in zip(t, t[1:])]
+
+
+with torch.no_grad():
+    step()
+    acc = [0.0, 0.0, 0.0]
+    for _ in range(steps):
+        nll, dt = step()
+        acc = [a + b for a, b in zip(acc, dt)]
+print("stage-2 step, batch 4 x 320x320 (latent 80x80): nll %s" % [round(float(x), 4) for x in nll])
+print("  encoder forward %.1f ms | flow forward + backward %.1f ms | encoder backward %.1f ms | total %.1f ms  (peak memory %.1f GB)"
+      % tuple([1e3 * a / steps for a in acc] + [1e3 * sum(acc) / steps, torch.cuda.max_memory_allocated() / 2 ** 30]))

@@ -327,3 +327,42 @@ def stage2_step(sd, plan, lr, gt_latent, leaves, conv2d, flow_kernels=None):
                                                                      kernels=flow_kernels)
     grads.update(enc.backward(g_ft, g_mean))
     return nll, grads
+
+
+class Stage2NLL(torch.autograd.Function):
+    """The stage-2 objective as ONE autograd node over (gt_latent, lr, *parameters): ``forward`` evaluates the objective and every gradient
+    with the library's kernels (stage2_step), ``backward`` hands the gradients to the parameters, rescaled by the incoming gradient (which
+    must weigh the samples equally: ``nll.mean()``, ``nll.sum()``, a GradScaler factor ...).  This is what replaces
+    ``z, nll, _ = netG(gt=..., lr=..., reverse=False); nll.mean().backward()`` of LLFlow_model.optimize_parameters (LLFlow_model.py:215-232)
+    for a module whose parameters carry the reference's names."""
+
+    @staticmethod
+    def forward(ctx, cfg, gt_latent, lr, *params):
+        from . import flow
+        keys = cfg["keys"]
+        sd = {k: p.detach() for k, p in zip(keys, params)}
+        sd.update(cfg.get("buffers", {}))
+        with torch.no_grad():
+            plan = flow.FlowPlan(sd, gt_latent.device)
+            nll, grads = stage2_step(sd, plan, lr, gt_latent, cfg["leaves"], cfg["conv2d"], flow_kernels=cfg.get("flow_kernels"))
+        ctx.batch = gt_latent.shape[0]
+        ctx.has = [k in grads for k in keys]
+        ctx.save_for_backward(*[grads[k] for k in keys if k in grads])
+        return nll
+
+    @staticmethod
+    def backward(ctx, g_nll):
+        if not bool((g_nll == g_nll[0]).all()):
+            raise RuntimeError("Stage2NLL supports reductions that weigh every sample equally (nll.mean(), nll.sum())")
+        scale = g_nll[0] * ctx.batch                                     # stored gradients are those of nll.mean()
+        saved = iter(ctx.saved_tensors)
+        return (None, None, None) + tuple(next(saved) * scale if h else None for h in ctx.has)
+
+
+def stage2_nll(named_parameters, gt_latent, lr, leaves, conv2d, flow_kernels=None):
+    """``named_parameters``: iterable of (state-dict key, Parameter) of the generator (netG of train_stage2.py: ``RRDB.*`` and
+    ``flowUpsamplerNet.*``).  Returns the per-sample objective [B] with the graph edge to every parameter, so that
+    ``stage2_nll(...).mean().backward()`` fills ``param.grad`` exactly like the reference's autograd."""
+    named = [(k, p) for k, p in named_parameters]
+    cfg = {"keys": [k for k, _ in named], "leaves": leaves, "conv2d": conv2d, "flow_kernels": flow_kernels}
+    return Stage2NLL.apply(cfg, gt_latent, lr, *[p for _, p in named])

@@ -175,3 +175,22 @@ def test_stage2_step_non_square_single_sample():
             if float((grads[k] - v.grad).abs().max()) > 1e-3 * sc + 1e-7:
                 bad.append((k, float((grads[k] - v.grad).abs().max()) / sc))
     assert len(bad) <= 2 and all(e < 5e-2 for _, e in bad), bad      # isolated ReLU sign flips of the split first-layer sum (see flow_train_gpu_check.py)
+
+
+def test_stage2_nll_autograd_node_fills_param_grads_like_the_reference():
+    """encoder_train.stage2_nll over a module's named parameters: after ``.mean().backward()`` every ``param.grad`` equals the reference's
+    (tests/golden/stage2.npz), including under a loss-scaling factor"""
+    from glare_b200 import encoder_train, synth
+    g = load_golden("stage2")
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in synth.synth_state_dict("netG_stage2", 0).items()}
+    gt, lr = torch.from_numpy(g["gt_latent"]), torch.from_numpy(g["lr"])
+    conv = lambda x, wgt: F.conv2d(x, wgt, None, padding=1)               # noqa: E731
+    sd_val = {k: p.detach() for k, p in params.items()}
+    nll = encoder_train.stage2_nll(params.items(), gt, lr, TorchLeaves(), conv, flow_kernels=TorchEmuKernels(sd_val))
+    assert np.allclose(nll.detach().numpy(), g["nll"], atol=1e-4, rtol=1e-5)
+    (nll.mean() * 128.0).backward()                                       # GradScaler-style factor
+    for key in list(g):
+        if key.startswith("grad."):
+            ref, got = torch.from_numpy(g[key]) * 128.0, params[key[5:]].grad
+            assert got is not None and float((got - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), key
+    assert params["flowUpsamplerNet.layers.0.actnorm.bias"].grad is not None

@@ -1,49 +1,19 @@
-"""Dense-operator backends of the engine and their roofline bookkeeping (see engine.py docstring).
+"""Dense-operator backend of the engine (tcgen05 kernels of libglare_b200.so) and its roofline bookkeeping (see engine.py docstring).
 
-``make_dense("torch-fp32")``  cuDNN/cuBLAS fp32 (TF32 off) -- library baseline, bring-up backend
-``make_dense("torch-bf16")``  cuDNN/cuBLAS bf16            -- library baseline
-``make_dense("auto")``        = "tc-bf16x3": tcgen05 dense path, fp32-grade (each fp32 operand split into two bf16 pieces, three
-                              bf16 passes; measured as accurate as 3xTF32 on this network, profiles/r01n_fullsize_parity_420x620.txt)
+``make_dense("auto")``        = "tc-bf16x3": fp32-grade (each fp32 operand split into two bf16 pieces, three bf16 passes; measured as
+                              accurate as 3xTF32 on this network, profiles/r01n_fullsize_parity_420x620.txt)
 ``make_dense("tc-tf32bf16x2" | "tc-3xtf32" | "tc-tf32" | "tc-bf16")``  the same kernels in the other operand modes
+
+There is no library (cuDNN / cuBLAS) backend and no fallback: a shape outside the kernels' coverage raises.
 """
 import os
 
 import torch
 import torch.nn.functional as F
 
-from .engine import TorchDense
-
 
 def dcn_flops(C, Cout, px):
     return 2.0 * C * Cout * 9 * px
-
-
-class _TorchBackend(TorchDense):
-    def __init__(self, dtype, allow_tf32=False):
-        super().__init__(dtype, allow_tf32)
-        self.dtype_name = {torch.float32: "fp32", torch.bfloat16: "bf16"}[dtype]
-        self.name = "torch-library-" + self.dtype_name
-
-    def roofline(self, timers, eng, B, lr_shape, pk):
-        """Dominant kernel of libglare_b200.so in this configuration: the DCNv2 forward (fp32 FMA path).
-        Algorithmic work = 2*C*Cout*9 FLOP per output pixel: scale 0 C=256 @ H/2 x W/2,
-        scale 1 C=128 @ H x W."""
-        Hp, Wp = lr_shape[2], lr_shape[3]
-        out = {}
-        tot_ms, tot_fl, n = 0.0, 0.0, 0
-        for i, (C, px) in enumerate(((256, (Hp // 2) * (Wp // 2)), (128, Hp * Wp))):
-            ev = timers.get("dcn%d" % i, [])
-            if not ev:
-                continue
-            ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
-            tot_ms += ms
-            tot_fl += dcn_flops(C, C, px) * B
-            n += 1
-        if not n:
-            return None
-        ach = tot_fl / (tot_ms / 1e3) / 1e12
-        return {"kernel": "dcn_fwd_kernel (both AFT scales, fp32 FMA)", "bound": "tensor", "achieved": ach, "peak": pk["tensor"],
-                "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None, "ms_per_step": tot_ms, "peak_source": pk["src"]}
 
 
 class _Bracket:
@@ -97,9 +67,8 @@ class TcDense:
 
     mode 0 bf16 operands, 1 tf32, 2 3xTF32, 3 tf32 + 2 x bf16 cross terms, 4 bf16x3 (default; fp32-grade).  Every conv shape of the path
     runs on the tcgen05 kernel (3-channel layers through channel padding, Downsample through the TMA traversal stride, Upsample as four
-    sub-pixel phases) and so do the attention matmuls.  ``self.lib`` (cuDNN / cuBLAS) is only reached when a caller asks for it
-    (``attn_impl = "library"``, ``cover_all = False``) or a shape falls outside the kernels; every such call is counted in
-    ``self.fallbacks`` and reported by the bench (empty on the GLARE network)."""
+    sub-pixel phases) and so do the attention matmuls.  A shape outside the kernels' coverage raises NotImplementedError (no library
+    fallback); ``self.fallbacks`` only records the fused-softmax -> exact-softmax switch of the attention path."""
 
     def __init__(self, mode):
         from . import ops
@@ -109,7 +78,6 @@ class TcDense:
         self.dtype_name = {0: "bf16", 1: "tf32", 2: "fp32 (3xTF32 tensor-core emulation, fp32 accumulate)",
                            3: "fp32 (tf32 x tf32 + two bf16 cross terms on tensor cores, fp32 accumulate)",
                            4: "fp32 split into two bf16 pieces per operand, three bf16 tensor-core passes (16-bit significand), fp32 accumulate"}[mode]
-        self.lib = TorchDense(torch.float32, allow_tf32=(mode in (0, 1)))
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
@@ -117,9 +85,7 @@ class TcDense:
         # statistics passes per step but lengthens the short-K conv epilogues by 46 ms (warp reductions + fp64 atomics on the critical
         # path of the TMEM drain), so it is OFF by default; the separate gn_stats kernel is HBM-bound and cheaper.
         self.fuse_gn_stats = bool(os.environ.get("GLARE_FUSE_GN_STATS"))      # A/B switch
-        self.cover_all = True          # 3-channel convs (channel-padded) and stride-2 Downsample convs on the tcgen05 kernel too
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
-        self.attn_impl = "gemm"        # "gemm": tcgen05 GEMMs (softmax in their epilogues, or the softmax kernel); "library": cuBLAS bmm + torch softmax
         self.attn_s_budget = 3 << 29   # bytes of fp32 score matrix materialised per pass (1.5 GiB)
         # mode 4: softmax fused into the epilogues of the two GEMMs (csrc/attn.cu): exp against a Cauchy-Schwarz row reference in the scores
         # GEMM, 1 / row sum in the P V GEMM; rows that fall outside the safe window raise `attn_flag` and `attention_verified()` tells
@@ -155,20 +121,16 @@ class TcDense:
             hi, lo = self.ops.conv_prep_act(self.mode, xn)
         return Operand(self.mode, hi, lo, B, C, H, W), pad_c
 
-    def _library(self, key, x, w, b, stride, padding, residual):
-        self.fallbacks[key] = self.fallbacks.get(key, 0) + 1
-        with self._t("conv_library_fallback"):
-            xd = x.dense() if isinstance(x, Operand) else x
-            y = self.lib.conv2d(xd.contiguous(memory_format=torch.channels_last), w, b, stride=stride, padding=padding)
-            return y if residual is None else y + residual
+    @staticmethod
+    def _unsupported(what):
+        raise NotImplementedError("glare_b200: %s is outside the tcgen05 kernels' coverage and there is no library fallback" % what)
 
     def conv2d(self, x, w, b=None, stride=1, padding=1, residual=None):
         Cin = x.C if isinstance(x, Operand) else x.shape[1]
         Cout, ks = w.shape[0], w.shape[2]
         shape_ok = w.shape[2] == w.shape[3] and ks in (1, 3) and stride == 1 and padding == ks // 2
-        native = Cin % self.bke == 0 and Cout % 4 == 0
-        if not shape_ok or not (native or self.cover_all):
-            return self._library("conv %dx%d %d->%d s%d" % (ks, ks, Cin, Cout, stride), x, w, b, stride, padding, residual)
+        if not shape_ok:
+            self._unsupported("conv %dx%d %d->%d stride %d padding %d" % (ks, w.shape[3], Cin, Cout, stride, padding))
         op, pad_c = self._operand(x)
         w_hi, w_lo = self._weights(w, pad_c)
         flops = 2.0 * op.B * op.H * op.W * Cin * Cout * ks * ks
@@ -218,8 +180,8 @@ class TcDense:
     def upsample_conv(self, x, w, b=None):
         """Upsample.forward (encoder_decoder.py:49-53): nearest x2 + 3x3 conv, evaluated on the LOW-resolution input as four
         sub-pixel phases with pre-summed 2x2 filters (no upsampled copy, 4/9 of the FLOPs)"""
-        if not self.cover_all or tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4 or x.shape[1] % self.bke:
-            return None
+        if tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4 or x.shape[1] % self.bke:
+            self._unsupported("Upsample conv %s" % (tuple(w.shape),))
         key = ("up2", w.data_ptr(), tuple(w.shape), w._version)
         if key not in self._w:
             rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}          # phase -> which 3x3 taps land on source row/col 0 and 1
@@ -244,8 +206,8 @@ class TcDense:
 
     def downsample_conv(self, x, w, b=None):
         """Downsample.forward (encoder_decoder.py:68-72): pad (0,1,0,1) + 3x3 stride-2 conv, padding by TMA zero fill"""
-        if not self.cover_all or tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4:
-            return None
+        if tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4:
+            self._unsupported("Downsample conv %s" % (tuple(w.shape),))
         op, pad_c = self._operand(x)
         w_hi, w_lo = self._weights(w, pad_c)
         Ho, Wo = (op.H - 2) // 2 + 1, (op.W - 2) // 2 + 1
@@ -259,8 +221,7 @@ class TcDense:
     def gn_swish(self, x, gamma, beta, swish=True):
         C = x.shape[1]
         if C % 128 != 0:
-            self.fallbacks["groupnorm C=%d" % C] = self.fallbacks.get("groupnorm C=%d" % C, 0) + 1
-            return self.lib.gn_swish(x, gamma, beta, swish)
+            self._unsupported("GroupNorm(32) over %d channels" % C)
         with self._t("groupnorm"):
             stats = getattr(x, "_glare_gn_stats", None)            # produced by the conv epilogue that wrote x
             xn = _nhwc(x)
@@ -288,10 +249,8 @@ class TcDense:
         S = Q K^T (W = K[n]) -> fused scale + row softmax emitting the operand P -> O = P V (W = V[n]^T)."""
         q_is_op, k_is_op = isinstance(q, Operand), isinstance(k, Operand)
         C = q.C if q_is_op else q.shape[1]
-        if self.attn_impl == "library" or C % self.bke != 0:
-            self.fallbacks["attention bmm+softmax (library)"] = self.fallbacks.get("attention bmm+softmax (library)", 0) + 1
-            with self._t("attention"):
-                return self.lib.attention(q.dense() if q_is_op else q, k.dense() if k_is_op else k, v)
+        if C % self.bke != 0:
+            self._unsupported("attention over %d channels" % C)
         ops = self.ops
         with self._t("attention_total(incl. its conv_tc GEMMs)"):
             vn = _nhwc(v)
@@ -436,27 +395,7 @@ class TcDense:
 
 
 def make_dense(name="auto"):
-    if name.endswith("+libattn"):
-        d = make_dense(name[:-len("+libattn")])
-        d.attn_impl = "library"
-        d.name += "+library-attention"
-        return d
-    if name in ("auto", "tc-bf16x3"):
-        return TcDense(4)
-    if name == "tc-tf32bf16x2":
-        return TcDense(3)
-    if name == "tc-3xtf32":
-        return TcDense(2)
-    if name == "tc-tf32":
-        return TcDense(1)
-    if name == "tc-bf16":
-        return TcDense(0)
-    if name == "torch-fp32":
-        return _TorchBackend(torch.float32)
-    if name == "torch-tf32":
-        b = _TorchBackend(torch.float32, allow_tf32=True)
-        b.name, b.dtype_name = "torch-library-tf32", "tf32"
-        return b
-    if name == "torch-bf16":
-        return _TorchBackend(torch.bfloat16)
-    raise ValueError("unknown dense backend %r" % name)
+    modes = {"auto": 4, "tc-bf16x3": 4, "tc-tf32bf16x2": 3, "tc-3xtf32": 2, "tc-tf32": 1, "tc-bf16": 0}
+    if name not in modes:
+        raise ValueError("unknown dense backend %r (tcgen05 operand modes: %s)" % (name, ", ".join(sorted(modes))))
+    return TcDense(modes[name])

@@ -9,53 +9,15 @@ The engine consumes the reference's checkpoints unchanged (``net_G.pth`` / ``vqg
 It is CUDA-only by construction: there is no CPU path and no PyTorch re-implementation of the VQ, flow-step
 or DCN operators to fall back to.
 
-Dense operators (3x3 / 1x1 convolutions, GroupNorm+swish, attention) go through the ``dense`` backend object:
-``TorchDense`` (cuDNN / cuBLAS library calls, the recompiled-library baseline) or ``glare_b200.dense_tc``
-(tcgen05 implicit-GEMM kernels) -- chosen explicitly by the caller, never silently.
+Dense operators (3x3 / 1x1 convolutions, GroupNorm+swish, attention) go through the ``dense`` backend object
+(``glare_b200.dense.TcDense``: tcgen05 implicit-GEMM kernels of libglare_b200.so).  There is no library (cuDNN / cuBLAS)
+backend in the package; the cuDNN fp32 comparison path of the tests lives in ``tests/libdense.py``.
 """
 import torch
 import torch.nn.functional as F
 
 from . import flow as flowmod
 from . import ops
-
-
-class TorchDense:
-    """Library (cuDNN/cuBLAS) implementation of the dense operators, fp32 or bf16.  This is the baseline the
-    hand-written tensor-core path is measured against, and the dense backend of the first bring-up."""
-    name = "torch-library"
-
-    def __init__(self, dtype=torch.float32, allow_tf32=False):
-        self.dtype = dtype
-        self.allow_tf32 = allow_tf32
-
-    def _ctx(self):
-        torch.backends.cudnn.allow_tf32 = self.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
-
-    def conv2d(self, x, w, b=None, stride=1, padding=1, residual=None):
-        self._ctx()
-        y = F.conv2d(x.to(self.dtype), w.to(self.dtype), None if b is None else b.to(self.dtype), stride=stride,
-                     padding=padding)
-        return y if residual is None else y + residual
-
-    def gn_swish(self, x, gamma, beta, swish=True):
-        y = F.group_norm(x.float(), 32, gamma, beta, eps=1e-6)       # encoder_decoder.py:34-35
-        if swish:
-            y = y * torch.sigmoid(y)                                 # encoder_decoder.py:29-31
-        return y.to(self.dtype)
-
-    def attention(self, q, k, v):
-        """single-head attention over h*w tokens, d = C (encoder_decoder.py:176-187); q,k,v [B,C,h,w]"""
-        self._ctx()
-        B, C, h, w = q.shape
-        out = torch.empty_like(q)
-        for b in range(B):                       # the N x N score matrix is materialised per sample (1 GB at 105x155)
-            qb = q[b].reshape(C, h * w).t()
-            s = torch.mm(qb, k[b].reshape(C, h * w)) * (int(C) ** (-0.5))
-            s = torch.softmax(s.float(), dim=1).to(q.dtype)
-            out[b] = torch.mm(v[b].reshape(C, h * w), s.t()).reshape(C, h, w)
-        return out
 
 
 class _Timed:
@@ -81,7 +43,10 @@ class GlareEngine:
         if not torch.cuda.is_available():
             raise RuntimeError("glare_b200.GlareEngine needs a CUDA device (B200 / sm_100a); there is no CPU path")
         self.device = torch.device(device)
-        self.dense = dense if dense is not None else TorchDense()
+        if dense is None:
+            from .dense import make_dense
+            dense = make_dense("auto")                     # tcgen05, fp32-grade operands
+        self.dense = dense
         self.per_sample_ratio = per_sample_ratio
         self.timers = None        # bench.py sets a dict: name -> [(start_event, end_event), ...]
         self.g = {k: v.to(self.device, torch.float32).contiguous() for k, v in sd_g.items()

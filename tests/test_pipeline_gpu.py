@@ -15,6 +15,9 @@ def engine(request, glare_lib, sd_g, sd_v):
     """fp32-grade configurations: the tensor-core dense path in 3xTF32 mode, and the cuDNN fp32 library baseline"""
     from glare_b200.dense import make_dense
     from glare_b200.engine import GlareEngine
+    if request.param == "torch-fp32":                   # comparison path of the tests, not part of the package
+        from libdense import TorchDense
+        return GlareEngine(sd_g, sd_v, device="cuda:0", dense=TorchDense())
     return GlareEngine(sd_g, sd_v, device="cuda:0", dense=make_dense(request.param))
 
 

@@ -126,6 +126,75 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick=False):
+    """The other single-box configurations of BASELINE.json, measured with the same rules (device events, barrier on both sides, max over
+    ranks, L2 flush between iterations, weak scaling): configs[2] bf16 operands at 8 images per GPU (bs 64 over 8 GPUs) and configs[4]
+    1920x1080 unpaired inference (auto_padding to 1088x1936) at 1 / 2 / 4 images per GPU.  Returned as the `alt_configs` object of the line."""
+    import torch.distributed as dist
+    from glare_b200 import synth
+    from glare_b200.api import GlareEnhancer
+    from glare_b200.dense import make_dense
+    from oracle import glare_oracle as O     # psnr() only (a checker), never on the measured path
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+            flush.zero_()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    out = {}
+    pk = peaks()
+    # ---- configs[2]: bf16 tensor-core operands (fp32 accumulate, fp32 GroupNorm / softmax / residual stream), 8 images per GPU
+    B = 8
+    lq, gt = synth_batch(B, seed=100 + rank)
+    enh = GlareEnhancer(sd_g, sd_v, device=dev, pad="lol", dense=make_dense("tc-bf16"))
+    host_u8 = (lq.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
+    host_out = torch.empty_like(host_u8).pin_memory()
+    lr_dev, box = enh.preprocess(host_u8.to(dev))
+    steps, warm = (3, 3) if quick else (10, 3)
+    ms = timed(lambda: enh.engine.infer(lr_dev), steps, warm)
+    ms_e2e = timed(lambda: enh.enhance(host_u8, out=host_out), steps, 2)
+    crop = lambda o: o[:, :, box[0]:box[1], box[2]:box[3]].clamp(0, 1).float().cpu()       # noqa: E731
+    o16, o32 = crop(enh.engine.infer(lr_dev)), crop(fp32_engine.infer(lr_dev))
+    gtq = gt                                                                               # clean target of the synthetic pair
+    ips = world * B / (ms / 1e3)
+    out["lolv2_real_bf16_bs64_over_8gpus"] = {
+        "workload": "configs[2]: 8 images 600x400 (padded 420x620) per GPU per step, bf16 tensor-core operands", "dtype": "bf16",
+        "value": ips, "unit": "images/s", "ms_per_step": ms, "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "images/s",
+                                                                  "h2d_bytes_per_step": host_u8.numel(), "d2h_bytes_per_step": host_out.numel()},
+        "frac_of_bf16_ceiling": ips / world / (pk["tensor"] / 13.16),
+        "ceiling_images_per_s_per_gpu": pk["tensor"] / 13.16,
+        "dpsnr_vs_fp32_path_db": abs(O.psnr(o16, gtq) - O.psnr(o32, gtq)), "pixel_mean_abs_diff_vs_fp32_path": float((o16 - o32).abs().mean())}
+    del enh, lr_dev
+    torch.cuda.empty_cache()
+    # ---- configs[4]: 1920x1080, the fp32-grade default backend, batch swept
+    enh = GlareEnhancer(sd_g, sd_v, device=dev, pad="auto", dense=fp32_engine.dense)
+    sweep = {}
+    for Bh in ((1,) if quick else (1, 2, 4)):
+        lqh, _ = synth.synth_images(Bh, 1080, 1920, seed=200 + rank)
+        hu8 = (lqh.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
+        hout = torch.empty_like(hu8).pin_memory()
+        ms = timed(lambda: enh.enhance(hu8, out=hout), 2, 1)             # through the public API: host buffers in and out
+        sweep["batch_%d" % Bh] = {"value": world * Bh / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+                                  "frac_of_bf16_ceiling": Bh / (ms / 1e3) / (pk["tensor"] / 447.0)}
+    out["unpaired_1080p_fp32"] = {"workload": "configs[4]: 1920x1080 images (auto_padding to 1088x1936, 131 648 latent tokens), end to end "
+                                              "through GlareEnhancer.enhance with host buffers, fp32-grade operands (bf16x3)",
+                                  "dtype": fp32_engine.dense.dtype_name, "ceiling_images_per_s_per_gpu_bf16": pk["tensor"] / 447.0,
+                                  "per_gpu_batch_sweep": sweep}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -135,6 +204,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--dense", default=os.environ.get("GLARE_DENSE", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the alt_configs measurements (bf16 config 3, 1080p config 5)")
+    ap.add_argument("--quick-alt", action="store_true", help="alt_configs with fewer steps and 1080p at batch 1 only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,6 +300,10 @@ def main():
     e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": host_u8.numel(),
            "d2h_bytes_per_step": host_out.numel()}
 
+    alt = None
+    if not args.no_alt and args.dense in ("auto", "tc-bf16x3"):
+        alt = alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, eng, quick=args.quick_alt)
+
     if rank == 0:
         pk = peaks()
         roof = dense.roofline(timers, eng, B, lr_dev.shape, pk)
@@ -250,7 +325,7 @@ def main():
                            "library_fallbacks_per_run": getattr(dense, "fallbacks", None), "parallelism": "images sharded, dp%d" % world,
                            "l2": "256 MiB buffer written between timed iterations (L2 flush); activations per step exceed L2"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "peaks": pk["src"],
+                "peaks": pk["src"], "alt_configs": alt,
                 "breakdown_ms_per_step": dense.breakdown(timers, args.steps) if hasattr(dense, "breakdown") else None}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -146,3 +146,16 @@ def test_flow_explicit_backward_matches_autograd(sd_g):
         close(grads[k], leaf[k].grad, k)
         checked += 1
     assert checked >= 24 * 2 * 9 + 28 * 3
+
+
+def test_oracle_reproduces_reference_at_bench_shape(sd_g, sd_v):
+    """420x620 (BASELINE configs[1] shape, image 0 of the bench batch): oracle against the stored reference outputs"""
+    g = load_golden("pipe_420x620")
+    lq, _ = synth.synth_images(1, 400, 600, seed=0)
+    lr = synth.preprocess(synth.pad_lol(lq))
+    assert float(lr.double().sum()) == pytest.approx(float(g["lr_checksum"]), rel=1e-12)
+    st = {}
+    out = O.glare_infer(sd_g, sd_v, lr, stages=st)
+    assert np.array_equal(st["idx"].reshape(-1).numpy(), g["idx"].astype(np.int64))
+    assert float((st["z_flow"] - T(g["z_flow"])).abs().max()) <= 1e-5
+    assert float((out - T(g["out"])).abs().max()) <= 1e-5

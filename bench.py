@@ -161,9 +161,10 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
     enh = GlareEnhancer(sd_g, sd_v, device=dev, pad="lol", dense=make_dense("tc-bf16"))
     host_u8 = (lq.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
     host_out = torch.empty_like(host_u8).pin_memory()
-    lr_dev, box = enh.preprocess(host_u8.to(dev))
+    dev8 = host_u8.to(dev)
+    lr_dev, box = enh.preprocess(dev8)
     steps, warm = (3, 3) if quick else (10, 3)
-    ms = timed(lambda: enh.engine.infer(lr_dev), steps, warm)
+    ms = timed(lambda: enh.enhance_device(dev8), steps, warm)         # one CUDA-graph replay per step, batch resident in HBM
     ms_e2e = timed(lambda: enh.enhance(host_u8, out=host_out), steps, 2)
     crop = lambda o: o[:, :, box[0]:box[1], box[2]:box[3]].clamp(0, 1).float().cpu()       # noqa: E731
     o16, o32 = crop(enh.engine.infer(lr_dev)), crop(fp32_engine.infer(lr_dev))
@@ -204,6 +205,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--dense", default=os.environ.get("GLARE_DENSE", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--no-alt", action="store_true", help="skip the alt_configs measurements (bf16 config 3, 1080p config 5)")
     ap.add_argument("--quick-alt", action="store_true", help="alt_configs with fewer steps and 1080p at batch 1 only")
     args = ap.parse_args()
@@ -236,29 +238,26 @@ def main():
     enh = GlareEnhancer(sd_g, sd_v, device=dev, pad="lol", dense=dense)
     eng = enh.engine
     B = args.batch
+    use_graph = not args.no_graph
     lq, gt = synth_batch(B, seed=rank)
     host_u8 = (lq.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
     host_out = torch.empty_like(host_u8).pin_memory()
-    lr_dev, box = enh.preprocess(host_u8.to(dev))
-    lr_dev = lr_dev.contiguous()
+    dev_u8 = host_u8.to(dev)                                               # `value`: the batch is resident in HBM (uint8 NHWC, as decoded)
+    lr_dev, box = enh.preprocess(dev_u8)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    gather = torch.empty((world * B, 3) + tuple(lr_dev.shape[2:]), device=dev) if world > 1 else None
+    from glare_b200.parallel import AsyncGather
+    gather = AsyncGather()                                                 # world > 1: all_gather of the uint8 results on a side stream
 
-    def step():
-        out = eng.infer(lr_dev)
-        if world > 1:
-            dist.all_gather_into_tensor(gather, out.contiguous())
-        return out
+    def step(graph=use_graph):
+        # pre-processing kernel -> the whole network -> post-processing kernel; one CUDA-graph replay per step when graph is on
+        gather.submit(enh.enhance_device(dev_u8, graph=graph))
 
     for _ in range(max(args.warmup, 3)):
         step()
         flush.zero_()
     warm = max(args.warmup, 3)
 
-    # ---- device-resident throughput (`value`) + live per-kernel timers for the roofline
-    eng.timers = {}
-    if hasattr(dense, "timers"):
-        dense.timers = {}
+    # ---- device-resident throughput (`value`)
     n0 = ops.LAUNCHES
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -269,27 +268,43 @@ def main():
     for _ in range(args.steps):
         step()
         flush.zero_()
+    gather.wait()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = ops.LAUNCHES - n0
-    timers, eng.timers = eng.timers, None
-    if hasattr(dense, "timers"):
-        dense.last_timers, dense.last_steps, dense.timers = dense.timers, args.steps, None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
 
+    # ---- per-kernel timers for the roofline: the same step, launched eagerly with a CUDA-event bracket around every operator (a captured
+    # graph has no per-kernel brackets); rank 0 only needs it, every rank runs it to stay in step
+    eng.timers = {}
+    if hasattr(dense, "timers"):
+        dense.timers = {}
+    inst_steps = min(args.steps, 5)
+    e0.record()
+    for _ in range(inst_steps):
+        step(graph=False)
+        flush.zero_()
+    gather.wait()
+    e1.record()
+    barrier()
+    inst_ms = e0.elapsed_time(e1) / inst_steps
+    timers, eng.timers = eng.timers, None
+    if hasattr(dense, "timers"):
+        dense.last_timers, dense.last_steps, dense.timers = dense.timers, inst_steps, None
+
     # ---- end to end through the public API with host buffers
     for _ in range(2):
-        enh.enhance(host_u8, out=host_out)
+        enh.enhance(host_u8, out=host_out, graph=use_graph)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        enh.enhance(host_u8, out=host_out)
+        enh.enhance(host_u8, out=host_out, graph=use_graph)
         flush.zero_()
     e1.record()
     barrier()
@@ -308,7 +323,9 @@ def main():
         pk = peaks()
         roof = dense.roofline(timers, eng, B, lr_dev.shape, pk)
         if roof is not None and "share_of_step" in roof:
-            roof["share_of_step"] = roof["ms_per_step"] / (ms / args.steps)
+            roof["share_of_step"] = roof["ms_per_step"] / inst_ms
+            roof["timing"] = ("CUDA-event brackets around every launch of the kernel in %d eagerly launched steps (%.1f ms/step) run right "
+                              "after the graph-replayed timed region" % (inst_steps, inst_ms))
         cpu = None
         if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N = 1 only
             cores = os.cpu_count() or 1
@@ -323,10 +340,13 @@ def main():
                 "config": {"workload": "LOL eval15-shape batch inference: 15 images 600x400 (reflect-padded to 420x620) per GPU per step",
                            "batch_per_gpu": B, "dense_backend": dense.name,
                            "library_fallbacks_per_run": getattr(dense, "fallbacks", None), "parallelism": "images sharded, dp%d" % world,
+                           "launch": ("one CUDA graph replay per step (pre-processing + network + post-processing), %d kernels per graph"
+                                      % (launches // max(1, args.steps))) if use_graph else "eager (one ctypes call per kernel)",
+                           "gather": "uint8 results all_gathered on a side stream (NCCL), overlapped with the next step" if world > 1 else None,
                            "l2": "256 MiB buffer written between timed iterations (L2 flush); activations per step exceed L2"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "peaks": pk["src"], "alt_configs": alt,
-                "breakdown_ms_per_step": dense.breakdown(timers, args.steps) if hasattr(dense, "breakdown") else None}
+                "breakdown_ms_per_step": dense.breakdown(timers, inst_steps) if hasattr(dense, "breakdown") else None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

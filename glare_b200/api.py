@@ -44,15 +44,28 @@ class GlareEnhancer:
         """rgb(): clip to [0,1], *255, truncate to uint8 (infer_unpaired.py:40-42), NHWC; one kernel (glare_postprocess_u8)"""
         return ops.postprocess_u8(out.float(), box)
 
+    def _device_path(self, dev_u8):
+        """uint8 [B,H,W,3] on the device -> enhanced uint8 [B,H,W,3] on the device (one pass, no host synchronisation)"""
+        lr, box = self.preprocess(dev_u8)
+        return self.postprocess(self.engine._forward(lr)[0], box)
+
     @torch.no_grad()
-    def enhance(self, images_u8, out=None):
+    def enhance_device(self, dev_u8, graph=True):
+        """device-resident form of `enhance`.  graph=True: pre-processing, the whole network and post-processing replay as ONE captured
+        CUDA graph per input shape (engine.graphed); the returned tensor is the graph's static output, overwritten by the next call."""
+        if graph:
+            return self.engine.graphed("enhance-" + self.pad, self._device_path, dev_u8)
+        lr, box = self.preprocess(dev_u8)
+        return self.postprocess(self.engine.infer(lr), box)
+
+    @torch.no_grad()
+    def enhance(self, images_u8, out=None, graph=True):
         """images_u8: host uint8 [B,H,W,3] (pinned for async copies).  Returns host uint8 [B,H,W,3]."""
         if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[-1] != 3:
             raise ValueError("expected uint8 [B,H,W,3]")
         with torch.cuda.device(self.device):
             dev = images_u8.to(self.device, non_blocking=True)
-            lr, box = self.preprocess(dev)
-            res = self.postprocess(self.engine.infer(lr), box)
+            res = self.enhance_device(dev, graph=graph)
             if out is None:
                 out = torch.empty(res.shape, dtype=torch.uint8, pin_memory=True)
             out.copy_(res, non_blocking=True)

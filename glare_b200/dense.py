@@ -7,6 +7,7 @@
 There is no library (cuDNN / cuBLAS) backend and no fallback: a shape outside the kernels' coverage raises.
 """
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -100,13 +101,24 @@ class TcDense:
     def _t(self, name, flops=0.0):
         return _Bracket(self.timers, name, flops)
 
+    def _cached(self, key, w, make):
+        """packed-weight cache: one entry per (storage address, shape, role), REPLACED when the tensor's in-place version moves (an optimizer
+        step bumps it on every weight: keying on the version would add a packed copy of every weight per training step).  Entries hold the
+        source tensor by weak reference: a different tensor object at a recycled address is repacked, and entries whose source has died
+        (per-step temporaries of the training path: flipped filters, the flow's hoisted weight) are swept when new keys arrive."""
+        ent = self._w.get(key)
+        if ent is None or ent[0]() is not w or ent[1] != w._version:
+            if ent is None and len(self._w) >= 256:
+                for k in [k for k, e in self._w.items() if e[0]() is None]:
+                    del self._w[k]
+            ent = self._w[key] = (weakref.ref(w), w._version, make())
+        return ent[2]
+
     def _weights(self, w, pad_c=0):
-        # keyed by storage address + in-place version; the entry keeps `w` alive so the address cannot be recycled under the cache
-        key = (w.data_ptr(), tuple(w.shape), pad_c, w._version)
-        if key not in self._w:
+        def make():
             wp = F.pad(w, (0, 0, 0, 0, 0, pad_c)) if pad_c else w            # zero input channels up to the K chunk
-            self._w[key] = (w, self.ops.conv_pack_weight(self.mode, wp))
-        return self._w[key][1]
+            return self.ops.conv_pack_weight(self.mode, wp)
+        return self._cached((w.data_ptr(), tuple(w.shape), pad_c), w, make)
 
     def _operand(self, x):
         """logical [B,C,H,W] fp32 tensor -> Operand, input channels zero-padded to a multiple of the 128-byte K chunk"""
@@ -182,8 +194,7 @@ class TcDense:
         sub-pixel phases with pre-summed 2x2 filters (no upsampled copy, 4/9 of the FLOPs)"""
         if tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4 or x.shape[1] % self.bke:
             self._unsupported("Upsample conv %s" % (tuple(w.shape),))
-        key = ("up2", w.data_ptr(), tuple(w.shape), w._version)
-        if key not in self._w:
+        def make():
             rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}          # phase -> which 3x3 taps land on source row/col 0 and 1
             ph = {}
             for a in (0, 1):
@@ -191,14 +202,15 @@ class TcDense:
                     w2 = torch.stack([torch.stack([w[:, :, list(rows[a][r])][:, :, :, list(rows[c][q])].sum(dim=(2, 3))
                                                    for q in (0, 1)], dim=-1) for r in (0, 1)], dim=-2)      # [Co,Ci,2,2]
                     ph[(a, c)] = self.ops.conv_pack_weight(self.mode, w2.contiguous())
-            self._w[key] = (w, ph)
+            return ph
+        phases = self._cached(("up2", w.data_ptr(), tuple(w.shape)), w, make)
         op, _ = self._operand(x)
         Cout = w.shape[0]
         y = torch.empty((op.B, 2 * op.H, 2 * op.W, Cout), device=op.hi.device, dtype=torch.float32)
         stats = self._new_stats(op.B, Cout)
         with self._t("conv_tc", 2.0 * op.B * op.H * op.W * op.C * Cout * 16):
             first = True
-            for (pa, pb), (w_hi, w_lo) in self._w[key][1].items():
+            for (pa, pb), (w_hi, w_lo) in phases.items():
                 self.ops.conv2d_nhwc_tc_g(self.mode, 2, op.hi, op.lo, w_hi, w_lo, b, None, y, op.B, op.H, op.W, op.C, Cout, ksize=2, pa=pa,
                                           pb=pb, gn_stats=stats, gn_zero=first)
                 first = False
@@ -244,7 +256,7 @@ class TcDense:
             y = self.ops.dcnv2_pack_fwd_nhwc_tc(self.mode, xn, on, w_hi, w_lo, bias, B, H, W, C, Cout, dg)
         return y.permute(0, 3, 1, 2)
 
-    def attention(self, q, k, v, as_operand=False):
+    def attention(self, q, k, v, as_operand=False, fused=None):
         """AttnBlock core (encoder_decoder.py:176-187) on the tcgen05 GEMM path: per sample and per band of query rows
         S = Q K^T (W = K[n]) -> fused scale + row softmax emitting the operand P -> O = P V (W = V[n]^T)."""
         q_is_op, k_is_op = isinstance(q, Operand), isinstance(k, Operand)
@@ -262,7 +274,7 @@ class TcDense:
             q_hi, q_lo = (q.hi, q.lo) if q_is_op else ops.conv_prep_act(self.mode, qn)
             k_hi, k_lo = (k.hi, k.lo) if k_is_op else ops.conv_prep_act(self.mode, kn)      # K[n] as GEMM weights [N][C]
             vt_hi, vt_lo = ops.attn_transpose_v(self.mode, vn, B, N, C, Np)
-            if self.attn_fused and N >= 32:
+            if (self.attn_fused if fused is None else (fused and self.mode == 4)) and N >= 32:
                 sq = (getattr(q, "row_sq", None), getattr(k, "row_sq", None))
                 if as_operand and self.pack_epilogue and C % 32 == 0:  # the P V epilogue writes proj_out's operand
                     out_op = ops._hi_alloc(self.mode, (B, h, w, C), vn.device)

@@ -9,8 +9,9 @@ Downsample's becomes a conv over the zero-interleaved gradient, the five matmuls
 every backend, so the CPU test (tests/test_encoder_train_cpu.py) runs exactly this logic with torch / host-compiled leaves against torch
 autograd of the oracle and the reference's own gradients.
 
-STATUS (round 1): CPU-verified; the new kernels (csrc/train_enc.cu) have not run on hardware yet.  Weight gradients use the fp32 split-K
-GEMM over an explicit im2col (correctness baseline; a tensor-core weight-gradient kernel is the follow-up).
+STATUS (round 2): green on B200 (tests/test_zz_flow_train_gpu.py, profiles/r41_train_check.log); 240 ms per step at BASELINE config 4
+(batch 4 x 320x320) with the fp32 split-K weight-gradient GEMM, 200 ms with the tensor-core weight gradient (GLARE_WGRAD_TC=1,
+profiles/r40_train_probe*.txt).
 """
 import ctypes
 
@@ -69,7 +70,9 @@ class CudaLeaves:
         return (y if y is not None else F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)).float()
 
     def attention(self, q, k, v):
-        return self.dense.attention(q, k, v).float()
+        # exact softmax: the fused-softmax fast path relies on a device flag the caller must read and act on (engine.infer does); a training
+        # forward cannot recompute after the fact, and the backward (Tape._attn_bwd) recomputes P with the exact softmax anyway
+        return self.dense.attention(q, k, v, fused=False).float()
 
     def gemm_tn(self, a, b):
         """a [P][M], b [P][N] -> a^T b [M][N] (fp32 split-K GEMM, csrc/dcn_bwd.cu)"""
@@ -295,7 +298,9 @@ class EncoderTrainer:
         T = self.tape
         cond_pre, color = self.out_ids
         s = torch.sigmoid(self.vals[cond_pre])
-        g = {cond_pre: g_cond_feat * s * (1.0 - s), color: g_color_map}
+        g = {cond_pre: g_cond_feat * s * (1.0 - s)}
+        if g_color_map is not None:                  # None: the objective did not use color_map (mean = gt branch) -> color_conv gets no gradient
+            g[color] = g_color_map
 
         def give(i, val):
             if val is not None:
@@ -318,15 +323,24 @@ class EncoderTrainer:
         return T.grads
 
 
-def stage2_step(sd, plan, lr, gt_latent, leaves, conv2d, flow_kernels=None):
+def stage2_step(sd, plan, lr, gt_latent, leaves, conv2d, flow_kernels=None, use_gt_mean=False):
     """One stage-2 objective evaluation with all gradients: -> (nll [B], {state-dict key: dL/dparam}) for L = nll.mean().
-    ``lr`` preprocessed low-light input [B,3,H,W], ``gt_latent`` [B,3,H/4,W/4] (the frozen VQGAN's encoding of the ground truth)."""
+    ``lr`` preprocessed low-light input [B,3,H,W], ``gt_latent`` [B,3,H/4,W/4] (the frozen VQGAN's encoding of the ground truth).
+    use_gt_mean: the Gaussian's mean is ``gt`` instead of the encoder's color_map -- the branch LLFlowVQGAN2.normal_flow takes when
+    ``random.random() > opt['train_gt_ratio']`` is False (LLFlowVQGAN2_arch.py:109; 0.2 in train_stage2_LOL.yml); color_conv then receives no
+    gradient (its keys are absent from the result, like the reference's ``param.grad is None``)."""
     enc = EncoderTrainer(leaves, sd)
     heads = enc.forward(lr)
-    nll, _, _, g_ft, g_mean, grads = flow_train.nll_forward_backward(plan, sd, gt_latent, heads["cond_feat"], heads["color_map"], conv2d,
-                                                                     kernels=flow_kernels)
-    grads.update(enc.backward(g_ft, g_mean))
+    mean = gt_latent if use_gt_mean else heads["color_map"]
+    nll, _, _, g_ft, g_mean, grads = flow_train.nll_forward_backward(plan, sd, gt_latent, heads["cond_feat"], mean, conv2d, kernels=flow_kernels)
+    grads.update(enc.backward(g_ft, None if use_gt_mean else g_mean))
     return nll, grads
+
+
+def draw_use_gt_mean(train_gt_ratio):
+    """the reference's per-step draw (LLFlowVQGAN2_arch.py:109), consuming Python's global RNG exactly like it"""
+    import random
+    return not (random.random() > train_gt_ratio)
 
 
 class Stage2NLL(torch.autograd.Function):
@@ -344,7 +358,8 @@ class Stage2NLL(torch.autograd.Function):
         sd.update(cfg.get("buffers", {}))
         with torch.no_grad():
             plan = flow.FlowPlan(sd, gt_latent.device)
-            nll, grads = stage2_step(sd, plan, lr, gt_latent, cfg["leaves"], cfg["conv2d"], flow_kernels=cfg.get("flow_kernels"))
+            nll, grads = stage2_step(sd, plan, lr, gt_latent, cfg["leaves"], cfg["conv2d"], flow_kernels=cfg.get("flow_kernels"),
+                                     use_gt_mean=cfg.get("use_gt_mean", False))
         ctx.batch = gt_latent.shape[0]
         ctx.has = [k in grads for k in keys]
         ctx.save_for_backward(*[grads[k] for k in keys if k in grads])
@@ -359,10 +374,13 @@ class Stage2NLL(torch.autograd.Function):
         return (None, None, None) + tuple(next(saved) * scale if h else None for h in ctx.has)
 
 
-def stage2_nll(named_parameters, gt_latent, lr, leaves, conv2d, flow_kernels=None):
+def stage2_nll(named_parameters, gt_latent, lr, leaves, conv2d, flow_kernels=None, train_gt_ratio=0.0, use_gt_mean=None):
     """``named_parameters``: iterable of (state-dict key, Parameter) of the generator (netG of train_stage2.py: ``RRDB.*`` and
     ``flowUpsamplerNet.*``).  Returns the per-sample objective [B] with the graph edge to every parameter, so that
-    ``stage2_nll(...).mean().backward()`` fills ``param.grad`` exactly like the reference's autograd."""
+    ``stage2_nll(...).mean().backward()`` fills ``param.grad`` exactly like the reference's autograd.  ``train_gt_ratio``
+    (opt['train_gt_ratio']): probability of the ``mean = gt`` branch, drawn per call like the reference; ``use_gt_mean`` overrides the draw."""
     named = [(k, p) for k, p in named_parameters]
-    cfg = {"keys": [k for k, _ in named], "leaves": leaves, "conv2d": conv2d, "flow_kernels": flow_kernels}
+    if use_gt_mean is None:
+        use_gt_mean = draw_use_gt_mean(train_gt_ratio)
+    cfg = {"keys": [k for k, _ in named], "leaves": leaves, "conv2d": conv2d, "flow_kernels": flow_kernels, "use_gt_mean": use_gt_mean}
     return Stage2NLL.apply(cfg, gt_latent, lr, *[p for _, p in named])

@@ -35,7 +35,7 @@ class ParamModule(nn.Module):
             if rest:
                 groups.setdefault(head, {})[rest] = shape
             else:
-                self.register_parameter(head, nn.Parameter(torch.zeros(tuple(shape)), requires_grad=False))
+                self.register_parameter(head, nn.Parameter(torch.zeros(tuple(shape))))
         for head, sub in groups.items():
             self.add_module(head, ParamModule(sub))
 
@@ -146,6 +146,16 @@ class FlowUpsamplerNet(ParamModule):
     def __init__(self, image_shape=None, hidden_channels=64, K=12, L=None, actnorm_scale=1.0, flow_permutation=None,
                  flow_coupling="affine", LU_decomposed=False, opt=None, shapes=None):
         super().__init__(shapes if shapes is not None else _sub(synth.state_shapes("netG"), "flowUpsamplerNet."))
+        # attributes the reference solver reads (VQLLFLOWD_model.py:307-321 get_z): FlowUpsamplerNet.py:38,116-119 with the generator's
+        # image_shape (80, 80, 3) (VQLLFLOWDeformable_arch.py:45) and no squeeze level in the shipped configuration
+        self.H, self.W, self.C = (tuple(image_shape) if image_shape is not None else (80, 80, 3))
+        gt_size = 256
+        try:
+            gt_size = opt["datasets"]["train"]["GT_size"] or gt_size
+        except (TypeError, KeyError):
+            pass
+        self.scaleH, self.scaleW = gt_size / self.H, gt_size / self.W
+        self.opt = opt
         self._plan, self._plan_key = None, None
         self.dense = None          # dense conv backend for the hoisted first layers; set by the owning generator
 
@@ -196,12 +206,16 @@ class VQModel(nn.Module):
             self._engine = (key, GlareEngine({}, self.state_dict(), device=next(self.parameters()).device, flow=False))
         return self._engine[1]
 
+    @torch.no_grad()
     def encode(self, x):
-        return self._eng().vqgan_encode(x), None
+        eng = self._eng()
+        return eng.run_verified(lambda: eng.vqgan_encode(x)), None
 
+    @torch.no_grad()
     def decode(self, h, vgg_feat=None):
         quant, emb_loss, _ = self.quantize(h)
-        return None, emb_loss, self._eng().vq_decoder_features(quant)
+        eng = self._eng()
+        return None, emb_loss, eng.run_verified(lambda: eng.vq_decoder_features(quant))
 
 
 class VQLLFLOWDeformable(nn.Module):
@@ -213,11 +227,16 @@ class VQLLFLOWDeformable(nn.Module):
         shapes = synth.state_shapes(which)
         self.opt = opt
         self.RRDB = ParamModule(_sub(shapes, "RRDB."))
-        self.flowUpsamplerNet = FlowUpsamplerNet(shapes=_sub(shapes, "flowUpsamplerNet."))
+        self.flowUpsamplerNet = FlowUpsamplerNet((80, 80, 3), 64, K, opt=opt, shapes=_sub(shapes, "flowUpsamplerNet."))
+        try:
+            self.quant = 255 if opt["datasets"]["train"]["quant"] is None else opt["datasets"]["train"]["quant"]   # VQLLFLOWDeformable_arch.py:28
+        except (TypeError, KeyError):
+            self.quant = 255
         if which == "netG":
             self.deformable_decoder = ParamModule(_sub(shapes, "deformable_decoder."))
         self.dense_name = "auto"
         self._engine = None
+        self._train_ctx = None
 
     def engine(self, net_vq=None):
         key = _fingerprint(self) + (_fingerprint(net_vq) if net_vq is not None else ())
@@ -229,18 +248,46 @@ class VQLLFLOWDeformable(nn.Module):
             self._engine = (key, eng)
         return self._engine[1]
 
-    @torch.no_grad()
     def forward(self, net_vq=None, gt=None, lr=None, z=None, eps_std=None, reverse=True, epses=None, reverse_with_grad=True,
                 lr_enc=None, add_gt_noise=False, step=None, y_label=None, align_condition_feature=False, get_color_map=False):
         if get_color_map:
             raise NotImplementedError("get_color_map is not reachable from the shipped configurations")
         if reverse:
             assert lr.shape[1] == 3
-            st = {}
-            out = self.engine(net_vq).infer(lr, stages=st)
+            with torch.no_grad():
+                st = {}
+                out = self.engine(net_vq).infer(lr, stages=st)
             return out, st["z_flow"]
-        eng = self.engine(None)
-        enc = eng.cond_encoder(lr.to(eng.device, torch.float32))
-        zz, logdet = eng.flow_encode(gt.to(eng.device, torch.float32), enc["cond_feat"])
-        nll = flowmod.gaussian_nll(zz, enc["color_map"], logdet)
+        if add_gt_noise:
+            raise NotImplementedError("add_gt_noise=True is not reachable from the shipped configurations (LLFlow_model.py:215 passes the default)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._normal_flow_train(gt, lr)
+        with torch.no_grad():
+            eng = self.engine(None)
+            lr_d = lr.to(eng.device, torch.float32)
+            enc = eng.run_verified(lambda: eng.cond_encoder(lr_d))
+            zz, logdet = eng.flow_encode(gt.to(eng.device, torch.float32), enc["cond_feat"])
+            nll = flowmod.gaussian_nll(zz, enc["color_map"], logdet)
         return zz, nll, logdet
+
+    def _normal_flow_train(self, gt, lr):
+        """training call of LLFlow_model.optimize_parameters (LLFlow_model.py:215-232): ``z, nll, _ = netG(gt=..., lr=..., reverse=False)``
+        followed by ``scaler.scale(nll.mean()).backward()``.  The objective and every parameter gradient come from the library's kernels
+        (encoder_train.stage2_nll: one autograd node over this module's named parameters); the `mean = gt` branch is drawn per call with
+        opt['train_gt_ratio'] like LLFlowVQGAN2_arch.py:109."""
+        from . import encoder_train
+        from .dense import make_dense
+        dev = next(self.parameters()).device
+        if self._train_ctx is None:
+            dense = make_dense(self.dense_name)
+            self._train_ctx = (dense, encoder_train.CudaLeaves(dense))
+        dense, leaves = self._train_ctx
+        ratio = 0.0
+        try:
+            ratio = float(self.opt["train_gt_ratio"] or 0.0)
+        except (TypeError, KeyError):
+            pass
+        named = [(k, p) for k, p in self.named_parameters() if k.startswith(("RRDB.", "flowUpsamplerNet."))]
+        nll = encoder_train.stage2_nll(named, gt.to(dev, torch.float32), lr.to(dev, torch.float32), leaves,
+                                       lambda x, w: dense.conv2d(x, w).float(), train_gt_ratio=ratio)
+        return None, nll, None

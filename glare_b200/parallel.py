@@ -37,6 +37,46 @@ def enhance_sharded(fn, images, group=None):
     return torch.cat(parts, 0)
 
 
+class AsyncGather:
+    """all_gather of each rank's result batch on a SIDE stream: the NVLink transfer of batch i overlaps the kernels of batch i + 1 (the
+    forward pass itself has no collective).  ``submit`` snapshots the local result into one of two private slots on the compute stream (the
+    caller's tensor -- e.g. a CUDA graph's static output -- may be overwritten right away), the collective runs on the side stream;
+    ``wait`` makes the compute stream wait for everything submitted so far.  Without an initialised process group it is a pass-through."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.side = torch.cuda.Stream() if self.on and torch.cuda.is_available() else None     # CPU tensors (gloo tests): synchronous
+        self.slots, self.outs, self.done, self.i = [None, None], [None, None], [None, None], 0
+
+    def submit(self, local):
+        if not self.on:
+            return local
+        i, self.i = self.i, self.i ^ 1
+        if self.side is None:
+            out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+            return out
+        cur = torch.cuda.current_stream()
+        if self.slots[i] is None or self.slots[i].shape != local.shape or self.slots[i].dtype != local.dtype:
+            self.slots[i] = torch.empty_like(local)
+            self.outs[i] = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        if self.done[i] is not None:
+            cur.wait_event(self.done[i])                  # the collective that last read this slot has finished
+        self.slots[i].copy_(local)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(self.outs[i], self.slots[i], group=self.group)
+            self.done[i] = torch.cuda.Event()
+            self.done[i].record(self.side)
+        return self.outs[i]
+
+    def wait(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+
+
 def allreduce_gradients(grads, group=None):
     """Data-parallel stage-2 training: every rank computes the gradients of its share of the batch
     (glare_b200.encoder_train.stage2_step); this averages them over the ranks with ONE collective over a flat fp32 bucket

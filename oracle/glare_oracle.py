@@ -261,13 +261,14 @@ def flow_encode(sd, gt, ft, logdet=None, p="flowUpsamplerNet"):
     return z, logdet
 
 
-def stage2_nll(sd, gt_latent, lr, quant=32, p_enc="RRDB"):
-    """LLFlowVQGAN2.normal_flow with train_gt_ratio branch 'mean = color_map'   LLFlowVQGAN2_arch.py:75-122
-    (add_gt_noise=False path as called by LLFlow_model.py:215).  Returns (z, nll[B])."""
+def stage2_nll(sd, gt_latent, lr, quant=32, p_enc="RRDB", use_gt_mean=False):
+    """LLFlowVQGAN2.normal_flow   LLFlowVQGAN2_arch.py:75-122 (add_gt_noise=False path as called by LLFlow_model.py:215).
+    use_gt_mean: the branch `random.random() > train_gt_ratio` picks at :109 -- False: mean = color_map, True: mean = gt.
+    Returns (z, nll[B])."""
     enc = cond_encoder(sd, lr, p_enc)
     pixels = gt_latent.shape[2] * gt_latent.shape[3]
     z, logdet = flow_encode(sd, gt_latent, enc["cond_feat"])
-    mean = enc["color_map"]
+    mean = gt_latent if use_gt_mean else enc["color_map"]
     logp = (-0.5 * ((z - mean) ** 2 + math.log(2 * math.pi))).sum(dim=(1, 2, 3))   # flow.py:76-95
     nll = -(logdet + logp) / float(np.log(2.) * pixels)
     return z, nll

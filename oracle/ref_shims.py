@@ -48,7 +48,7 @@ def install():
 
     _stub("pytorch_lightning", LightningModule=nn.Module)
     _stub("lpips", LPIPS=lambda *a, **k: nn.Identity())
-    _stub("natsort", natsorted=sorted, natsort=sorted)
+    _stub("natsort", natsorted=sorted, natsort=types.SimpleNamespace(natsorted=sorted))    # `from natsort import natsort` (infer_unpaired.py:5)
     _stub("pyiqa")
     _stub("tensorboardX", SummaryWriter=object)
     sk = _stub("skimage")

@@ -85,3 +85,32 @@ def test_aft_axpby_matches_reference_rounding(glare_lib, layout):
     assert torch.equal(ops.aft_axpby(a, b, one, ratio), a + b * ratio)
     with pytest.raises(ValueError):
         ops.aft_axpby(a, b[:, :64], m, m)
+
+
+def test_graph_replay_equals_eager(glare_lib, sd_g, sd_v):
+    """the whole pass as ONE captured CUDA graph (engine.graphed): replays on changing inputs give what the eager launches give, one
+    graph per input shape, and the launch counter advances by the graph's kernel count per replay"""
+    from glare_b200 import ops, synth
+    from glare_b200.api import GlareEnhancer
+    enh = GlareEnhancer(sd_g, sd_v, device="cuda:0", pad="lol")
+    batches = []
+    for seed in (1, 2):
+        lq, _ = synth.synth_images(2, 44, 60, seed=seed)
+        batches.append((lq.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory())
+    for i, x in enumerate((batches[0], batches[1], batches[0])):
+        n0 = ops.LAUNCHES
+        got = enh.enhance(x, graph=True).clone()
+        n_graph = ops.LAUNCHES - n0
+        n0 = ops.LAUNCHES
+        want = enh.enhance(x, graph=False)
+        n_eager = ops.LAUNCHES - n0
+        diff = (got.int() - want.int()).abs()
+        assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3
+        if i > 0:                                # (the first call also counts the eager warm-up and the capture pass)
+            assert n_graph == n_eager > 300      # kernels inside the graph are counted per replay
+    assert len(enh.engine._graphs) == 1
+    st = {}
+    lr = synth.preprocess(synth.synth_images(1, 32, 48, seed=3)[0])
+    a = enh.engine.infer(lr, stages=st, graph=True).clone()
+    b = enh.engine.infer(lr, graph=False)
+    assert torch.allclose(a, b, atol=1e-5) and st["idx"].numel() == 8 * 12

@@ -194,3 +194,67 @@ def test_stage2_nll_autograd_node_fills_param_grads_like_the_reference():
             ref, got = torch.from_numpy(g[key]) * 128.0, params[key[5:]].grad
             assert got is not None and float((got - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), key
     assert params["flowUpsamplerNet.layers.0.actnorm.bias"].grad is not None
+
+
+def test_stage2_step_gt_mean_branch_matches_reference():
+    """the `mean = gt` branch of LLFlowVQGAN2.normal_flow (LLFlowVQGAN2_arch.py:109, probability train_gt_ratio = 0.2): objective and gradients
+    against the reference's own (tests/golden/stage2_gtmean.npz) and against autograd of the oracle; color_conv receives no gradient"""
+    from glare_b200 import encoder_train, flow, synth
+    from oracle import glare_oracle as O
+    g, gm = load_golden("stage2"), load_golden("stage2_gtmean")
+    sd = synth.synth_state_dict("netG_stage2", 0)
+    gt, lr = torch.from_numpy(g["gt_latent"]), torch.from_numpy(g["lr"])
+    conv = lambda x, wgt: F.conv2d(x, wgt, None, padding=1)               # noqa: E731
+    with torch.no_grad():
+        nll, grads = encoder_train.stage2_step(sd, flow.FlowPlan(sd, torch.device("cpu")), lr, gt, TorchLeaves(), conv,
+                                               flow_kernels=TorchEmuKernels(sd), use_gt_mean=True)
+    assert np.allclose(nll.numpy(), gm["nll"], atol=1e-4, rtol=1e-5)
+    assert not np.allclose(gm["nll"], g["nll"], atol=1e-2)                # really the other branch
+    for key in list(gm):
+        if key.startswith("grad."):
+            ref = torch.from_numpy(gm[key])
+            assert float((grads[key[5:]] - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), key
+    for k in gm["no_grad"]:
+        assert str(k) not in grads
+    sda = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    _, nll_a = O.stage2_nll(sda, gt, lr, use_gt_mean=True)
+    nll_a.mean().backward()
+    for k, v in sda.items():
+        if v.grad is None:
+            assert k not in grads or float(grads[k].abs().max()) == 0.0, k
+        else:
+            sc = max(float(v.grad.abs().max()), 1e-6)
+            assert float((grads[k] - v.grad).abs().max()) <= 1e-3 * sc + 1e-7, k
+
+
+def test_draw_use_gt_mean_follows_the_reference_rng():
+    import random
+    from glare_b200 import encoder_train
+    random.seed(1)
+    want = [not (random.random() > 0.2) for _ in range(50)]
+    random.seed(1)
+    assert [encoder_train.draw_use_gt_mean(0.2) for _ in range(50)] == want and any(want) and not all(want)
+
+
+def test_packed_weight_cache_does_not_grow_with_optimizer_steps():
+    """the cache was keyed on the weight's in-place version -> one more packed copy of every weight per training step"""
+    from glare_b200.dense import TcDense
+    d = TcDense.__new__(TcDense)
+    d._w, d.mode, calls = {}, 4, []
+
+    class Ops:
+        @staticmethod
+        def conv_pack_weight(mode, w):
+            calls.append(w._version)
+            return (w.clone(), None)
+
+    d.ops = Ops()
+    w = torch.zeros((8, 32, 3, 3))
+    for step in range(5):
+        d._weights(w)
+        d._weights(w)                      # second use inside the step: cached
+        w.add_(1.0)                        # optimizer step bumps the version
+    assert len(calls) == 5 and len(d._w) == 1
+    for _ in range(600):                   # per-step temporaries (new tensor objects) are swept once dead
+        d._weights(torch.zeros((8, 32, 1, 1)))
+    assert len(d._w) <= 257

@@ -1,0 +1,94 @@
+"""GPU: the drop-in nn.Module mirrors (glare_b200/modules.py) called the way the reference calls them -- VERDICT r1 weak #9:
+  * VQLLFLOWDeformable.forward(net_vq=..., lr=..., z=..., eps_std=..., reverse=True, ...)  (VQLLFLOWD_model.py:296-305 get_sr_with_z, with
+    z from the get_z recipe :307-321 that reads flowUpsamplerNet.scaleH / scaleW) against the reference's own output (golden pipeline);
+  * VQModel.encode / decode (LLFlow_model.py:201, VQLLFLOWDeformable_arch.py:246) against the oracle / the golden decoder features;
+  * DCNv2Pack.forward (deformableDecoder_arch.py:141-152) against the oracle's restatement of the reference kernel;
+  * the stage-2 generator mirror TRAINED as dropped in: nll = netG(gt=..., lr=..., reverse=False)[1]; nll.mean().backward() fills
+    param.grad with the reference's own gradients (LLFlow_model.py:215-232; tests/golden/stage2.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nets(glare_lib, sd_g, sd_v):
+    from glare_b200 import modules
+    netG, net_hq = modules.VQLLFLOWDeformable().cuda(), modules.VQModel().cuda()
+    netG.load_state_dict(sd_g, strict=True)
+    net_hq.load_state_dict(sd_v, strict=True)
+    return netG.eval(), net_hq.eval()
+
+
+def test_generator_reverse_call_like_get_sr(nets):
+    netG, net_hq = nets
+    g = load_golden("pipe_64x96")
+    lq = torch.from_numpy(g["lr"]).cuda()
+    # VQLLFLOWD_model.get_z (heat 0, no split): zeros [B, 3 * 2^L * 2^L, scale * H // scaleH, scale * W // scaleW]
+    f = netG.flowUpsamplerNet
+    z = torch.zeros((lq.shape[0], 3 * 16, int(1 * lq.shape[2] // f.scaleH), int(1 * lq.shape[3] // f.scaleW)))
+    with torch.no_grad():
+        sr, enc_feat = netG(net_vq=net_hq, lr=lq, z=z, eps_std=0, reverse=True, reverse_with_grad=False, epses=None)
+    assert float((sr.cpu() - torch.from_numpy(g["out"])).abs().max()) < 1e-3
+    assert float((enc_feat.cpu() - torch.from_numpy(g["z_flow"])).abs().max()) < 2e-3
+
+
+def test_vqmodel_encode_decode(nets, sd_v):
+    from oracle import glare_oracle as O
+    _, net_hq = nets
+    g = load_golden("pipe_64x96")
+    x = torch.from_numpy(g["gt"])
+    h, _ = net_hq.encode(x.cuda())
+    want = O._conv(sd_v, "quant_conv", O.encoder(sd_v, "encoder", x)[0], padding=0)       # VQModel.encode, VQModel_arch.py:74-79
+    assert float((h.cpu() - want).abs().max()) < 1e-3 * max(1.0, float(want.abs().max()))
+    _, emb_loss, feats = net_hq.decode(torch.from_numpy(g["z_flow"]).cuda())
+    assert torch.allclose(feats[0].float().cpu()[:, ::16], torch.from_numpy(g["vq_feat1"]), atol=1e-3)
+    assert torch.allclose(feats[1].float().cpu()[:, ::16], torch.from_numpy(g["vq_feat0"]), atol=1e-3)
+    assert torch.isfinite(emb_loss)
+
+
+def test_dcnv2pack_module_forward(glare_lib):
+    from glare_b200 import modules
+    from oracle import glare_oracle as O
+    gen = torch.Generator().manual_seed(4)
+    m = modules.DCNv2Pack(16, 16, 3, stride=1, padding=1, deformable_groups=4)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(m.weight.shape, generator=gen) * 0.1)
+        m.bias.copy_(torch.randn(16, generator=gen) * 0.1)
+        m.conv_offset.weight.copy_(torch.randn(m.conv_offset.weight.shape, generator=gen) * 0.1)
+        m.conv_offset.bias.copy_(torch.randn(108, generator=gen) * 0.1)
+    x, feat = torch.randn((2, 16, 9, 12), generator=gen), torch.randn((2, 16, 9, 12), generator=gen)
+    out = torch.nn.functional.conv2d(feat, m.conv_offset.weight.detach(), m.conv_offset.bias.detach(), padding=1)
+    o1, o2, mk = torch.chunk(out, 3, dim=1)
+    want = O.modulated_deform_conv(x, torch.cat((o1, o2), 1), torch.sigmoid(mk), m.weight.detach(), m.bias.detach(), dg=4)
+    torch.backends.cudnn.allow_tf32 = False
+    got = m.cuda()(x.cuda(), feat.cuda())
+    assert float((got.detach().cpu() - want).abs().max()) < 1e-4
+
+
+def test_stage2_mirror_trains_as_dropped_in(glare_lib):
+    from glare_b200 import modules, synth
+    g = load_golden("stage2")
+    netG = modules.VQLLFLOWDeformable(which="netG_stage2", opt={"train_gt_ratio": 0.0, "datasets": {"train": {"GT_size": 256, "quant": 32}}}).cuda()
+    netG.load_state_dict(synth.synth_state_dict("netG_stage2", 0), strict=True)
+    netG.train()
+    opt = torch.optim.Adam([p for p in netG.parameters() if p.requires_grad], lr=5e-5, betas=(0.9, 0.99))
+    opt.zero_grad()
+    _, nll, _ = netG(gt=torch.from_numpy(g["gt_latent"]).cuda(), lr=torch.from_numpy(g["lr"]).cuda(), reverse=False)
+    assert np.allclose(nll.detach().cpu().numpy(), g["nll"], atol=2e-4, rtol=2e-5)
+    nll.mean().backward()
+    named = dict(netG.named_parameters())
+    for key in list(g):
+        if key.startswith("grad."):
+            ref, got = torch.from_numpy(g[key]), named[key[5:]].grad
+            assert got is not None and float((got.cpu() - ref).abs().max()) <= 2e-3 * max(float(ref.abs().max()), 1e-3), key
+    before = named["RRDB.cond_conv.0.weight"].detach().clone()
+    opt.step()
+    assert not torch.equal(before, named["RRDB.cond_conv.0.weight"].detach())
+    # evaluation call of the same module (get_encode_nll, VQLLFLOWD_model.py:270-275): no graph, (z, nll, logdet)
+    with torch.no_grad():
+        z, nll2, logdet = netG(gt=torch.from_numpy(g["gt_latent"]).cuda(), lr=torch.from_numpy(g["lr"]).cuda(), reverse=False)
+    assert z.shape == (2, 3, 8, 8) and nll2.shape == (2,) and logdet.shape == (2,)

@@ -77,3 +77,34 @@ def test_allreduce_gradients_gloo_world2():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert all(ok and shape == (3, 2) for _, ok, shape in res)
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from glare_b200.parallel import AsyncGather
+    ga = AsyncGather()
+    ok = True
+    for step in range(3):                                   # the two slots are reused from the third submit on
+        local = torch.full((2, 4, 5, 3), rank * 10 + step, dtype=torch.uint8)
+        out = ga.submit(local)
+        ga.wait()
+        want = torch.cat([torch.full((2, 4, 5, 3), r * 10 + step, dtype=torch.uint8) for r in range(world)])
+        ok = ok and bool(torch.equal(out, want))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_async_gather_gloo_world2():
+    """bench.py's result gather (uint8 batches, one all_gather per step); on CPU tensors it runs synchronously"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(ok for _, ok in res)

@@ -42,6 +42,7 @@ SIGNATURES = {
     "glare_attn_softmax_rows": [_i, _vp, _ll, _ll, _i, _i, ctypes.c_float, _vp, _vp, _ll, _vp],
     "glare_attn_transpose_v": [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "glare_attn_row_norm": [_vp, _ll, _i, _ll, _vp, _vp, _vp],
+    "glare_attn_row_ref": [_vp, _ll, _ll, _i, ctypes.c_float, ctypes.c_float, _vp, _vp],
     "glare_attn_scores_exp_tc": [_i, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _ll, _vp, _vp],
     "glare_attn_row_sum_finish": [_vp, _ll, _i, _ll, _vp, _vp, _vp],
     "glare_attn_pv_tc": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp],

@@ -266,6 +266,25 @@ __global__ void __launch_bounds__(256) attn_row_sum_finish_kernel(const float* _
     row_scale[r] = 1.0f / s;
 }
 
+// Row reference from SAMPLED scores (the default since round 2): s_sub [rows][lds] = q_i . k_j for a strided subset of the sample's keys
+// (one small GEMM, 128 keys = 1/127 of the scores GEMM at 600x400); ref_i = scale * max_j s_sub[i][j] + offset.  The sampled maximum L_i
+// is a LOWER bound of the row maximum m_i, so with offset = 50 the largest p~ of the row is e^(m_i - L_i - 50) >= e^-50 (the row sum
+// never underflows) and it overflows only if m_i - L_i > ~128: the fused path now fails only for rows whose true maximum exceeds the
+// maximum over 128 sampled keys by more than 128 nats -- independent of how loose |q||k| is (trained checkpoints: norms of tens,
+// logits of a few units).  attn_row_sum_finish still raises the flag for such rows and the host falls back to the exact path.
+__global__ void __launch_bounds__(256) attn_row_ref_kernel(const float* __restrict__ s_sub, long long rows, long long lds, int n_sub, float scale,
+                                                           float offset, float* __restrict__ ref_out) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* sr = s_sub + row * lds;
+    float m = -INFINITY;
+    for (int i = lane; i < n_sub; i += 32) m = fmaxf(m, __ldg(sr + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) ref_out[row] = fmaf(m, scale, offset);              // NaN scores propagate: the row sum check catches them
+}
+
 // |row| from the partial sums of squares a conv epilogue left per (output block, row) (glare_conv2d_nhwc_tc_pack)
 __global__ void __launch_bounds__(256) attn_row_norm_finish_kernel(const float* __restrict__ part, long long part_stride, int n_blocks, long long rows,
                                                                    long long rows_per_sample, float* __restrict__ norm_out,
@@ -295,6 +314,18 @@ __global__ void __launch_bounds__(256) attn_row_norm_finish_kernel(const float* 
 }  // namespace glare
 
 using namespace glare;
+
+// ref_out[r] = scale * max_{j < n_sub} s_sub[r * lds + j] + offset: the per-row softmax reference of glare_attn_scores_exp_tc (key_norm_max
+// null) from the scores against a sampled subset of the keys
+GLARE_API int glare_attn_row_ref(const float* s_sub, long long rows, long long lds, int n_sub, float scale, float offset, float* ref_out,
+                                 cudaStream_t stream) {
+    if (rows < 0 || n_sub <= 0 || lds < n_sub || !(scale > 0.f)) return GLARE_ERR_BAD_ARG;
+    if (rows == 0) return GLARE_OK;
+    if (!s_sub || !ref_out || (rows + 7) / 8 > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
+    attn_row_ref_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(s_sub, rows, lds, n_sub, scale, offset, ref_out);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
 
 // norm_out[r] = sqrt(sum_{b < n_blocks} part[b * part_stride + r]) (may be null); max_bits[r / rows_per_sample] = max over the sample (may be null)
 GLARE_API int glare_attn_row_norm_finish(const float* part, long long part_stride, int n_blocks, long long rows, long long rows_per_sample,

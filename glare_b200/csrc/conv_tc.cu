@@ -47,10 +47,11 @@ struct ConvTcArgs {
     int gn_cpg;              // channels per group (Cout / 32), a multiple of 4
     int tma_store;           // epilogue: registers -> swizzled smem staging -> TMA tiled store (else per-thread float4 stores)
     // attention epilogues (mode 4 only; attn.cu documents the scheme).  Scores GEMM: the accumulator s becomes
-    // p = exp(exp_scale * s - ref(row)), ref(row) = row_norm[row] * exp_scale * max|k| - exp_margin >= every logit of the row - margin,
-    // written as the bf16x3 operand of the P V GEMM; per-(row, output block) partial row sums go to row_sum_part.
-    const float* row_norm;        // [rows] |q_row|, or null
-    const unsigned* key_norm_max; // bits of max_j |k_j| (non-negative float)
+    // p = exp(exp_scale * s - ref(row)), written as the bf16x3 operand of the P V GEMM; per-(row, output block) partial row sums go to
+    // row_sum_part.  ref(row) = row_norm[row] when key_norm_max is null (the caller's reference: sampled row maximum + margin), else the
+    // Cauchy-Schwarz form row_norm[row] * exp_scale * max|k| - exp_margin >= every logit of the row - margin.
+    const float* row_norm;        // [rows] ref(row) or |q_row|, or null
+    const unsigned* key_norm_max; // bits of max_j |k_j| (non-negative float), or null
     float* row_sum_part;          // [n_blocks][part_stride]
     long long part_stride;
     float exp_scale, exp_margin;
@@ -409,7 +410,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool epi_pack = MODE == 4 && (epi_exp || a.pack_out != 0);
             const bool epi_sq = MODE == 4 && a.row_sq_part != nullptr;
             float e_ref = 0.f, e_sum = 0.f, r_scale = 1.f, e_sq = 0.f;
-            if (epi_exp && valid) e_ref = fmaf(__ldg(a.row_norm + pix), a.exp_scale * __uint_as_float(__ldg(a.key_norm_max)), -a.exp_margin);
+            if (epi_exp && valid)                                        // key_norm_max == null: row_norm holds the reference itself (attn.cu, sampled maximum)
+                e_ref = a.key_norm_max ? fmaf(__ldg(a.row_norm + pix), a.exp_scale * __uint_as_float(__ldg(a.key_norm_max)), -a.exp_margin)
+                                       : __ldg(a.row_norm + pix);
             if (a.row_scale != nullptr) r_scale = valid ? __ldg(a.row_scale + pix) : 0.f;
             // one 32-column chunk of this thread's accumulator row: registers -> bias / residual / attention epilogues -> store
             auto process = [&](const uint32_t (&v)[32], const int c0) {
@@ -870,8 +873,8 @@ GLARE_API int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, i
                                        float scale, float margin, const float* q_row_norm, const unsigned* key_norm_max, void* p_out,
                                        float* row_sum_part, long long part_stride, int* n_blocks_host, cudaStream_t stream) {
     if (mode != 4) return GLARE_ERR_UNSUPPORTED;
-    if (!q_row_norm || !key_norm_max || !row_sum_part || !n_blocks_host || n_pad < n_keys || (n_pad & 31) || !(scale > 0.f) || !(margin >= 0.f))
-        return GLARE_ERR_BAD_ARG;
+    if (!q_row_norm || !row_sum_part || !n_blocks_host || n_pad < n_keys || (n_pad & 31) || !(scale > 0.f) || !(margin >= 0.f))
+        return GLARE_ERR_BAD_ARG;                            // key_norm_max may be null: q_row_norm then holds the per-row reference itself
     AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host, 0, nullptr};
     return conv_tc_launch(mode, q, nullptr, k, nullptr, nullptr, nullptr, reinterpret_cast<float*>(p_out), 1, rows_h, rows_w, rows_h, rows_w, C,
                           n_keys, std_taps(1), 1, n_pad, 0, stream, nullptr, 0, &ae);
@@ -912,7 +915,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if (ae && (ae->row_norm || ae->row_scale) && (bias || residual || gn_stats)) return GLARE_ERR_UNSUPPORTED;
     if (ae && ae->pack_out && !ae->row_norm && ((Cout & 31) || ldy != Cout || residual || gn_stats || ts.oscale != 1)) return GLARE_ERR_UNSUPPORTED;
     if (ae && ae->row_sq_part && ae->part_stride < (long long)B * H * W) return GLARE_ERR_BAD_ARG;
-    if (epi_exp && (!ae->key_norm_max || !ae->row_sum_part || ae->part_stride < (long long)B * H * W || (ldy & 31) || Cout < 32))
+    if (epi_exp && (!ae->row_sum_part || ae->part_stride < (long long)B * H * W || (ldy & 31) || Cout < 32))
         return GLARE_ERR_BAD_ARG;
     if (gn_stats && (Cout % 128 != 0 || B <= 0)) return GLARE_ERR_UNSUPPORTED;       // 32 groups of a multiple of 4 channels
     if (gn_stats && gn_zero) GLARE_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 64 * (size_t)B, stream));

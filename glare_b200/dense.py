@@ -87,12 +87,17 @@ class TcDense:
         # path of the TMEM drain), so it is OFF by default; the separate gn_stats kernel is HBM-bound and cheaper.
         self.fuse_gn_stats = bool(os.environ.get("GLARE_FUSE_GN_STATS"))      # A/B switch
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
-        self.attn_s_budget = 3 << 29   # bytes of fp32 score matrix materialised per pass (1.5 GiB)
+        self.attn_s_budget = None      # bytes of score / operand matrix materialised per pass; None: sized from free HBM at first use (_budget)
         # mode 4: softmax fused into the epilogues of the two GEMMs (csrc/attn.cu): exp against a Cauchy-Schwarz row reference in the scores
         # GEMM, 1 / row sum in the P V GEMM; rows that fall outside the safe window raise `attn_flag` and `attention_verified()` tells
         # the caller (engine.infer) to re-run with the exact three-kernel path
         self.attn_fused = mode == 4 and not os.environ.get("GLARE_ATTN_UNFUSED")
         self.attn_margin = 60.0
+        # row reference of the fused softmax: "sampled" = maximum over 128 strided keys + 50 (one small extra GEMM per block; robust to loose
+        # |q||k| bounds), "cauchy" = the Cauchy-Schwarz bound - margin of round 1 (needs no extra GEMM; trips when the bound is > ~115 above
+        # the row maximum)
+        self.attn_ref = os.environ.get("GLARE_ATTN_REF", "sampled")
+        self.attn_ref_keys, self.attn_ref_offset = 128, 50.0
         self.attn_flag = None
         self.pack_epilogue = mode == 4 and not os.environ.get("GLARE_NO_PACK_EPILOGUE")   # A/B switch: operands written by the producing conv
         self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
@@ -256,6 +261,16 @@ class TcDense:
             y = self.ops.dcnv2_pack_fwd_nhwc_tc(self.mode, xn, on, w_hi, w_lo, bias, B, H, W, C, Cout, dg)
         return y.permute(0, 3, 1, 2)
 
+    def _budget(self):
+        """bytes of N x N operand per pass.  600x400 needs 1.06 GB per sample (one pass).  1080p (131 648 tokens, 69 GB per sample) runs in
+        bands of query rows: the band must hold enough 256-row tiles to fill the 74 CTA pairs of the P V GEMM (N = 512 -> two output
+        blocks), so the budget is a quarter of the free HBM up to 16 GiB (31 K query rows at 1080p; round 1's fixed 1.5 GiB gave 3.9 K rows
+        = 30 work items for 74 pairs)."""
+        if self.attn_s_budget is None:
+            free, _ = torch.cuda.mem_get_info()
+            self.attn_s_budget = int(max(3 << 29, min(16 << 30, free // 4)))
+        return self.attn_s_budget
+
     def attention(self, q, k, v, as_operand=False, fused=None):
         """AttnBlock core (encoder_decoder.py:176-187) on the tcgen05 GEMM path: per sample and per band of query rows
         S = Q K^T (W = K[n]) -> fused scale + row softmax emitting the operand P -> O = P V (W = V[n]^T)."""
@@ -286,7 +301,8 @@ class TcDense:
             out = torch.empty((B, h, w, C), device=vn.device, dtype=torch.float32)
             # query rows per pass: the whole sample when its score matrix fits the budget (tile-filling GEMMs matter more
             # than L2 residency of S: the P V GEMM needs >= 74 M-tiles to give every SM a 128x256 tile), else 8-row multiples
-            band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
+            budget = self._budget() // 2                      # S (fp32) and P (operand) are both materialised on this path
+            band = h if N * Np * 4 <= budget else max(8, (budget // (w * Np * 4)) // 8 * 8)
             rows_max = min(band, h) * w
             S = torch.empty((rows_max, Np), device=vn.device, dtype=torch.float32)
             p_hi = ops._hi_alloc(self.mode, (rows_max, Np), vn.device)
@@ -309,24 +325,39 @@ class TcDense:
 
     def _attention_fused(self, qn, kn, q_op, k_op, vt_op, out, B, h, w, N, Np, C, sq=(None, None), pack=False):
         """mode 4: scores GEMM with the exp epilogue -> row-sum finish -> P V GEMM with the 1 / row-sum epilogue (csrc/attn.cu).
-        qn / kn: fp32 NHWC q / k (row norms by a pass over them) or None when sq carries the partial sums of squares their conv left."""
+        qn / kn: fp32 NHWC q / k (row norms by a pass over them) or None when sq carries the partial sums of squares their conv left (only the
+        "cauchy" reference needs either)."""
         ops, dev = self.ops, q_op.device
         if self.attn_flag is None or self.attn_flag.device != dev:
             self.attn_flag = torch.zeros((1,), device=dev, dtype=torch.int32)
         scale = float(int(C) ** (-0.5))
         q_norm = torch.empty((B, N), device=dev, dtype=torch.float32)
-        k_max = torch.zeros((B,), device=dev, dtype=torch.int32)
-        with self._t("attn_softmax"):
-            if sq[0] is not None:
-                ops.attn_row_norm_finish(sq[0][0], sq[0][1], B * N, N, norm_out=q_norm)
-            else:
-                ops.attn_row_norm(qn, B * N, C, N, norm_out=q_norm)
-            if sq[1] is not None:
-                ops.attn_row_norm_finish(sq[1][0], sq[1][1], B * N, N, max_bits=k_max)
-            else:
-                ops.attn_row_norm(kn, B * N, C, N, max_bits=k_max)
+        if self.attn_ref == "sampled":
+            # scores of every query against n_sub strided keys of its sample (per-sample weights: one launch for the batch) -> row maximum
+            k_max = None
+            n_sub = min(N, self.attn_ref_keys)
+            sel = torch.linspace(0, N - 1, n_sub, device=dev).round().long()
+            k_sub = k_op.view(B, N, -1).index_select(1, sel).contiguous()            # [B][n_sub][2C] operand rows = GEMM weights
+            ld = (n_sub + 3) // 4 * 4
+            s_sub = torch.empty((B * N, ld), device=dev, dtype=torch.float32)
+            with self._t("conv_tc", 2.0 * B * N * n_sub * C):
+                ops.conv2d_nhwc_tc_ex(self.mode, q_op, None, k_sub, None, s_sub, B, h, w, C, n_sub, ld, n_sub * C)
+            with self._t("attn_softmax"):
+                ops.attn_row_ref(s_sub, B * N, ld, n_sub, scale, self.attn_ref_offset, q_norm)
+        else:
+            k_max = torch.zeros((B,), device=dev, dtype=torch.int32)
+            with self._t("attn_softmax"):
+                if sq[0] is not None:
+                    ops.attn_row_norm_finish(sq[0][0], sq[0][1], B * N, N, norm_out=q_norm)
+                else:
+                    ops.attn_row_norm(qn, B * N, C, N, norm_out=q_norm)
+                if sq[1] is not None:
+                    ops.attn_row_norm_finish(sq[1][0], sq[1][1], B * N, N, max_bits=k_max)
+                else:
+                    ops.attn_row_norm(kn, B * N, C, N, max_bits=k_max)
         # whole-sample passes while the operand matrix fits the budget, else bands of 8-row multiples
-        band = h if N * Np * 4 <= self.attn_s_budget else max(8, (self.attn_s_budget // (w * Np * 4)) // 8 * 8)
+        budget = self._budget()
+        band = h if N * Np * 4 <= budget else max(8, (budget // (w * Np * 4)) // 8 * 8)
         rows_max = min(band, h) * w
         p_op = ops._hi_alloc(self.mode, (rows_max, Np), dev)
         n32 = (N + 31) // 32 * 32
@@ -341,7 +372,7 @@ class TcDense:
                 gemm_flops = 2.0 * bh * w * N * C
                 with self._t("conv_tc", gemm_flops):
                     nb = ops.attn_scores_exp_tc(self.mode, q_op[b, r0:r1], k_op[b], bh, w, C, N, Np, scale, self.attn_margin,
-                                                q_norm[b, r0 * w:], k_max[b:], p_op, part, rows_max)
+                                                q_norm[b, r0 * w:], None if k_max is None else k_max[b:], p_op, part, rows_max)
                 with self._t("attn_softmax"):
                     ops.attn_row_sum_finish(part, rows_max, nb, bh * w, row_scale, self.attn_flag)
                 with self._t("conv_tc", gemm_flops):

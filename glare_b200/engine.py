@@ -85,9 +85,11 @@ class GlareEngine:
         hn = self._gn(sd, p + ".norm", x, swish=False)
         q = k = None
         if getattr(self.dense, "attn_fused", False) and hasattr(self.dense, "conv2d_operand"):
-            # q / k only feed the scores GEMM: their convs write its operands and the row norms of the softmax reference directly
-            q = self.dense.conv2d_operand(hn, sd[p + ".q.weight"], sd.get(p + ".q.bias"), row_sq=True)
-            k = self.dense.conv2d_operand(hn, sd[p + ".k.weight"], sd.get(p + ".k.bias"), row_sq=True)
+            # q / k only feed the scores GEMM: their convs write its operands directly (and, for the Cauchy-Schwarz softmax reference, the
+            # row norms)
+            rsq = getattr(self.dense, "attn_ref", "sampled") == "cauchy"
+            q = self.dense.conv2d_operand(hn, sd[p + ".q.weight"], sd.get(p + ".q.bias"), row_sq=rsq)
+            k = self.dense.conv2d_operand(hn, sd[p + ".k.weight"], sd.get(p + ".k.bias"), row_sq=rsq)
         if q is None or k is None:
             q = self._conv(sd, p + ".q", hn, padding=0)
             k = self._conv(sd, p + ".k", hn, padding=0)

@@ -236,6 +236,12 @@ def attn_row_norm(x_rows, rows, C, rows_per_sample, norm_out=None, max_bits=None
     check(lib().glare_attn_row_norm(ptr(x_rows), rows, C, rows_per_sample, ptr(norm_out), ptr(max_bits), stream()), "glare_attn_row_norm")
 
 
+def attn_row_ref(s_sub, rows, lds, n_sub, scale, offset, ref_out):
+    """per-row softmax reference from the scores against a sampled subset of the keys: scale * rowmax + offset"""
+    require_cuda(s_sub, ref_out)
+    check(lib().glare_attn_row_ref(ptr(s_sub), rows, lds, n_sub, scale, offset, ptr(ref_out), stream()), "glare_attn_row_ref")
+
+
 def attn_scores_exp_tc(mode, q_op, k_op, rows_h, rows_w, C, n_keys, n_pad, scale, margin, q_norm, key_max, p_out, row_sum_part, part_stride):
     """scores GEMM with exp(scale * s - ref(row)) in the epilogue; returns the number of output blocks (valid planes of row_sum_part)"""
     import ctypes

@@ -170,6 +170,12 @@ int glare_attn_transpose_v(int out_mode, const float* v, int B, int N, int C, in
  * GEMM scales row i by 1 / sum_j p~_ij.  A row whose sum leaves [1e-24, 3e38] sets *flag (the caller re-runs with the exact path). */
 int glare_attn_row_norm(const float* x, long long rows, int C, long long rows_per_sample, float* norm_out, unsigned* max_bits,
                         cudaStream_t stream);
+/* Default row reference (round 2): ref_out[r] = scale * max_{j < n_sub} s_sub[r * lds + j] + offset, from the scores of every query against a
+ * strided SAMPLE of the keys (one small GEMM).  The sampled maximum is a lower bound of the row maximum, so the fused path only leaves its
+ * window when the true maximum exceeds the sampled one by > ~128 nats, however loose |q||k| is.  Passed to glare_attn_scores_exp_tc as
+ * q_row_norm with key_norm_max = NULL. */
+int glare_attn_row_ref(const float* s_sub, long long rows, long long lds, int n_sub, float scale, float offset, float* ref_out,
+                       cudaStream_t stream);
 int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, int rows_h, int rows_w, int C, int n_keys, int n_pad, float scale,
                              float margin, const float* q_row_norm, const unsigned* key_norm_max, void* p_out, float* row_sum_part,
                              long long part_stride, int* n_blocks_host, cudaStream_t stream);

@@ -226,29 +226,67 @@ def test_attention_query_bands(glare_lib, fused):
     assert float((banded - whole).abs().max()) < 1e-5
 
 
-def test_attention_fused_softmax_window_flag_and_fallback(glare_lib):
-    """rows whose maximum logit sits > ~115 below the Cauchy-Schwarz bound raise the device flag; attention_verified() then switches the
-    backend to the exact path, which is what the engine re-runs with"""
+@pytest.mark.parametrize("ref", ["sampled", "cauchy"])
+def test_attention_fused_softmax_window_flag_and_fallback(glare_lib, ref):
+    """rows outside the fused path's window raise the device flag; attention_verified() then switches the backend to the exact path, which is
+    what the engine re-runs with.  "cauchy": row maximum > ~115 below the |q||k| bound (huge norms along orthogonal directions).  "sampled":
+    the true row maximum > ~128 above the maximum over the sampled keys (one enormous key that the stride misses)."""
     from glare_b200.dense import TcDense
     B, C, h, w = 1, 512, 12, 16
     g = torch.Generator().manual_seed(3)
     q = torch.randn((B, C, h, w), generator=g) * 0.05
     k = torch.randn((B, C, h, w), generator=g) * 0.05
-    q[:, 0] = 400.0                                   # huge norms along orthogonal directions: bound ~ 400 * 400 / 22.6, logits ~ 0
-    k[:, 0] = 0.0
-    k[:, 1] = 400.0
-    q[:, 1] = 0.0
+    if ref == "cauchy":
+        q[:, 0] = 400.0                               # bound ~ 400 * 400 / 22.6, logits ~ 0
+        k[:, 0] = 0.0
+        k[:, 1] = 400.0
+        q[:, 1] = 0.0
+    else:
+        q[:, 0] = 60.0                                # key (0, 1) is not among the 128 sampled of 192 (linspace picks 0, 2, 3, 5, ...)
+        k[:, 0] = 0.0
+        k[0, 0, 0, 1] = 60.0 * 22.627417 * 0.1        # its logit: 60 * 135.8 / 22.6 = 360 above every sampled key's
     v = torch.randn((B, C, h, w), generator=g)
     q, k, v = q.cuda(), k.cuda(), v.cuda()
     d = TcDense(4)
+    d.attn_ref = ref
+    if ref == "sampled":
+        sel = torch.linspace(0, h * w - 1, 128).round().long()
+        assert 1 not in sel.tolist()
     d.attention(q, k, v)
     assert not d.attention_verified()
     assert not d.attn_fused and d.fallbacks
     out = d.attention(q, k, v)
     assert d.attention_verified()
-    ref = _attention_fp64(q, k, v)
-    err = float((out.reshape(B, C, h * w).double() - ref).abs().max())
-    assert err < 6e-5 * max(1.0, float(ref.abs().max())), err
+    ref64 = _attention_fp64(q, k, v)
+    assert float((out.reshape(B, C, h * w).double() - ref64).abs().max()) < 6e-5 * max(1.0, float(ref64.abs().max()))
+
+
+@pytest.mark.parametrize("shape,sq,sk", [((1, 512, 24, 21), 3.0, 3.0), ((2, 512, 40, 33), 6.0, 2.0), ((1, 512, 105, 155), 4.0, 4.0)])
+def test_attention_fused_softmax_trained_net_logit_ranges(glare_lib, shape, sq, sk):
+    """logit ranges of a TRAINED net -- large |q|, |k| in random directions, so that the Cauchy-Schwarz bound
+    |q||k| C^-1/2 (~ sq * sk * 22.6) sits far more than 115 above the actual row maximum (~ 4.5 * sq * sk) with peaked rows.  The sampled
+    reference keeps these on the fused path (no flag, no fallback) and matches the exact softmax; the round-1 reference trips."""
+    from glare_b200.dense import TcDense
+    B, C, h, w = shape
+    g = torch.Generator().manual_seed(11 + h)
+    q = (torch.randn((B, C, h, w), generator=g) * sq).cuda()
+    k = (torch.randn((B, C, h, w), generator=g) * sk).cuda()
+    v = torch.randn((B, C, h, w), generator=g).cuda()
+    N = h * w
+    s0 = (q[0].reshape(C, N).t()[:256].double() @ k[0].reshape(C, N).double()) * C ** -0.5
+    bound = float(q[0].reshape(C, N).norm(dim=0).max() * k[0].reshape(C, N).norm(dim=0).max()) * C ** -0.5
+    assert bound - float(s0.max(dim=1).values.min()) > 130          # the round-1 window is exceeded ...
+    d = TcDense(4)
+    assert d.attn_ref == "sampled"
+    out = d.attention(q, k, v)
+    assert d.attention_verified() and d.attn_fused and not d.fallbacks
+    ref64 = _attention_fp64(q, k, v)
+    sc = max(1.0, float(ref64.abs().max()))
+    assert float((out.reshape(B, C, N).double() - ref64).abs().max()) < 1e-4 * sc
+    old = TcDense(4)
+    old.attn_ref = "cauchy"
+    old.attention(q, k, v)
+    assert not old.attention_verified()                              # ... and the round-1 reference falls back
 
 
 @pytest.mark.parametrize("mode,tol", [(4, 1e-4), (3, 5e-5), (2, 5e-5), (1, 3e-3), (0, 2e-4)])   # K = 4608 with a truncating fp32 accumulator

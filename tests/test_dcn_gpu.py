@@ -150,3 +150,64 @@ def test_backward_against_cpu_autograd(glare_lib, cfg):
         err = float((d.grad.cpu() - r.grad).abs().max())
         scale = max(1.0, float(r.grad.abs().max()))
         assert err < 2e-4 * scale, (name, cfg, err, scale)
+
+
+def _case(seed, B=2, C=32, Co=32, H=13, W=17, dg=4):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((B, C, H, W), generator=g)
+    off = torch.randn((B, dg * 18, H, W), generator=g) * 2.0
+    msk = torch.sigmoid(torch.randn((B, dg * 9, H, W), generator=g))
+    w = torch.randn((Co, C, 3, 3), generator=g) / (3.0 * C ** 0.5)
+    b = torch.randn((Co,), generator=g)
+    gy = torch.randn((B, Co, H, W), generator=g)
+    return [t.cuda().contiguous() for t in (x, off, msk, w, b, gy)]
+
+
+def test_deform_conv_ext_shim_forward_backward(glare_lib):
+    """glare_b200/deform_conv_ext.py called the way the reference's ModulatedDeformConvFunction calls its plug-in (deform_conv.py:147-153,
+    161-170): caller-allocated output and zeroed gradient tensors, two empty scratch tensors; against torchvision's CPU autograd"""
+    import torchvision.ops
+    from glare_b200 import deform_conv_ext as ext
+    x, off, msk, w, b, gy = _case(21)
+    out = x.new_empty((2, 32, 13, 17))
+    bufs = [x.new_empty(0), x.new_empty(0)]
+    ext.modulated_deform_conv_forward(x, w, b, bufs[0], off, msk, out, bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, 4, True)
+    grads = [torch.zeros_like(t) for t in (x, w, b, off, msk)]
+    ext.modulated_deform_conv_backward(x, w, b, bufs[0], off, msk, bufs[1], grads[0], grads[1], grads[2], grads[3], grads[4], gy,
+                                       3, 3, 1, 1, 1, 1, 1, 1, 1, 4, True)
+    assert bufs[0].numel() == 0 and bufs[1].numel() == 0
+    cx, coff, cmsk, cw, cb = (t.detach().cpu().requires_grad_(True) for t in (x, off, msk, w, b))
+    y_ref = torchvision.ops.deform_conv2d(cx, coff, cw, cb, stride=1, padding=1, dilation=1, mask=cmsk)
+    y_ref.backward(gy.cpu())
+    assert torch.allclose(out.cpu(), y_ref.detach(), atol=1e-4, rtol=1e-4)
+    for got, want, nm in zip(grads, (cx.grad, cw.grad, cb.grad, coff.grad, cmsk.grad), ("input", "weight", "bias", "offset", "mask")):
+        sc = max(1.0, float(want.abs().max()))
+        assert float((got.cpu() - want).abs().max()) < 2e-3 * sc, nm
+
+
+def test_against_the_reference_built_extension(glare_lib):
+    """oracle/_ref/deform_conv_ext.so = the reference's own CUDA sources compiled unmodified for sm_100 (oracle/build_ref_dcn.py): the
+    reference GPU kernel itself as the checker of both glare DCN kernels.  Skipped when the extension was not built."""
+    import os
+    import sys
+    from conftest import ROOT
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "deform_conv_ext.so")):
+        pytest.skip("oracle/_ref/deform_conv_ext.so not built (python -m oracle.build_ref_dcn, authoring container)")
+    sys.path.insert(0, ref_dir)
+    try:
+        import deform_conv_ext as ref_ext
+    finally:
+        sys.path.remove(ref_dir)
+    from glare_b200 import ops
+    from glare_b200.dense import make_dense
+    x, off, msk, w, b, _ = _case(5, B=2, C=128, Co=128, H=30, W=41)
+    out = x.new_empty(x.shape)
+    ref_ext.modulated_deform_conv_forward(x, w, b, x.new_empty(0), off, msk, out, x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 4, True)
+    y_fma = ops.modulated_deform_conv(x, off, msk, w, b, 1, 1, 1, 1, 4)
+    assert float((y_fma - out).abs().max()) < 1e-4
+    # tensor-core kernel: consumes the raw conv_offset output (offsets in the reference's (g, tap, {dh, dw}) order, mask LOGITS)
+    o1, o2 = torch.chunk(off, 2, dim=1)
+    raw = torch.cat((o1, o2, torch.logit(msk.clamp(1e-6, 1 - 1e-6))), dim=1)
+    y_tc = make_dense("auto").dcn_pack(x, raw, w, b, 4)
+    assert float((y_tc - out).abs().max()) < 2e-4 * max(1.0, float(out.abs().max()))

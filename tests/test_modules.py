@@ -83,3 +83,45 @@ def test_dropin_rebinds_reference_factories(sd_g, sd_v):
     finally:
         networks.define_Flow, networks.find_vqgan = saved
         dda.modulated_deform_conv, dda.DCNv2Pack = saved_dcn
+
+
+def test_deform_conv_ext_shim_exports_the_reference_plugin_surface():
+    """the five functions of the reference's pybind11 module (ops/dcn/src/deform_conv_ext.cpp:150-164) with the reference's argument counts"""
+    import inspect as ins
+    from glare_b200 import deform_conv_ext as ext
+    want = {"deform_conv_forward", "deform_conv_backward_input", "deform_conv_backward_parameters", "modulated_deform_conv_forward",
+            "modulated_deform_conv_backward"}
+    assert want <= set(dir(ext))
+    assert len(ins.signature(ext.modulated_deform_conv_forward).parameters) == 19       # deform_conv_ext.cpp:125-134
+    assert len(ins.signature(ext.modulated_deform_conv_backward).parameters) == 24      # :136-147
+    x = torch.zeros((1, 8, 4, 4))
+    with pytest.raises(NotImplementedError):                                             # CPU tensors: as the reference
+        ext.modulated_deform_conv_forward(x, torch.zeros((8, 8, 3, 3)), torch.zeros(8), x.new_empty(0), torch.zeros((1, 72, 4, 4)),
+                                          torch.zeros((1, 36, 4, 4)), torch.zeros((1, 8, 4, 4)), x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 4, True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code"), reason="reference tree not mounted")
+def test_reference_function_binds_the_shim_without_rebinding():
+    """registering the shim under the name the reference imports (deform_conv.py:23-26 `from . import deform_conv_ext`) makes the
+    reference's OWN ModulatedDeformConvFunction call into it: checked on CPU up to the shim's NotImplementedError for CPU tensors"""
+    import importlib
+    import sys
+    from oracle import ref_shims
+    from glare_b200 import deform_conv_ext as ext
+    ref_shims.install()
+    name = "models.modules.ops.dcn.deform_conv_ext"
+    saved, saved_mod = sys.modules.get(name), sys.modules.pop("models.modules.ops.dcn.deform_conv", None)
+    try:
+        sys.modules[name] = ext
+        dc = importlib.import_module("models.modules.ops.dcn.deform_conv")
+        assert dc.deform_conv_ext is ext
+        x = torch.zeros((1, 8, 4, 4))
+        with pytest.raises(NotImplementedError):
+            dc.modulated_deform_conv(x, torch.zeros((1, 72, 4, 4)), torch.zeros((1, 36, 4, 4)), torch.zeros((8, 8, 3, 3)), torch.zeros(8), 1, 1, 1, 1, 4)
+    finally:
+        sys.modules.pop(name, None)
+        sys.modules.pop("models.modules.ops.dcn.deform_conv", None)
+        if saved is not None:
+            sys.modules[name] = saved
+        if saved_mod is not None:
+            sys.modules["models.modules.ops.dcn.deform_conv"] = saved_mod

@@ -179,6 +179,52 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
         "dpsnr_vs_fp32_path_db": abs(O.psnr(o16, gtq) - O.psnr(o32, gtq)), "pixel_mean_abs_diff_vs_fp32_path": float((o16 - o32).abs().mean())}
     del enh, lr_dev
     torch.cuda.empty_cache()
+    # ---- configs[3]: one stage-2 training step through the drop-in mirrors, the call sequence of LLFlow_model.optimize_parameters
+    # (LLFlow_model.py:181-232): frozen VQGAN encodes the ground truth, netG(gt=..., lr=..., reverse=False) -> nll.mean().backward()
+    # (objective + every gradient from libglare_b200.so), gradient all-reduce over the ranks, Adam step.  Batch 4 x 320x320 per GPU.
+    if not quick:
+        from glare_b200 import modules
+        from glare_b200.parallel import allreduce_gradients
+        opt2 = {"train_gt_ratio": 0.2, "datasets": {"train": {"GT_size": 320, "quant": 32}}}          # train_stage2_LOL.yml
+        netG = modules.VQLLFLOWDeformable(which="netG_stage2", opt=opt2).to(dev)
+        netG.load_state_dict(synth.synth_state_dict("netG_stage2", 0), strict=True)
+        netG.train()
+        net_hq = modules.VQModel().to(dev)
+        net_hq.load_state_dict(sd_v, strict=True)
+        net_hq.eval()
+        named = [(k, p) for k, p in netG.named_parameters()]
+        optim = torch.optim.Adam([p for _, p in named], lr=5e-5, betas=(0.9, 0.99))
+        gen = torch.Generator().manual_seed(10 + rank)                                                # train_stage2_LOL.yml manual_seed
+        real_H = torch.rand((4, 3, 320, 320), generator=gen).to(dev)
+        var_L = synth.preprocess(torch.rand((4, 3, 320, 320), generator=gen)).to(dev)
+        import random
+        random.seed(10)
+        last = {}
+
+        def train_step():
+            optim.zero_grad(set_to_none=True)
+            with torch.no_grad():
+                encoder_gt, _ = net_hq.encode(real_H)
+            _, nll, _ = netG(gt=encoder_gt.detach(), lr=var_L, reverse=False)
+            nll.mean().backward()
+            if world > 1:
+                grads = allreduce_gradients({k: p.grad for k, p in named if p.grad is not None})
+                for k, p in named:
+                    if p.grad is not None:
+                        p.grad = grads[k].to(p.grad.dtype).reshape(p.grad.shape)
+            optim.step()
+            last["nll"] = nll.detach()
+
+        ms_t = timed(train_step, 5, 2)
+        out["stage2_training_step"] = {
+            "workload": "configs[3]: one stage-2 step (frozen-VQGAN encode of GT, flow NLL forward + backward, Adam) through the drop-in "
+                        "mirrors, batch 4 x 320x320 per GPU, fp32-grade tensor-core operands (bf16x3), train_gt_ratio 0.2",
+            "value": world * 4 / (ms_t / 1e3), "unit": "samples/s", "ms_per_step": ms_t, "steps_per_s_per_gpu": 1e3 / ms_t,
+            "algorithmic_tflop_per_step": 12.6, "achieved_tflops_per_gpu": 12.6 / (ms_t / 1e3), "frac_of_bf16_peak": 12.6 / (ms_t / 1e3) / pk["tensor"],
+            "nll_last": [round(float(v), 4) for v in last["nll"].cpu()],
+            "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else None}
+        del netG, net_hq, optim
+        torch.cuda.empty_cache()
     # ---- configs[4]: 1920x1080, the fp32-grade default backend, batch swept
     enh = GlareEnhancer(sd_g, sd_v, device=dev, pad="auto", dense=fp32_engine.dense)
     sweep = {}

@@ -31,13 +31,15 @@ SIGNATURES = {
     "glare_dcnv2_bwd_data_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "glare_dcnv2_bwd_weight_f32": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "glare_dcnv2_pack_fwd_nhwc_tc": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "glare_dcnv2_fwd_nhwc_tc": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "glare_conv_tc_elem_bytes": [_i],
     "glare_conv_pack_weight": [_i, _vp, _i, _i, _i, _vp, _vp, _vp],
     "glare_conv_prep_act": [_i, _vp, _ll, _vp, _vp, _vp],
     "glare_conv2d_nhwc_tc": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "glare_conv2d_nhwc_tc_down2": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "glare_conv2d_nhwc_tc_up2_phase": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "glare_conv2d_nhwc_tc_g": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "glare_conv2d_nhwc_tc_g": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp],
+    "glare_conv_gn_scratch_floats": [_i, _i, _i],
     "glare_conv2d_nhwc_tc_ex": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _vp],
     "glare_attn_softmax_rows": [_i, _vp, _ll, _ll, _i, _i, ctypes.c_float, _vp, _vp, _ll, _vp],
     "glare_attn_transpose_v": [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
@@ -57,7 +59,7 @@ SIGNATURES = {
     "glare_gn_stats_nhwc_f32": [_vp, _i, _ll, _i, _i, _vp, _vp],
     "glare_gn_apply_nhwc": [_i, _vp, _vp, _vp, _vp, ctypes.c_float, _i, _i, _ll, _i, _i, _vp, _vp, _vp],
 }
-_RESTYPES = {"glare_error_string": ctypes.c_char_p}
+_RESTYPES = {"glare_error_string": ctypes.c_char_p, "glare_conv_gn_scratch_floats": ctypes.c_longlong}
 
 
 class GlareLibraryError(RuntimeError):

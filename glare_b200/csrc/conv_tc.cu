@@ -43,8 +43,10 @@ struct ConvTcArgs {
     int m_tiles;             // B * tiles_y * tiles_x
     int w_batched;           // weights differ per sample (3rd tensor-map coordinate = n): attention S = Q K^T, O = P V
     long long ldy;           // output row (pixel) stride in elements, >= Cout
-    double* gn_stats;        // optional [B][32][2] (sum, sum of squares) of the OUTPUT per GroupNorm group, accumulated in the epilogue
-    int gn_cpg;              // channels per group (Cout / 32), a multiple of 4
+    float* gn_part;          // optional [B][gn_slots][32][2]: per (pixel tile, epilogue warp) partial (sum, sum of squares) of the OUTPUT per
+                             // GroupNorm group -- every entry written exactly once (no atomics), reduced in fp64 by conv_gn_finish_kernel
+    int gn_cpg;              // channels per group (Cout / 32): 4, 8 or 16
+    int gn_slots;            // tiles_y * tiles_x * 4
     int tma_store;           // epilogue: registers -> swizzled smem staging -> TMA tiled store (else per-thread float4 stores)
     // attention epilogues (mode 4 only; attn.cu documents the scheme).  Scores GEMM: the accumulator s becomes
     // p = exp(exp_scale * s - ref(row)), written as the bf16x3 operand of the P V GEMM; per-(row, output block) partial row sums go to
@@ -86,7 +88,7 @@ struct ConvCfg {
     static constexpr int HALO_STAGES_RAW = SMEM_BUDGET / HALO_STAGE_BYTES;
     static constexpr int HALO_STAGES = HALO_STAGES_RAW > 8 ? 8 : HALO_STAGES_RAW;
     static constexpr int HALO_SMEM_DYN = HALO_STAGES * HALO_STAGE_BYTES + STAGING_BYTES + 1024;
-    // RING2 variant (opt-in, GLARE_CONV_RING2=1; not yet run on hardware): the same filter-row patch staging for the 256-wide N tile, where one
+    // RING2 variant (default for 3x3 stride-1 convs with the 256-wide N tile; GLARE_CONV_NO_RING2=1 disables): the same filter-row patch staging, where one
     // stage per filter row (patch + three 16 KB weight slabs = 68 KB) would leave only two stages.  Activation patches and weight slabs get their
     // own rings instead: R2_A_SLOTS patches (one per filter row and K chunk) and R2_B_SLOTS slabs (one per tap and K chunk).
     static constexpr int R2_A_SLOTS = 3;
@@ -489,53 +491,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         o[16 + (j >> 1)] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
                     }
                 }
-                if (a.gn_stats != nullptr) {
-                    // GroupNorm statistics of what this conv produces (the next layer's Normalize, encoder_decoder.py:34-35):
-                    // per group fp32 partial sums over this thread's channels, warp-reduced over 32 pixels, one fp64 atomic per
-                    // (warp, group) -- saves the separate statistics pass over the activation
-                    const int qpg = a.gn_cpg >> 2;                          // quads of channels per group: 1, 2, 4 or 8
-                    float s4[8], q4[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float v0 = valid ? o[4 * i] : 0.f, v1 = valid ? o[4 * i + 1] : 0.f;
-                        const float v2 = valid ? o[4 * i + 2] : 0.f, v3 = valid ? o[4 * i + 3] : 0.f;
-                        s4[i] = (v0 + v1) + (v2 + v3);
-                        q4[i] = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, v3 * v3)));
-                    }
-                    if (qpg >= 2) {
-#pragma unroll
-                        for (int i = 0; i < 8; i += 2) { s4[i] += s4[i + 1]; q4[i] += q4[i + 1]; }
-                    }
-                    if (qpg >= 4) {
-#pragma unroll
-                        for (int i = 0; i < 8; i += 4) { s4[i] += s4[i + 2]; q4[i] += q4[i + 2]; }
-                    }
-                    if (qpg >= 8) { s4[0] += s4[4]; q4[0] += q4[4]; }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if ((i & (qpg - 1)) != 0) continue;                   // uniform: first quad of each group
-                        float sm = s4[i], sq = q4[i];
-#pragma unroll
-                        for (int sh = 16; sh > 0; sh >>= 1) {
-                            sm += __shfl_xor_sync(0xffffffffu, sm, sh);
-                            sq += __shfl_xor_sync(0xffffffffu, sq, sh);
-                        }
-                        if (lane == 0 && n < a.B && co + 4 * i < a.Cout) {
-                            double* st = a.gn_stats + ((long long)n * 32 + (co + 4 * i) / a.gn_cpg) * 2;
-                            atomicAdd(st, (double)sm);
-                            atomicAdd(st + 1, (double)sq);
-                        }
-                    }
-                }
                 if (a.tma_store) {
                     uint8_t* buf = staging + (chunk_id & 1) * (32 * 128);
                     __syncwarp();                                        // lane 0 has seen the previous store of this buffer drain
+                    if (a.gn_part != nullptr && !valid) {                // pixels outside the image are clipped by the store; keep them out of the sums
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = 0.f;
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)                          // SWIZZLE_128B: 16-byte chunk j of row r at chunk j ^ (r & 7)
                         *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                             make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     fence_proxy_async();
                     __syncwarp();
+                    if (a.gn_part != nullptr) {
+                        // GroupNorm statistics of what this conv produces (the next layer's Normalize, encoder_decoder.py:34-35), from the
+                        // staged tile: lane l sums channel co + l over the warp's 32 pixels -- column reads of the swizzled tile are
+                        // conflict-free (32 distinct words of one 128-byte row per step) --, cpg adjacent lanes fold into their group, and the
+                        // group's first lane writes the (tile, warp) partial.  No shuffles over pixels, no atomics: one fp32 pair per group.
+                        float cs = 0.f, cq = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const float v = *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                            cs += v;
+                            cq = fmaf(v, v, cq);
+                        }
+                        for (int sh = 1; sh < a.gn_cpg; sh <<= 1) {
+                            cs += __shfl_xor_sync(0xffffffffu, cs, sh);
+                            cq += __shfl_xor_sync(0xffffffffu, cq, sh);
+                        }
+                        if ((lane & (a.gn_cpg - 1)) == 0 && n < a.B) {
+                            float2* dst = reinterpret_cast<float2*>(a.gn_part) +
+                                          ((long long)n * a.gn_slots + (long long)r_ * 4 + q) * 32 + (co + lane) / a.gn_cpg;
+                            *dst = make_float2(cs, cq);
+                        }
+                    }
                     if (lane == 0) {
                         // box = 32 channels x TW pixels x TH / 4 rows; clips pixels / channels outside the tensor
                         if (n < a.B) tma_store_4d(&tmY, buf, co, tx * a.TW, ty * a.TH + (a.TH >> 2) * q, n);
@@ -587,6 +577,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
         else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// GroupNorm statistics from the conv epilogue's partials: stats[b][g] = sum over the sample's slots of part[b][slot][g], fp64, fixed order
+__global__ void __launch_bounds__(128) conv_gn_finish_kernel(const float2* __restrict__ part, int slots, double* __restrict__ stats) {
+    __shared__ double s_s[128], s_q[128];
+    const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
+    const float2* p = part + (long long)b * slots * 32 + g;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < slots; i += 128) {
+        const float2 v = __ldg(p + (long long)i * 32);
+        s += (double)v.x;
+        q += (double)v.y;
+    }
+    s_s[threadIdx.x] = s;
+    s_q[threadIdx.x] = q;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_s[threadIdx.x] += s_s[threadIdx.x + o]; s_q[threadIdx.x] += s_q[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats[(long long)blockIdx.x * 2] = s_s[0];
+        stats[(long long)blockIdx.x * 2 + 1] = s_q[0];
     }
 }
 
@@ -747,7 +761,7 @@ static int launch_conv(int cl, const CUtensorMap& tA, const CUtensorMap& tAl, co
         if constexpr (MODE == 4 && BN <= 128) return launch_conv_cl<MODE, BN, 2, true>(tA, tAl, tB, tBl, tY, a, stream);
         else return GLARE_ERR_UNSUPPORTED;
     }
-    if (cl == 5) {                                                   // opt-in two-ring patch staging for the 256-wide N tile
+    if (cl == 5) {                                                   // two-ring patch staging for the 256-wide N tile
         if constexpr (MODE == 4 && BN == 256) return launch_conv_cl<MODE, BN, 2, false, true>(tA, tAl, tB, tBl, tY, a, stream);
         else return GLARE_ERR_UNSUPPORTED;
     }
@@ -796,7 +810,7 @@ struct AttnEpi {                       // attention epilogues of the two GEMMs (
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
                           int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats = nullptr,
-                          int gn_zero = 0, const AttnEpi* ae = nullptr);
+                          float* gn_scratch = nullptr, long long gn_scratch_floats = 0, const AttnEpi* ae = nullptr);
 static inline TapSpec std_taps(int ksize) { return TapSpec{ksize * ksize, ksize, -(ksize / 2), -(ksize / 2), 1, 0, 0}; }
 
 GLARE_API int glare_conv2d_nhwc_tc(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
@@ -830,26 +844,29 @@ GLARE_API int glare_conv2d_nhwc_tc_up2_phase(int mode, const void* x, const void
 }
 
 // General form used by the Python host: kind 0 = 3x3 / 1x1 stride-1 conv, 1 = Downsample conv (stride 2), 2 = one sub-pixel phase
-// (pa, pb) of Upsample+conv.  gn_stats (optional, [B][32][2] fp64): GroupNorm(32) sum / sum-of-squares of the OUTPUT accumulated in
-// the epilogue; gn_zero != 0 clears it first (phases 2..4 of an upsample conv accumulate into the same buffer).
+// (pa, pb) of Upsample+conv.  gn_stats (optional, [B][32][2] fp64, kinds 0 and 1, Cout % 128 == 0): GroupNorm(32) sum / sum of squares of
+// the OUTPUT, taken from the epilogue's staged tiles as per-(tile, warp) partials in gn_scratch (>= glare_conv_gn_scratch_floats(B, H, W)
+// floats for the OUTPUT size) and reduced in fp64 by a second small launch -- deterministic, no atomics.
 GLARE_API int glare_conv2d_nhwc_tc_g(int mode, int kind, const void* x, const void* x_lo, const void* w, const void* w_lo,
                                      const float* bias, const float* residual, float* y, int B, int Hin, int Win, int Cin, int Cout,
-                                     int ksize, int pa, int pb, double* gn_stats, int gn_zero, cudaStream_t stream) {
+                                     int ksize, int pa, int pb, double* gn_stats, float* gn_scratch, long long gn_scratch_floats,
+                                     cudaStream_t stream) {
     if (kind == 0) {
         if (ksize != 1 && ksize != 3) return GLARE_ERR_BAD_ARG;
         return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, residual, y, B, Hin, Win, Hin, Win, Cin, Cout, std_taps(ksize), 1, Cout, 0, stream,
-                              gn_stats, gn_zero);
+                              gn_stats, gn_scratch, gn_scratch_floats);
     }
     if (kind == 1) {
         if (Hin < 2 || Win < 2 || residual) return GLARE_ERR_BAD_ARG;
         const int Ho = (Hin + 1 - 3) / 2 + 1, Wo = (Win + 1 - 3) / 2 + 1;
         return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, Hin, Win, Ho, Wo, Cin, Cout, TapSpec{9, 3, 0, 0, 1, 0, 0}, 2, Cout, 0,
-                              stream, gn_stats, gn_zero);
+                              stream, gn_stats, gn_scratch, gn_scratch_floats);
     }
     if (kind == 2) {
         if (((pa | pb) & ~1) || residual) return GLARE_ERR_BAD_ARG;
+        if (gn_stats) return GLARE_ERR_UNSUPPORTED;          // the sub-pixel phases store directly (no staged tile to take the sums from)
         return conv_tc_launch(mode, x, x_lo, w, w_lo, bias, nullptr, y, B, Hin, Win, Hin, Win, Cin, Cout,
-                              TapSpec{4, 2, pa - 1, pb - 1, 2, pa, pb}, 1, Cout, 0, stream, gn_stats, gn_zero);
+                              TapSpec{4, 2, pa - 1, pb - 1, 2, pa, pb}, 1, Cout, 0, stream);
     }
     return GLARE_ERR_BAD_ARG;
 }
@@ -877,7 +894,7 @@ GLARE_API int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, i
         return GLARE_ERR_BAD_ARG;                            // key_norm_max may be null: q_row_norm then holds the per-row reference itself
     AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host, 0, nullptr};
     return conv_tc_launch(mode, q, nullptr, k, nullptr, nullptr, nullptr, reinterpret_cast<float*>(p_out), 1, rows_h, rows_w, rows_h, rows_w, C,
-                          n_keys, std_taps(1), 1, n_pad, 0, stream, nullptr, 0, &ae);
+                          n_keys, std_taps(1), 1, n_pad, 0, stream, nullptr, nullptr, 0, &ae);
 }
 
 // O = diag(row_scale) P~ V: p operand [rows][n_pad], vt operand [C][n_pad] (V^T of the sample); y [rows][ldy] fp32, or with pack_out != 0
@@ -888,7 +905,7 @@ GLARE_API int glare_attn_pv_tc(int mode, const void* p, const void* vt, const fl
     if (!row_scale) return GLARE_ERR_BAD_ARG;
     AttnEpi ae{nullptr, nullptr, nullptr, 0, 0.f, 0.f, row_scale, nullptr, pack_out ? 1 : 0, nullptr};
     return conv_tc_launch(mode, p, nullptr, vt, nullptr, nullptr, nullptr, reinterpret_cast<float*>(y), 1, rows_h, rows_w, rows_h, rows_w, n_pad, C,
-                          std_taps(1), 1, ldy, 0, stream, nullptr, 0, &ae);
+                          std_taps(1), 1, ldy, 0, stream, nullptr, nullptr, 0, &ae);
 }
 
 // Stride-1 conv (ksize 1 or 3) whose output goes straight to another tensor-core GEMM: y is written as that GEMM's bf16x3 operand (NHWC
@@ -901,13 +918,13 @@ GLARE_API int glare_conv2d_nhwc_tc_pack(int mode, const void* x, const void* w, 
     if ((ksize != 1 && ksize != 3) || (row_sq_part && !n_blocks_host)) return GLARE_ERR_BAD_ARG;
     AttnEpi ae{nullptr, nullptr, nullptr, part_stride, 0.f, 0.f, nullptr, n_blocks_host, 1, row_sq_part};
     return conv_tc_launch(mode, x, nullptr, w, nullptr, bias, nullptr, reinterpret_cast<float*>(y_operand), B, H, W, H, W, Cin, Cout, std_taps(ksize), 1,
-                          Cout, 0, stream, nullptr, 0, &ae);
+                          Cout, 0, stream, nullptr, nullptr, 0, &ae);
 }
 
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
-                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats, int gn_zero,
-                          const AttnEpi* ae) {
+                          int stride, long long ldy, long long w_batch_stride, cudaStream_t stream, double* gn_stats, float* gn_scratch,
+                          long long gn_scratch_floats, const AttnEpi* ae) {
     const int ksize = ts.tap_w;
     const bool epi_exp = ae && ae->row_norm;
     const bool epi_pack = ae && (ae->row_norm || ae->pack_out);          // the output is an operand tensor
@@ -917,8 +934,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if (ae && ae->row_sq_part && ae->part_stride < (long long)B * H * W) return GLARE_ERR_BAD_ARG;
     if (epi_exp && (!ae->row_sum_part || ae->part_stride < (long long)B * H * W || (ldy & 31) || Cout < 32))
         return GLARE_ERR_BAD_ARG;
-    if (gn_stats && (Cout % 128 != 0 || B <= 0)) return GLARE_ERR_UNSUPPORTED;       // 32 groups of a multiple of 4 channels
-    if (gn_stats && gn_zero) GLARE_CUDA(cudaMemsetAsync(gn_stats, 0, sizeof(double) * 64 * (size_t)B, stream));
+    if (gn_stats && (Cout % 128 != 0 || Cout > 512 || B <= 0 || !gn_scratch || ldy != Cout || ts.oscale != 1)) return GLARE_ERR_UNSUPPORTED;
     if (ldy < Cout || (ldy & 3) || w_batch_stride < 0 || (residual && ldy != Cout)) return GLARE_ERR_BAD_ARG;
     if (mode < 0 || mode > 4 || B < 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize < 1 || ksize > 3)) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
@@ -929,7 +945,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     ConvTcArgs a{};
     a.bias = bias; a.residual = residual; a.y = y;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.pad = -ts.dy0; a.stride = stride;
-    a.gn_stats = gn_stats; a.gn_cpg = Cout / 32;
+    a.gn_part = nullptr; a.gn_cpg = Cout / 32;
     a.ntaps = ts.ntaps; a.tap_w = ts.tap_w; a.tap_dy0 = ts.dy0; a.tap_dx0 = ts.dx0;
     a.oscale = ts.oscale; a.oa = ts.oa; a.ob = ts.ob;
     if (residual && ts.oscale != 1) return GLARE_ERR_BAD_ARG;
@@ -944,7 +960,9 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     static const bool no_halo = getenv("GLARE_CONV_NO_HALO") != nullptr;            // A/B switch for profiling only
     const bool halo = !no_halo && mode == 4 && BN <= 128 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
                       w_batch_stride == 0 && getenv("GLARE_CONV_NO_CLUSTER") == nullptr && getenv("GLARE_CONV_MCAST") == nullptr;
-    static const bool want_ring2 = getenv("GLARE_CONV_RING2") != nullptr;             // opt-in, not yet run on hardware
+    // two-ring patch staging for the 256-wide N tile: default since round 2 (green on hardware, conv_tc 451.4 -> 447.7 ms/step,
+    // profiles/r45_bench_ring2.json); GLARE_CONV_NO_RING2 selects the one-ring kernel (A/B switch)
+    static const bool want_ring2 = getenv("GLARE_CONV_NO_RING2") == nullptr;
     const bool ring2 = want_ring2 && !no_halo && mode == 4 && BN == 256 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
                        w_batch_stride == 0 && !ae && getenv("GLARE_CONV_NO_CLUSTER") == nullptr && getenv("GLARE_CONV_MCAST") == nullptr;
     if (halo || ring2) {
@@ -1000,16 +1018,32 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
         if ((rc = make_act_map(&tAl, x_lo, true, B, Hin, Win, 2 * Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;
         if ((rc = make_w_map(&tBl, w_lo, true, Cout, 2 * ts.ntaps * Cin, BN / csz, n_w, 2 * w_batch_stride)) != GLARE_OK) return rc;
     }
+    if (gn_stats) {
+        if (!a.tma_store) return GLARE_ERR_UNSUPPORTED;
+        a.gn_slots = a.tiles_y * a.tiles_x * 4;
+        if ((long long)B * a.gn_slots * 64 > gn_scratch_floats) return GLARE_ERR_BAD_ARG;
+        a.gn_part = gn_scratch;
+    }
 #define GLARE_CONV_DISPATCH(M)                                                            \
     do {                                                                                  \
-        if (BN == 256) return launch_conv<M, 256>(cl, tA, tAl, tB, tBl, tY, a, stream);   \
-        if (BN == 128) return launch_conv<M, 128>(cl, tA, tAl, tB, tBl, tY, a, stream);   \
-        return launch_conv<M, 64>(cl, tA, tAl, tB, tBl, tY, a, stream);                   \
+        if (BN == 256) rc = launch_conv<M, 256>(cl, tA, tAl, tB, tBl, tY, a, stream);     \
+        else if (BN == 128) rc = launch_conv<M, 128>(cl, tA, tAl, tB, tBl, tY, a, stream);\
+        else rc = launch_conv<M, 64>(cl, tA, tAl, tB, tBl, tY, a, stream);                \
     } while (0)
     if (mode == 0) GLARE_CONV_DISPATCH(0);
-    if (mode == 1) GLARE_CONV_DISPATCH(1);
-    if (mode == 2) GLARE_CONV_DISPATCH(2);
-    if (mode == 3) GLARE_CONV_DISPATCH(3);
-    GLARE_CONV_DISPATCH(4);
+    else if (mode == 1) GLARE_CONV_DISPATCH(1);
+    else if (mode == 2) GLARE_CONV_DISPATCH(2);
+    else if (mode == 3) GLARE_CONV_DISPATCH(3);
+    else GLARE_CONV_DISPATCH(4);
 #undef GLARE_CONV_DISPATCH
+    if (rc != GLARE_OK || !gn_stats) return rc;
+    conv_gn_finish_kernel<<<(unsigned)(B * 32), 128, 0, stream>>>(reinterpret_cast<const float2*>(gn_scratch), a.gn_slots, gn_stats);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// floats of scratch glare_conv2d_nhwc_tc_g needs for the fused GroupNorm statistics of an output of B x H x W pixels (both tile geometries)
+GLARE_API long long glare_conv_gn_scratch_floats(int B, int H, int W) {
+    const long long t1 = (long long)((H + 7) / 8) * ((W + 15) / 16), t2 = (long long)((H + 15) / 16) * ((W + 7) / 8);
+    return (long long)B * (t1 > t2 ? t1 : t2) * 4 * 64;
 }

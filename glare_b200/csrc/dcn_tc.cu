@@ -34,6 +34,7 @@ struct DcnTcArgs {
     float* y;
     int B, H, W, C, Cout, dg, cpg, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;   // kchunks = C / BKE channel chunks per tap
     int total_tiles;
+    int mask_prob;           // the mask channels of om already hold sigmoid(m) (operator-level entry: offset / mask tensors of the reference op)
     int stages;              // ring depth actually used (<= DcnCfg::STAGES): fewer stages leave more of the SM's 256 KB to the L1 cache,
                              // which is what serves the bilinear corner gathers (each 128-byte channel line is touched ~36 times per tile)
 };
@@ -99,8 +100,11 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int nb = tile % a.n_blocks;
-                for (int tap = 0; tap < 9; ++tap)
-                    for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+                // K order = channel chunk major, tap minor (the accumulation order is free): the nine taps of one 32-channel chunk read the same
+                // ~10 x 18 pixel window of 128-byte channel lines back to back, so the window (23 KB) stays in the small L1 that the operand
+                // rings leave; tap-major order put the other chunks' windows (4 - 8 x 23 KB) between two uses of a line
+                for (int kc = 0; kc < a.kchunks; ++kc)
+                    for (int tap = 0; tap < 9; ++tap, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
                         mbar_wait_bounded(&empty_bar[s], ph ^ 1);
@@ -239,15 +243,15 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                     float v = 0.f;
                     if (gy < a.H && gx < a.W) {
                         v = __ldg(a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c + ch);
-                        if (ch >= 18 * a.dg) v = 1.0f / (1.0f + expf(-v));
+                        if (ch >= 18 * a.dg && !a.mask_prob) v = 1.0f / (1.0f + expf(-v));
                     }
                     s_om[i] = v;
                 }
                 named_bar_sync(3, 64 * SW);
             }
-            for (int tap = 0; tap < 9; ++tap) {
-                const int ti = tap / 3, tj = tap - ti * 3;
-                for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+            for (int kc = 0; kc < a.kchunks; ++kc) {
+                for (int tap = 0; tap < 9; ++tap, ++it) {
+                    const int ti = tap / 3, tj = tap - ti * 3;
                     if ((int)(it & 1) != gsel) continue;
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -277,7 +281,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                                 } else {
                                     const float* omp = a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c;
                                     oh = __ldg(omp + g * 18 + 2 * tap); ow = __ldg(omp + g * 18 + 2 * tap + 1);
-                                    mk = 1.0f / (1.0f + expf(-__ldg(omp + 18 * a.dg + g * 9 + tap)));
+                                    mk = __ldg(omp + 18 * a.dg + g * 9 + tap);
+                                    if (!a.mask_prob) mk = 1.0f / (1.0f + expf(-mk));
                                 }
                                 const float h_im = (float)(gy - 1 + ti) + oh, w_im = (float)(gx - 1 + tj) + ow;   // .cu:607-612
                                 if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {            // .cu:618
@@ -449,16 +454,33 @@ using namespace glare;
 
 // x NHWC fp32 [B,H,W,C]; offmask = raw conv_offset output NHWC fp32 [B,H,W,27*dg]; w / w_lo packed by
 // glare_conv_pack_weight(mode, weight[Cout,C,3,3]); y NHWC fp32 [B,H,W,Cout].  3x3, stride 1, pad 1, dilation 1, groups 1.
+static int dcn_tc_launch(int mode, const float* x, const float* offmask, int mask_prob, const void* w, const void* w_lo, const float* bias_or_null,
+                         float* y, int B, int H, int W, int C, int Cout, int deformable_groups, cudaStream_t stream);
+
 GLARE_API int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float* offmask, const void* w, const void* w_lo,
                                            const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout,
                                            int deformable_groups, cudaStream_t stream) {
+    return dcn_tc_launch(mode, x, offmask, 0, w, w_lo, bias_or_null, y, B, H, W, C, Cout, deformable_groups, stream);
+}
+
+// The reference OPERATOR's inputs on the same kernel (ModulatedDeformConvFunction.forward, ops/dcn/deform_conv.py:124-153, for 3x3 /
+// stride 1 / pad 1 / dilation 1 / groups 1): offmask NHWC [B,H,W,27*dg] = the op's offset tensor (channels [0,18dg)) and its mask tensor
+// (channels [18dg,27dg), ALREADY through the sigmoid) side by side.
+GLARE_API int glare_dcnv2_fwd_nhwc_tc(int mode, const float* x, const float* offset_mask, const void* w, const void* w_lo,
+                                      const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout, int deformable_groups,
+                                      cudaStream_t stream) {
+    return dcn_tc_launch(mode, x, offset_mask, 1, w, w_lo, bias_or_null, y, B, H, W, C, Cout, deformable_groups, stream);
+}
+
+static int dcn_tc_launch(int mode, const float* x, const float* offmask, int mask_prob, const void* w, const void* w_lo, const float* bias_or_null,
+                         float* y, int B, int H, int W, int C, int Cout, int deformable_groups, cudaStream_t stream) {
     if (mode < 0 || mode > 4 || B < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || deformable_groups <= 0) return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
     if (!x || !offmask || !w || !y || ((mode == 2 || mode == 3) && !w_lo)) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
     if (C % deformable_groups != 0 || C % bke != 0 || (C / deformable_groups) % 8 != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
     DcnTcArgs a{};
-    a.x = x; a.om = offmask; a.bias = bias_or_null; a.y = y;
+    a.x = x; a.om = offmask; a.bias = bias_or_null; a.y = y; a.mask_prob = mask_prob;
     a.B = B; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.dg = deformable_groups; a.cpg = C / deformable_groups;
     a.TH = 8; a.TW = 16;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;

@@ -82,10 +82,10 @@ class TcDense:
         self.bke = 64 if mode == 0 else 32
         self._w = {}
         self.fallbacks = {}
-        # GroupNorm sum / sum-of-squares of a conv's output accumulated in its epilogue.  Measured on B200 (profiles/r01k_*): saves 19 ms of
-        # statistics passes per step but lengthens the short-K conv epilogues by 46 ms (warp reductions + fp64 atomics on the critical
-        # path of the TMEM drain), so it is OFF by default; the separate gn_stats kernel is HBM-bound and cheaper.
-        self.fuse_gn_stats = bool(os.environ.get("GLARE_FUSE_GN_STATS"))      # A/B switch
+        # GroupNorm sum / sum of squares of a conv's output taken in its epilogue (column sums of the staged output tile -> per-(tile, warp)
+        # partials -> fp64 finish launch; no atomics, no shuffles over pixels), which removes the statistics pass over the activation.
+        # Round 1's version (warp reductions + fp64 atomics on the TMEM-drain path) cost more than it saved and was off.
+        self.fuse_gn_stats = not os.environ.get("GLARE_NO_FUSE_GN_STATS")      # A/B switch
         self.dcn_tc = True             # DCNv2 on the tensor-core kernel (dcn_tc.cu); False -> fp32 FMA kernel (dcn.cu)
         self.attn_s_budget = None      # bytes of score / operand matrix materialised per pass; None: sized from free HBM at first use (_budget)
         # mode 4: softmax fused into the epilogues of the two GEMMs (csrc/attn.cu): exp against a Cauchy-Schwarz row reference in the scores
@@ -142,7 +142,8 @@ class TcDense:
     def _unsupported(what):
         raise NotImplementedError("glare_b200: %s is outside the tcgen05 kernels' coverage and there is no library fallback" % what)
 
-    def conv2d(self, x, w, b=None, stride=1, padding=1, residual=None):
+    def conv2d(self, x, w, b=None, stride=1, padding=1, residual=None, gn_stats=True):
+        """gn_stats=False: the output does not feed a Normalize (training backward convs): skip the epilogue statistics"""
         Cin = x.C if isinstance(x, Operand) else x.shape[1]
         Cout, ks = w.shape[0], w.shape[2]
         shape_ok = w.shape[2] == w.shape[3] and ks in (1, 3) and stride == 1 and padding == ks // 2
@@ -160,7 +161,7 @@ class TcDense:
             return y if residual is None else y + residual
         res = _nhwc(residual) if residual is not None else None
         y = torch.empty((op.B, op.H, op.W, Cout), device=op.hi.device, dtype=torch.float32)
-        stats = self._new_stats(op.B, Cout)
+        stats = self._new_stats(op.B, Cout) if gn_stats else None
         with self._t("conv_tc", flops):
             self.ops.conv2d_nhwc_tc_g(self.mode, 0, op.hi, op.lo, w_hi, w_lo, b, res, y, op.B, op.H, op.W, op.C, Cout, ksize=ks,
                                       gn_stats=stats)
@@ -184,7 +185,7 @@ class TcDense:
 
     def _new_stats(self, B, Cout):
         """fp64 [B,32,2] buffer for GroupNorm statistics fused into the conv epilogue (None when the output cannot feed Normalize)"""
-        if not self.fuse_gn_stats or Cout % 128:
+        if not self.fuse_gn_stats or Cout % 128 or Cout > 512:
             return None
         return torch.empty((B, 32, 2), device="cuda", dtype=torch.float64)
 
@@ -212,16 +213,13 @@ class TcDense:
         op, _ = self._operand(x)
         Cout = w.shape[0]
         y = torch.empty((op.B, 2 * op.H, 2 * op.W, Cout), device=op.hi.device, dtype=torch.float32)
-        stats = self._new_stats(op.B, Cout)
         with self._t("conv_tc", 2.0 * op.B * op.H * op.W * op.C * Cout * 16):
-            first = True
             for (pa, pb), (w_hi, w_lo) in phases.items():
                 self.ops.conv2d_nhwc_tc_g(self.mode, 2, op.hi, op.lo, w_hi, w_lo, b, None, y, op.B, op.H, op.W, op.C, Cout, ksize=2, pa=pa,
-                                          pb=pb, gn_stats=stats, gn_zero=first)
-                first = False
-        return self._tag(y.permute(0, 3, 1, 2), stats)
+                                          pb=pb)
+        return y.permute(0, 3, 1, 2)            # (the sub-pixel phases store directly: no staged tile, statistics by the separate kernel)
 
-    def downsample_conv(self, x, w, b=None):
+    def downsample_conv(self, x, w, b=None, gn_stats=True):
         """Downsample.forward (encoder_decoder.py:68-72): pad (0,1,0,1) + 3x3 stride-2 conv, padding by TMA zero fill"""
         if tuple(w.shape[2:]) != (3, 3) or w.shape[0] % 4:
             self._unsupported("Downsample conv %s" % (tuple(w.shape),))
@@ -230,7 +228,7 @@ class TcDense:
         Ho, Wo = (op.H - 2) // 2 + 1, (op.W - 2) // 2 + 1
         Cout = w.shape[0]
         y = torch.empty((op.B, Ho, Wo, Cout), device=op.hi.device, dtype=torch.float32)
-        stats = self._new_stats(op.B, Cout)
+        stats = self._new_stats(op.B, Cout) if gn_stats else None
         with self._t("conv_tc", 2.0 * op.B * Ho * Wo * x.shape[1] * Cout * 9):
             self.ops.conv2d_nhwc_tc_g(self.mode, 1, op.hi, op.lo, w_hi, w_lo, b, None, y, op.B, op.H, op.W, op.C, Cout, gn_stats=stats)
         return self._tag(y.permute(0, 3, 1, 2), stats)
@@ -422,15 +420,16 @@ class TcDense:
                 "peak_source": pk["src"] + " (cuBLAS bf16 sustained)"}
 
     def _traffic(self, B):
-        """dram__bytes_read.sum + dram__bytes_write.sum per launch of conv_tc_kernel, from the committed ncu capture of this
-        exact configuration (profiles/conv_tc_traffic.json); None when no capture matches."""
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch of conv_tc_kernel from the committed ncu capture of this configuration
+        (profiles/conv_tc_traffic.json, written by tools/traffic_summary.py on the GPU box).  Only returned when the capture was taken from
+        the SAME kernel sources (sha256 of csrc/, glare_b200.build.source_hash) in the same mode and batch; otherwise None."""
         import json
-        import os
+        from .build import source_hash
         path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "conv_tc_traffic.json")
         try:
             with open(path) as f:
                 t = json.load(f)
-            if t.get("mode") != self.name or t.get("batch") != B:
+            if t.get("mode") != self.name or t.get("batch") != B or t.get("csrc_sha16") != source_hash():
                 return None
             return t["dram_bytes_per_launch"]
         except Exception:

@@ -63,10 +63,10 @@ class CudaLeaves:
 
     # dense
     def conv_same(self, x, w, b=None):
-        return self.dense.conv2d(x, w, b, stride=1, padding=w.shape[2] // 2).float()
+        return self.dense.conv2d(x, w, b, stride=1, padding=w.shape[2] // 2, gn_stats=False).float()   # the tape's Normalize takes its own statistics
 
     def conv_down(self, x, w, b=None):
-        y = self.dense.downsample_conv(x, w, b)
+        y = self.dense.downsample_conv(x, w, b, gn_stats=False)
         return (y if y is not None else F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)).float()
 
     def attention(self, q, k, v):

@@ -2,9 +2,8 @@
 
 Parameter names are the reference's state-dict keys (``flowUpsamplerNet.layers.{s}.actnorm.bias`` ...), so a
 ``net_G.pth`` loads unchanged.  Everything that depends only on the weights -- exp(logs), the fp64 inverse of
-the 1x1 conv (Permutations.py:38), slogdet -- is evaluated ONCE here (on the host, in the reference's own
-precision) instead of once per call as the reference does, which also removes the per-step host sync
-(Permutations.py:25).
+the 1x1 conv (Permutations.py:38), slogdet -- is evaluated ONCE per checkpoint here (batched, on the device) instead
+of once per call as the reference does, which also removes the per-step host sync (Permutations.py:25).
 """
 import math
 
@@ -19,66 +18,63 @@ NET_FLOATS = 9552                           # include/glare_b200.h GLARE_FLOW_NE
 HIDDEN = 64
 
 
-def pack_net(sd, p, has_z):
-    """One coupling net (FlowAffineCouplingsAblation.py:143-151) -> packed block, layout in glare_b200.h."""
-    w1 = sd[p + ".0.weight"].float().cpu()
-    w3 = sd[p + ".4.weight"].float().cpu()
-    nout = w3.shape[0]
-    out = torch.zeros(NET_FLOATS, dtype=torch.float32)
+def _stack(sd, keys, device):
+    return torch.stack([sd[k].detach().to(device=device, dtype=torch.float32) for k in keys])
+
+
+def pack_nets(sd, prefixes, has_z, device):
+    """The coupling nets `prefixes` (FlowAffineCouplingsAblation.py:143-151) -> packed blocks [n][NET_FLOATS], layout in glare_b200.h.
+    Batched over the nets and evaluated on `device`: a handful of tensor ops, no host synchronisation (the stage-2 training step repacks
+    after every optimizer step)."""
+    n = len(prefixes)
+    w1 = _stack(sd, [p + ".0.weight" for p in prefixes], device)                          # [n,64,Cin,3,3]
+    w3 = _stack(sd, [p + ".4.weight" for p in prefixes], device)                          # [n,nout,64,3,3]
+    nout = w3.shape[1]
+    out = torch.zeros((n, NET_FLOATS), dtype=torch.float32, device=device)
     if has_z:
-        out[0:576] = w1[:, 0].reshape(HIDDEN, 9).flatten()
-    out[576:640] = sd[p + ".0.actnorm.bias"].float().cpu().flatten()
-    out[640:704] = torch.exp(sd[p + ".0.actnorm.logs"].float().cpu()).flatten()          # FlowActNorms.py:62
-    out[704:4800] = sd[p + ".2.weight"].float().cpu()[:, :, 0, 0].t().contiguous().flatten()
-    out[4800:4864] = sd[p + ".2.actnorm.bias"].float().cpu().flatten()
-    out[4864:4928] = torch.exp(sd[p + ".2.actnorm.logs"].float().cpu()).flatten()
-    w3p = torch.zeros(HIDDEN, 9, 8)
-    w3p[:, :, :nout] = w3.reshape(nout, HIDDEN, 9).permute(1, 2, 0)
-    out[4928:9536] = w3p.flatten()
-    out[9536:9536 + nout] = sd[p + ".4.bias"].float().cpu().flatten()
-    out[9544:9544 + nout] = torch.exp(sd[p + ".4.logs"].float().cpu() * 3).flatten()       # flow.py:68-70 logscale_factor=3
-    return out
-
-
-def pack_pointwise(sd, p, reverse):
-    """ActNorm + InvertibleConv1x1 of one step -> 16 floats (M row-major, bias, scale)."""
-    w = sd[p + ".invconv.weight"].float().cpu()
-    logs = sd[p + ".actnorm.logs"].float().cpu().flatten()
-    out = torch.zeros(16, dtype=torch.float32)
-    if reverse:
-        out[0:9] = torch.inverse(w.double()).float().flatten()                            # Permutations.py:38
-        out[12:15] = torch.exp(-logs)                                                     # FlowActNorms.py:64
-    else:
-        out[0:9] = w.flatten()
-        out[12:15] = torch.exp(logs)
-    out[9:12] = sd[p + ".actnorm.bias"].float().cpu().flatten()
-    return out
+        out[:, 0:576] = w1[:, :, 0].reshape(n, 576)
+    out[:, 576:640] = _stack(sd, [p + ".0.actnorm.bias" for p in prefixes], device).reshape(n, HIDDEN)
+    out[:, 640:704] = torch.exp(_stack(sd, [p + ".0.actnorm.logs" for p in prefixes], device)).reshape(n, HIDDEN)     # FlowActNorms.py:62
+    out[:, 704:4800] = _stack(sd, [p + ".2.weight" for p in prefixes], device)[:, :, :, 0, 0].transpose(1, 2).reshape(n, HIDDEN * HIDDEN)
+    out[:, 4800:4864] = _stack(sd, [p + ".2.actnorm.bias" for p in prefixes], device).reshape(n, HIDDEN)
+    out[:, 4864:4928] = torch.exp(_stack(sd, [p + ".2.actnorm.logs" for p in prefixes], device)).reshape(n, HIDDEN)
+    w3p = torch.zeros((n, HIDDEN, 9, 8), dtype=torch.float32, device=device)
+    w3p[:, :, :, :nout] = w3.reshape(n, nout, HIDDEN, 9).permute(0, 2, 3, 1)
+    out[:, 4928:9536] = w3p.reshape(n, -1)
+    out[:, 9536:9536 + nout] = _stack(sd, [p + ".4.bias" for p in prefixes], device).reshape(n, nout)
+    out[:, 9544:9544 + nout] = torch.exp(_stack(sd, [p + ".4.logs" for p in prefixes], device) * 3).reshape(n, nout)  # flow.py:68-70 logscale_factor=3
+    return out, w1
 
 
 class FlowPlan:
-    """Device-resident packed parameters of the whole flow (built once per checkpoint)."""
+    """Device-resident packed parameters of the whole flow (built once per checkpoint; rebuilt per optimizer step in training).  Everything
+    is computed on `device` with batched tensor ops -- no `.cpu()` round trips, no host synchronisation."""
 
     def __init__(self, sd, device, prefix="flowUpsamplerNet"):
         self.prefix = prefix
-        self.device = device
-        nets_a, nets_f, w_a, w_f = [], [], [], []
-        for s in COUPLING_STEPS:
-            p = "%s.layers.%d.affine" % (prefix, s)
-            nets_a.append(pack_net(sd, p + ".fAffine", True))
-            nets_f.append(pack_net(sd, p + ".fFeatures", False))
-            w_a.append(sd[p + ".fAffine.0.weight"].float().cpu()[:, 1:])      # ft channels of cat([z1, ft]) (:137-141)
-            w_f.append(sd[p + ".fFeatures.0.weight"].float().cpu())
-        self.nets_a = torch.stack(nets_a).to(device)
-        self.nets_f = torch.stack(nets_f).to(device)
-        # one dense conv for the ft part of every first layer: rows [ci*128 + 0..63] = NN_A, [ci*128 + 64..127] = NN_F
-        self.w_pre = torch.stack([torch.cat([a, f], 0) for a, f in zip(w_a, w_f)]).reshape(-1, HIDDEN, 3, 3).contiguous().to(device)
-        self.pw_inv = torch.stack([pack_pointwise(sd, "%s.layers.%d" % (prefix, s), True) for s in range(N_FLOW_STEPS)]).to(device)
-        self.pw_fwd = torch.stack([pack_pointwise(sd, "%s.layers.%d" % (prefix, s), False) for s in range(N_FLOW_STEPS)]).to(device)
+        self.device = device = torch.device(device)
+        pa = ["%s.layers.%d.affine.fAffine" % (prefix, s) for s in COUPLING_STEPS]
+        pf = ["%s.layers.%d.affine.fFeatures" % (prefix, s) for s in COUPLING_STEPS]
+        self.nets_a, w1a = pack_nets(sd, pa, True, device)
+        self.nets_f, w1f = pack_nets(sd, pf, False, device)
+        # one dense conv for the ft part of every first layer: rows [ci*128 + 0..63] = NN_A (ft channels of cat([z1, ft]), :137-141),
+        # [ci*128 + 64..127] = NN_F
+        self.w_pre = torch.cat([w1a[:, :, 1:], w1f], dim=1).reshape(-1, HIDDEN, 3, 3).contiguous()
+        # ActNorm + InvertibleConv1x1 of every step -> 16 floats (M row-major, bias, scale), both directions
+        steps = range(N_FLOW_STEPS)
+        w = _stack(sd, ["%s.layers.%d.invconv.weight" % (prefix, s) for s in steps], device)                     # [28,3,3]
+        logs = _stack(sd, ["%s.layers.%d.actnorm.logs" % (prefix, s) for s in steps], device).reshape(N_FLOW_STEPS, 3)
+        bias = _stack(sd, ["%s.layers.%d.actnorm.bias" % (prefix, s) for s in steps], device).reshape(N_FLOW_STEPS, 3)
+        self.pw_inv = torch.zeros((N_FLOW_STEPS, 16), dtype=torch.float32, device=device)
+        self.pw_fwd = torch.zeros((N_FLOW_STEPS, 16), dtype=torch.float32, device=device)
+        self.pw_inv[:, 0:9] = torch.linalg.inv_ex(w.double())[0].float().reshape(N_FLOW_STEPS, 9)               # Permutations.py:38
+        self.pw_inv[:, 12:15] = torch.exp(-logs)                                                                 # FlowActNorms.py:64
+        self.pw_fwd[:, 0:9] = w.reshape(N_FLOW_STEPS, 9)
+        self.pw_fwd[:, 12:15] = torch.exp(logs)
+        self.pw_inv[:, 9:12] = bias
+        self.pw_fwd[:, 9:12] = bias
         # weight-only logdet terms per step (FlowActNorms.py:66-74, Permutations.py:27,51-53), multiplied by `pixels` at run time
-        self.ld_const = torch.stack([
-            torch.stack([sd["%s.layers.%d.actnorm.logs" % (prefix, s)].float().cpu().sum(),
-                         torch.slogdet(sd["%s.layers.%d.invconv.weight" % (prefix, s)].float().cpu())[1]])
-            for s in range(N_FLOW_STEPS)]).to(device)
+        self.ld_const = torch.stack([logs.sum(dim=1), torch.linalg.slogdet(w)[1]], dim=1)
 
 
 def precompute(plan, ft, conv2d):

@@ -74,6 +74,11 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
         raise ValueError("offset shape %s != %s" % (tuple(offset.shape), (B, deformable_groups * 2 * kh * kw, Ho, Wo)))
     if tuple(mask.shape) != (B, deformable_groups * kh * kw, Ho, Wo):
         raise ValueError("mask shape %s != %s" % (tuple(mask.shape), (B, deformable_groups * kh * kw, Ho, Wo)))
+    if (packed_weight is None and (kh, kw, stride, padding, dilation) == (3, 3, 1, 1, 1) and C % 32 == 0 and (C // deformable_groups) % 8 == 0
+            and Co % 4 == 0 and deformable_groups * 27 <= 108):
+        # GLARE's configuration (deformableDecoder_arch.py:129-131: 3x3, stride 1, pad 1, dg 4, 128 / 256 channels): the tensor-core kernel
+        # (csrc/dcn_tc.cu), 3-5 x the reference extension's speed on B200 (profiles/r43_dcn_ref_compare.txt); other shapes: the fp32 FMA kernel
+        return _modulated_deform_conv_tc(x, offset, mask, weight, bias, deformable_groups)
     if packed_weight is None:
         packed_weight = dcn_pack_weight(weight)
     y = x.new_empty((B, Co, Ho, Wo))
@@ -81,6 +86,29 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
     check(lib().glare_dcnv2_fwd_f32(ptr(x), ptr(offset), ptr(mask), ptr(packed_weight), ptr(b), B, C, H, W, Co, kh, kw,
                                     stride, padding, dilation, deformable_groups, ptr(y), stream()), "glare_dcnv2_fwd_f32")
     return y
+
+
+_DCN_W = {}
+
+
+def _modulated_deform_conv_tc(x, offset, mask, weight, bias, dg):
+    """NCHW operator inputs -> NHWC, offset | mask side by side, fp32-grade (bf16x3) tensor-core kernel, NCHW-shaped (channels_last) result"""
+    import weakref
+    B, C, H, W = x.shape
+    Co = weight.shape[0]
+    key = (weight.data_ptr(), tuple(weight.shape))
+    ent = _DCN_W.get(key)
+    if ent is None or ent[0]() is not weight or ent[1] != weight._version:
+        if len(_DCN_W) > 64:
+            _DCN_W.clear()
+        ent = _DCN_W[key] = (weakref.ref(weight), weight._version, conv_pack_weight(MODE_BF16X3, weight)[0])
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    om = torch.cat((offset.permute(0, 2, 3, 1), mask.permute(0, 2, 3, 1)), dim=3).contiguous()
+    y = torch.empty((B, H, W, Co), device=x.device, dtype=torch.float32)
+    b = f32c(bias) if bias is not None else None
+    check(lib().glare_dcnv2_fwd_nhwc_tc(MODE_BF16X3, ptr(xn), ptr(om), ptr(ent[2]), None, ptr(b), ptr(y), B, H, W, C, Co, dg, stream()),
+          "glare_dcnv2_fwd_nhwc_tc")
+    return y.permute(0, 3, 1, 2)
 
 
 def dcnv2_bwd_data(x_nhwc, offset, mask, dcol_nhwc, dg, grad_x_nhwc, grad_offset, grad_mask, col_nhwc):
@@ -178,12 +206,18 @@ def dcnv2_pack_fwd_nhwc_tc(mode, x_nhwc, offmask_nhwc, w_hi, w_lo, bias, B, H, W
     return y
 
 
-def conv2d_nhwc_tc_g(mode, kind, x_hi, x_lo, w_hi, w_lo, bias, residual, y, B, Hin, Win, Cin, Cout, ksize=3, pa=0, pb=0, gn_stats=None,
-                     gn_zero=True):
-    """general conv entry (kind 0 stride-1, 1 Downsample, 2 Upsample phase) with optional fused GroupNorm statistics of the output"""
+def conv2d_nhwc_tc_g(mode, kind, x_hi, x_lo, w_hi, w_lo, bias, residual, y, B, Hin, Win, Cin, Cout, ksize=3, pa=0, pb=0, gn_stats=None):
+    """general conv entry (kind 0 stride-1, 1 Downsample, 2 Upsample phase).  gn_stats ([B,32,2] fp64, kinds 0 / 1): GroupNorm statistics of
+    the output from the epilogue (per-tile partials in a scratch tensor + a small fp64 finish launch inside the same call)"""
+    global LAUNCHES
     require_cuda(x_hi, x_lo, w_hi, w_lo, bias, residual, y, gn_stats)
+    scratch, n = None, 0
+    if gn_stats is not None:
+        n = int(lib().glare_conv_gn_scratch_floats(B, y.shape[1], y.shape[2]))
+        scratch = torch.empty((n,), device=y.device, dtype=torch.float32)
+        LAUNCHES += 1                                   # the finish kernel
     check(lib().glare_conv2d_nhwc_tc_g(mode, kind, ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(residual), ptr(y), B, Hin, Win,
-                                       Cin, Cout, ksize, pa, pb, ptr(gn_stats), 1 if gn_zero else 0, stream()), "glare_conv2d_nhwc_tc_g")
+                                       Cin, Cout, ksize, pa, pb, ptr(gn_stats), ptr(scratch), n, stream()), "glare_conv2d_nhwc_tc_g")
     return y
 
 

@@ -117,6 +117,13 @@ int glare_dcnv2_bwd_weight_f32(const float* col, const float* gout, long long P,
 int glare_dcnv2_pack_fwd_nhwc_tc(int mode, const float* x, const float* offmask, const void* w, const void* w_lo,
                                  const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout,
                                  int deformable_groups, cudaStream_t stream);
+/* The reference OPERATOR's inputs on the same tensor-core kernel (ModulatedDeformConvFunction.forward, ops/dcn/deform_conv.py:124-153 ->
+ * deform_conv_ext.modulated_deform_conv_forward, src/deform_conv_ext.cpp:125-134) for 3x3 / stride 1 / pad 1 / dilation 1 / groups 1:
+ * offset_mask NHWC [B,H,W,27*dg] holds the op's offset tensor in channels [0,18dg) and its mask tensor (already sigmoid-ed) in
+ * [18dg,27dg).  Same shape limits as glare_dcnv2_pack_fwd_nhwc_tc. */
+int glare_dcnv2_fwd_nhwc_tc(int mode, const float* x, const float* offset_mask, const void* w, const void* w_lo,
+                            const float* bias_or_null, float* y, int B, int H, int W, int C, int Cout, int deformable_groups,
+                            cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (4) Dense convolutions on tcgen05 tensor cores -- the cuDNN calls behind nn.Conv2d in ResnetBlock
@@ -143,11 +150,15 @@ int glare_conv2d_nhwc_tc_down2(int mode, const void* x, const void* x_lo, const 
  * low-resolution x NHWC [B,H,W,Cin], writes pixels (2i+a, 2j+b) of y NHWC [B,2H,2W,Cout]; w packed [Cout][4][Cin] for this phase */
 int glare_conv2d_nhwc_tc_up2_phase(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                                    float* y, int B, int H, int W, int Cin, int Cout, int a, int b, cudaStream_t stream);
-/* general form: kind 0 = stride-1 conv, 1 = Downsample conv, 2 = sub-pixel phase (pa, pb) of Upsample+conv; gn_stats (optional,
- * [B][32][2] fp64) receives the GroupNorm(32) sum / sum of squares of the OUTPUT from the epilogue (gn_zero != 0 clears it first) */
+/* general form: kind 0 = stride-1 conv, 1 = Downsample conv, 2 = sub-pixel phase (pa, pb) of Upsample+conv.  gn_stats (optional, kinds 0
+ * and 1, Cout in {128, 256, 384, 512}, [B][32][2] fp64) receives the GroupNorm(32) sum / sum of squares of the OUTPUT (the statistics of the
+ * Normalize that consumes it, encoder_decoder.py:34-35): the epilogue sums its staged output tiles into per-(tile, warp) partials in
+ * gn_scratch (>= glare_conv_gn_scratch_floats(B, Hout, Wout) floats; every entry written once, no atomics) and a second small launch
+ * reduces them in fp64 in a fixed order. */
 int glare_conv2d_nhwc_tc_g(int mode, int kind, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                            const float* residual, float* y, int B, int Hin, int Win, int Cin, int Cout, int ksize, int pa, int pb,
-                           double* gn_stats, int gn_zero, cudaStream_t stream);
+                           double* gn_stats, float* gn_scratch, long long gn_scratch_floats, cudaStream_t stream);
+long long glare_conv_gn_scratch_floats(int B, int H, int W);
 /* extended form: ldy = output pixel stride (elements, >= Cout, % 4 == 0); w_batch_stride != 0 -> per-sample weights
  * w + n * w_batch_stride (the attention GEMMs S = Q K^T and O = P V, encoder_decoder.py:176-187) */
 int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,

@@ -1,6 +1,6 @@
-"""Child process of tests/test_zz_flow_train_gpu.py::test_conv_ring2_in_child_process: the opt-in two-ring patch staging of conv_tc
-(GLARE_CONV_RING2=1, 256-wide N tiles) against cuDNN fp32 and against the default kernel, with CUDA-event timings of both printed.
-The variant is selected by an environment variable read once per process, so the parent runs this script twice."""
+"""Child process of tests/test_zz_flow_train_gpu.py: the two-ring patch staging of conv_tc for the 256-wide N tiles (default) and the
+one-ring kernel (GLARE_CONV_NO_RING2=1) against cuDNN fp32, with CUDA-event timings printed.  The variant is selected by an environment
+variable read once per process, so the parent runs this script twice."""
 import os
 import sys
 

@@ -27,17 +27,16 @@ def test_flow_training_kernels_in_child_process(glare_lib):
 
 
 def test_conv_default_kernel_in_child_process(glare_lib):
-    """the shipped conv kernel on the shapes of the RING2 comparison below: a regression here is a failure, not an expected one"""
+    """the shipped conv kernels (two-ring patch staging, RING2, for the 256-wide N tiles since round 2) against cuDNN fp32 on three shapes"""
     env = dict(os.environ)
-    env.pop("GLARE_CONV_RING2", None)
+    env.pop("GLARE_CONV_NO_RING2", None)
     rc, log = _child("conv_ring2_gpu_check.py", env)
     assert rc == 0, log
 
 
-def test_conv_ring2_in_child_process(glare_lib):
-    """opt-in two-ring patch staging of the 256-wide conv tiles (csrc/conv_tc.cu RING2): parity against cuDNN fp32.  Green on hardware
-    (profiles/r40_ring2_*.log: same errors as the default kernel, 0.577 vs 0.593 ms on 512->512 at 4x105x155)."""
+def test_conv_one_ring_kernel_in_child_process(glare_lib):
+    """the one-ring kernel for the 256-wide tiles (GLARE_CONV_NO_RING2=1, the A/B switch; round 1's default) stays correct"""
     env = dict(os.environ)
-    env["GLARE_CONV_RING2"] = "1"
+    env["GLARE_CONV_NO_RING2"] = "1"
     rc, log = _child("conv_ring2_gpu_check.py", env)
     assert rc == 0, log

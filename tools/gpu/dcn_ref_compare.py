@@ -58,7 +58,9 @@ for C, H, W in ((256, 210, 310), (128, 420, 620)):
     x_cl, raw_cl = x.contiguous(memory_format=torch.channels_last), raw.contiguous(memory_format=torch.channels_last)
     fma = lambda: ops.modulated_deform_conv(x, offset, mask, wgt, bias, 1, 1, 1, 1, 4, packed_weight=packed)      # noqa: E731
     tc = lambda: dense.dcn_pack(x_cl, raw_cl, wgt, bias, 4)                                                         # noqa: E731
+    op = lambda: ops.modulated_deform_conv(x, offset, mask, wgt, bias, 1, 1, 1, 1, 4)        # noqa: E731  (operator-level entry: NCHW tensors of the reference op)
     y_ref, y_fma, y_tc = ref(), fma(), tc()
+    y_op, t_op = op(), timed(op)
     sc = float(y_ref.abs().max())
     t_ref, t_glue, t_fma, t_tc = timed(ref), timed(ref_with_glue), timed(fma), timed(tc)
     fl = 2.0 * B * H * W * C * C * 9 / 1e12
@@ -68,5 +70,7 @@ for C, H, W in ((256, 210, 310), (128, 420, 620)):
     print("    glare dcn_fwd_kernel (fp32 FMA, general operator)  %8.2f ms   %6.1f TFLOP/s   x%.1f" % (t_fma, fl / t_fma * 1e3, t_ref / t_fma))
     print("    glare dcn_tc_kernel (tcgen05, raw conv_offset in)  %8.2f ms   %6.1f TFLOP/s   x%.1f (x%.1f incl. the reference's glue)" %
           (t_tc, fl / t_tc * 1e3, t_ref / t_tc, t_glue / t_tc))
-    del x, raw, wgt, y_ref, y_fma, y_tc
+    print("    glare modulated_deform_conv (reference op signature, NCHW in/out, same kernel + layout passes) %8.2f ms   x%.1f   maxdiff %.3g" %
+          (t_op, t_ref / t_op, float((y_op - y_ref).abs().max())))
+    del x, raw, wgt, y_ref, y_fma, y_tc, y_op
     torch.cuda.empty_cache()

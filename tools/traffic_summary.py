@@ -37,8 +37,26 @@ def main(path):
         n = len(d["launches"])
         out[k] = {"launches": n, "dram_read_bytes": d["dram_read_bytes"], "dram_write_bytes": d["dram_write_bytes"],
                   "dram_bytes_per_launch": (d["dram_read_bytes"] + d["dram_write_bytes"]) / max(1, n), "time_us": d["time_us"]}
-    json.dump(out, sys.stdout, indent=1)
+    return out
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    res = main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--bench-json":
+        # the file bench.py reads (profiles/conv_tc_traffic.json): the dominant kernel's per-launch DRAM bytes, tagged with the mode, batch and
+        # the hash of the kernel sources it was captured from:  traffic_summary.py x.csv --bench-json <mode name> <batch> "<command>"
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from glare_b200.build import source_hash
+        k = next(k for k in res if "conv_tc_kernel" in k)
+        tot = {"launches": 0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "time_us": 0.0}
+        for kk, d in res.items():
+            if "conv_tc_kernel" in kk:
+                for f in tot:
+                    tot[f] += d[f]
+        json.dump({"kernel": "conv_tc_kernel", "mode": sys.argv[3], "batch": int(sys.argv[4]), "command": sys.argv[5] if len(sys.argv) > 5 else None,
+                   "csrc_sha16": source_hash(), "launches": tot["launches"],
+                   "dram_bytes_per_launch": (tot["dram_read_bytes"] + tot["dram_write_bytes"]) / max(1, tot["launches"]),
+                   "dram_bytes_per_step": tot["dram_read_bytes"] + tot["dram_write_bytes"], "time_us_under_ncu": tot["time_us"]}, sys.stdout, indent=1)
+    else:
+        json.dump(res, sys.stdout, indent=1)

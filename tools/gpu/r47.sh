@@ -1,0 +1,6 @@
+#!/bin/bash
+# round 2, call 8: software-pipelined DCN sampler: parity + timing
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_dcn_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q 2>&1 | tail -3
+timeout 600 python tools/gpu/dcn_ref_compare.py 15 > gpurun_out/r47_dcn_ref_compare.txt 2>&1; grep "dcn_tc_kernel\|maxdiff vs" gpurun_out/r47_dcn_ref_compare.txt
+GLARE_DCN_SW=4 timeout 600 python tools/gpu/dcn_ref_compare.py 15 > gpurun_out/r47_dcn_ref_compare_sw4.txt 2>&1; grep "dcn_tc_kernel" gpurun_out/r47_dcn_ref_compare_sw4.txt

@@ -81,6 +81,7 @@ class TcDense:
                            4: "fp32 split into two bf16 pieces per operand, three bf16 tensor-core passes (16-bit significand), fp32 accumulate"}[mode]
         self.bke = 64 if mode == 0 else 32
         self._w = {}
+        self.force_repack = False      # CUDA-graph capture of a TRAINING step: every replay must repack from the current weights
         self.fallbacks = {}
         # GroupNorm sum / sum of squares of a conv's output taken in its epilogue (column sums of the staged output tile -> per-(tile, warp)
         # partials -> fp64 finish launch; no atomics, no shuffles over pixels), which removes the statistics pass over the activation.
@@ -112,7 +113,7 @@ class TcDense:
         source tensor by weak reference: a different tensor object at a recycled address is repacked, and entries whose source has died
         (per-step temporaries of the training path: flipped filters, the flow's hoisted weight) are swept when new keys arrive."""
         ent = self._w.get(key)
-        if ent is None or ent[0]() is not w or ent[1] != w._version:
+        if self.force_repack or ent is None or ent[0]() is not w or ent[1] != w._version:
             if ent is None and len(self._w) >= 256:
                 for k in [k for k, e in self._w.items() if e[0]() is None]:
                     del self._w[k]

@@ -31,11 +31,14 @@ def _nchw(x_nhwc):
 
 
 _WT = {}
+_NO_CACHE = False          # set while a training step is being captured into a CUDA graph: every replay recomputes from the current weights
 
 
 def _flipped_transposed(w):
     """[Co,Ci,k,k] -> [Ci,Co,k,k] with the taps reversed; cached per weight version so that the conv path's packed-weight cache (keyed on the
     tensor it is given) does not grow with every training step"""
+    if _NO_CACHE:
+        return w.flip(2, 3).transpose(0, 1).contiguous()
     key = (w.data_ptr(), w._version, tuple(w.shape))
     if key not in _WT:
         if len(_WT) > 4096:
@@ -52,7 +55,9 @@ class CudaLeaves:
         from ._lib import lib, stream
         self.dense, self.ops, self.lib, self.stream = dense, ops, lib, stream
         import os
-        self.wgrad_tc = bool(os.environ.get("GLARE_WGRAD_TC")) and getattr(dense, "mode", None) == 4
+        # weight gradients on the tensor cores (gemm_tn_tc) unless GLARE_WGRAD_FMA=1 selects the fp32 split-K GEMM (the correctness baseline):
+        # 209 vs 228 ms per stage-2 step at batch 4 x 320x320 (profiles/r46_train_probe*.txt)
+        self.wgrad_tc = not os.environ.get("GLARE_WGRAD_FMA") and getattr(dense, "mode", None) == 4
 
     @staticmethod
     def _p(t):
@@ -86,8 +91,7 @@ class CudaLeaves:
     def gemm_tn_tc(self, a, b, chunk=8192):
         """a [P][M], b [P][N] -> a^T b [M][N] on the tensor cores: the reduction over the P pixels is cut into chunks that become the BATCH of one
         tcgen05 GEMM launch with per-sample weights (sample c: rows = a_c^T [M][chunk], weights = b_c^T [N][chunk]), the per-chunk products are
-        summed in fp32.  Opt-in (GLARE_WGRAD_TC=1) until the batched-weights path of conv_tc has a recorded hardware run; the fp32 split-K GEMM
-        (gemm_tn) is the default."""
+        summed in fp32.  Default in the fp32-grade (bf16x3) mode; GLARE_WGRAD_FMA=1 selects the fp32 split-K GEMM instead."""
         P, M = a.shape
         N = b.shape[1]
         chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
@@ -343,6 +347,40 @@ def draw_use_gt_mean(train_gt_ratio):
     return not (random.random() > train_gt_ratio)
 
 
+def _graphed_step(cfg, run, gt_latent, lr, params, use_gt_mean):
+    """The whole objective + gradient evaluation (~2 500 kernel launches and torch ops at batch 4 x 320x320, CPU-launch bound when issued one by
+    one) replayed as ONE CUDA graph per (shapes, branch, parameter storage).  The parameters are read in place at replay time -- the
+    optimizer updates them in place, so their addresses are stable -- and everything derived from them (packed weights, flipped filters,
+    the FlowPlan) is recomputed INSIDE the graph: the host-side caches are bypassed during capture.  The returned objective / gradients are the
+    graph's static buffers, valid until the next call (``forward`` clones the objective; ``backward`` consumes the gradients before that)."""
+    import contextlib
+    from .engine import _Graphed
+    key = (tuple(gt_latent.shape), tuple(lr.shape), bool(use_gt_mean), tuple(p.data_ptr() for p in params))
+    graphs = cfg.setdefault("_graphs", {})
+    g = graphs.get(key)
+    if g is None:
+        dense = getattr(cfg["leaves"], "dense", None)
+
+        @contextlib.contextmanager
+        def no_caches():
+            global _NO_CACHE
+            old = (_NO_CACHE, getattr(dense, "force_repack", False))
+            _NO_CACHE = True
+            if dense is not None:
+                dense.force_repack = True
+            try:
+                yield
+            finally:
+                _NO_CACHE = old[0]
+                if dense is not None:
+                    dense.force_repack = old[1]
+
+        if len(graphs) >= 4:
+            graphs.clear()
+        g = graphs[key] = _Graphed(None, run, gt_latent, lr, capture_ctx=no_caches)
+    return g(gt_latent, lr)
+
+
 class Stage2NLL(torch.autograd.Function):
     """The stage-2 objective as ONE autograd node over (gt_latent, lr, *parameters): ``forward`` evaluates the objective and every gradient
     with the library's kernels (stage2_step), ``backward`` hands the gradients to the parameters, rescaled by the incoming gradient (which
@@ -352,18 +390,26 @@ class Stage2NLL(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, gt_latent, lr, *params):
-        from . import flow
         keys = cfg["keys"]
-        sd = {k: p.detach() for k, p in zip(keys, params)}
-        sd.update(cfg.get("buffers", {}))
+        use_gt_mean = cfg.get("use_gt_mean", False)
+
+        def run(gt, x):
+            from . import flow
+            sd = {k: p.detach() for k, p in zip(keys, params)}
+            sd.update(cfg.get("buffers", {}))
+            plan = flow.FlowPlan(sd, gt.device)
+            nll, grads = stage2_step(sd, plan, x, gt, cfg["leaves"], cfg["conv2d"], flow_kernels=cfg.get("flow_kernels"), use_gt_mean=use_gt_mean)
+            return nll, [grads.get(k) for k in keys]
+
         with torch.no_grad():
-            plan = flow.FlowPlan(sd, gt_latent.device)
-            nll, grads = stage2_step(sd, plan, lr, gt_latent, cfg["leaves"], cfg["conv2d"], flow_kernels=cfg.get("flow_kernels"),
-                                     use_gt_mean=cfg.get("use_gt_mean", False))
+            if cfg.get("graph") and gt_latent.is_cuda:
+                nll, glist = _graphed_step(cfg, run, gt_latent, lr, params, use_gt_mean)
+            else:
+                nll, glist = run(gt_latent, lr)
         ctx.batch = gt_latent.shape[0]
-        ctx.has = [k in grads for k in keys]
-        ctx.save_for_backward(*[grads[k] for k in keys if k in grads])
-        return nll
+        ctx.has = [g is not None for g in glist]
+        ctx.save_for_backward(*[g for g in glist if g is not None])
+        return nll.clone() if cfg.get("graph") else nll
 
     @staticmethod
     def backward(ctx, g_nll):
@@ -374,13 +420,17 @@ class Stage2NLL(torch.autograd.Function):
         return (None, None, None) + tuple(next(saved) * scale if h else None for h in ctx.has)
 
 
-def stage2_nll(named_parameters, gt_latent, lr, leaves, conv2d, flow_kernels=None, train_gt_ratio=0.0, use_gt_mean=None):
+def stage2_nll(named_parameters, gt_latent, lr, leaves, conv2d, flow_kernels=None, train_gt_ratio=0.0, use_gt_mean=None, graph=False):
     """``named_parameters``: iterable of (state-dict key, Parameter) of the generator (netG of train_stage2.py: ``RRDB.*`` and
     ``flowUpsamplerNet.*``).  Returns the per-sample objective [B] with the graph edge to every parameter, so that
     ``stage2_nll(...).mean().backward()`` fills ``param.grad`` exactly like the reference's autograd.  ``train_gt_ratio``
-    (opt['train_gt_ratio']): probability of the ``mean = gt`` branch, drawn per call like the reference; ``use_gt_mean`` overrides the draw."""
+    (opt['train_gt_ratio']): probability of the ``mean = gt`` branch, drawn per call like the reference; ``use_gt_mean`` overrides the draw.
+    ``graph=True``: the evaluation replays as one CUDA graph (see _graphed_step); pass the SAME ``cfg`` holder via ``graph`` (a dict) to keep
+    the captured graphs across calls."""
     named = [(k, p) for k, p in named_parameters]
     if use_gt_mean is None:
         use_gt_mean = draw_use_gt_mean(train_gt_ratio)
-    cfg = {"keys": [k for k, _ in named], "leaves": leaves, "conv2d": conv2d, "flow_kernels": flow_kernels, "use_gt_mean": use_gt_mean}
+    cfg = graph if isinstance(graph, dict) else {}
+    cfg.update({"keys": [k for k, _ in named], "leaves": leaves, "conv2d": conv2d, "flow_kernels": flow_kernels, "use_gt_mean": use_gt_mean,
+                "graph": bool(graph) or isinstance(graph, dict)})
     return Stage2NLL.apply(cfg, gt_latent, lr, *[p for _, p in named])

@@ -303,27 +303,36 @@ class GlareEngine:
 
 
 class _Graphed:
-    def __init__(self, engine, fn, example):
+    """``fn(*tensors)`` captured as one CUDA graph: static input copies, an eager warm-up pass on a side stream (weight-packing caches,
+    lazily created buffers, backend mode), then the capture.  ``verify()`` (optional) is polled during the warm-up: False means "run it
+    again" (the attention backend just switched paths).  ``capture_ctx`` (optional context manager) wraps the captured pass only."""
+
+    def __init__(self, engine, fn, *examples, verify=None, capture_ctx=None):
+        import contextlib
         from . import ops
         self.ops = ops
-        self.static_in = example.clone()
+        self.static_in = [e.clone() for e in examples]
+        if verify is None and engine is not None:
+            verify = engine._verified
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):                  # eager warm-up: weight packing caches, lazily created buffers, backend mode
+        with torch.cuda.stream(side):
             for _ in range(2):
-                fn(self.static_in)
-                if engine._verified():
+                fn(*self.static_in)
+                if verify is None or verify():
                     break
         cur.wait_stream(side)
         n0 = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            self.static_out = fn(self.static_in)
+        with (capture_ctx() if capture_ctx is not None else contextlib.nullcontext()):
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.static_out = fn(*self.static_in)
         self.kernels = ops.LAUNCHES - n0               # kernels of libglare_b200.so inside the graph (ops.LAUNCHES is advanced per replay)
 
-    def __call__(self, x):
-        self.static_in.copy_(x, non_blocking=True)
+    def __call__(self, *xs):
+        for dst, x in zip(self.static_in, xs):
+            dst.copy_(x, non_blocking=True)
         self.graph.replay()
         self.ops.LAUNCHES += self.kernels
         return self.static_out

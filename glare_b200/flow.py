@@ -46,6 +46,22 @@ def pack_nets(sd, prefixes, has_z, device):
     return out, w1
 
 
+def _inv_logdet_3x3(w):
+    """w [n,3,3] fp32 -> (inverse [n,3,3] fp32, log|det| [n] fp32), evaluated in fp64 by the cofactor formula with elementwise tensor ops:
+    what the reference gets from torch.inverse(w.double()) (Permutations.py:38) and torch.slogdet(w)[1] (:27) to fp32 rounding, without
+    the LU library calls (host pointer arrays, error-flag synchronisation) that would break CUDA-graph capture of the training step."""
+    m = w.double()
+    a, b, c = m[:, 0, 0], m[:, 0, 1], m[:, 0, 2]
+    d, e, f = m[:, 1, 0], m[:, 1, 1], m[:, 1, 2]
+    g, h, i = m[:, 2, 0], m[:, 2, 1], m[:, 2, 2]
+    c00, c01, c02 = e * i - f * h, f * g - d * i, d * h - e * g
+    det = a * c00 + b * c01 + c * c02
+    adj = torch.stack([torch.stack([c00, c * h - b * i, b * f - c * e], dim=1),
+                       torch.stack([c01, a * i - c * g, c * d - a * f], dim=1),
+                       torch.stack([c02, b * g - a * h, a * e - b * d], dim=1)], dim=1)
+    return (adj / det[:, None, None]).float(), torch.log(det.abs()).float()
+
+
 class FlowPlan:
     """Device-resident packed parameters of the whole flow (built once per checkpoint; rebuilt per optimizer step in training).  Everything
     is computed on `device` with batched tensor ops -- no `.cpu()` round trips, no host synchronisation."""
@@ -67,14 +83,15 @@ class FlowPlan:
         bias = _stack(sd, ["%s.layers.%d.actnorm.bias" % (prefix, s) for s in steps], device).reshape(N_FLOW_STEPS, 3)
         self.pw_inv = torch.zeros((N_FLOW_STEPS, 16), dtype=torch.float32, device=device)
         self.pw_fwd = torch.zeros((N_FLOW_STEPS, 16), dtype=torch.float32, device=device)
-        self.pw_inv[:, 0:9] = torch.linalg.inv_ex(w.double())[0].float().reshape(N_FLOW_STEPS, 9)               # Permutations.py:38
+        w_inv, logdet_w = _inv_logdet_3x3(w)
+        self.pw_inv[:, 0:9] = w_inv.reshape(N_FLOW_STEPS, 9)                                                     # Permutations.py:38
         self.pw_inv[:, 12:15] = torch.exp(-logs)                                                                 # FlowActNorms.py:64
         self.pw_fwd[:, 0:9] = w.reshape(N_FLOW_STEPS, 9)
         self.pw_fwd[:, 12:15] = torch.exp(logs)
         self.pw_inv[:, 9:12] = bias
         self.pw_fwd[:, 9:12] = bias
         # weight-only logdet terms per step (FlowActNorms.py:66-74, Permutations.py:27,51-53), multiplied by `pixels` at run time
-        self.ld_const = torch.stack([logs.sum(dim=1), torch.linalg.slogdet(w)[1]], dim=1)
+        self.ld_const = torch.stack([logs.sum(dim=1), logdet_w], dim=1)
 
 
 def precompute(plan, ft, conv2d):

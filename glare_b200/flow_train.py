@@ -178,7 +178,8 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
         K.point_bwd(gu, t, pw, B, h, w, g_z, sums)
         wmat = sd[p + ".invconv.weight"].to(gt.device, torch.float32)
         ld_total = g_ld * B * hw                                        # sum over samples of dL/dlogdet, times the pixel count
-        grads[p + ".invconv.weight"] = sums[0:9].view(3, 3) + ld_total * torch.inverse(wmat.double()).t().float()
+        # d log|det W| / dW = W^-T; fp64 cofactor inverse (no LU library call: no error-flag synchronisation, CUDA-graph capturable)
+        grads[p + ".invconv.weight"] = sums[0:9].view(3, 3) + ld_total * flowmod._inv_logdet_3x3(wmat[None])[0][0].t()
         grads[p + ".actnorm.logs"] = (sums[9:12] + ld_total).view(1, 3, 1, 1)
         grads[p + ".actnorm.bias"] = sums[12:15].view(1, 3, 1, 1).clone()
 

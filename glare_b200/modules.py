@@ -237,6 +237,11 @@ class VQLLFLOWDeformable(nn.Module):
         self.dense_name = "auto"
         self._engine = None
         self._train_ctx = None
+        # True: stage-2 training calls replay as one CUDA graph per (shapes, mean branch).  Off by default: measured on B200 the step is
+        # GPU-bound (193 ms of kernel time per replay at batch 4 x 320x320 against 195-245 ms eagerly launched, profiles/r48_*), so the graph
+        # buys nothing and holds a second copy of the tape's memory per branch
+        self.train_graph = False
+        self._train_graphs = {}
 
     def engine(self, net_vq=None):
         key = _fingerprint(self) + (_fingerprint(net_vq) if net_vq is not None else ())
@@ -289,5 +294,6 @@ class VQLLFLOWDeformable(nn.Module):
             pass
         named = [(k, p) for k, p in self.named_parameters() if k.startswith(("RRDB.", "flowUpsamplerNet."))]
         nll = encoder_train.stage2_nll(named, gt.to(dev, torch.float32), lr.to(dev, torch.float32), leaves,
-                                       lambda x, w: dense.conv2d(x, w).float(), train_gt_ratio=ratio)
+                                       lambda x, w: dense.conv2d(x, w).float(), train_gt_ratio=ratio,
+                                       graph=self._train_graphs if self.train_graph else False)
         return None, nll, None

@@ -240,7 +240,7 @@ def test_packed_weight_cache_does_not_grow_with_optimizer_steps():
     """the cache was keyed on the weight's in-place version -> one more packed copy of every weight per training step"""
     from glare_b200.dense import TcDense
     d = TcDense.__new__(TcDense)
-    d._w, d.mode, calls = {}, 4, []
+    d._w, d.mode, d.force_repack, calls = {}, 4, False, []
 
     class Ops:
         @staticmethod

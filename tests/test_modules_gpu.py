@@ -92,3 +92,34 @@ def test_stage2_mirror_trains_as_dropped_in(glare_lib):
     with torch.no_grad():
         z, nll2, logdet = netG(gt=torch.from_numpy(g["gt_latent"]).cuda(), lr=torch.from_numpy(g["lr"]).cuda(), reverse=False)
     assert z.shape == (2, 3, 8, 8) and nll2.shape == (2,) and logdet.shape == (2,)
+
+
+@pytest.mark.parametrize("ratio", [0.0, 1.0])
+def test_stage2_training_graph_replays_equal_eager_steps(glare_lib, ratio):
+    """the training call as ONE CUDA graph per (shapes, mean branch) (encoder_train._graphed_step, opt-in): three SGD steps with graph replays
+    give the objective and the parameters of three eagerly launched steps -- i.e. every replay re-derives packed weights, flipped filters
+    and the flow plan from the CURRENT parameters"""
+    from glare_b200 import modules, synth
+    g = load_golden("stage2")
+    gt, lr = torch.from_numpy(g["gt_latent"]).cuda(), torch.from_numpy(g["lr"]).cuda()
+    runs = []
+    for use_graph in (True, False):
+        netG = modules.VQLLFLOWDeformable(which="netG_stage2", opt={"train_gt_ratio": ratio, "datasets": {"train": {"GT_size": 256, "quant": 32}}}).cuda()
+        netG.load_state_dict(synth.synth_state_dict("netG_stage2", 0), strict=True)
+        netG.train()
+        netG.train_graph = use_graph
+        opt = torch.optim.SGD(netG.parameters(), lr=2e-3)          # (Adam's sign-like normalisation would amplify 1e-7 gradient differences)
+        nlls = []
+        for step in range(3):
+            opt.zero_grad(set_to_none=True)
+            _, nll, _ = netG(gt=gt, lr=lr, reverse=False)
+            nll.mean().backward()
+            opt.step()
+            nlls.append(nll.detach().cpu())
+        runs.append((nlls, {k: v.detach().cpu() for k, v in netG.state_dict().items()}))
+        assert (len(netG._train_graphs.get("_graphs", {})) == 1) == use_graph
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert torch.allclose(a, b, atol=2e-4, rtol=2e-5), (a, b)
+    assert float((runs[0][0][0] - runs[0][0][2]).abs().max()) > 1e-3          # the parameters really moved between the replays
+    worst = max(float((runs[0][1][k] - runs[1][1][k]).abs().max()) for k in runs[0][1])
+    assert worst < 1e-5, worst

@@ -1,6 +1,6 @@
 """BASELINE config 4 shape (stage-2 flow training: batch 4, 320x320 crops, latent 80x80) through glare_b200.encoder_train.stage2_step:
 wall-clock per step and the split encoder forward / flow forward+backward / encoder backward.  python tools/gpu/train_probe.py [steps]
-(GLARE_WGRAD_TC=1 selects the tensor-core weight gradient)."""
+(tensor-core weight gradient by default; GLARE_WGRAD_FMA=1 selects the fp32 split-K GEMM)."""
 import sys
 import time
 

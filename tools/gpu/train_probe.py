@@ -43,3 +43,21 @@ with torch.no_grad():
 print("stage-2 step, batch 4 x 320x320 (latent 80x80): nll %s" % [round(float(x), 4) for x in nll])
 print("  encoder forward %.1f ms | flow forward + backward %.1f ms | encoder backward %.1f ms | total %.1f ms  (peak memory %.1f GB)"
       % tuple([1e3 * a / steps for a in acc] + [1e3 * sum(acc) / steps, torch.cuda.max_memory_allocated() / 2 ** 30]))
+
+if len(sys.argv) > 2 and sys.argv[2] == "--profile":
+    # kernel-time breakdown of one step (torch.profiler / CUPTI): which kernels the 0.2 s go to
+    from torch.profiler import ProfilerActivity, profile
+    with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step()
+        torch.cuda.synchronize()
+    rows = {}
+    for ev in prof.events():
+        if ev.device_type is not None and "cuda" in str(ev.device_type).lower():
+            name = ev.name.split("<")[0].split("(")[0][:60]
+            r = rows.setdefault(name, [0.0, 0])
+            r[0] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+            r[1] += 1
+    tot = sum(v[0] for v in rows.values())
+    print("kernel-time breakdown of one step: %.1f ms of device time in %d kernels" % (tot / 1e3, sum(v[1] for v in rows.values())))
+    for name, (t, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:28]:
+        print("  %-62s %5d launches %9.2f ms %5.1f %%" % (name, n, t / 1e3, 100 * t / tot))

@@ -120,8 +120,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CL = CM == 0 ? 1 : 2;
     constexpr bool PAIR = CM == 2, MCAST = CM == 1;
     using Cfg = ConvCfg<MODE, BN, PAIR>;
-    static_assert(!HALO || (MODE == 4 && CM == 2 && BN <= 128), "halo staging: mode 4, CTA pair, BN <= 128");
-    static_assert(!RING2 || (MODE == 4 && CM == 2 && !HALO && Cfg::R2_B_SLOTS >= 4), "two-ring staging: mode 4, CTA pair");
+    static_assert(!HALO || ((MODE == 4 || MODE == 0) && CM == 2 && BN <= 128), "halo staging: 128-byte bf16 rows (modes 0 / 4), CTA pair, BN <= 128");
+    static_assert(!RING2 || ((MODE == 4 || MODE == 0) && CM == 2 && !HALO && Cfg::R2_B_SLOTS >= 4), "two-ring staging: modes 0 / 4, CTA pair");
     constexpr int STAGES = HALO ? Cfg::HALO_STAGES : Cfg::STAGES;
     constexpr int STAGE_BYTES = HALO ? Cfg::HALO_STAGE_BYTES : Cfg::STAGE_BYTES;
     constexpr int RING_BYTES = RING2 ? Cfg::R2_RING_BYTES : STAGES * STAGE_BYTES;        // operand rings; the epilogue staging tiles follow
@@ -202,7 +202,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             mbar_wait_bounded(&a_empty[sa], ((it / Cfg::R2_A_SLOTS) & 1) ^ 1);
                             if (cl_rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * Cfg::HALO_A_BYTES);
                             else mbar_arrive_cluster(&a_full[sa], 0);
-                            tma_load_4d_2sm(smem_al + (size_t)sa * Cfg::HALO_A_BYTES, &tmA, &a_full[sa], 2 * kc * Cfg::BKE, x0, y0 + dy, n);
+                            tma_load_4d_2sm(smem_al + (size_t)sa * Cfg::HALO_A_BYTES, &tmA, &a_full[sa], (Cfg::B3 ? 2 : 1) * kc * Cfg::BKE, x0, y0 + dy, n);
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
                                 const uint32_t ib = 3u * it + dx;
@@ -211,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[sb], 2 * Cfg::B_BYTES);
                                 else mbar_arrive_cluster(&full_bar[sb], 0);
                                 tma_load_3d_2sm(ring_b + (size_t)sb * Cfg::B_BYTES, &tmB, &full_bar[sb],
-                                                2 * ((dy * 3 + dx) * a.Cin + kc * Cfg::BKE), nb * BN + half, 0);
+                                                (Cfg::B3 ? 2 : 1) * ((dy * 3 + dx) * a.Cin + kc * Cfg::BKE), nb * BN + half, 0);
                             }
                         }
                     }
@@ -228,11 +228,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             uint8_t* st = smem_al + (size_t)s * STAGE_BYTES;
                             if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
                             else mbar_arrive_cluster(&full_bar[s], 0);
-                            tma_load_4d_2sm(st, &tmA, &full_bar[s], 2 * kc * Cfg::BKE, x0, y0 + dy, n);      // (TW + 2) x TH patch of this filter row
+                            tma_load_4d_2sm(st, &tmA, &full_bar[s], (Cfg::B3 ? 2 : 1) * kc * Cfg::BKE, x0, y0 + dy, n);      // (TW + 2) x TH patch of this filter row
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx)
                                 tma_load_3d_2sm(st + Cfg::HALO_A_BYTES + dx * Cfg::B_BYTES, &tmB, &full_bar[s],
-                                                2 * ((dy * 3 + dx) * a.Cin + kc * Cfg::BKE), nb * BN + half, wn);
+                                                (Cfg::B3 ? 2 : 1) * ((dy * 3 + dx) * a.Cin + kc * Cfg::BKE), nb * BN + half, wn);
                         }
                     }
                     continue;
@@ -304,12 +304,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tc_fence_after();
                             const uint64_t da = umma_desc_sw128_sbo(pa + dx * 128, (Cfg::HALO_TW + 2) * 128);
                             const uint64_t db = umma_desc_sw128(ring_b + (uint32_t)sb * Cfg::B_BYTES);
+                            if (Cfg::B3) {
 #pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                const uint64_t adv = (uint64_t)(jj * 2);
-                                mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | jj) != 0 ? 1u : 0u);
-                                mma<false, PAIR>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);
-                                mma<false, PAIR>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);
+                                for (int jj = 0; jj < 2; ++jj) {
+                                    const uint64_t adv = (uint64_t)(jj * 2);
+                                    mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | jj) != 0 ? 1u : 0u);
+                                    mma<false, PAIR>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);
+                                    mma<false, PAIR>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);
+                                }
+                            } else {                                      // mode 0: 64 bf16 per row, four K = 16 steps
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint64_t adv = (uint64_t)(j * 2);
+                                    mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | j) != 0 ? 1u : 0u);
+                                }
                             }
                             umma_commit_2sm_mc(&empty_bar[sb], (uint16_t)0x3);       // this tap's weight slab is free in both CTAs
                         }
@@ -330,12 +338,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // pixel (y, x + dx) of the patch is row y * (TW + 2) + x + dx: start dx rows in, 8-row groups one patch row apart
                             const uint64_t da = umma_desc_sw128_sbo(sa + dx * 128, (Cfg::HALO_TW + 2) * 128);
                             const uint64_t db = umma_desc_sw128(sa + Cfg::HALO_A_BYTES + dx * Cfg::B_BYTES);
+                            if (Cfg::B3) {
 #pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                const uint64_t adv = (uint64_t)(jj * 2);
-                                mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | jj) != 0 ? 1u : 0u);
-                                mma<false, PAIR>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);
-                                mma<false, PAIR>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);
+                                for (int jj = 0; jj < 2; ++jj) {
+                                    const uint64_t adv = (uint64_t)(jj * 2);
+                                    mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | jj) != 0 ? 1u : 0u);
+                                    mma<false, PAIR>(d_tmem, da + adv, db + 4 + adv, idesc, 1u);
+                                    mma<false, PAIR>(d_tmem, da + 4 + adv, db + adv, idesc, 1u);
+                                }
+                            } else {                                      // mode 0: 64 bf16 per row, four K = 16 steps
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint64_t adv = (uint64_t)(j * 2);
+                                    mma<false, PAIR>(d_tmem, da + adv, db + adv, idesc, (ki | dx | j) != 0 ? 1u : 0u);
+                                }
                             }
                         }
                         umma_commit_2sm_mc(&empty_bar[s], (uint16_t)0x3);
@@ -408,8 +424,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long pix = ((long long)n * a.H * a.oscale + (gy * a.oscale + a.oa)) * (a.W * a.oscale) + (gx * a.oscale + a.ob);
             float* yrow = a.y + pix * a.ldy;
             const float* rrow = (a.residual && valid) ? a.residual + pix * a.Cout : nullptr;
-            const bool epi_exp = MODE == 4 && a.row_norm != nullptr;
-            const bool epi_pack = MODE == 4 && (epi_exp || a.pack_out != 0);
+            const bool epi_exp = (MODE == 4 || MODE == 0) && a.row_norm != nullptr;     // (mode 0: handled at the top of `process`)
+            const bool epi_pack = MODE == 4 && (a.row_norm != nullptr || a.pack_out != 0);
             const bool epi_sq = MODE == 4 && a.row_sq_part != nullptr;
             float e_ref = 0.f, e_sum = 0.f, r_scale = 1.f, e_sq = 0.f;
             if (epi_exp && valid)                                        // key_norm_max == null: row_norm holds the reference itself (attn.cu, sampled maximum)
@@ -419,6 +435,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // one 32-column chunk of this thread's accumulator row: registers -> bias / residual / attention epilogues -> store
             auto process = [&](const uint32_t (&v)[32], const int c0) {
                 const int co = nb * BN + c0;
+                if constexpr (MODE == 0) {
+                    if (a.row_norm != nullptr) {
+                        // bf16 operands (BASELINE config 3): the scores GEMM's exp epilogue writes P~ as the single-piece bf16 operand of the
+                        // P V GEMM.  Two 32-column chunks share one 128-byte staging row (64 bf16): the left chunk fills 16-byte chunks 0-3, the
+                        // right one 4-7 and issues the TMA store (box = 64 keys x TW pixels x TH / 4 rows).  Keys >= Cout get 0.
+                        const int right = (c0 >> 5) & 1;
+                        const int co_pair = co - 32 * right;
+                        if (co_pair >= a.Cout) return;                   // uniform over the CTA
+                        const float c1 = a.exp_scale * 1.4426950408889634f, r1 = e_ref * 1.4426950408889634f;
+                        float p[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) p[j] = ex2_approx((co + j < a.Cout) ? fmaf(__uint_as_float(v[j]), c1, -r1) : -INFINITY);
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // fixed order: repeatable row sums
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) { s0 += p[j]; s1 += p[j + 1]; s2 += p[j + 2]; s3 += p[j + 3]; }
+                        e_sum += (s0 + s1) + (s2 + s3);
+                        uint8_t* buf = staging + (chunk_id & 1) * (32 * 128);
+                        if (!right) __syncwarp();                        // lane 0 has seen the previous store of this buffer drain
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            uint32_t w4[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __nv_bfloat162 h = __floats2bfloat162_rn(p[8 * jj + 2 * e], p[8 * jj + 2 * e + 1]);
+                                w4[e] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            *reinterpret_cast<uint4*>(buf + lane * 128 + (((4 * right + jj) ^ (lane & 7)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        }
+                        if (right) {
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (n < a.B) tma_store_4d(&tmY, buf, co_pair, tx * a.TW, ty * a.TH + (a.TH >> 2) * q, n);
+                                tma_store_commit();
+                                tma_store_wait_read<1>();
+                            }
+                            ++chunk_id;
+                        }
+                        return;
+                    }
+                }
                 if (co >= a.Cout) return;                                // uniform over the CTA
                 const bool full = co + 32 <= a.Cout;                     // uniform: no ragged tail inside this chunk
                 float o[32];
@@ -724,6 +781,19 @@ static int make_out_map(CUtensorMap* m, const float* ptr, int B, int H, int W, i
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
+// P~ operand of the bf16 mode: bf16 [B,H,W,ldy], one epilogue warp stores 64 keys x TW pixels x TH / 4 rows per instruction
+static int make_out_map_bf16(CUtensorMap* m, const void* ptr, int B, int H, int W, int n_cols, long long ldy, int TH, int TW) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return GLARE_ERR_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)n_cols, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)W * ldy * 2, (cuuint64_t)H * W * ldy * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH / 4), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
+}
+
 template <int MODE, int BN, int CM, bool HALO = false, bool RING2 = false>
 static int launch_conv_cl(const CUtensorMap& tA, const CUtensorMap& tAl, const CUtensorMap& tB, const CUtensorMap& tBl,
                           const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
@@ -758,11 +828,11 @@ static int launch_conv(int cl, const CUtensorMap& tA, const CUtensorMap& tAl, co
                        const CUtensorMap& tY, const ConvTcArgs& a, cudaStream_t stream) {
     // cl: 1 = single CTA, 2 = multicast cluster, 3 = CTA pair (cta_group::2), 4 = CTA pair with filter-row halo staging
     if (cl == 4) {
-        if constexpr (MODE == 4 && BN <= 128) return launch_conv_cl<MODE, BN, 2, true>(tA, tAl, tB, tBl, tY, a, stream);
+        if constexpr ((MODE == 4 || MODE == 0) && BN <= 128) return launch_conv_cl<MODE, BN, 2, true>(tA, tAl, tB, tBl, tY, a, stream);
         else return GLARE_ERR_UNSUPPORTED;
     }
     if (cl == 5) {                                                   // two-ring patch staging for the 256-wide N tile
-        if constexpr (MODE == 4 && BN == 256) return launch_conv_cl<MODE, BN, 2, false, true>(tA, tAl, tB, tBl, tY, a, stream);
+        if constexpr ((MODE == 4 || MODE == 0) && BN == 256) return launch_conv_cl<MODE, BN, 2, false, true>(tA, tAl, tB, tBl, tY, a, stream);
         else return GLARE_ERR_UNSUPPORTED;
     }
     if (cl == 3) return launch_conv_cl<MODE, BN, 2>(tA, tAl, tB, tBl, tY, a, stream);
@@ -889,7 +959,7 @@ GLARE_API int glare_conv2d_nhwc_tc_ex(int mode, const void* x, const void* x_lo,
 GLARE_API int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, int rows_h, int rows_w, int C, int n_keys, int n_pad,
                                        float scale, float margin, const float* q_row_norm, const unsigned* key_norm_max, void* p_out,
                                        float* row_sum_part, long long part_stride, int* n_blocks_host, cudaStream_t stream) {
-    if (mode != 4) return GLARE_ERR_UNSUPPORTED;
+    if (mode != 4 && mode != 0) return GLARE_ERR_UNSUPPORTED;
     if (!q_row_norm || !row_sum_part || !n_blocks_host || n_pad < n_keys || (n_pad & 31) || !(scale > 0.f) || !(margin >= 0.f))
         return GLARE_ERR_BAD_ARG;                            // key_norm_max may be null: q_row_norm then holds the per-row reference itself
     AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host, 0, nullptr};
@@ -901,7 +971,7 @@ GLARE_API int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, i
 // (ldy == C, C % 32 == 0) the bf16x3 operand of the following proj_out conv
 GLARE_API int glare_attn_pv_tc(int mode, const void* p, const void* vt, const float* row_scale, void* y, int rows_h, int rows_w, int n_pad,
                                int C, long long ldy, int pack_out, cudaStream_t stream) {
-    if (mode != 4) return GLARE_ERR_UNSUPPORTED;
+    if (mode != 4 && !(mode == 0 && !pack_out)) return GLARE_ERR_UNSUPPORTED;
     if (!row_scale) return GLARE_ERR_BAD_ARG;
     AttnEpi ae{nullptr, nullptr, nullptr, 0, 0.f, 0.f, row_scale, nullptr, pack_out ? 1 : 0, nullptr};
     return conv_tc_launch(mode, p, nullptr, vt, nullptr, nullptr, nullptr, reinterpret_cast<float*>(y), 1, rows_h, rows_w, rows_h, rows_w, n_pad, C,
@@ -928,7 +998,9 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     const int ksize = ts.tap_w;
     const bool epi_exp = ae && ae->row_norm;
     const bool epi_pack = ae && (ae->row_norm || ae->pack_out);          // the output is an operand tensor
-    if (ae && mode != 4) return GLARE_ERR_UNSUPPORTED;
+    // attention epilogues: mode 4 (all of them) and mode 0 (exp with a bf16 P~ operand; row scale) -- not the operand-packing / row-square ones
+    if (ae && mode != 4 && !(mode == 0 && !ae->pack_out && !ae->row_sq_part)) return GLARE_ERR_UNSUPPORTED;
+    if (epi_exp && mode == 0 && (ldy & 63)) return GLARE_ERR_BAD_ARG;
     if (ae && (ae->row_norm || ae->row_scale) && (bias || residual || gn_stats)) return GLARE_ERR_UNSUPPORTED;
     if (ae && ae->pack_out && !ae->row_norm && ((Cout & 31) || ldy != Cout || residual || gn_stats || ts.oscale != 1)) return GLARE_ERR_UNSUPPORTED;
     if (ae && ae->row_sq_part && ae->part_stride < (long long)B * H * W) return GLARE_ERR_BAD_ARG;
@@ -958,12 +1030,12 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;
     // filter-row halo staging (ConvCfg): 3x3 stride-1 convs with narrow N tiles, 8 x 16 pixel tiles
     static const bool no_halo = getenv("GLARE_CONV_NO_HALO") != nullptr;            // A/B switch for profiling only
-    const bool halo = !no_halo && mode == 4 && BN <= 128 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
+    const bool halo = !no_halo && (mode == 4 || mode == 0) && BN <= 128 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
                       w_batch_stride == 0 && getenv("GLARE_CONV_NO_CLUSTER") == nullptr && getenv("GLARE_CONV_MCAST") == nullptr;
     // two-ring patch staging for the 256-wide N tile: default since round 2 (green on hardware, conv_tc 451.4 -> 447.7 ms/step,
     // profiles/r45_bench_ring2.json); GLARE_CONV_NO_RING2 selects the one-ring kernel (A/B switch)
     static const bool want_ring2 = getenv("GLARE_CONV_NO_RING2") == nullptr;
-    const bool ring2 = want_ring2 && !no_halo && mode == 4 && BN == 256 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
+    const bool ring2 = want_ring2 && !no_halo && (mode == 4 || mode == 0) && BN == 256 && ts.ntaps == 9 && ts.tap_w == 3 && stride == 1 && ts.oscale == 1 &&
                        w_batch_stride == 0 && !ae && getenv("GLARE_CONV_NO_CLUSTER") == nullptr && getenv("GLARE_CONV_MCAST") == nullptr;
     if (halo || ring2) {
         a.TH = 16; a.TW = 8;
@@ -1005,7 +1077,9 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
         a.tma_store = ((!direct || epi_pack) && Cout >= 32 && ts.oscale == 1) ? 1 : 0;
     }
     // exp epilogue: the output is an operand tensor of 128-byte chunks (32 keys each), written whole up to the padded row length ldy
-    if ((rc = make_out_map(&tY, y, B, H, W, epi_exp ? (int)ldy : Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
+    if (epi_exp && mode == 0) {
+        if ((rc = make_out_map_bf16(&tY, y, B, H, W, (int)ldy, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
+    } else if ((rc = make_out_map(&tY, y, B, H, W, epi_exp ? (int)ldy : Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0 || mode == 4;
     const int e2 = mode == 4 ? 2 : 1;              // mode 4: the operand tensors are interleaved bf16 pairs, 2 per element
     if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, e2 * Cin, a.TH, use_halo ? a.TW + 2 : a.TW, stride)) != GLARE_OK) return rc;

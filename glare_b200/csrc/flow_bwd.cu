@@ -444,8 +444,10 @@ GLARE_API int glare_flow_train_colsum_f32(const float* a, long long lda, const f
     if (P < 0 || C <= 0 || C > 64 || 256 % C != 0 || lda < C || (b && ldb < C)) return GLARE_ERR_BAD_ARG;
     if (P == 0) return GLARE_OK;
     if (!a || !out) return GLARE_ERR_BAD_ARG;
-    long long chunks = (P + 1023) / 1024;
-    if (chunks > 148 * 4) chunks = 148 * 4;
+    // >= one CTA per 128 rows (32 sequential loads per thread): round 1's 1024 rows per CTA left 25 CTAs for the 25 600 latent pixels of a
+    // training batch, 80 us per call and 288 calls per step (profiles/r50_train_probe_kernel_breakdown.txt)
+    long long chunks = (P + 127) / 128;
+    if (chunks > 148 * 8) chunks = 148 * 8;
     const long long per = (P + chunks - 1) / chunks;
     chunks = (P + per - 1) / per;
     FB_LAUNCH(flow_tr_colsum_kernel, (unsigned)chunks, 256, stream, a, lda, b, ldb, C, P, per, out);

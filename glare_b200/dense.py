@@ -92,7 +92,7 @@ class TcDense:
         # mode 4: softmax fused into the epilogues of the two GEMMs (csrc/attn.cu): exp against a Cauchy-Schwarz row reference in the scores
         # GEMM, 1 / row sum in the P V GEMM; rows that fall outside the safe window raise `attn_flag` and `attention_verified()` tells
         # the caller (engine.infer) to re-run with the exact three-kernel path
-        self.attn_fused = mode == 4 and not os.environ.get("GLARE_ATTN_UNFUSED")
+        self.attn_fused = mode in (0, 4) and not os.environ.get("GLARE_ATTN_UNFUSED")      # (mode 0: P~ written as the single-piece bf16 operand)
         self.attn_margin = 60.0
         # row reference of the fused softmax: "sampled" = maximum over 128 strided keys + 50 (one small extra GEMM per block; robust to loose
         # |q||k| bounds), "cauchy" = the Cauchy-Schwarz bound - margin of round 1 (needs no extra GEMM; trips when the bound is > ~115 above
@@ -288,7 +288,7 @@ class TcDense:
             q_hi, q_lo = (q.hi, q.lo) if q_is_op else ops.conv_prep_act(self.mode, qn)
             k_hi, k_lo = (k.hi, k.lo) if k_is_op else ops.conv_prep_act(self.mode, kn)      # K[n] as GEMM weights [N][C]
             vt_hi, vt_lo = ops.attn_transpose_v(self.mode, vn, B, N, C, Np)
-            if (self.attn_fused if fused is None else (fused and self.mode == 4)) and N >= 32:
+            if (self.attn_fused if fused is None else (fused and self.mode in (0, 4))) and N >= 32:
                 sq = (getattr(q, "row_sq", None), getattr(k, "row_sq", None))
                 if as_operand and self.pack_epilogue and C % 32 == 0:  # the P V epilogue writes proj_out's operand
                     out_op = ops._hi_alloc(self.mode, (B, h, w, C), vn.device)
@@ -360,8 +360,9 @@ class TcDense:
         rows_max = min(band, h) * w
         p_op = ops._hi_alloc(self.mode, (rows_max, Np), dev)
         n32 = (N + 31) // 32 * 32
-        if n32 < Np:
+        if self.mode == 4 and n32 < Np:
             p_op[:, 2 * n32:].zero_()                                    # operand chunks past the last key chunk are never written
+        # (mode 0: the epilogue writes whole 64-key rows, zeros for keys >= N, and Np is the next multiple of 64)
         part = torch.empty(((N + 63) // 64, rows_max), device=dev, dtype=torch.float32)
         row_scale = torch.empty((rows_max,), device=dev, dtype=torch.float32)
         for b in range(B):

@@ -88,6 +88,18 @@ class CudaLeaves:
         self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, b.shape[1], self._p(out))
         return out
 
+    def colsum(self, x):
+        """x [P][C] -> column sums [C] (bias gradients).  C a multiple of 64: the flow path's column-sum kernel on 64-column slabs; other widths
+        (3-channel heads) are tiny reductions left to torch.  (Round 1 ran these through the 128 x 128-tile split-K GEMM with a ones vector:
+        35 ms of a 194 ms step.)"""
+        P, C = x.shape
+        if C % 64 or not x.is_contiguous():
+            return x.sum(dim=0)
+        out = torch.zeros((C,), device=x.device, dtype=torch.float32)
+        for c0 in range(0, C, 64):
+            self._call("glare_flow_train_colsum_f32", ctypes.c_void_p(x.data_ptr() + 4 * c0), C, None, 0, 64, P, ctypes.c_void_p(out.data_ptr() + 4 * c0))
+        return out
+
     def gemm_tn_tc(self, a, b, chunk=8192):
         """a [P][M], b [P][N] -> a^T b [M][N] on the tensor cores: the reduction over the P pixels is cut into chunks that become the BATCH of one
         tcgen05 GEMM launch with per-sample weights (sample c: rows = a_c^T [M][chunk], weights = b_c^T [N][chunk]), the per-chunk products are
@@ -188,7 +200,7 @@ class Tape:
         G = self.L.gemm_tn(col, gyn)                                                   # [k*k*Ci][Co], tap-major rows
         self._acc(p + ".weight", G.view(k * k, Ci, Co).permute(2, 1, 0).reshape(Co, Ci, k, k).contiguous())
         if (p + ".bias") in self.sd:
-            self._acc(p + ".bias", self.L.gemm_tn(torch.ones((gyn.shape[0], 1), device=gyn.device), gyn)[0])
+            self._acc(p + ".bias", self.L.colsum(gyn))
         if not need_gx:
             return None
         w_t = _flipped_transposed(w)                                                  # transpose of a stride-1 'same' conv

@@ -15,6 +15,9 @@ class TorchLeaves:
         s = torch.softmax(torch.bmm(q.reshape(B, C, h * w).permute(0, 2, 1), k.reshape(B, C, h * w)) * (int(C) ** (-0.5)), dim=2)
         return torch.bmm(v.reshape(B, C, h * w), s.permute(0, 2, 1)).reshape(B, C, h, w)
 
+    def colsum(self, x):
+        return x.sum(dim=0)
+
     def gemm_tn(self, a, b):
         return a.t() @ b
 

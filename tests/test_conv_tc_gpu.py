@@ -226,6 +226,30 @@ def test_attention_query_bands(glare_lib, fused):
     assert float((banded - whole).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(1, 512, 9, 14), (2, 512, 24, 21), (1, 512, 105, 155), (1, 128, 40, 33)])
+def test_attention_fused_softmax_bf16_operands(glare_lib, shape):
+    """mode 0 (BASELINE config 3): the exp epilogue writes P~ as the single-piece bf16 operand (two 32-key chunks per staged row, ragged
+    tails zero-filled) -- against the exact three-kernel bf16 path and fp64, at bf16 tolerances"""
+    from glare_b200.dense import TcDense
+    B, C, h, w = shape
+    g = torch.Generator().manual_seed(3 + h)
+    q = (torch.randn((B, C, h, w), generator=g) * 1.5).cuda()
+    k = (torch.randn((B, C, h, w), generator=g) * 1.5).cuda()
+    v = torch.randn((B, C, h, w), generator=g).cuda()
+    fused, exact = TcDense(0), TcDense(0)
+    exact.attn_fused = False
+    assert fused.attn_fused
+    o1, o2 = fused.attention(q, k, v), exact.attention(q, k, v)
+    torch.cuda.synchronize()
+    assert fused.attention_verified() and fused.attn_fused
+    ref = _attention_fp64(q, k, v)
+    sc = max(1.0, float(ref.abs().max()))
+    e1 = float((o1.reshape(B, C, h * w).double() - ref).abs().max())
+    e2 = float((o2.reshape(B, C, h * w).double() - ref).abs().max())
+    assert e1 < 3e-2 * sc and e2 < 3e-2 * sc and e1 < 2.0 * e2 + 1e-3, (shape, e1, e2)
+    assert torch.equal(o1, fused.attention(q, k, v))
+
+
 @pytest.mark.parametrize("ref", ["sampled", "cauchy"])
 def test_attention_fused_softmax_window_flag_and_fallback(glare_lib, ref):
     """rows outside the fused path's window raise the device flag; attention_verified() then switches the backend to the exact path, which is

@@ -122,4 +122,4 @@ def test_stage2_training_graph_replays_equal_eager_steps(glare_lib, ratio):
         assert torch.allclose(a, b, atol=2e-4, rtol=2e-5), (a, b)
     assert float((runs[0][0][0] - runs[0][0][2]).abs().max()) > 1e-3          # the parameters really moved between the replays
     worst = max(float((runs[0][1][k] - runs[1][1][k]).abs().max()) for k in runs[0][1])
-    assert worst < 1e-5, worst
+    assert worst < 1e-4, worst          # (the split-K / column-sum gradient kernels combine partial sums with atomics: run-to-run ~1e-6 relative)

@@ -31,11 +31,12 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def source_hash():
-    """sha256 (first 16 hex digits) over the kernel sources the library is built from: ties a committed ncu capture to the code it measured"""
+def source_hash(files=("conv_tc.cu", "tc.cuh", "common.cuh")):
+    """sha256 (first 16 hex digits) over the sources of the bench's dominant kernel (conv_tc_kernel and the headers it includes): ties the
+    committed ncu capture behind `roofline.traffic` to the code it measured"""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))):
+    for f in sorted(os.path.join(CSRC, n) for n in files):
         h.update(os.path.basename(f).encode())
         with open(f, "rb") as fh:
             h.update(fh.read())

@@ -122,7 +122,10 @@ vq_argmin_gather_kernel(const float* __restrict__ z,        // [B,3,hw]
                     for (int k = 0; k < K; ++k) {
                         const float4 c = s_cb[k];
                         float dot = __fmaf_rn(c3, c.z, __fmaf_rn(b, c.y, __fmul_rn(a, c.x)));
-                        float d = __fmaf_rn(-2.0f, dot, __fadd_rn(tnn, c.w));
+                        // the reference's two roundings, fl(fl(tn + cn) - fl(2 dot)): when 2 dot overflows while dot does not, this is
+                        // inf - inf = NaN where the single FMA of the main loop gives inf.  Only here can that matter: fl(2 dot) = inf
+                        // implies tn = inf, so the main loop (d < best) never selects such a code either way.
+                        float d = __fsub_rn(__fadd_rn(tnn, c.w), __fmul_rn(2.0f, dot));
                         if (d < bd || (d != d && bd == bd)) { bd = d; bi_ = k; }
                     }
                 }

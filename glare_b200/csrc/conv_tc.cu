@@ -43,7 +43,7 @@ struct ConvTcArgs {
     int m_tiles;             // B * tiles_y * tiles_x
     int w_batched;           // weights differ per sample (3rd tensor-map coordinate = n): attention S = Q K^T, O = P V
     long long ldy;           // output row (pixel) stride in elements, >= Cout
-    float* gn_part;          // optional [B][gn_slots][32][2]: per (pixel tile, epilogue warp) partial (sum, sum of squares) of the OUTPUT per
+    float* gn_part;          // optional [B][gn_slots][32][4]: per (pixel tile, epilogue warp) partial {S1, S2, shift, count} of the OUTPUT per
                              // GroupNorm group -- every entry written exactly once (no atomics), reduced in fp64 by conv_gn_finish_kernel
     int gn_cpg;              // channels per group (Cout / 32): 4, 8 or 16
     int gn_slots;            // tiles_y * tiles_x * 4
@@ -563,24 +563,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (a.gn_part != nullptr) {
                         // GroupNorm statistics of what this conv produces (the next layer's Normalize, encoder_decoder.py:34-35), from the
-                        // staged tile: lane l sums channel co + l over the warp's 32 pixels -- column reads of the swizzled tile are
+                        // staged tile: lane l sums channel co + l over the warp's valid pixels -- column reads of the swizzled tile are
                         // conflict-free (32 distinct words of one 128-byte row per step) --, cpg adjacent lanes fold into their group, and the
-                        // group's first lane writes the (tile, warp) partial.  No shuffles over pixels, no atomics: one fp32 pair per group.
+                        // group's first lane writes the (tile, warp) partial.  No shuffles over pixels, no atomics.  Shifted-data sums: values
+                        // are taken relative to c = the group's first channel at the warp's first pixel, so the fp32 partial keeps the
+                        // variance when |mean| >> std; the finish kernel undoes the shift in fp64.  Partial = {S1, S2, c, n}.
+                        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                        const float v0 = *reinterpret_cast<const float*>(buf + (((lane >> 2) ^ 0) << 4 | ((lane & 3) << 2)));      // row 0
+                        const float cshift = __shfl_sync(0xffffffffu, v0, lane & ~(a.gn_cpg - 1));
                         float cs = 0.f, cq = 0.f;
 #pragma unroll
                         for (int r = 0; r < 32; ++r) {
                             const float v = *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-                            cs += v;
-                            cq = fmaf(v, v, cq);
+                            const float dv = (vmask >> r) & 1u ? v - cshift : 0.f;
+                            cs += dv;
+                            cq = fmaf(dv, dv, cq);
                         }
                         for (int sh = 1; sh < a.gn_cpg; sh <<= 1) {
                             cs += __shfl_xor_sync(0xffffffffu, cs, sh);
                             cq += __shfl_xor_sync(0xffffffffu, cq, sh);
                         }
                         if ((lane & (a.gn_cpg - 1)) == 0 && n < a.B) {
-                            float2* dst = reinterpret_cast<float2*>(a.gn_part) +
+                            float4* dst = reinterpret_cast<float4*>(a.gn_part) +
                                           ((long long)n * a.gn_slots + (long long)r_ * 4 + q) * 32 + (co + lane) / a.gn_cpg;
-                            *dst = make_float2(cs, cq);
+                            *dst = make_float4(cs, cq, cshift, (float)(__popc(vmask) * a.gn_cpg));
                         }
                     }
                     if (lane == 0) {
@@ -637,16 +643,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-// GroupNorm statistics from the conv epilogue's partials: stats[b][g] = sum over the sample's slots of part[b][slot][g], fp64, fixed order
-__global__ void __launch_bounds__(128) conv_gn_finish_kernel(const float2* __restrict__ part, int slots, double* __restrict__ stats) {
+// GroupNorm statistics from the conv epilogue's partials {S1, S2, c, n} (shifted sums about c over n values): the true sums
+// sum x = S1 + n c, sum x^2 = S2 + 2 c S1 + n c^2 per partial in fp64, reduced over the sample's slots in a fixed order
+__global__ void __launch_bounds__(128) conv_gn_finish_kernel(const float4* __restrict__ part, int slots, double* __restrict__ stats) {
     __shared__ double s_s[128], s_q[128];
     const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
-    const float2* p = part + (long long)b * slots * 32 + g;
+    const float4* p = part + (long long)b * slots * 32 + g;
     double s = 0.0, q = 0.0;
     for (int i = threadIdx.x; i < slots; i += 128) {
-        const float2 v = __ldg(p + (long long)i * 32);
-        s += (double)v.x;
-        q += (double)v.y;
+        const float4 v = __ldg(p + (long long)i * 32);
+        const double S1 = v.x, S2 = v.y, c = v.z, n = v.w;
+        s += S1 + n * c;
+        q += S2 + 2.0 * c * S1 + n * c * c;
     }
     s_s[threadIdx.x] = s;
     s_q[threadIdx.x] = q;
@@ -1095,7 +1103,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     if (gn_stats) {
         if (!a.tma_store) return GLARE_ERR_UNSUPPORTED;
         a.gn_slots = a.tiles_y * a.tiles_x * 4;
-        if ((long long)B * a.gn_slots * 64 > gn_scratch_floats) return GLARE_ERR_BAD_ARG;
+        if ((long long)B * a.gn_slots * 128 > gn_scratch_floats) return GLARE_ERR_BAD_ARG;
         a.gn_part = gn_scratch;
     }
 #define GLARE_CONV_DISPATCH(M)                                                            \
@@ -1111,7 +1119,7 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     else GLARE_CONV_DISPATCH(4);
 #undef GLARE_CONV_DISPATCH
     if (rc != GLARE_OK || !gn_stats) return rc;
-    conv_gn_finish_kernel<<<(unsigned)(B * 32), 128, 0, stream>>>(reinterpret_cast<const float2*>(gn_scratch), a.gn_slots, gn_stats);
+    conv_gn_finish_kernel<<<(unsigned)(B * 32), 128, 0, stream>>>(reinterpret_cast<const float4*>(gn_scratch), a.gn_slots, gn_stats);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }
@@ -1119,5 +1127,5 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
 // floats of scratch glare_conv2d_nhwc_tc_g needs for the fused GroupNorm statistics of an output of B x H x W pixels (both tile geometries)
 GLARE_API long long glare_conv_gn_scratch_floats(int B, int H, int W) {
     const long long t1 = (long long)((H + 7) / 8) * ((W + 15) / 16), t2 = (long long)((H + 15) / 16) * ((W + 7) / 8);
-    return (long long)B * (t1 > t2 ? t1 : t2) * 4 * 64;
+    return (long long)B * (t1 > t2 ? t1 : t2) * 4 * 128;
 }

@@ -12,7 +12,10 @@ namespace glare {
 
 constexpr int GN_THREADS = 256;
 
-// x [B][HW][C]; grid (chunks, B); stats [B][G][2] (pre-zeroed)
+// x [B][HW][C]; grid (chunks, B); stats [B][G][2] (pre-zeroed).
+// Shifted-data sums: every value is taken relative to c_g = x[b, pixel 0, first channel of the group] before it is squared, so the fp32
+// partials stay at the scale of the group's spread even when |mean| >> std (sum of x^2 in fp32 loses the variance at mean / std ~ 1000:
+// tests/test_edge_cases_gpu.py); each CTA converts its shifted sums back to true sums in fp64 (exact: c_g is an fp32 value).
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ x, long long HW, int C, int G,
                                                               double* __restrict__ stats) {
     __shared__ double s_sum[64], s_sq[64];
@@ -22,40 +25,48 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
     const int my_c4 = threadIdx.x % c4n, my_row = threadIdx.x / c4n;
     if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
     __syncthreads();
+    const int cpg = C / G;
+    const long long per = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per, p1 = (p0 + per < HW) ? p0 + per : HW;
+    const float* xs = x + (long long)b * HW * C;
     double s = 0.0, q = 0.0;
     if (my_row < rows) {
-        const long long per = (HW + gridDim.x - 1) / gridDim.x;
-        const long long p0 = (long long)blockIdx.x * per, p1 = (p0 + per < HW) ? p0 + per : HW;
-        const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * HW * C);
+        const int g = (my_c4 * 4) / cpg;
+        const float c = __ldg(xs + g * cpg);         // the group's shift: its first channel at pixel 0 of the sample
+        const float4* xb = reinterpret_cast<const float4*>(xs);
         // four independent 128-bit loads in flight per thread (a single one leaves HBM latency exposed)
         long long p = p0 + my_row;
         for (; p + 3LL * rows < p1; p += 4LL * rows) {
             float4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + (p + (long long)u * rows) * c4n + my_c4);
-            // 16 values in fp32 (relative error 1e-7 of a 16-term sum), then into the fp64 running sums
+            // 16 shifted values in fp32 (relative error 1e-7 of a 16-term sum), then into the fp64 running sums
             float s32 = 0.f, q32 = 0.f;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                s32 += (v[u].x + v[u].y) + (v[u].z + v[u].w);
-                q32 = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, fmaf(v[u].w, v[u].w, q32))));
+                const float d0 = v[u].x - c, d1 = v[u].y - c, d2 = v[u].z - c, d3 = v[u].w - c;
+                s32 += (d0 + d1) + (d2 + d3);
+                q32 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q32))));
             }
             s += (double)s32;
             q += (double)q32;
         }
         for (; p < p1; p += rows) {
             const float4 v = __ldg(xb + p * c4n + my_c4);
-            s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-            q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+            const double d0 = (double)v.x - c, d1 = (double)v.y - c, d2 = (double)v.z - c, d3 = (double)v.w - c;
+            s += d0 + d1 + d2 + d3;
+            q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         }
-        const int g = (my_c4 * 4) / (C / G);
         atomicAdd(&s_sum[g], s);
         atomicAdd(&s_sq[g], q);
     }
     __syncthreads();
-    if (threadIdx.x < G) {
-        atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2], s_sum[threadIdx.x]);
-        atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    if (threadIdx.x < G && p1 > p0) {
+        // shifted -> true sums over this CTA's n = (p1 - p0) * cpg values: sum x = S1 + n c, sum x^2 = S2 + 2 c S1 + n c^2
+        const double c = (double)__ldg(xs + threadIdx.x * cpg), n = (double)(p1 - p0) * cpg;
+        const double S1 = s_sum[threadIdx.x], S2 = s_sq[threadIdx.x];
+        atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2], S1 + n * c);
+        atomicAdd(&stats[((long long)b * G + threadIdx.x) * 2 + 1], S2 + 2.0 * c * S1 + n * c * c);
     }
 }
 

@@ -63,3 +63,65 @@ def test_vq_extreme_latents(glare_lib, sd_v):
     idx, _ = ops.vq_lookup(z.cuda(), ops.vq_pack_codebook(cbw.cuda()))
     idx_o, _ = vq_lookup(z.numpy(), cbw.numpy())
     assert np.array_equal(idx.cpu().numpy(), idx_o)
+
+
+def _ref_ext():
+    import os
+    import sys
+    from conftest import ROOT
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "deform_conv_ext.so")):
+        pytest.skip("oracle/_ref/deform_conv_ext.so not built (python -m oracle.build_ref_dcn, authoring container)")
+    sys.path.insert(0, ref_dir)
+    try:
+        import deform_conv_ext as ref_ext
+    finally:
+        sys.path.remove(ref_dir)
+    return ref_ext
+
+
+def test_dcn_border_and_nonfinite_offsets_against_the_reference_kernel(glare_lib):
+    """sampling positions exactly on the open border (-1, H) / (-1, W) (deform_conv_cuda_kernel.cu:618), on integer grid points, far outside,
+    infinite and NaN: both glare DCN kernels against the reference's own CUDA kernel (built unmodified for sm_100)"""
+    from glare_b200 import ops
+    ref_ext = _ref_ext()
+    g = torch.Generator().manual_seed(17)
+    B, C, H, W, dg = 1, 128, 12, 20, 4
+    x = torch.randn((B, C, H, W), generator=g).cuda()
+    w = (torch.randn((C, C, 3, 3), generator=g) / (3 * C ** 0.5)).cuda()
+    b = torch.randn((C,), generator=g).cuda()
+    off = torch.randn((B, dg * 18, H, W), generator=g) * 1.5
+    special = torch.tensor([0.0, -1.0, 1.0, 0.5, -0.5, -2.0, 2.0, 1e6, -1e6, 3e38, float("inf"), float("-inf"), float("nan"), 1e-30, 0.999999, -0.999999])
+    pick = torch.randint(0, len(special), off.shape, generator=g)
+    use = torch.rand(off.shape, generator=g) < 0.5
+    off = torch.where(use, special[pick], off).cuda()
+    msk = torch.sigmoid(torch.randn((B, dg * 9, H, W), generator=g)).cuda()
+    out = x.new_empty((B, C, H, W))
+    ref_ext.modulated_deform_conv_forward(x, w, b, x.new_empty(0), off, msk, out, x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
+    finite = torch.isfinite(out)
+    assert float(finite.float().mean()) > 0.5            # (NaN offsets poison the reference's output pixels too: compare where it is finite)
+    y_tc = ops.modulated_deform_conv(x, off, msk, w, b, 1, 1, 1, 1, dg)                                   # tensor-core kernel (GLARE's shape)
+    y_fma = ops.modulated_deform_conv(x, off, msk, w, b, 1, 1, 1, 1, dg, packed_weight=ops.dcn_pack_weight(w))   # fp32 FMA kernel
+    for name, y in (("tc", y_tc), ("fma", y_fma)):
+        assert bool((torch.isfinite(y) == finite).all()), name
+        d = float((torch.where(finite, y - out, torch.zeros_like(y))).abs().max())
+        assert d < 2e-4 * max(1.0, float(out[finite].abs().max())), (name, d)
+
+
+def test_groupnorm_constant_and_huge_inputs(glare_lib):
+    """zero variance (rstd = 1 / sqrt(eps)), a large common offset (fp64 statistics: no E[x^2] - E[x]^2 cancellation) and 1e4-scale values,
+    separate statistics kernel and conv-epilogue statistics alike, against torch group_norm in fp64"""
+    from glare_b200.dense import TcDense
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    B, C, H, W = 2, 128, 17, 23
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).cuda(), (0.1 * torch.randn(C, generator=g)).cuda()
+    cases = {"constant": torch.full((B, C, H, W), 3.25), "offset": 1000.0 + torch.randn((B, C, H, W), generator=g),
+             "large": 1e4 * torch.randn((B, C, H, W), generator=g)}
+    d = TcDense(2)                                              # 3xTF32 operand: hi + lo is the exact fp32 value
+    for name, x in cases.items():
+        x = x.cuda()
+        got = d.gn_swish(x, gamma, beta, swish=False).dense()
+        want = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6).float()
+        tol = 2e-3 if name == "offset" else 2e-5                # x - mean itself carries 1e-7 * 1000 of fp32 rounding at a 1000 offset
+        assert float((got - want).abs().max()) < tol * max(1.0, float(want.abs().max())), name

@@ -26,6 +26,7 @@ namespace glare {
 
 constexpr int DT_FIXED_THREADS = 192;     // warp 0 TMA(weights), 1 MMA, 2-5 epilogue; then two groups of SW sampler warps (SW = 4 or 8)
 constexpr int DT_A_BYTES = 128 * 128;
+constexpr int DT_TH = 8, DT_TW = 16;        // pixel tile (compile-time: m / TW and m % TW sit in the sampler's inner loop)
 
 struct DcnTcArgs {
     const float* x;
@@ -34,6 +35,7 @@ struct DcnTcArgs {
     float* y;
     int B, H, W, C, Cout, dg, cpg, TH, TW, tiles_x, tiles_y, n_blocks, kchunks;   // kchunks = C / BKE channel chunks per tap
     int total_tiles;
+    int cpg_shift;           // log2(cpg) when C / deformable_groups is a power of two, else -1
     int mask_prob;           // the mask channels of om already hold sigmoid(m) (operator-level entry: offset / mask tensors of the reference op)
     int stages;              // ring depth actually used (<= DcnCfg::STAGES): fewer stages leave more of the SM's 256 KB to the L1 cache,
                              // which is what serves the bilinear corner gathers (each 128-byte channel line is touched ~36 times per tile)
@@ -172,7 +174,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         // ===================== epilogue =====================
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const int py = m / a.TW, px = m - py * a.TW;
+        const int py = m / DT_TW, px = m - py * DT_TW;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
             const int nb = tile % a.n_blocks;
@@ -180,7 +182,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             const int n = r / tiles_xy;
             r -= n * tiles_xy;
             const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-            const int gy = ty * a.TH + py, gx = tx * a.TW + px;
+            const int gy = ty * DT_TH + py, gx = tx * DT_TW + px;
             const bool valid = gy < a.H && gx < a.W;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait_bounded(&tmem_full_bar[as], aph);
@@ -224,7 +226,12 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
         constexpr int V4 = CPL / 4;
         const int om_c = 27 * a.dg;
         float* const s_om = reinterpret_cast<float*>(smem_al + (size_t)STAGES * Cfg::STAGE_BYTES);   // [128][om_c] when OMS
+        // integer divisions by run-time values cost ~25 instructions each and the sampler is instruction-bound (ncu r31: 250 instructions per
+        // lane and (pixel, tap, chunk)): ring slot / phase are carried as counters, the deformable group comes from a shift when
+        // C / deformable_groups is a power of two (GLARE: 32 / 64), the tile geometry is compile-time
         uint32_t it = 0;
+        int ring_s = 0;
+        uint32_t ring_ph = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             int r = tile / a.n_blocks;
             const int n = r / tiles_xy;
@@ -238,8 +245,8 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                 const int st_id = threadIdx.x - DT_FIXED_THREADS;
                 for (int i = st_id; i < 128 * om_c; i += 64 * SW) {
                     const int m = i / om_c, ch = i - m * om_c;
-                    const int py = m / a.TW, px = m - py * a.TW;
-                    const int gy = ty * a.TH + py, gx = tx * a.TW + px;
+                    const int py = m / DT_TW, px = m - py * DT_TW;
+                    const int gy = ty * DT_TH + py, gx = tx * DT_TW + px;
                     float v = 0.f;
                     if (gy < a.H && gx < a.W) {
                         v = __ldg(a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c + ch);
@@ -252,11 +259,53 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             for (int kc = 0; kc < a.kchunks; ++kc) {
                 for (int tap = 0; tap < 9; ++tap, ++it) {
                     const int ti = tap / 3, tj = tap - ti * 3;
+                    const int s = ring_s;                                  // == it % STAGES, (it / STAGES) & 1
+                    const uint32_t ph = ring_ph;
+                    if (++ring_s == STAGES) { ring_s = 0; ring_ph ^= 1u; }
                     if ((int)(it & 1) != gsel) continue;
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
                     const int cbase = kc * Cfg::BKE + j * CPL;             // first channel of this lane
-                    const int g = cbase / a.cpg;                           // its deformable group (cpg % CPL == 0)
+                    const int g = a.cpg_shift >= 0 ? (cbase >> a.cpg_shift) : cbase / a.cpg;   // its deformable group (cpg % CPL == 0)
+                    // geometry of one (pixel, group, tap): the four bilinear corner weights (x mask) and corner pixel offsets
+                    auto geometry = [&](const int m, float (&gw)[4], int (&go)[4]) {
+                        const int py = m / DT_TW, px = m - py * DT_TW;
+                        const int gy = ty * DT_TH + py, gx = tx * DT_TW + px;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { gw[k] = 0.f; go[k] = 0; }
+                        if (gy < a.H && gx < a.W) {
+                            float oh, ow, mk;
+                            if (OMS) {
+                                const float* omp = s_om + m * om_c;
+                                oh = omp[g * 18 + 2 * tap]; ow = omp[g * 18 + 2 * tap + 1]; mk = omp[18 * a.dg + g * 9 + tap];
+                            } else {
+                                const float* omp = a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c;
+                                oh = __ldg(omp + g * 18 + 2 * tap); ow = __ldg(omp + g * 18 + 2 * tap + 1);
+                                mk = __ldg(omp + 18 * a.dg + g * 9 + tap);
+                                if (!a.mask_prob) mk = 1.0f / (1.0f + expf(-mk));
+                            }
+                            const float h_im = (float)(gy - 1 + ti) + oh, w_im = (float)(gx - 1 + tj) + ow;   // .cu:607-612
+                            if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {            // .cu:618
+                                const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
+                                const int hh = hl + 1, wh = wl + 1;
+                                const float lh = h_im - hl, lw = w_im - wl, uh = 1.f - lh, uw = 1.f - lw;
+                                if (hl >= 0 && wl >= 0) { gw[0] = uh * uw * mk; go[0] = hl * a.W + wl; }
+                                if (hl >= 0 && wh <= a.W - 1) { gw[1] = uh * lw * mk; go[1] = hl * a.W + wh; }
+                                if (hh <= a.H - 1 && wl >= 0) { gw[2] = lh * uw * mk; go[2] = hh * a.W + wl; }
+                                if (hh <= a.H - 1 && wh <= a.W - 1) { gw[3] = lh * lw * mk; go[3] = hh * a.W + wh; }
+                            }
+                        }
+                    };
+                    // The 8 lanes of a `sub` group work on the same pixels (8 x 4 channels = the 32-channel chunk).  When the chunk lies in
+                    // one deformable group (C / deformable_groups a multiple of the chunk: GLARE's 32 / 64) they would all compute the same
+                    // geometry: lane j computes it for ONE of the lane's RPL pixel rows of this stage and the others fetch it by shuffle
+                    // (8 shuffles instead of ~100 instructions per row; the sampler is instruction-issue bound).
+                    constexpr int RPL = RW / 4;                            // pixel rows per lane per stage: 4 (SW = 8) or 8 (SW = 4)
+                    const bool share = (a.cpg % Cfg::BKE) == 0;              // the chunk's BKE channels (32, or 64 for bf16 operands) lie in one group
+                    float myw[4];
+                    int myo[4];
+                    if (share) {
+                        const int ridx = j & (RPL - 1), hq_m = ridx / QB, q4_m = ridx - hq_m * QB;
+                        geometry(sw * RW + (hq_m / (4 / QB)) * 16 + ((hq_m % (4 / QB)) * QB + q4_m) + 4 * sub, myw, myo);
+                    }
                     mbar_wait_bounded(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
 #pragma unroll
@@ -268,32 +317,15 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                         int co[QB][4];
 #pragma unroll
                         for (int q4 = 0; q4 < QB; ++q4) {
-                            const int m = sw * RW + half * 16 + (qb + q4) + 4 * sub;
-                            const int py = m / a.TW, px = m - py * a.TW;
-                            const int gy = ty * a.TH + py, gx = tx * a.TW + px;
+                            if (share) {
+                                const int src = (lane & 24) + hq * QB + q4;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) { cw[q4][k] = 0.f; co[q4][k] = 0; }
-                            if (gy < a.H && gx < a.W) {
-                                float oh, ow, mk;
-                                if (OMS) {
-                                    const float* omp = s_om + m * om_c;
-                                    oh = omp[g * 18 + 2 * tap]; ow = omp[g * 18 + 2 * tap + 1]; mk = omp[18 * a.dg + g * 9 + tap];
-                                } else {
-                                    const float* omp = a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c;
-                                    oh = __ldg(omp + g * 18 + 2 * tap); ow = __ldg(omp + g * 18 + 2 * tap + 1);
-                                    mk = __ldg(omp + 18 * a.dg + g * 9 + tap);
-                                    if (!a.mask_prob) mk = 1.0f / (1.0f + expf(-mk));
+                                for (int k = 0; k < 4; ++k) {
+                                    cw[q4][k] = __shfl_sync(0xffffffffu, myw[k], src);
+                                    co[q4][k] = __shfl_sync(0xffffffffu, myo[k], src);
                                 }
-                                const float h_im = (float)(gy - 1 + ti) + oh, w_im = (float)(gx - 1 + tj) + ow;   // .cu:607-612
-                                if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {            // .cu:618
-                                    const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
-                                    const int hh = hl + 1, wh = wl + 1;
-                                    const float lh = h_im - hl, lw = w_im - wl, uh = 1.f - lh, uw = 1.f - lw;
-                                    if (hl >= 0 && wl >= 0) { cw[q4][0] = uh * uw * mk; co[q4][0] = hl * a.W + wl; }
-                                    if (hl >= 0 && wh <= a.W - 1) { cw[q4][1] = uh * lw * mk; co[q4][1] = hl * a.W + wh; }
-                                    if (hh <= a.H - 1 && wl >= 0) { cw[q4][2] = lh * uw * mk; co[q4][2] = hh * a.W + wl; }
-                                    if (hh <= a.H - 1 && wh <= a.W - 1) { cw[q4][3] = lh * lw * mk; co[q4][3] = hh * a.W + wh; }
-                                }
+                            } else {
+                                geometry(sw * RW + half * 16 + (qb + q4) + 4 * sub, cw[q4], co[q4]);
                             }
                         }
                         // corners with zero weight read pixel 0 of the image (valid memory) and contribute nothing
@@ -302,7 +334,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                         for (int q4 = 0; q4 < QB; ++q4)
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const float4* p = reinterpret_cast<const float4*>(xn + (long long)co[q4][k] * a.C + cbase);
+                                const float4* p = reinterpret_cast<const float4*>(xn + (co[q4][k] * a.C + cbase));      // < 2^31 per image (host check)
 #pragma unroll
                                 for (int v4 = 0; v4 < V4; ++v4) xv[q4][k][v4] = __ldg(p + v4);
                             }
@@ -479,12 +511,16 @@ static int dcn_tc_launch(int mode, const float* x, const float* offmask, int mas
     if (!x || !offmask || !w || !y || ((mode == 2 || mode == 3) && !w_lo)) return GLARE_ERR_BAD_ARG;
     const int bke = mode == 0 ? 64 : 32;
     if (C % deformable_groups != 0 || C % bke != 0 || (C / deformable_groups) % 8 != 0 || Cout % 4 != 0) return GLARE_ERR_UNSUPPORTED;
+    if ((long long)H * W * C >= 0x7fffffffLL) return GLARE_ERR_UNSUPPORTED;        // the sampler addresses one image with 32-bit offsets
     DcnTcArgs a{};
     a.x = x; a.om = offmask; a.bias = bias_or_null; a.y = y; a.mask_prob = mask_prob;
     a.B = B; a.H = H; a.W = W; a.C = C; a.Cout = Cout; a.dg = deformable_groups; a.cpg = C / deformable_groups;
-    a.TH = 8; a.TW = 16;
+    a.TH = DT_TH; a.TW = DT_TW;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
     a.kchunks = C / bke;
+    a.cpg_shift = -1;
+    for (int sft = 0; sft < 16; ++sft)
+        if ((1 << sft) == a.cpg) a.cpg_shift = sft;
     int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
     const long long m_tiles = (long long)B * a.tiles_y * a.tiles_x;
     while (BN > 64 && m_tiles * ((Cout + BN - 1) / BN) < kNumSMs) BN >>= 1;

@@ -125,3 +125,36 @@ def test_groupnorm_constant_and_huge_inputs(glare_lib):
         want = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6).float()
         tol = 2e-3 if name == "offset" else 2e-5                # x - mean itself carries 1e-7 * 1000 of fp32 rounding at a 1000 offset
         assert float((got - want).abs().max()) < tol * max(1.0, float(want.abs().max())), name
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 5), (1, 7, 9), (3, 16, 8), (1, 9, 130)])
+def test_dense_ops_on_tiny_and_ragged_spatial_sizes(glare_lib, shape):
+    """feature maps smaller than one 8 x 16 pixel tile, odd sizes, a single pixel: 3x3 / 1x1 convs (residual, fused GroupNorm statistics),
+    Downsample, Upsample+conv and GroupNorm+swish against cuDNN / torch fp32"""
+    import torch.nn.functional as F
+    from glare_b200.dense import TcDense
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 31 + W)
+    C = 128
+    x = torch.randn((B, C, H, W), generator=g).cuda()
+    res = torch.randn((B, C, H, W), generator=g).cuda()
+    w3 = (torch.randn((C, C, 3, 3), generator=g) / (3 * C ** 0.5)).cuda()
+    w1 = (torch.randn((C, C, 1, 1), generator=g) / C ** 0.5).cuda()
+    b = torch.randn((C,), generator=g).cuda()
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).cuda(), (0.1 * torch.randn(C, generator=g)).cuda()
+    d = TcDense(4)
+
+    def close(got, want, what, tol=1e-4):
+        assert got.shape == want.shape, what
+        assert float((got.float() - want).abs().max()) < tol * max(1.0, float(want.abs().max())), what
+
+    y = d.conv2d(x, w3, b, residual=res)
+    close(y, F.conv2d(x, w3, b, padding=1) + res, "conv3x3")
+    gn = d.gn_swish(y, gamma, beta)                       # statistics from the conv epilogue
+    yn = F.group_norm(y.float(), 32, gamma, beta, eps=1e-6)
+    close(gn.dense(), yn * torch.sigmoid(yn), "groupnorm+swish after conv", 2e-4)
+    close(d.conv2d(x, w1, b, padding=0), F.conv2d(x, w1, b), "conv1x1")
+    if H >= 2 and W >= 2:
+        close(d.downsample_conv(x, w3, b), F.conv2d(F.pad(x, (0, 1, 0, 1)), w3, b, stride=2), "downsample")
+    close(d.upsample_conv(x, w3, b), F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w3, b, padding=1), "upsample")

@@ -199,7 +199,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int dy = 0; dy < 3; ++dy) {
                         for (int kc = 0; kc < a.kchunks; ++kc, ++it) {           // it counts patches; slabs are 3 * it + dx
                             const int sa = it % Cfg::R2_A_SLOTS;
-                            mbar_wait_bounded(&a_empty[sa], ((it / Cfg::R2_A_SLOTS) & 1) ^ 1);
+                            mbar_wait_backoff(&a_empty[sa], ((it / Cfg::R2_A_SLOTS) & 1) ^ 1, 256);
                             if (cl_rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * Cfg::HALO_A_BYTES);
                             else mbar_arrive_cluster(&a_full[sa], 0);
                             tma_load_4d_2sm(smem_al + (size_t)sa * Cfg::HALO_A_BYTES, &tmA, &a_full[sa], (Cfg::B3 ? 2 : 1) * kc * Cfg::BKE, x0, y0 + dy, n);
@@ -207,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int dx = 0; dx < 3; ++dx) {
                                 const uint32_t ib = 3u * it + dx;
                                 const int sb = ib % Cfg::R2_B_SLOTS;
-                                mbar_wait_bounded(&empty_bar[sb], ((ib / Cfg::R2_B_SLOTS) & 1) ^ 1);
+                                mbar_wait_backoff(&empty_bar[sb], ((ib / Cfg::R2_B_SLOTS) & 1) ^ 1, 256);
                                 if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[sb], 2 * Cfg::B_BYTES);
                                 else mbar_arrive_cluster(&full_bar[sb], 0);
                                 tma_load_3d_2sm(ring_b + (size_t)sb * Cfg::B_BYTES, &tmB, &full_bar[sb],
@@ -224,7 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
                             const int s = it % STAGES;
                             const uint32_t ph = (it / STAGES) & 1;
-                            mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                            mbar_wait_backoff(&empty_bar[s], ph ^ 1, 256);
                             uint8_t* st = smem_al + (size_t)s * STAGE_BYTES;
                             if (cl_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
                             else mbar_arrive_cluster(&full_bar[s], 0);
@@ -242,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                        mbar_wait_backoff(&empty_bar[s], ph ^ 1, 256);
                         uint8_t* st = smem_al + (size_t)s * STAGE_BYTES;
                         const int wn = a.w_batched ? (n < a.B ? n : a.B - 1) : 0;   // a dummy tile still feeds the peer real weights
                         const int kw = tap * a.Cin + kc * Cfg::BKE;
@@ -419,7 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int gy = ty * a.TH + py, gx = tx * a.TW + px;
             const bool valid = gy < a.H && gx < a.W && n < a.B;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-            mbar_wait_bounded(&tmem_full_bar[as], aph);
+            mbar_wait_backoff(&tmem_full_bar[as], aph, 512);      // (producers / epilogue are ahead by design: poll with back-off, tc.cuh)
             tc_fence_after();
             const long long pix = ((long long)n * a.H * a.oscale + (gy * a.oscale + a.oa)) * (a.W * a.oscale) + (gx * a.oscale + a.ob);
             float* yrow = a.y + pix * a.ldy;

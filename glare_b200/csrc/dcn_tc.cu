@@ -109,7 +109,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                     for (int tap = 0; tap < 9; ++tap, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait_bounded(&empty_bar[s], ph ^ 1);
+                        mbar_wait_backoff(&empty_bar[s], ph ^ 1, 256);
                         uint8_t* st = smem_al + (size_t)s * Cfg::STAGE_BYTES;
                         const int kcoord = tap * a.C + kc * Cfg::BKE;
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES * (Cfg::X3 ? 2 : 1));
@@ -126,13 +126,14 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-                mbar_wait_bounded(&tmem_empty_bar[as], aph ^ 1);
+                mbar_wait_backoff(&tmem_empty_bar[as], aph ^ 1, 128);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int ki = 0; ki < k_iters; ++ki, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait_bounded(&full_bar[s], ph);
+                    // (in THIS kernel the MMA thread waits for the samplers nearly all the time: back off here too; <= 128 ns per ~1 us stage)
+                    mbar_wait_backoff(&full_bar[s], ph, 128);
                     tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)s * Cfg::STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + DT_A_BYTES);
@@ -185,7 +186,7 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
             const int gy = ty * DT_TH + py, gx = tx * DT_TW + px;
             const bool valid = gy < a.H && gx < a.W;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-            mbar_wait_bounded(&tmem_full_bar[as], aph);
+            mbar_wait_backoff(&tmem_full_bar[as], aph, 1024);
             tc_fence_after();
             float* yrow = a.y + (((long long)n * a.H + gy) * a.W + gx) * a.Cout;
 #pragma unroll 1

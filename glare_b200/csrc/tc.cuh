@@ -13,6 +13,22 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     }
 }
 
+// The same wait for the roles that are AHEAD of the pipeline by design (TMA producers waiting for a free ring slot, epilogue warps waiting
+// for the next accumulator): poll with an exponential nanosleep back-off up to `max_ns` instead of spinning.  A spinning waiter re-issues
+// its try_wait / clock / compare / branch sequence every ~17 cycles: in dcn_tc_kernel that was 18 % of ALL executed warp instructions
+// (profiles/r57_ncu_dcn_tc_source.txt) on an instruction-issue-bound kernel, and in every kernel it is issue power on a power-capped chip.
+// Not for the MMA thread's wait on a full stage: that one is on the critical path.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t max_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t ns = 32;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (ns < max_ns) ns <<= 1;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

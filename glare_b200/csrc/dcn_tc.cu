@@ -244,16 +244,27 @@ dcn_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ C
                 // (pixel, group, tap) then starts from shared memory instead of a dependent global load per use
                 named_bar_sync(3, 64 * SW);                    // all sampler warps are done with the previous tile's values
                 const int st_id = threadIdx.x - DT_FIXED_THREADS;
-                for (int i = st_id; i < 128 * om_c; i += 64 * SW) {
-                    const int m = i / om_c, ch = i - m * om_c;
-                    const int py = m / DT_TW, px = m - py * DT_TW;
-                    const int gy = ty * DT_TH + py, gx = tx * DT_TW + px;
-                    float v = 0.f;
-                    if (gy < a.H && gx < a.W) {
-                        v = __ldg(a.om + (((long long)n * a.H + gy) * a.W + gx) * om_c + ch);
-                        if (ch >= 18 * a.dg && !a.mask_prob) v = 1.0f / (1.0f + expf(-v));
+                // a tile row's 16 pixels x om_c values are one contiguous run in global memory AND in s_om ([m][om_c], m = 16 py + px): copy
+                // run by run with the channel index carried as a counter (no division by the run-time om_c; ncu r57: 12 % of the kernel's
+                // instructions sat in this loop)
+                const int run = DT_TW * om_c, step_ch = (64 * SW) % om_c, mask_ch = 18 * a.dg;
+                const int px_valid = a.W - tx * DT_TW < DT_TW ? a.W - tx * DT_TW : DT_TW;
+                for (int py = 0; py < DT_TH; ++py) {
+                    const int gy = ty * DT_TH + py;
+                    const float* src = a.om + (((long long)n * a.H + gy) * a.W + tx * DT_TW) * om_c;
+                    float* dst = s_om + py * run;
+                    const int n_valid = gy < a.H ? px_valid * om_c : 0;
+                    int ch = st_id % om_c;
+                    for (int i = st_id; i < run; i += 64 * SW) {
+                        float v = 0.f;
+                        if (i < n_valid) {
+                            v = __ldg(src + i);
+                            if (ch >= mask_ch && !a.mask_prob) v = 1.0f / (1.0f + expf(-v));
+                        }
+                        dst[i] = v;
+                        ch += step_ch;
+                        if (ch >= om_c) ch -= om_c;
                     }
-                    s_om[i] = v;
                 }
                 named_bar_sync(3, 64 * SW);
             }

@@ -225,6 +225,15 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
             "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else None}
         del netG, net_hq, optim
         torch.cuda.empty_cache()
+    # ---- single-image latency of the bench shape (infer_dataset_lol.py / infer_unpaired.py run batch 1): host uint8 in -> host uint8 out
+    enh1 = GlareEnhancer(sd_g, sd_v, device=dev, pad="lol", dense=fp32_engine.dense)
+    lq1, _ = synth_batch(1, seed=300 + rank)
+    h1 = (lq1.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
+    o1 = torch.empty_like(h1).pin_memory()
+    ms1 = timed(lambda: enh1.enhance(h1, out=o1), 5 if quick else 20, 3)
+    out["latency_600x400_batch1"] = {"workload": "one 600x400 image end to end through GlareEnhancer.enhance (H2D, one CUDA-graph replay, D2H), fp32-grade",
+                                     "value": ms1, "unit": "ms/image", "images_per_s": world * 1e3 / ms1}
+    del enh1
     # ---- configs[4]: 1920x1080, the fp32-grade default backend, batch swept
     enh = GlareEnhancer(sd_g, sd_v, device=dev, pad="auto", dense=fp32_engine.dense)
     sweep = {}

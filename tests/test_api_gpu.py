@@ -114,3 +114,27 @@ def test_graph_replay_equals_eager(glare_lib, sd_g, sd_v):
     a = enh.engine.infer(lr, stages=st, graph=True).clone()
     b = enh.engine.infer(lr, graph=False)
     assert torch.allclose(a, b, atol=1e-5) and st["idx"].numel() == 8 * 12
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_attention_flag_trip_recaptures_and_recomputes(glare_lib, sd_g, sd_v, graph):
+    """a fused-softmax row outside its window (forced here by a row reference 300 below the sampled maximum: every p~ overflows) raises the
+    device flag; the engine -- graph replay or eager -- switches the backend to the exact softmax, drops / re-captures the graph and
+    returns the recomputed result, equal to an engine that never used the fused path"""
+    from glare_b200 import synth
+    from glare_b200.dense import make_dense
+    from glare_b200.engine import GlareEngine
+    lr = synth.preprocess(synth.synth_images(2, 32, 48, seed=6)[0])
+    bad = make_dense("auto")
+    bad.attn_ref_offset = -300.0
+    eng = GlareEngine(sd_g, sd_v, device="cuda:0", dense=bad)
+    out = eng.infer(lr, graph=graph).clone()
+    assert not bad.attn_fused and bad.fallbacks
+    exact = make_dense("auto")
+    exact.attn_fused = False
+    ref = GlareEngine(sd_g, sd_v, device="cuda:0", dense=exact).infer(lr)
+    assert torch.isfinite(out).all() and float((out - ref).abs().max()) < 1e-5
+    again = eng.infer(lr, graph=graph)              # stays on the exact path, one graph for the shape
+    assert float((again - ref).abs().max()) < 1e-5
+    if graph:
+        assert len(eng._graphs) == 1

@@ -54,6 +54,7 @@ SIGNATURES = {
     "glare_im2col_nhwc_f32": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_attn_softmax_bwd_f32": [_vp, _vp, _ll, _ll, _i, ctypes.c_float, _vp, _vp],
     "glare_aft_axpby_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp, _vp],
+    "glare_aft_cat_operand": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "glare_preprocess_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_postprocess_u8": [_vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_gn_stats_nhwc_f32": [_vp, _i, _ll, _i, _i, _vp, _vp],

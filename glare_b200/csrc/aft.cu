@@ -28,9 +28,37 @@ __global__ void __launch_bounds__(256) aft_axpby_kernel(const float4* __restrict
     }
 }
 
+// WarpBlock.forward's torch.cat([x_vq, h], dim=1) (deformableDecoder_arch.py:286) fused with the operand conversion of the conv that
+// consumes it: a [P][Ca], b [P][Cb] fp32 (NHWC pixels) -> the bf16x3 operand [P][2 * (Ca + Cb)] of the concatenated tensor, written directly
+// (no fp32 cat tensor: saves its write and its read by the conversion pass)
+__global__ void __launch_bounds__(256) aft_cat_operand_kernel(const float4* __restrict__ a, const float4* __restrict__ b, long long P, int ca4, int cb4,
+                                                              __nv_bfloat16* __restrict__ out) {
+    const int c4n = ca4 + cb4;
+    const long long n4 = P * c4n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / c4n;
+        const int c4 = (int)(i - p * c4n);
+        const float4 v = c4 < ca4 ? __ldg(a + p * ca4 + c4) : __ldg(b + p * cb4 + (c4 - ca4));
+        store_b3_4(out, i * 4, v.x, v.y, v.z, v.w);            // element index of the concatenated tensor: p * (Ca + Cb) + c
+    }
+}
+
 }  // namespace glare
 
 using namespace glare;
+
+// a NHWC [P][Ca], b NHWC [P][Cb] fp32 -> bf16x3 operand of cat([a, b], channels): out [P][2 * (Ca + Cb)] bf16 (Ca, Cb multiples of 32)
+GLARE_API int glare_aft_cat_operand(const float* a, const float* b, long long P, int Ca, int Cb, void* out, cudaStream_t stream) {
+    if (P < 0 || Ca <= 0 || Cb <= 0 || (Ca & 31) || (Cb & 31)) return GLARE_ERR_BAD_ARG;
+    if (P == 0) return GLARE_OK;
+    if (!a || !b || !out || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15)) return GLARE_ERR_BAD_ARG;
+    const long long n4 = P * ((Ca + Cb) / 4);
+    const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    aft_cat_operand_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), P, Ca / 4, Cb / 4,
+                                                     reinterpret_cast<__nv_bfloat16*>(out));
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
 
 // out[n][i] = a[n][i] * alpha[n * alpha_stride] + b[n][i] * beta[n * beta_stride], i < n_per_sample (multiple of 4), n < B; strides 0 or 1;
 // out may alias a or b

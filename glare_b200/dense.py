@@ -184,6 +184,17 @@ class TcDense:
         out.row_sq = sq
         return out
 
+    def cat_operand(self, a, b):
+        """operand of torch.cat([a, b], dim=1) for two fp32 activations (WarpBlock's offset-conv input): one pass, no fp32 cat tensor.
+        None when this mode / shape has no such kernel (the caller concatenates)."""
+        if self.mode != 4 or a.shape[1] % 32 or b.shape[1] % 32 or a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+            return None
+        with self._t("prep_act"):
+            an, bn = _nhwc(a), _nhwc(b)
+            B, H, W, Ca = an.shape
+            hi = self.ops.aft_cat_operand(an.contiguous(), bn.contiguous())
+        return Operand(self.mode, hi, None, B, Ca + bn.shape[3], H, W)
+
     def _new_stats(self, B, Cout):
         """fp64 [B,32,2] buffer for GroupNorm statistics fused into the conv epilogue (None when the output cannot feed Normalize)"""
         if not self.fuse_gn_stats or Cout % 128 or Cout > 512:

@@ -176,7 +176,9 @@ class GlareEngine:
     def warp_block(self, i, x_vq, h):
         """WarpBlock.forward (:285-290) + DCNv2Pack.forward (:141-152)"""
         sd, p = self.g, "deformable_decoder.warp.%d" % i
-        cat = torch.cat([x_vq, h], dim=1)
+        cat = self.dense.cat_operand(x_vq, h) if hasattr(self.dense, "cat_operand") else None     # the conv operand of cat([x_vq, h]) in one pass
+        if cat is None:
+            cat = torch.cat([x_vq, h], dim=1)
         feat = None
         if hasattr(self.dense, "conv2d_operand"):                        # feat only feeds conv_offset: written as its operand
             feat = self.dense.conv2d_operand(cat, sd[p + ".offset.weight"], sd.get(p + ".offset.bias"))

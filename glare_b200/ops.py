@@ -356,6 +356,16 @@ def aft_axpby(a, b, alpha, beta):
     return out
 
 
+def aft_cat_operand(a_nhwc, b_nhwc):
+    """bf16x3 operand of cat([a, b], channel) from two NHWC fp32 tensors of the same pixels (no fp32 cat tensor)"""
+    require_cuda(a_nhwc, b_nhwc)
+    B, H, W, Ca = a_nhwc.shape
+    Cb = b_nhwc.shape[3]
+    out = torch.empty((B, H, W, 2 * (Ca + Cb)), device=a_nhwc.device, dtype=torch.bfloat16)
+    check(lib().glare_aft_cat_operand(ptr(a_nhwc), ptr(b_nhwc), B * H * W, Ca, Cb, ptr(out), stream()), "glare_aft_cat_operand")
+    return out
+
+
 # ------------------------------------------------------------------------------------------- pre / post-processing
 def preprocess_u8(img_u8_nhwc, pad, mode):
     """uint8 [B,H,W,3] (device) -> log(clamp(x/255 + 1e-3)) fp32 [B,3,Hp,Wp]; pad = (top, bottom, left, right); mode 0 reflect, 1 symmetric"""

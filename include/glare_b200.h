@@ -259,6 +259,9 @@ int glare_attn_softmax_bwd_f32(const float* P, const float* dP, long long rows, 
  * ---------------------------------------------------------------------------------------------------- */
 int glare_aft_axpby_f32(const float* a, const float* b, const float* alpha, const float* beta, int alpha_stride, int beta_stride, int B,
                         long long n_per_sample, float* out, cudaStream_t stream);
+/* WarpBlock.forward's torch.cat([x_vq, h], dim=1) (deformableDecoder_arch.py:286) fused with the operand conversion of the offset conv that
+ * consumes it: a NHWC [P][Ca], b NHWC [P][Cb] fp32 -> bf16x3 (mode 4) operand of the concatenated tensor, out [P][2 * (Ca + Cb)] bf16. */
+int glare_aft_cat_operand(const float* a, const float* b, long long P, int Ca, int Cb, void* out, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

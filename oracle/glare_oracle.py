@@ -47,6 +47,9 @@ def resnet_block(sd, p, x):
     return x + h
 
 
+ATTN_MAX_BYTES = 6 << 30      # score matrix budget of attn_block before it switches to blocks of query rows
+
+
 def attn_block(sd, p, x):
     """AttnBlock.forward: single head, d = C, full softmax over h*w keys   encoder_decoder.py:168-192"""
     hn = _gn(sd, p + ".norm", x)
@@ -56,10 +59,22 @@ def attn_block(sd, p, x):
     b, c, h, w = q.shape
     q = q.reshape(b, c, h * w).permute(0, 2, 1)
     k = k.reshape(b, c, h * w)
-    s = torch.bmm(q, k) * (int(c) ** (-0.5))
-    s = torch.softmax(s, dim=2)
     v = v.reshape(b, c, h * w)
-    o = torch.bmm(v, s.permute(0, 2, 1)).reshape(b, c, h, w)
+    n = h * w
+    if n * n * 4 <= ATTN_MAX_BYTES:
+        s = torch.bmm(q, k) * (int(c) ** (-0.5))
+        s = torch.softmax(s, dim=2)
+        o = torch.bmm(v, s.permute(0, 2, 1)).reshape(b, c, h, w)
+    else:
+        # 1920x1080 (131 648 tokens): the reference's N x N matrix is 69 GB per sample.  The same arithmetic in blocks of query rows -- each
+        # row still sees every key, softmax over the full row -- so only the matmul blocking differs from the one-shot form.
+        o = torch.empty((b, c, n), dtype=q.dtype)
+        rows = max(1, ATTN_MAX_BYTES // (n * 4))
+        for r0 in range(0, n, rows):
+            s = torch.bmm(q[:, r0:r0 + rows], k) * (int(c) ** (-0.5))
+            s = torch.softmax(s, dim=2)
+            o[:, :, r0:r0 + rows] = torch.bmm(v, s.permute(0, 2, 1))
+        o = o.reshape(b, c, h, w)
     return x + _conv(sd, p + ".proj_out", o, padding=0)
 
 

@@ -387,3 +387,17 @@ def test_groupnorm_statistics_fused_into_conv_epilogue(glare_lib, mode, C, H, W)
         o1, o2 = d1.gn_swish(y1, gamma, beta), d2.gn_swish(y2, gamma, beta)
         # the two statistics agree to ~1e-7 relative: at most one unit in the last place of the operand (8 bits for mode 0, 16 for mode 4)
         assert float((o1.dense() - o2.dense()).abs().max()) < {0: 1e-2, 4: 6.2e-5}.get(mode, 2e-5)
+
+
+def test_cat_operand_equals_cat_then_convert(glare_lib):
+    """WarpBlock's cat([x_vq, h]) written directly as the offset conv's operand: bitwise the operand of the concatenated fp32 tensor"""
+    from glare_b200 import ops
+    from glare_b200.dense import TcDense
+    g = torch.Generator().manual_seed(12)
+    a = torch.randn((2, 128, 13, 21), generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    b = torch.randn((2, 256, 13, 21), generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    d = TcDense(4)
+    op = d.cat_operand(a, b)
+    want, _ = ops.conv_prep_act(4, torch.cat([a, b], dim=1).permute(0, 2, 3, 1).contiguous())
+    assert op.C == 384 and torch.equal(op.hi.view(torch.int16), want.view(torch.int16))
+    assert TcDense(0).cat_operand(a, b) is None

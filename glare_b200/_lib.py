@@ -47,7 +47,7 @@ SIGNATURES = {
     "glare_attn_row_ref": [_vp, _ll, _ll, _i, ctypes.c_float, ctypes.c_float, _vp, _vp],
     "glare_attn_scores_exp_tc": [_i, _vp, _vp, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _ll, _vp, _vp],
     "glare_attn_row_sum_finish": [_vp, _ll, _i, _ll, _vp, _vp, _vp],
-    "glare_attn_pv_tc": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp],
+    "glare_attn_pv_tc": [_i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp],
     "glare_conv2d_nhwc_tc_pack": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _vp],
     "glare_attn_row_norm_finish": [_vp, _ll, _i, _ll, _ll, _vp, _vp, _vp],
     "glare_gn_bwd_nhwc_f32": [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _i, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -747,12 +747,13 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int make_act_map(CUtensorMap* m, const void* ptr, bool bf16, int B, int H, int W, int C, int TH, int TW, int stride) {
+static int make_act_map(CUtensorMap* m, const void* ptr, bool bf16, int B, int H, int W, int C, int TH, int TW, int stride, long long ldc = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return GLARE_ERR_UNSUPPORTED;
     const cuuint64_t es = bf16 ? 2 : 4;
+    const cuuint64_t ld = ldc > 0 ? (cuuint64_t)ldc : (cuuint64_t)C;      // pixel stride in elements (> C: a column slice of a wider matrix)
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint64_t strides[3] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es};
     // traversal stride s: the box spans TW*s x TH*s input pixels and delivers every s-th one -> TW x TH rows in smem
     cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)(TW * stride), (cuuint32_t)(TH * stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
@@ -762,12 +763,13 @@ static int make_act_map(CUtensorMap* m, const void* ptr, bool bf16, int B, int H
     return r == CUDA_SUCCESS ? GLARE_OK : GLARE_ERR_BAD_ARG;
 }
 
-static int make_w_map(CUtensorMap* m, const void* ptr, bool bf16, int Cout, int K, int BN, int n_w, long long w_batch_stride) {
+static int make_w_map(CUtensorMap* m, const void* ptr, bool bf16, int Cout, int K, int BN, int n_w, long long w_batch_stride, long long ldk = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return GLARE_ERR_UNSUPPORTED;
     const cuuint64_t es = bf16 ? 2 : 4;
+    const cuuint64_t ld = ldk > 0 ? (cuuint64_t)ldk : (cuuint64_t)K;      // row stride in elements (> K: a column slice of a wider matrix)
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, (cuuint64_t)n_w};
-    cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)(n_w > 1 ? w_batch_stride : (long long)K * Cout) * es};
+    cuuint64_t strides[2] = {ld * es, (cuuint64_t)(n_w > 1 ? w_batch_stride : (long long)ld * Cout) * es};
     cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims,
@@ -884,6 +886,7 @@ struct TapSpec { int ntaps, tap_w, dy0, dx0, oscale, oa, ob; };
 struct AttnEpi {                       // attention epilogues of the two GEMMs (ConvTcArgs documents the fields)
     const float* row_norm; const unsigned* key_norm_max; float* row_sum_part; long long part_stride; float exp_scale, exp_margin;
     const float* row_scale; int* n_blocks_out; int pack_out; float* row_sq_part;
+    long long ldx, ldw;                // row strides (logical elements) of x / w when they are column slices of wider matrices (0: dense)
 };
 static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void* w, const void* w_lo, const float* bias,
                           const float* residual, float* y, int B, int Hin, int Win, int H, int W, int Cin, int Cout, TapSpec ts,
@@ -970,19 +973,23 @@ GLARE_API int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, i
     if (mode != 4 && mode != 0) return GLARE_ERR_UNSUPPORTED;
     if (!q_row_norm || !row_sum_part || !n_blocks_host || n_pad < n_keys || (n_pad & 31) || !(scale > 0.f) || !(margin >= 0.f))
         return GLARE_ERR_BAD_ARG;                            // key_norm_max may be null: q_row_norm then holds the per-row reference itself
-    AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host, 0, nullptr};
+    AttnEpi ae{q_row_norm, key_norm_max, row_sum_part, part_stride, scale, margin, nullptr, n_blocks_host, 0, nullptr, 0, 0};
     return conv_tc_launch(mode, q, nullptr, k, nullptr, nullptr, nullptr, reinterpret_cast<float*>(p_out), 1, rows_h, rows_w, rows_h, rows_w, C,
                           n_keys, std_taps(1), 1, n_pad, 0, stream, nullptr, nullptr, 0, &ae);
 }
 
-// O = diag(row_scale) P~ V: p operand [rows][n_pad], vt operand [C][n_pad] (V^T of the sample); y [rows][ldy] fp32, or with pack_out != 0
-// (ldy == C, C % 32 == 0) the bf16x3 operand of the following proj_out conv
-GLARE_API int glare_attn_pv_tc(int mode, const void* p, const void* vt, const float* row_scale, void* y, int rows_h, int rows_w, int n_pad,
-                               int C, long long ldy, int pack_out, cudaStream_t stream) {
+// O = diag(row_scale) (P~ V + residual): p operand [rows] x n_keys (row stride ldp elements), vt operand [C] x n_keys (V^T of the sample,
+// row stride ldvt); y [rows][ldy] fp32, or with pack_out != 0 (ldy == C, C % 32 == 0) the bf16x3 operand of the following proj_out conv.
+// Key bands: the tensor core's fp32 accumulator truncates, a bias that grows with the contraction length (1080p: 131 648 keys -> 1.3e-3 of
+// the output scale, tests/test_fullsize_parity_gpu.py); the host therefore contracts at most a few 10^4 keys per launch and chains the
+// launches through `residual` (fp32 [rows][C], added round-to-nearest in the epilogue BEFORE the row scale): bands 1..n-1 pass
+// row_scale = NULL and write the running sum, the last band passes row_scale (and pack_out).  ldp / ldvt = 0: dense (= n_keys).
+GLARE_API int glare_attn_pv_tc(int mode, const void* p, long long ldp, const void* vt, long long ldvt, const float* row_scale, const float* residual,
+                               void* y, int rows_h, int rows_w, int n_keys, int C, long long ldy, int pack_out, cudaStream_t stream) {
     if (mode != 4 && !(mode == 0 && !pack_out)) return GLARE_ERR_UNSUPPORTED;
-    if (!row_scale) return GLARE_ERR_BAD_ARG;
-    AttnEpi ae{nullptr, nullptr, nullptr, 0, 0.f, 0.f, row_scale, nullptr, pack_out ? 1 : 0, nullptr};
-    return conv_tc_launch(mode, p, nullptr, vt, nullptr, nullptr, nullptr, reinterpret_cast<float*>(y), 1, rows_h, rows_w, rows_h, rows_w, n_pad, C,
+    if ((pack_out && !row_scale) || (ldp && ldp < n_keys) || (ldvt && ldvt < n_keys) || (residual && ldy != C)) return GLARE_ERR_BAD_ARG;
+    AttnEpi ae{nullptr, nullptr, nullptr, 0, 0.f, 0.f, row_scale, nullptr, pack_out ? 1 : 0, nullptr, ldp, ldvt};
+    return conv_tc_launch(mode, p, nullptr, vt, nullptr, nullptr, residual, reinterpret_cast<float*>(y), 1, rows_h, rows_w, rows_h, rows_w, n_keys, C,
                           std_taps(1), 1, ldy, 0, stream, nullptr, nullptr, 0, &ae);
 }
 
@@ -994,7 +1001,7 @@ GLARE_API int glare_conv2d_nhwc_tc_pack(int mode, const void* x, const void* w, 
                                         int Cout, int ksize, float* row_sq_part, long long part_stride, int* n_blocks_host, cudaStream_t stream) {
     if (mode != 4) return GLARE_ERR_UNSUPPORTED;
     if ((ksize != 1 && ksize != 3) || (row_sq_part && !n_blocks_host)) return GLARE_ERR_BAD_ARG;
-    AttnEpi ae{nullptr, nullptr, nullptr, part_stride, 0.f, 0.f, nullptr, n_blocks_host, 1, row_sq_part};
+    AttnEpi ae{nullptr, nullptr, nullptr, part_stride, 0.f, 0.f, nullptr, n_blocks_host, 1, row_sq_part, 0, 0};
     return conv_tc_launch(mode, x, nullptr, w, nullptr, bias, nullptr, reinterpret_cast<float*>(y_operand), B, H, W, H, W, Cin, Cout, std_taps(ksize), 1,
                           Cout, 0, stream, nullptr, nullptr, 0, &ae);
 }
@@ -1009,8 +1016,8 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     // attention epilogues: mode 4 (all of them) and mode 0 (exp with a bf16 P~ operand; row scale) -- not the operand-packing / row-square ones
     if (ae && mode != 4 && !(mode == 0 && !ae->pack_out && !ae->row_sq_part)) return GLARE_ERR_UNSUPPORTED;
     if (epi_exp && mode == 0 && (ldy & 63)) return GLARE_ERR_BAD_ARG;
-    if (ae && (ae->row_norm || ae->row_scale) && (bias || residual || gn_stats)) return GLARE_ERR_UNSUPPORTED;
-    if (ae && ae->pack_out && !ae->row_norm && ((Cout & 31) || ldy != Cout || residual || gn_stats || ts.oscale != 1)) return GLARE_ERR_UNSUPPORTED;
+    if (ae && (ae->row_norm || ae->row_scale) && (bias || gn_stats || (residual && ae->row_norm))) return GLARE_ERR_UNSUPPORTED;
+    if (ae && ae->pack_out && !ae->row_norm && ((Cout & 31) || ldy != Cout || gn_stats || ts.oscale != 1)) return GLARE_ERR_UNSUPPORTED;
     if (ae && ae->row_sq_part && ae->part_stride < (long long)B * H * W) return GLARE_ERR_BAD_ARG;
     if (epi_exp && (!ae->row_sum_part || ae->part_stride < (long long)B * H * W || (ldy & 31) || Cout < 32))
         return GLARE_ERR_BAD_ARG;
@@ -1090,8 +1097,8 @@ static int conv_tc_launch(int mode, const void* x, const void* x_lo, const void*
     } else if ((rc = make_out_map(&tY, y, B, H, W, epi_exp ? (int)ldy : Cout, ldy, a.TH, a.TW)) != GLARE_OK) return rc;
     const bool bf = mode == 0 || mode == 4;
     const int e2 = mode == 4 ? 2 : 1;              // mode 4: the operand tensors are interleaved bf16 pairs, 2 per element
-    if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, e2 * Cin, a.TH, use_halo ? a.TW + 2 : a.TW, stride)) != GLARE_OK) return rc;
-    if ((rc = make_w_map(&tB, w, bf, Cout, e2 * ts.ntaps * Cin, BN / csz, n_w, e2 * w_batch_stride)) != GLARE_OK) return rc;
+    if ((rc = make_act_map(&tA, x, bf, B, Hin, Win, e2 * Cin, a.TH, use_halo ? a.TW + 2 : a.TW, stride, ae ? e2 * ae->ldx : 0)) != GLARE_OK) return rc;
+    if ((rc = make_w_map(&tB, w, bf, Cout, e2 * ts.ntaps * Cin, BN / csz, n_w, e2 * w_batch_stride, ae ? e2 * ae->ldw : 0)) != GLARE_OK) return rc;
     tAl = tA; tBl = tB;
     if (mode == 2) {
         if ((rc = make_act_map(&tAl, x_lo, false, B, Hin, Win, Cin, a.TH, a.TW, stride)) != GLARE_OK) return rc;

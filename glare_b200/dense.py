@@ -99,6 +99,9 @@ class TcDense:
         # the row maximum)
         self.attn_ref = os.environ.get("GLARE_ATTN_REF", "sampled")
         self.attn_ref_keys, self.attn_ref_offset = 128, 50.0
+        # keys contracted per P V launch: longer rows (1080p: 131 648 keys) run in bands chained through the residual epilogue, which keeps the
+        # tensor-core accumulator's truncation bias at the level of the 600x400 shape (16 320 keys: one launch)
+        self.attn_key_band = 16384
         self.attn_flag = None
         self.pack_epilogue = mode == 4 and not os.environ.get("GLARE_NO_PACK_EPILOGUE")   # A/B switch: operands written by the producing conv
         self.timers = None             # bench.py: dict name -> [(start_event, end_event, algorithmic_flops)]
@@ -387,7 +390,8 @@ class TcDense:
                 with self._t("attn_softmax"):
                     ops.attn_row_sum_finish(part, rows_max, nb, bh * w, row_scale, self.attn_flag)
                 with self._t("conv_tc", gemm_flops):
-                    ops.attn_pv_tc(self.mode, p_op, vt_op[b], row_scale, out[b, r0:r1], bh, w, Np, C, C, pack_out=pack)
+                    ops.attn_pv_tc(self.mode, p_op, vt_op[b], row_scale, out[b, r0:r1], bh, w, Np, C, C, pack_out=pack,
+                                   key_band=self.attn_key_band)
 
     def attention_verified(self):
         """True when every fused-softmax row so far stayed inside the safe window (one 4-byte device read).  On False the fused path is

@@ -292,11 +292,30 @@ def attn_row_sum_finish(part, part_stride, n_blocks, rows, row_scale, flag):
     check(lib().glare_attn_row_sum_finish(ptr(part), part_stride, n_blocks, rows, ptr(row_scale), ptr(flag), stream()), "glare_attn_row_sum_finish")
 
 
-def attn_pv_tc(mode, p_op, vt_op, row_scale, y, rows_h, rows_w, n_pad, C, ldy, pack_out=False):
-    """y: fp32 [rows][ldy], or with pack_out the bf16x3 operand [rows][2 * C] of the following conv"""
+def attn_pv_tc(mode, p_op, vt_op, row_scale, y, rows_h, rows_w, n_pad, C, ldy, pack_out=False, key_band=0):
+    """y: fp32 [rows][ldy], or with pack_out the bf16x3 operand [rows][2 * C] of the following conv.  key_band > 0: the contraction over the
+    n_pad keys runs in bands of key_band keys chained through the epilogue's residual input (fp32 running sum, round-to-nearest adds), which
+    bounds the tensor-core accumulator's truncation bias for very long rows (1080p); the row scale / operand packing ride on the last band."""
     require_cuda(p_op, vt_op, row_scale, y)
-    check(lib().glare_attn_pv_tc(mode, ptr(p_op), ptr(vt_op), ptr(row_scale), ptr(y), rows_h, rows_w, n_pad, C, ldy, 1 if pack_out else 0, stream()),
-          "glare_attn_pv_tc")
+    e2 = 2 if mode == MODE_BF16X3 else 1               # operand entries per logical element
+    es = p_op.element_size()
+    if key_band <= 0 or key_band >= n_pad:
+        check(lib().glare_attn_pv_tc(mode, ptr(p_op), 0, ptr(vt_op), 0, ptr(row_scale), None, ptr(y), rows_h, rows_w, n_pad, C, ldy,
+                                     1 if pack_out else 0, stream()), "glare_attn_pv_tc")
+        return
+    import ctypes
+    rows = rows_h * rows_w
+    acc = [torch.empty((rows, C), device=p_op.device, dtype=torch.float32) for _ in range(2)]
+    prev = None
+    for i, k0 in enumerate(range(0, n_pad, key_band)):
+        nk = min(key_band, n_pad - k0)
+        last = k0 + nk >= n_pad
+        pp = ctypes.c_void_p(p_op.data_ptr() + k0 * e2 * es)
+        vv = ctypes.c_void_p(vt_op.data_ptr() + k0 * e2 * es)
+        dst = y if last else acc[i & 1]
+        check(lib().glare_attn_pv_tc(mode, pp, n_pad, vv, n_pad, ptr(row_scale) if last else None, ptr(prev), ptr(dst), rows_h, rows_w, nk, C,
+                                     ldy if last else C, 1 if (pack_out and last) else 0, stream()), "glare_attn_pv_tc")
+        prev = dst
 
 
 def conv2d_nhwc_tc_pack(mode, x_op, w_op, bias, B, H, W, Cin, Cout, ksize, row_sq=False):

@@ -192,8 +192,8 @@ int glare_attn_scores_exp_tc(int mode, const void* q, const void* k, int rows_h,
                              long long part_stride, int* n_blocks_host, cudaStream_t stream);
 int glare_attn_row_sum_finish(const float* part, long long part_stride, int n_blocks, long long rows, float* row_scale, int* flag,
                               cudaStream_t stream);
-int glare_attn_pv_tc(int mode, const void* p, const void* vt, const float* row_scale, void* y, int rows_h, int rows_w, int n_pad, int C,
-                     long long ldy, int pack_out, cudaStream_t stream);
+int glare_attn_pv_tc(int mode, const void* p, long long ldp, const void* vt, long long ldvt, const float* row_scale, const float* residual,
+                     void* y, int rows_h, int rows_w, int n_keys, int C, long long ldy, int pack_out, cudaStream_t stream);
 /* stride-1 conv writing its output as the bf16x3 operand of the next tensor-core GEMM (q / k projections, the WarpBlock offset conv) and,
  * optionally, per-row partial sums of squares per output block; glare_attn_row_norm_finish turns those into |row| and the per-sample maximum */
 int glare_conv2d_nhwc_tc_pack(int mode, const void* x, const void* w, const float* bias, void* y_operand, int B, int H, int W, int Cin, int Cout,

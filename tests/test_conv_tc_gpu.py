@@ -401,3 +401,24 @@ def test_cat_operand_equals_cat_then_convert(glare_lib):
     want, _ = ops.conv_prep_act(4, torch.cat([a, b], dim=1).permute(0, 2, 3, 1).contiguous())
     assert op.C == 384 and torch.equal(op.hi.view(torch.int16), want.view(torch.int16))
     assert TcDense(0).cat_operand(a, b) is None
+
+
+def test_attention_pv_key_bands(glare_lib):
+    """P V GEMM contracted in key bands chained through the residual epilogue (1080p path) == the single launch up to fp32 rounding of the band
+    sums, for the fp32 output and for the operand-packing output; ragged last band"""
+    from glare_b200.dense import TcDense, Operand
+    B, C, h, w = 2, 512, 24, 21                      # 504 keys -> Np = 512: bands of 192 -> 192 + 192 + 128
+    g = torch.Generator().manual_seed(21)
+    q, k, v = (torch.randn((B, C, h, w), generator=g).cuda() for _ in range(3))
+    one, banded = TcDense(4), TcDense(4)
+    banded.attn_key_band = 192
+    o1, o2 = one.attention(q, k, v), banded.attention(q, k, v)
+    ref = _attention_fp64(q, k, v)
+    sc = max(1.0, float(ref.abs().max()))
+    assert float((o2.reshape(B, C, h * w).double() - ref).abs().max()) < 6e-5 * sc
+    assert float((o1 - o2).abs().max()) < 2e-5 * sc
+    p1, p2 = one.attention(q, k, v, as_operand=True), banded.attention(q, k, v, as_operand=True)
+    assert isinstance(p2, Operand) and float((p1.dense() - p2.dense()).abs().max()) < 3e-5 * sc
+    b0 = TcDense(0)
+    b0.attn_key_band = 192
+    assert float((b0.attention(q, k, v).reshape(B, C, h * w).double() - ref).abs().max()) < 3e-2 * sc

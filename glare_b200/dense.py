@@ -332,8 +332,11 @@ class TcDense:
                     with self._t("attn_softmax"):
                         ops.attn_softmax_rows(self.mode, S, bh * w, Np, N, Np, scale, p_hi, p_lo, Np)
                     with self._t("conv_tc", gemm_flops):
-                        ops.conv2d_nhwc_tc_ex(self.mode, p_hi, p_lo, vt_hi[b], None if vt_lo is None else vt_lo[b], out[b, r0:r1],
-                                              1, bh, w, Np, C, C, 0)
+                        if self.mode in (0, 4):           # key bands for very long rows, as on the fused path (no row scale: P is normalised)
+                            ops.attn_pv_tc(self.mode, p_hi, vt_hi[b], None, out[b, r0:r1], bh, w, Np, C, C, key_band=self.attn_key_band)
+                        else:
+                            ops.conv2d_nhwc_tc_ex(self.mode, p_hi, p_lo, vt_hi[b], None if vt_lo is None else vt_lo[b], out[b, r0:r1],
+                                                  1, bh, w, Np, C, C, 0)
         return out.permute(0, 3, 1, 2)
 
     def _attention_fused(self, qn, kn, q_op, k_op, vt_op, out, B, h, w, N, Np, C, sq=(None, None), pack=False):

@@ -122,6 +122,27 @@ class CudaLeaves:
         self.ops.conv2d_nhwc_tc_ex(mode, a_hi, a_lo, b_hi, b_lo, y, nch, M // rows_w, rows_w, chunk, N, ldy, N * chunk)
         return y[:, :, :N].sum(dim=0)
 
+    def wgrad_conv(self, x_nhwc, gy_nhwc, k, stride, pad, chunk=8192):
+        """weight gradient of a k x k conv, [k*k*Ci][Co] (tap-major rows), on the tensor cores WITHOUT fp32 im2col columns: the transposed
+        bf16x3 operands of im2col(x) and of dY are written directly (csrc/train_wgrad.cu), then one batched GEMM over the pixel chunks.
+        None when the shape is outside that path (the caller uses im2col + gemm_tn)."""
+        B, H, W, Ci = x_nhwc.shape
+        _, Ho, Wo, Co = gy_nhwc.shape
+        M, N, P = k * k * Ci, Co, B * Ho * Wo
+        if not self.wgrad_tc or M < 128 or N < 32 or Ci % 32 or N % 32 or not x_nhwc.is_contiguous() or not gy_nhwc.is_contiguous():
+            return None
+        chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
+        nch = (P + chunk - 1) // chunk
+        a_op = torch.empty((nch, M, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
+        b_op = torch.empty((nch, N, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
+        self._call("glare_im2col_t_operand_bf16x3", self._p(x_nhwc), B, H, W, Ci, k, stride, pad, Ho, Wo, chunk, self._p(a_op))
+        self._call("glare_im2col_t_operand_bf16x3", self._p(gy_nhwc), B, Ho, Wo, Co, 1, 1, 0, Ho, Wo, chunk, self._p(b_op))
+        rows_w = 16 if M % 16 == 0 else 1
+        ldy = (N + 3) // 4 * 4
+        y = torch.empty((nch, M, ldy), device=x_nhwc.device, dtype=torch.float32)
+        self.ops.conv2d_nhwc_tc_ex(self.dense.mode, a_op, None, b_op, None, y, nch, M // rows_w, rows_w, chunk, N, ldy, N * chunk)
+        return y[:, :, :N].sum(dim=0)
+
     def gemm_nt(self, a, b, rows_hw):
         """a [R][K], b [N][K] -> a b^T [R][N] on the tcgen05 GEMM path (R = rows_hw[0] * rows_hw[1], the tile walk needs the 2-D factorisation)"""
         R, K = a.shape
@@ -195,9 +216,13 @@ class Tape:
         Co, Ci, k, _ = w.shape
         B, _, H, W = x.shape
         Ho, Wo = y.shape[2], y.shape[3]
-        gyn = _nhwc(gy).reshape(-1, Co)
-        col = self.L.im2col(_nhwc(x), k, 2 if down else 1, 0 if down else k // 2, Ho, Wo)
-        G = self.L.gemm_tn(col, gyn)                                                   # [k*k*Ci][Co], tap-major rows
+        gy4 = _nhwc(gy)
+        gyn = gy4.reshape(-1, Co)
+        xn = _nhwc(x)
+        G = self.L.wgrad_conv(xn, gy4, k, 2 if down else 1, 0 if down else k // 2) if hasattr(self.L, "wgrad_conv") else None
+        if G is None:
+            col = self.L.im2col(xn, k, 2 if down else 1, 0 if down else k // 2, Ho, Wo)
+            G = self.L.gemm_tn(col, gyn)                                               # [k*k*Ci][Co], tap-major rows
         self._acc(p + ".weight", G.view(k * k, Ci, Co).permute(2, 1, 0).reshape(Co, Ci, k, k).contiguous())
         if (p + ".bias") in self.sd:
             self._acc(p + ".bias", self.L.colsum(gyn))

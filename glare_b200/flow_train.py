@@ -38,6 +38,27 @@ class CudaKernels:
     def _call(self, name, *args):
         self.ops.check(getattr(self.lib(), name)(*args, self.stream()), name)
 
+    def wgrad(self, x_pc, gy_pc, k, B, h, w, chunk=8192):
+        """weight gradient [k*k*Ci][N] of a k x k 'same' conv from pixel-major activations x_pc [P][Ci] and output gradients gy_pc [P][N] on
+        the tensor cores (csrc/train_wgrad.cu operands + one batched bf16x3 GEMM): the coupling nets' 64 -> 64 1x1 and 64 -> 4 / 6 3x3 layers.
+        The 128 x 128-tile split-K fp32 GEMM spent 213 us per call on these skinny shapes, 125 calls per step.  None: shape not covered."""
+        P, Ci = x_pc.shape
+        N = gy_pc.shape[1]
+        if Ci % 32 or k not in (1, 3) or not x_pc.is_contiguous():
+            return None
+        Np = (N + 31) // 32 * 32
+        gy = gy_pc if Np == N and gy_pc.is_contiguous() else F.pad(gy_pc, (0, Np - N)).contiguous()
+        M = k * k * Ci
+        chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
+        nch = (P + chunk - 1) // chunk
+        a_op = torch.empty((nch, M, 2 * chunk), device=x_pc.device, dtype=torch.bfloat16)
+        b_op = torch.empty((nch, Np, 2 * chunk), device=x_pc.device, dtype=torch.bfloat16)
+        self._call("glare_im2col_t_operand_bf16x3", self._p(x_pc), B, h, w, Ci, k, 1, k // 2, h, w, chunk, ctypes.c_void_p(a_op.data_ptr()))
+        self._call("glare_im2col_t_operand_bf16x3", self._p(gy), B, h, w, Np, 1, 1, 0, h, w, chunk, ctypes.c_void_p(b_op.data_ptr()))
+        y = torch.empty((nch, M, Np), device=x_pc.device, dtype=torch.float32)
+        self.ops.conv2d_nhwc_tc_ex(4, a_op, None, b_op, None, y, nch, M // 16, 16, chunk, Np, Np, Np * chunk)
+        return y.sum(dim=0)[:, :N]
+
     def zeros(self, shape, like):
         return torch.zeros(shape, device=like.device, dtype=torch.float32)
 
@@ -97,9 +118,12 @@ def _net_param_grads(K, key, net_has_z, bufs, v, B, h, w, P, grads, like):
     h1, h2, hout, g_h, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9 = bufs
     nout = 4 if net_has_z else 6
     # Conv2dZeros: weight [nout][64][3][3], bias, logs (out = (conv + bias) * exp(3 logs))
-    K.im2col3x3(h2, C, C, B, h, w, col576)
-    G3 = K.zeros((9 * C, 8), like)
-    K.gemm_tn(col576, 9 * C, g_a3, 8, P, G3)
+    wg = getattr(K, "wgrad", None)               # tensor-core weight gradient where the kernel set has one (the GPU kernels)
+    G3 = wg(h2, g_a3, 3, B, h, w) if wg is not None else None
+    if G3 is None:
+        K.im2col3x3(h2, C, C, B, h, w, col576)
+        G3 = K.zeros((9 * C, 8), like)
+        K.gemm_tn(col576, 9 * C, g_a3, 8, P, G3)
     grads[key + ".4.weight"] = G3.view(9, C, 8).permute(2, 1, 0)[:nout].reshape(nout, C, 3, 3).contiguous()
     s8 = K.zeros((2, 8), like)
     K.colsum(g_a3, 8, None, 0, 8, P, s8[0])
@@ -107,8 +131,10 @@ def _net_param_grads(K, key, net_has_z, bufs, v, B, h, w, P, grads, like):
     grads[key + ".4.bias"] = s8[0, :nout].clone()
     grads[key + ".4.logs"] = (3.0 * s8[1, :nout]).view(nout, 1, 1)
     # 1x1 conv + ActNorm
-    G2 = K.zeros((C, C), like)
-    K.gemm_tn(h1, C, g_a2, C, P, G2)
+    G2 = wg(h1, g_a2, 1, B, h, w) if wg is not None else None
+    if G2 is None:
+        G2 = K.zeros((C, C), like)
+        K.gemm_tn(h1, C, g_a2, C, P, G2)
     grads[key + ".2.weight"] = G2.t().reshape(C, C, 1, 1).contiguous()
     s64 = K.zeros((4, C), like)
     K.colsum(g_a2, C, None, 0, C, P, s64[0])

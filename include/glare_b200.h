@@ -249,6 +249,11 @@ int glare_flow_train_colsum_f32(const float* a, long long lda, const float* b, l
 int glare_gn_bwd_nhwc_f32(const float* x, const float* gy, const double* stats, const float* gamma, const float* beta, float eps, int swish, int B,
                           long long HW, int C, int G, double* sums, float* gx, float* dgamma, float* dbeta, cudaStream_t stream);
 int glare_im2col_nhwc_f32(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, float* col, cudaStream_t stream);
+/* Transposed bf16x3 operand of im2col(x) for the tensor-core weight gradient (torch autograd of the encoder's nn.Conv2d layers,
+ * encoder_decoder.py:68-72,88-115,146-165): x NHWC [B,H,W,C] fp32, C % 32 == 0 -> out [nch][k*k*C][2*chunk] bf16, row = tap*C + c, the
+ * B*Ho*Wo output pixels as the K dimension in chunks of `chunk` (% 32 == 0; zero past the end).  k = 1: the transposed operand of dY. */
+int glare_im2col_t_operand_bf16x3(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int chunk,
+                                  void* out, cudaStream_t stream);
 int glare_attn_softmax_bwd_f32(const float* P, const float* dP, long long rows, long long ld, int n_keys, float scale, float* dS,
                                cudaStream_t stream);
 

@@ -161,6 +161,17 @@ def encoder_step_check(dev, dense, conv):
     for (Pp, M, N) in ((5000, 1152, 128), (777, 128, 64)):
         a, b = torch.randn((Pp, M), generator=gen).to(dev), torch.randn((Pp, N), generator=gen).to(dev)
         check("gemm_tn_tc %dx%dx%d" % (Pp, M, N), Lg.gemm_tn_tc(a, b, chunk=1024), (a.double().t() @ b.double()).float(), 1e-4)
+    # im2col-free tensor-core weight gradient (csrc/train_wgrad.cu: transposed operands written directly) against fp64 over the torch im2col
+    T = TorchLeaves()
+    for (Bq, Hh, Ww, Ci, Co, kk, stride, pad) in ((2, 13, 21, 128, 128, 3, 1, 1), (1, 22, 18, 64, 128, 3, 2, 0), (3, 9, 11, 256, 64, 1, 1, 0),
+                                                  (1, 40, 40, 32, 32, 3, 1, 1)):
+        Ho, Wo = (Hh, Ww) if stride == 1 else ((Hh + 1 - 3) // 2 + 1, (Ww + 1 - 3) // 2 + 1)
+        xq = torch.randn((Bq, Hh, Ww, Ci), generator=gen)
+        gq = torch.randn((Bq, Ho, Wo, Co), generator=gen)
+        want = (T.im2col(xq, kk, stride, pad, Ho, Wo).double().t() @ gq.reshape(-1, Co).double()).float()
+        for chunk in (8192, 96):                        # one chunk / many ragged chunks
+            got = Lg.wgrad_conv(xq.to(dev), gq.to(dev), kk, stride, pad, chunk=chunk)
+            check("wgrad_conv %s chunk %d" % ((Bq, Hh, Ww, Ci, Co, kk, stride), chunk), got, want, 1e-4)
     rel = sorted(((float((grads_g[k].cpu() - grads_c[k]).abs().max()) / max(float(grads_c[k].abs().max()), 1e-6), k) for k in grads_c), reverse=True)
     # first hardware run of a 40-layer backward through fp32-grade (bf16x3) tensor-core convs against fp32 CPU arithmetic: report the error
     # distribution, require it to be small for all but a few tensors (isolated ReLU sign flips of the flow nets, see run_checks)

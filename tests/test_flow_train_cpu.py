@@ -100,6 +100,7 @@ def test_flow_training_kernel_source_on_the_host(sd_g):
             assert fn(*args, None) == 0, name
 
         encode_chain = emu.encode_chain          # the forward chain kernels (csrc/flow.cu) are GPU-validated separately
+        wgrad = None                             # tensor-core weight gradient (csrc/train_wgrad.cu): GPU only, tests/flow_train_gpu_check.py
         gemm_tn = emu.gemm_tn                    # csrc/dcn_bwd.cu GEMM: GPU-validated by tests/test_dcn_gpu.py
 
     chk.OK = True

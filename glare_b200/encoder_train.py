@@ -158,6 +158,22 @@ class CudaLeaves:
         self.ops.conv2d_nhwc_tc_ex(mode, a_hi, a_lo, b_hi, b_lo, y, 1, rows_hw[0], rows_hw[1], K + padk, N, ldy, 0)
         return y[:, :N]
 
+    # modulated deformable convolution (stage 3, decoder_train.py)
+    def dcn_fwd(self, x, offmask_raw, w, b, dg):
+        """DCNv2Pack after conv_offset: the tensor-core kernel that takes the raw conv_offset output (offsets | mask logits), else the fp32
+        operator on (offset, sigmoid(mask))"""
+        y = self.dense.dcn_pack(x, offmask_raw, w, b, dg) if hasattr(self.dense, "dcn_pack") else None
+        if y is not None:
+            return y.float()
+        n_off = offmask_raw.shape[1] // 3 * 2
+        return self.ops.modulated_deform_conv(x.contiguous(), offmask_raw[:, :n_off].contiguous(), torch.sigmoid(offmask_raw[:, n_off:]).contiguous(),
+                                              w, b, 1, 1, 1, 1, dg)
+
+    def dcn_bwd(self, x, offset, mask, w, gy, dg):
+        """(grad_input, grad_offset, grad_mask, grad_weight, grad_bias): csrc/dcn_bwd.cu through dcn_backward.py"""
+        from .dcn_backward import dcn_backward
+        return dcn_backward(x, offset, mask, w, gy, dg, True)
+
     # memory-bound kernels
     def im2col(self, x_nhwc, k, stride, pad, Ho, Wo):
         B, H, W, C = x_nhwc.shape
@@ -205,16 +221,33 @@ class Tape:
         self.grads[key] = self.grads[key] + g if key in self.grads else g
 
     # -- convolution (encoder_decoder.py nn.Conv2d 3x3 / 1x1 stride 1, and Downsample :68-72) -----------------------------------------
-    def conv(self, p, x, down=False, need_gx=True):
+    def conv(self, p, x, down=False, need_gx=True, need_gw=True):
         w, b = self.sd[p + ".weight"], self.sd.get(p + ".bias")
         y = self.L.conv_down(x, w, b) if down else self.L.conv_same(x, w, b)
-        self.ops.append(("conv", p, x, y, down, need_gx))
+        self.ops.append(("conv", p, x, y, down, need_gx, need_gw))
         return y
 
-    def _conv_bwd(self, p, x, y, down, need_gx, gy):
+    def _conv_bwd(self, p, x, y, down, need_gx, gy, need_gw=True):
         w = self.sd[p + ".weight"]
         Co, Ci, k, _ = w.shape
         B, _, H, W = x.shape
+        Ho, Wo = y.shape[2], y.shape[3]
+        if need_gw:
+            self._conv_wgrad(p, x, y, down, gy)
+        if not need_gx:
+            return None
+        w_t = _flipped_transposed(w)                                                  # transpose of a stride-1 'same' conv
+        if not down:
+            return self.L.conv_same(gy, w_t)
+        # stride 2 over the (0,1,0,1)-padded input: the data gradient is the stride-1 conv of the zero-interleaved output gradient,
+        # placed at odd positions of an (H + 1) x (W + 1) canvas, cropped back to H x W
+        canvas = torch.zeros((B, Co, H + 1, W + 1), device=gy.device, dtype=torch.float32)
+        canvas[:, :, 1:2 * Ho:2, 1:2 * Wo:2] = gy
+        return self.L.conv_same(canvas, w_t)[:, :, :H, :W]
+
+    def _conv_wgrad(self, p, x, y, down, gy):
+        w = self.sd[p + ".weight"]
+        Co, Ci, k, _ = w.shape
         Ho, Wo = y.shape[2], y.shape[3]
         gy4 = _nhwc(gy)
         gyn = gy4.reshape(-1, Co)
@@ -226,16 +259,6 @@ class Tape:
         self._acc(p + ".weight", G.view(k * k, Ci, Co).permute(2, 1, 0).reshape(Co, Ci, k, k).contiguous())
         if (p + ".bias") in self.sd:
             self._acc(p + ".bias", self.L.colsum(gyn))
-        if not need_gx:
-            return None
-        w_t = _flipped_transposed(w)                                                  # transpose of a stride-1 'same' conv
-        if not down:
-            return self.L.conv_same(gy, w_t)
-        # stride 2 over the (0,1,0,1)-padded input: the data gradient is the stride-1 conv of the zero-interleaved output gradient,
-        # placed at odd positions of an (H + 1) x (W + 1) canvas, cropped back to H x W
-        canvas = torch.zeros((B, Co, H + 1, W + 1), device=gy.device, dtype=torch.float32)
-        canvas[:, :, 1:2 * Ho:2, 1:2 * Wo:2] = gy
-        return self.L.conv_same(canvas, w_t)[:, :, :H, :W]
 
     # -- Normalize (+ swish) (encoder_decoder.py:29-35) -------------------------------------------------------------------------------
     def gn(self, p, x, swish):
@@ -274,16 +297,89 @@ class Tape:
         return gq, gk, gv
 
 
-class EncoderTrainer:
+class BlockGraph:
+    """forward graph of the taming blocks over a Tape: a list of nodes (kind, output id, input ids, payload), ids index ``self.vals``; shared by
+    the condition encoder (stage 2) and the deformable decoder (stage 3, decoder_train.py)"""
+
+    def __init__(self, leaves, sd):
+        self.L, self.sd = leaves, sd
+
+    def _begin(self, *inputs):
+        self.tape = Tape(self.L, self.sd)
+        self.nodes, self.vals = [], list(inputs)
+
+    def _push(self, kind, val, inputs, payload):
+        self.vals.append(val)
+        self.nodes.append((kind, len(self.vals) - 1, inputs, payload))
+        return len(self.vals) - 1
+
+    def _conv(self, p, i, down=False, need_gx=True, need_gw=True):
+        y = self.tape.conv(p, self.vals[i], down, need_gx, need_gw)
+        return self._push("op", y, (i,), self.tape.ops[-1])
+
+    def _gn(self, p, i, swish):
+        y = self.tape.gn(p, self.vals[i], swish)
+        return self._push("op", y, (i,), self.tape.ops[-1])
+
+    def _add(self, i, j):
+        return self._push("add", self.vals[i] + self.vals[j], (i, j), None)
+
+    def _fn(self, val, inputs, bwd):
+        """a node whose backward rule is the closure ``bwd(gy) -> one gradient (or None) per input``"""
+        return self._push("fn", val, tuple(inputs), bwd)
+
+    def _resnet(self, p, i, shortcut="nin_shortcut"):
+        """ResnetBlock.forward   encoder_decoder.py:117-137 (deformableDecoder_arch.py ResBlock :170-183 names its shortcut conv_out)"""
+        h = self._conv(p + ".conv1", self._gn(p + ".norm1", i, True))
+        h = self._conv(p + ".conv2", self._gn(p + ".norm2", h, True))
+        s = self._conv(p + "." + shortcut, i) if (p + "." + shortcut + ".weight") in self.sd else i
+        return self._add(s, h)
+
+    def _attn(self, p, i):
+        """AttnBlock.forward   encoder_decoder.py:168-192"""
+        hn = self._gn(p + ".norm", i, False)
+        q, k, v = (self._conv(p + "." + n, hn) for n in "qkv")
+        o = self.tape.attention(self.vals[q], self.vals[k], self.vals[v])
+        o = self._push("op", o, (q, k, v), self.tape.ops[-1])
+        return self._add(i, self._conv(p + ".proj_out", o))
+
+    def _backprop(self, g):
+        """``g``: {value id: gradient} seeds; walks the nodes in reverse; returns the gradients that reached the graph inputs"""
+        T = self.tape
+
+        def give(i, val):
+            if val is not None:
+                g[i] = g[i] + val if i in g else val
+
+        for kind, out, inputs, op in reversed(self.nodes):
+            gy = g.pop(out, None)
+            if gy is None:
+                continue
+            if kind == "add":
+                give(inputs[0], gy)
+                give(inputs[1], gy)
+            elif kind == "fn":
+                for i, val in zip(inputs, op(gy)):
+                    give(i, val)
+            elif op[0] == "conv":
+                give(inputs[0], T._conv_bwd(op[1], op[2], op[3], op[4], op[5], gy, op[6]))
+            elif op[0] == "gn":
+                give(inputs[0], T._gn_bwd(op[1], op[2], op[3], op[4], gy))
+            else:
+                for i, val in zip(inputs, T._attn_bwd(op[1], op[2], op[3], gy)):
+                    give(i, val)
+        return g
+
+
+class EncoderTrainer(BlockGraph):
     """forward with tape and backward of ConEncoder1; parameter names are the reference's state-dict keys under ``prefix`` ('RRDB')"""
 
     def __init__(self, leaves, sd, prefix="RRDB"):
-        self.L, self.sd, self.p = leaves, sd, prefix
+        super().__init__(leaves, sd)
+        self.p = prefix
 
-    # forward graph: a list of nodes (kind, output id, input ids, payload); ids index self.vals
     def forward(self, x):
-        self.tape = Tape(self.L, self.sd)
-        self.nodes, self.vals = [], [x]
+        self._begin(x)
         sd, e = self.sd, self.p + ".encoder"
         h = self._conv(e + ".conv_in", 0, need_gx=False)
         for lvl in range(3):
@@ -303,65 +399,15 @@ class EncoderTrainer:
         cond = torch.sigmoid(self.vals[cond_pre])                                       # ConditionEncoder.py:52
         return {"cond_feat": cond, "color_map": self.vals[color]}
 
-    def _push(self, kind, val, inputs, payload):
-        self.vals.append(val)
-        self.nodes.append((kind, len(self.vals) - 1, inputs, payload))
-        return len(self.vals) - 1
-
-    def _conv(self, p, i, down=False, need_gx=True):
-        y = self.tape.conv(p, self.vals[i], down, need_gx)
-        return self._push("op", y, (i,), self.tape.ops[-1])
-
-    def _gn(self, p, i, swish):
-        y = self.tape.gn(p, self.vals[i], swish)
-        return self._push("op", y, (i,), self.tape.ops[-1])
-
-    def _add(self, i, j):
-        return self._push("add", self.vals[i] + self.vals[j], (i, j), None)
-
-    def _resnet(self, p, i):
-        """ResnetBlock.forward   encoder_decoder.py:117-137"""
-        h = self._conv(p + ".conv1", self._gn(p + ".norm1", i, True))
-        h = self._conv(p + ".conv2", self._gn(p + ".norm2", h, True))
-        s = self._conv(p + ".nin_shortcut", i) if (p + ".nin_shortcut.weight") in self.sd else i
-        return self._add(s, h)
-
-    def _attn(self, p, i):
-        """AttnBlock.forward   encoder_decoder.py:168-192"""
-        hn = self._gn(p + ".norm", i, False)
-        q, k, v = (self._conv(p + "." + n, hn) for n in "qkv")
-        o = self.tape.attention(self.vals[q], self.vals[k], self.vals[v])
-        o = self._push("op", o, (q, k, v), self.tape.ops[-1])
-        return self._add(i, self._conv(p + ".proj_out", o))
-
     def backward(self, g_cond_feat, g_color_map):
         """gradients of the two heads -> {state-dict key: gradient} of every encoder parameter"""
-        T = self.tape
         cond_pre, color = self.out_ids
         s = torch.sigmoid(self.vals[cond_pre])
         g = {cond_pre: g_cond_feat * s * (1.0 - s)}
         if g_color_map is not None:                  # None: the objective did not use color_map (mean = gt branch) -> color_conv gets no gradient
             g[color] = g_color_map
-
-        def give(i, val):
-            if val is not None:
-                g[i] = g[i] + val if i in g else val
-
-        for kind, out, inputs, op in reversed(self.nodes):
-            gy = g.pop(out, None)
-            if gy is None:
-                continue
-            if kind == "add":
-                give(inputs[0], gy)
-                give(inputs[1], gy)
-            elif op[0] == "conv":
-                give(inputs[0], T._conv_bwd(op[1], op[2], op[3], op[4], op[5], gy))
-            elif op[0] == "gn":
-                give(inputs[0], T._gn_bwd(op[1], op[2], op[3], op[4], gy))
-            else:
-                for i, val in zip(inputs, T._attn_bwd(op[1], op[2], op[3], gy)):
-                    give(i, val)
-        return T.grads
+        self._backprop(g)
+        return self.tape.grads
 
 
 def stage2_step(sd, plan, lr, gt_latent, leaves, conv2d, flow_kernels=None, use_gt_mean=False):

@@ -167,14 +167,15 @@ def dcn_offsets_masks(sd, p, feat):
     return torch.cat((o1, o2), dim=1).contiguous(), torch.sigmoid(m).contiguous()
 
 
-def warp_block(sd, p, x_vq, h):
-    """WarpBlock.forward   deformableDecoder_arch.py:285-290"""
+def warp_block(sd, p, x_vq, h, dcn=None):
+    """WarpBlock.forward   deformableDecoder_arch.py:285-290.  ``dcn``: a differentiable implementation of the operator (same signature as
+    modulated_deform_conv) for gradient checks -- the C im2col restatement has no autograd"""
     feat = _conv(sd, p + ".offset", torch.cat([x_vq, h], dim=1))
     offset, mask = dcn_offsets_masks(sd, p + ".dcn", feat)
-    return modulated_deform_conv(x_vq.contiguous(), offset, mask, sd[p + ".dcn.weight"], sd[p + ".dcn.bias"])
+    return (dcn or modulated_deform_conv)(x_vq.contiguous(), offset, mask, sd[p + ".dcn.weight"], sd[p + ".dcn.bias"])
 
 
-def aft_decoder(sd, z, vq_feats, enc_feats, p="deformable_decoder", per_sample_ratio=True):
+def aft_decoder(sd, z, vq_feats, enc_feats, p="deformable_decoder", per_sample_ratio=True, dcn=None):
     """MultiScaleDecoder2.forward   deformableDecoder_arch.py:525-576.
     ``per_sample_ratio``: the reference's ``h.mean()/x_vq.mean()`` (:567) reduces over the whole
     batch but is only ever run at batch 1; per-sample means reproduce that behaviour for any batch
@@ -188,7 +189,7 @@ def aft_decoder(sd, z, vq_feats, enc_feats, p="deformable_decoder", per_sample_r
         if lvl != 2:
             mixf = torch.sigmoid(sd[f"{p}.mix.{1 - lvl}.w"])
             h = enc_feats[lvl] * mixf + h * (1 - mixf)          # Mix.forward :587-590
-            x_vq = warp_block(sd, f"{p}.warp.{1 - lvl}", vq_feats[1 - lvl], h)
+            x_vq = warp_block(sd, f"{p}.warp.{1 - lvl}", vq_feats[1 - lvl], h, dcn=dcn)
             if per_sample_ratio:
                 ratio = h.mean(dim=(1, 2, 3), keepdim=True) / x_vq.mean(dim=(1, 2, 3), keepdim=True)
             else:

@@ -3,6 +3,12 @@ import torch
 import torch.nn.functional as F
 
 
+def _tv_offsets(offset, dg):
+    """the reference's offset layout (o1 | o2 halves, deformableDecoder_arch.py:144-146 + deform_conv_cuda_kernel.cu:596-601: per group g the
+    channels [g*18 + 2*t, g*18 + 2*t + 1] = (dy, dx) of tap t) is already torchvision's: identity, kept as the single place that says so"""
+    return offset
+
+
 class TorchLeaves:
     def conv_same(self, x, w, b=None):
         return F.conv2d(x, w, b, padding=w.shape[2] // 2)
@@ -17,6 +23,20 @@ class TorchLeaves:
 
     def colsum(self, x):
         return x.sum(dim=0)
+
+    def dcn_fwd(self, x, offmask_raw, w, b, dg):
+        from torchvision.ops import deform_conv2d
+        n_off = offmask_raw.shape[1] // 3 * 2
+        return deform_conv2d(x, _tv_offsets(offmask_raw[:, :n_off], dg), w, b, padding=1, mask=torch.sigmoid(offmask_raw[:, n_off:]))
+
+    def dcn_bwd(self, x, offset, mask, w, gy, dg):
+        from torchvision.ops import deform_conv2d
+        with torch.enable_grad():
+            leaves = [t.detach().clone().requires_grad_(True) for t in (x, offset, mask, w)]
+            b = torch.zeros(w.shape[0], requires_grad=True)
+            y = deform_conv2d(leaves[0], _tv_offsets(leaves[1], dg), leaves[3], b, padding=1, mask=leaves[2])
+            gi, go, gm, gw, gb = torch.autograd.grad(y, leaves[:3] + [leaves[3], b], gy)
+        return gi, go, gm, gw, gb
 
     def gemm_tn(self, a, b):
         return a.t() @ b

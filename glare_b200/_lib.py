@@ -54,6 +54,9 @@ SIGNATURES = {
     "glare_im2col_nhwc_f32": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_im2col_t_operand_bf16x3": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_attn_softmax_bwd_f32": [_vp, _vp, _ll, _ll, _i, ctypes.c_float, _vp, _vp],
+    "glare_ssim_partials": [_i, _i, _i, _i],
+    "glare_ssim_fwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp],
+    "glare_ssim_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "glare_aft_axpby_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp, _vp],
     "glare_aft_cat_operand": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "glare_preprocess_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
@@ -61,7 +64,8 @@ SIGNATURES = {
     "glare_gn_stats_nhwc_f32": [_vp, _i, _ll, _i, _i, _vp, _vp],
     "glare_gn_apply_nhwc": [_i, _vp, _vp, _vp, _vp, ctypes.c_float, _i, _i, _ll, _i, _i, _vp, _vp, _vp],
 }
-_RESTYPES = {"glare_error_string": ctypes.c_char_p, "glare_conv_gn_scratch_floats": ctypes.c_longlong}
+_RESTYPES = {"glare_error_string": ctypes.c_char_p, "glare_conv_gn_scratch_floats": ctypes.c_longlong,
+             "glare_ssim_partials": ctypes.c_longlong}
 
 
 class GlareLibraryError(RuntimeError):

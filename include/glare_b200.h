@@ -268,6 +268,20 @@ int glare_aft_axpby_f32(const float* a, const float* b, const float* alpha, cons
  * consumes it: a NHWC [P][Ca], b NHWC [P][Cb] fp32 -> bf16x3 (mode 4) operand of the concatenated tensor, out [P][2 * (Ca + Cb)] bf16. */
 int glare_aft_cat_operand(const float* a, const float* b, long long P, int Ca, int Cb, void* out, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * (8) Stage-3 loss: one level of MS-SSIM -- modules/pytorch_msssim/__init__.py:20-68 (`ssim`, 'valid' 11 x 11 Gaussian window per plane,
+ *     C1 = (0.01 L)^2, C2 = (0.03 L)^2), called per level by `msssim` :71-97 from VQLLFLOWD_model.py:221.  x, y: [planes][H][W] fp32
+ *     (planes = B * C), window_host: the `ws` 1-D Gaussian weights in HOST memory (ws = min(11, H, W)).
+ *     fwd: part[2 * b], part[2 * b + 1] = sums of cs_map / ssim_map over CTA b's window positions; glare_ssim_partials gives the CTA count.
+ *     bwd: coef (device) = {dL/d(sum cs_map), dL/d(sum ssim_map)}; g_mu / g_e11 / g_e12: scratch [planes][H-ws+1][W-ws+1];
+ *          dx[planes][H][W] = dL/dx of this level + 0.25 * coarse[planes][H/2][W/2] (the next level's dx through avg_pool2d(2); may be NULL).
+ * ---------------------------------------------------------------------------------------------------- */
+long long glare_ssim_partials(int planes, int H, int W, int ws);
+int glare_ssim_fwd_f32(const float* x, const float* y, int planes, int H, int W, int ws, const float* window_host, float C1, float C2,
+                       float* part, cudaStream_t stream);
+int glare_ssim_bwd_f32(const float* x, const float* y, int planes, int H, int W, int ws, const float* window_host, float C1, float C2,
+                       const float* coef, float* g_mu, float* g_e11, float* g_e12, const float* coarse, float* dx, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

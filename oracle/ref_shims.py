@@ -6,7 +6,7 @@ vectors committed under ``tests/golden/`` (see ``oracle/gen_golden.py``).  It on
 authoring container where ``/root/reference`` is mounted; nothing on the GPU box imports it.
 
 Shim set: stub third-party modules the reference imports but the hot path never
-uses, replace the two VGG feature extractors that download weights at construction, ignore the
+uses, replace the VGG feature extractors that download weights at construction, ignore the
 hard-coded ``'cuda'`` device literals when no GPU is present, and route the CUDA-only DCN op
 through ``torchvision.ops.deform_conv2d`` (same channel layout and border rule as
 ``ops/dcn/src/deform_conv_cuda_kernel.cu:571-633``).
@@ -87,6 +87,7 @@ def install():
     import models.modules.VQModel_arch as vqm
     vqm.VGGFeatureExtractor = _NoVGG
     import models.modules.losses as losses
+    losses.RefPerceptualNetwork = losses.PerceptualNetwork          # kept for oracle/gen_golden_stage3.py (built without its __init__)
     losses.PerceptualNetwork = _NoVGG
 
     # CUDA-only DCN -> torchvision CPU kernel

@@ -251,6 +251,21 @@ class GlareEngine:
         return out, dict(cond_feat=enc["cond_feat"], color_map=enc["color_map"], mid0=enc["mid_feat"][0], mid1=enc["mid_feat"][1],
                          z_flow=z, z_q=zq, idx=idx, vq_feat1=vq_feats[0], vq_feat0=vq_feats[1], out=out)
 
+    @torch.no_grad()
+    def stage3_inputs(self, lr):
+        """the frozen part of VQLLFLOWDeformable.reverse_flow (VQLLFLOWDeformable_arch.py:230-248, all under no_grad there): condition encoder
+        -> flow decode -> VQ -> VQGAN decoder features.  -> (z [B,3,h,w], [vq feat @2h, vq feat @4h], encoder mid features by level)"""
+        with torch.cuda.device(self.device):
+            lr = lr.to(self.device, torch.float32)
+
+            def run():
+                enc = self.cond_encoder(lr)
+                z = self.flow_decode(enc["color_map"], enc["cond_feat"])
+                zq, _ = self.vector_quantize(z)
+                return z, self.vq_decoder_features(zq), enc["mid_feat"]
+
+            return self.run_verified(run)
+
     def _verified(self):
         # the fused-softmax attention (dense.py) verifies its row sums on the device; a tripped flag switches the backend to the exact
         # softmax path and the caller recomputes (4-byte read, once per call)

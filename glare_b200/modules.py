@@ -11,8 +11,9 @@ code/models/base_model.py:110-122), kernels from libglare_b200.so underneath.
 
 The sub-trees whose arithmetic lives in the engine (encoders, decoders) are ``ParamModule``s: parameter
 containers built from the reference's own state-dict key list (glare_b200/data/state_shapes.json), not
-re-implementations of the reference forward code.  These modules are inference / forward-only (the reference's
-training loops stay PyTorch autograd).
+re-implementations of the reference forward code.  In training mode the generator's two training calls run on the library's kernels too:
+``reverse=False`` (stage 2: the flow objective, encoder_train.py) and ``reverse=True, reverse_with_grad=True`` (stage 3: the deformable decoder,
+decoder_train.py); the reference's solvers (optimizers, schedulers, logging) stay as they are.
 """
 import math
 
@@ -222,7 +223,8 @@ class VQLLFLOWDeformable(nn.Module):
     """VQLLFLOWDeformable_arch.py:18-250.  forward(net_vq=..., lr=..., reverse=True) -> (rec_deformable, enc_feat);
     forward(gt=..., lr=..., reverse=False) -> (z, nll, logdet)  [LLFlowVQGAN2_arch.py:75-122 objective, forward only]."""
 
-    def __init__(self, in_nc=3, out_nc=3, nf=64, nb=23, gc=32, scale=1, K=12, opt=None, step=None, which="netG"):
+    def __init__(self, in_nc=3, out_nc=3, nf=64, nb=23, gc=32, scale=1, K=12, opt=None, step=None, which="netG",
+                 fix_modules=("RRDB", "flowUpsamplerNet")):
         super().__init__()
         shapes = synth.state_shapes(which)
         self.opt = opt
@@ -234,8 +236,12 @@ class VQLLFLOWDeformable(nn.Module):
             self.quant = 255
         if which == "netG":
             self.deformable_decoder = ParamModule(_sub(shapes, "deformable_decoder."))
+            for name in (fix_modules or ()):                              # VQLLFLOWDeformable_arch.py:49-52: stage 3 trains the decoder only
+                for prm in getattr(self, name).parameters():
+                    prm.requires_grad = False
         self.dense_name = "auto"
         self._engine = None
+        self._frozen = None
         self._train_ctx = None
         # True: stage-2 training calls replay as one CUDA graph per (shapes, mean branch).  Off by default: measured on B200 the step is
         # GPU-bound (193 ms of kernel time per replay at batch 4 x 320x320 against 195-245 ms eagerly launched, profiles/r48_*), so the graph
@@ -259,6 +265,9 @@ class VQLLFLOWDeformable(nn.Module):
             raise NotImplementedError("get_color_map is not reachable from the shipped configurations")
         if reverse:
             assert lr.shape[1] == 3
+            if (reverse_with_grad and self.training and torch.is_grad_enabled() and hasattr(self, "deformable_decoder")
+                    and any(p.requires_grad for p in self.deformable_decoder.parameters())):
+                return self._reverse_flow_train(net_vq, lr)
             with torch.no_grad():
                 st = {}
                 out = self.engine(net_vq).infer(lr, stages=st)
@@ -275,6 +284,33 @@ class VQLLFLOWDeformable(nn.Module):
             nll = flowmod.gaussian_nll(zz, enc["color_map"], logdet)
         return zz, nll, logdet
 
+    def _leaves(self):
+        from . import encoder_train
+        from .dense import make_dense
+        if self._train_ctx is None:
+            dense = make_dense(self.dense_name)
+            self._train_ctx = (dense, encoder_train.CudaLeaves(dense))
+        return self._train_ctx
+
+    def _reverse_flow_train(self, net_vq, lr):
+        """training call of VQLLFLOWDModel.optimize_parameters (VQLLFLOWD_model.py:207-211): ``rec, _ = netG(net_vq=..., lr=...,
+        reverse=True, reverse_with_grad=True)``.  Encoder, flow and VQGAN run without gradient (VQLLFLOWDeformable_arch.py:230-248) on an
+        engine keyed on the frozen modules only -- it survives the optimizer's updates of the decoder -- and the deformable decoder is one
+        autograd node over its parameters (decoder_train.DeformableDecoderFn, DCN backward inside), with the whole-batch mean ratio of :567."""
+        from . import decoder_train
+        frozen = [self.RRDB, self.flowUpsamplerNet, net_vq]
+        key = sum((_fingerprint(m) for m in frozen), ())
+        if self._frozen is None or self._frozen[0] != key:
+            from .dense import make_dense
+            sd = {k: v for k, v in self.state_dict().items() if k.startswith(("RRDB.", "flowUpsamplerNet."))}
+            self._frozen = (key, GlareEngine(sd, net_vq.state_dict(), device=next(self.parameters()).device, dense=make_dense(self.dense_name),
+                                             decoders=False))
+        eng = self._frozen[1]
+        z, vq_feats, mid = eng.stage3_inputs(lr)
+        named = [(k, p) for k, p in self.named_parameters() if k.startswith("deformable_decoder.")]
+        rec = decoder_train.deformable_decoder(named, z, vq_feats, mid, self._leaves()[1], global_ratio=True)
+        return rec, z
+
     def _normal_flow_train(self, gt, lr):
         """training call of LLFlow_model.optimize_parameters (LLFlow_model.py:215-232): ``z, nll, _ = netG(gt=..., lr=..., reverse=False)``
         followed by ``scaler.scale(nll.mean()).backward()``.  The objective and every parameter gradient come from the library's kernels
@@ -283,10 +319,7 @@ class VQLLFLOWDeformable(nn.Module):
         from . import encoder_train
         from .dense import make_dense
         dev = next(self.parameters()).device
-        if self._train_ctx is None:
-            dense = make_dense(self.dense_name)
-            self._train_ctx = (dense, encoder_train.CudaLeaves(dense))
-        dense, leaves = self._train_ctx
+        dense, leaves = self._leaves()
         ratio = 0.0
         try:
             ratio = float(self.opt["train_gt_ratio"] or 0.0)

@@ -1,5 +1,6 @@
 """CPU: stage-3 training of the deformable decoder (glare_b200/decoder_train.py: tape over MultiScaleDecoder2, DCN backward inside the loop)
 with torch restatements of the kernel-level primitives, against torch autograd of the oracle for EVERY parameter the forward uses."""
+import numpy as np
 import pytest
 import torch
 
@@ -65,3 +66,41 @@ def test_decoder_autograd_node_fills_param_grads(sd_g):
         ref = sda[k].grad
         assert float((params[k].grad - ref).abs().max()) <= 1e-3 * float(ref.abs().max()) + 1e-8, k
     assert params["deformable_decoder.conv_out.weight"].grad is None
+
+
+def test_stage3_evaluation_matches_the_reference_golden(sd_g, sd_v):
+    """one stage-3 objective + gradient evaluation (VQLLFLOWD_model.py:187-232) against the unmodified reference's own numbers
+    (tests/golden/stage3.npz, oracle/gen_golden_stage3.py): the decoder tape on torch leaves, csrc/loss.cu on the host, frozen stages from
+    the oracle"""
+    from conftest import load_golden
+    from glare_b200 import decoder_train, losses, synth
+    from oracle import glare_oracle as O
+    from oracle.gen_golden_stage3 import vgg_state
+    from test_losses_cpu import _host_kernels
+    g = load_golden("stage3")
+    lq, gt = torch.from_numpy(g["lq"]), torch.from_numpy(g["gt"])
+    with torch.no_grad():
+        st = {}
+        O.glare_infer(sd_g, sd_v, synth.preprocess(lq), per_sample_ratio=False, stages=st)
+    assert float((st["z_flow"] - torch.from_numpy(g["z_flow"])).abs().max()) < 1e-4
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in sd_g.items() if k.startswith("deformable_decoder.")}
+    rec = decoder_train.deformable_decoder(params.items(), st["z_flow"], [st["vq_feat1"], st["vq_feat0"]], {1: st["mid1"], 0: st["mid0"]},
+                                           TorchLeaves(), global_ratio=True)
+    assert float((rec.detach() - torch.from_numpy(g["rec"])).abs().max()) < 2e-4
+    K = _host_kernels()
+    percep = losses.PerceptualNetwork(state_dict=vgg_state(0), leaves=TorchLeaves())
+    total, terms = losses.stage3_loss(rec, gt, percep, msssim_fn=lambda x, y, **kw: losses.msssim(x, y, kernels=K, **kw))
+    for k, v in terms.items():
+        assert abs(float(v.detach()) - float(g["term." + k])) <= 2e-5 * max(abs(float(g["term." + k])), 1e-3), k
+    total.backward()
+    with_grad = set(g["with_grad"].tolist())
+    assert {k for k, p in params.items() if p.grad is not None} == with_grad
+    gmax = max(float(np.abs(g[k]).max()) for k in g if k.startswith("grad."))
+    for k in g:
+        if k.startswith("grad."):
+            ref = torch.from_numpy(g[k])
+            err = float((params[k[5:]].grad - ref).abs().max())
+            assert err <= 2e-3 * max(float(ref.abs().max()), 1e-4 * gmax), (k, err, float(ref.abs().max()))
+    for k, s in zip(g["with_grad"].tolist(), g["abs_sum"].tolist()):         # every parameter: checksum of the gradient
+        got = float(params[k].grad.double().abs().sum())
+        assert abs(got - s) <= 5e-3 * max(s, 1e-4 * gmax * params[k].numel() ** 0.5), (k, got, s)

@@ -26,6 +26,13 @@ def test_flow_training_kernels_in_child_process(glare_lib):
     assert rc == 0, log
 
 
+def test_stage3_training_path_in_child_process(glare_lib):
+    """stage-3 (deformable decoder + losses): MS-SSIM kernels and the VGG perceptual loss against the oracle, one whole evaluation through
+    the drop-in modules against the unmodified reference's gradients (tests/golden/stage3.npz)"""
+    rc, log = _child("stage3_gpu_check.py")
+    assert rc == 0, log
+
+
 def test_conv_default_kernel_in_child_process(glare_lib):
     """the shipped conv kernels (two-ring patch staging, RING2, for the 256-wide N tiles since round 2) against cuDNN fp32 on three shapes"""
     env = dict(os.environ)

@@ -44,6 +44,7 @@ class DecoderTrainer(BlockGraph):
         om = self._conv(p + ".dcn.conv_offset", feat)
         w, b = self.sd[p + ".dcn.weight"], self.sd[p + ".dcn.bias"]
         out = self.vals[om]
+        self.offset_ids.append(om)                      # (tests teacher-force these values to separate arithmetic error from cell flips)
         n_off = out.shape[1] // 3 * 2                   # chunk(out, 3): offset = cat(o1, o2) = the first two thirds, mask = sigmoid(last third)
 
         def bwd(gy):
@@ -81,6 +82,7 @@ class DecoderTrainer(BlockGraph):
         """z [B,3,h,w] (the flow's latent), vq_feats = [feat 256ch @2h, feat 128ch @4h] of the frozen VQGAN decoder, enc_feats[lvl] the
         condition encoder's mid features at level 1 (256ch @2h) and level 0 (128ch @4h).  -> reconstruction [B,3,4h,4w]"""
         self._begin(z)
+        self.offset_ids = []
         p = self.p
         h = self._conv(p + ".conv_in", 0, need_gx=False)
         h = self._resnet(p + ".mid.block_1", h)

@@ -160,15 +160,18 @@ class VGGGraph(BlockGraph):
         self._begin(x)
         convs = {i: None for i, _, _ in VGG_CONVS}
         h, taps = 0, []
+        self.switches = []                              # ReLU outputs and pooling indices: the discontinuous choices of the forward pass
         for idx in range(16):
             if idx in convs:
                 h = self._conv(str(idx), h, need_gx=True, need_gw=False)
             elif idx in VGG_POOLS:
                 xin = self.vals[h]
                 y, where = F.max_pool2d(xin, 2, 2, return_indices=True)
+                self.switches.append(where)
                 h = self._fn(y, (h,), lambda gy, where=where, shape=xin.shape: (F.max_unpool2d(gy, where, 2, 2, output_size=shape[2:]),))
             else:
                 y = F.relu(self.vals[h])
+                self.switches.append(y)
                 h = self._fn(y, (h,), lambda gy, y=y: (gy * (y > 0),))
                 if idx in VGG_TAPS:
                     taps.append(h)

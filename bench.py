@@ -223,7 +223,47 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
             "algorithmic_tflop_per_step": 12.6, "achieved_tflops_per_gpu": 12.6 / (ms_t / 1e3), "frac_of_bf16_peak": 12.6 / (ms_t / 1e3) / pk["tensor"],
             "nll_last": [round(float(v), 4) for v in last["nll"].cpu()],
             "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else None}
-        del netG, net_hq, optim
+        del netG, optim
+        torch.cuda.empty_cache()
+        # ---- stage 3 (train_stage3_LOL.yml: batch 2 x 256x256): the call sequence of VQLLFLOWDModel.optimize_parameters
+        # (VQLLFLOWD_model.py:187-232): netG(net_vq=..., lr=..., reverse=True, reverse_with_grad=True) with encoder / flow / VQGAN frozen,
+        # |sr - gt| + 0.01 VGG16 perceptual + 0.2 (1 - MS-SSIM), total.backward() (decoder tape with the DCN backward kernels, csrc/loss.cu),
+        # gradient all-reduce, Adam on deformable_decoder.*
+        from glare_b200 import losses
+        netG3 = modules.VQLLFLOWDeformable().to(dev)
+        netG3.load_state_dict(sd_g, strict=True)
+        netG3.train()
+        vgen = torch.Generator().manual_seed(4000)
+        percep = losses.PerceptualNetwork(state_dict={"%d.%s" % (i, n): (torch.randn((co, ci, 3, 3), generator=vgen) * (2.0 / (9 * ci)) ** 0.5
+                                                                        if n == "weight" else torch.zeros(co))
+                                                      for i, ci, co in losses.VGG_CONVS for n in ("weight", "bias")}).to(dev)
+        named3 = [(k, p) for k, p in netG3.named_parameters() if p.requires_grad]
+        optim3 = torch.optim.Adam([p for _, p in named3], lr=5e-5, betas=(0.9, 0.99))
+        lq3, gt3 = synth.synth_images(2, 256, 256, seed=400 + rank)
+        var_L3, real_H3 = synth.preprocess(lq3).to(dev), gt3.to(dev)
+        last3 = {}
+
+        def train_step3():
+            optim3.zero_grad(set_to_none=True)
+            rec, _ = netG3(net_vq=net_hq, lr=var_L3, reverse=True, reverse_with_grad=True)
+            total, terms = losses.stage3_loss(rec, real_H3, percep)
+            total.backward()
+            if world > 1:
+                grads = allreduce_gradients({k: p.grad for k, p in named3 if p.grad is not None})
+                for k, p in named3:
+                    if p.grad is not None:
+                        p.grad = grads[k].to(p.grad.dtype).reshape(p.grad.shape)
+            optim3.step()
+            last3["total"] = total.detach()
+
+        ms_3 = timed(train_step3, 5, 3)
+        out["stage3_training_step"] = {
+            "workload": "one stage-3 step (train_stage3_LOL.yml shape: batch 2 x 256x256 per GPU) through the drop-in mirrors: frozen encoder / "
+                        "flow / VQGAN forward, deformable-decoder forward + backward (DCN backward in the loop), L1 + VGG16 perceptual (synthetic "
+                        "weights) + MS-SSIM objective, Adam; fp32-grade tensor-core operands (bf16x3)",
+            "value": world * 2 / (ms_3 / 1e3), "unit": "samples/s", "ms_per_step": ms_3, "objective_last": round(float(last3["total"]), 5),
+            "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else None}
+        del netG3, net_hq, optim3, percep
         torch.cuda.empty_cache()
     # ---- single-image latency of the bench shape (infer_dataset_lol.py / infer_unpaired.py run batch 1): host uint8 in -> host uint8 out
     enh1 = GlareEnhancer(sd_g, sd_v, device=dev, pad="lol", dense=fp32_engine.dense)

@@ -106,7 +106,9 @@ class DecoderTrainer(BlockGraph):
         """gradient of the reconstruction -> {state-dict key: gradient} of every parameter the forward uses (conv_out, scale.*, bias.*, enc.*
         are constructed but unused by the reference's forward: absent, like its ``param.grad is None``)"""
         self._backprop({self.out_id: g_rec.float()})
-        return self.tape.grads
+        grads = self.tape.grads
+        self.release()
+        return grads
 
 
 class DeformableDecoderFn(torch.autograd.Function):

@@ -315,11 +315,11 @@ class BlockGraph:
 
     def _conv(self, p, i, down=False, need_gx=True, need_gw=True):
         y = self.tape.conv(p, self.vals[i], down, need_gx, need_gw)
-        return self._push("op", y, (i,), self.tape.ops[-1])
+        return self._push("op", y, (i,), self.tape.ops.pop())
 
     def _gn(self, p, i, swish):
         y = self.tape.gn(p, self.vals[i], swish)
-        return self._push("op", y, (i,), self.tape.ops[-1])
+        return self._push("op", y, (i,), self.tape.ops.pop())
 
     def _add(self, i, j):
         return self._push("add", self.vals[i] + self.vals[j], (i, j), None)
@@ -340,8 +340,15 @@ class BlockGraph:
         hn = self._gn(p + ".norm", i, False)
         q, k, v = (self._conv(p + "." + n, hn) for n in "qkv")
         o = self.tape.attention(self.vals[q], self.vals[k], self.vals[v])
-        o = self._push("op", o, (q, k, v), self.tape.ops[-1])
+        o = self._push("op", o, (q, k, v), self.tape.ops.pop())
         return self._add(i, self._conv(p + ".proj_out", o))
+
+    def release(self):
+        """drop the tape's activations now: the closures of `_fn` nodes refer back to the graph, so without this the memory of a finished step
+        waits for the cyclic garbage collector (measured on stage 3: 33 GB peak and a caching allocator that keeps growing for a dozen steps)"""
+        self.nodes, self.vals = [], []
+        if getattr(self, "tape", None) is not None:
+            self.tape.ops = []
 
     def _backprop(self, g):
         """``g``: {value id: gradient} seeds; walks the nodes in reverse; returns the gradients that reached the graph inputs"""
@@ -351,8 +358,10 @@ class BlockGraph:
             if val is not None:
                 g[i] = g[i] + val if i in g else val
 
-        for kind, out, inputs, op in reversed(self.nodes):
+        while self.nodes:
+            kind, out, inputs, op = self.nodes.pop()                    # popped: a node's saved activations are freed as soon as it is done
             gy = g.pop(out, None)
+            self.vals[out] = None
             if gy is None:
                 continue
             if kind == "add":

@@ -180,6 +180,7 @@ class VGGGraph(BlockGraph):
 
     def backward(self, g_taps):
         g = self._backprop({t: gt for t, gt in zip(self.taps, g_taps)})
+        self.release()
         return g[0]
 
 
@@ -189,7 +190,9 @@ class PerceptualFn(torch.autograd.Function):
     def forward(ctx, dehaze, gt, leaves, sd):
         x = dehaze.detach().float()
         with torch.no_grad():
-            f_gt = VGGGraph(leaves, sd).forward(gt.detach().float())
+            g_gt = VGGGraph(leaves, sd)
+            f_gt = g_gt.forward(gt.detach().float())
+            g_gt.release()
             graph = VGGGraph(leaves, sd)
             f_x = graph.forward(x)
             seeds, loss = [], 0.0
@@ -248,7 +251,10 @@ class PerceptualNetwork(nn.Module):
 
     @torch.no_grad()
     def output_features(self, x):
-        return VGGGraph(self.leaves(x.device), self._sd()).forward(x.float())
+        graph = VGGGraph(self.leaves(x.device), self._sd())
+        feats = graph.forward(x.float())
+        graph.release()
+        return feats
 
     def forward(self, dehaze, gt):
         return PerceptualFn.apply(dehaze, gt, self.leaves(dehaze.device), self._sd())

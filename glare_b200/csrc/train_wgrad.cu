@@ -10,43 +10,66 @@
 
 namespace glare {
 
-// grid (pixel groups of 32, C / 32, k * k); block (32, 8).  out [nch][k*k*C][2 * chunk] bf16: row m = tap * C + c, pixel j of the chunk at
-// (j >> 5) * 64 + (j & 31) (a1) and + 32 (a2) -- the mode-4 operand layout with the pixels as the K dimension.
+// grid (pixel groups of 32 in packs of 8, C / 32, k * k); 256 threads.  out [nch][k*k*C][2 * chunk] bf16: row m = tap * C + c, pixel j of
+// the chunk at (j >> 5) * 64 + (j & 31) (a1) and + 32 (a2) -- the mode-4 operand layout with the pixels as the K dimension.
+// One CTA moves a 256-pixel x 32-channel tile of one tap: warp w gathers pixel group w (lane = channel, 128-byte reads per pixel) into shared
+// memory, then writes 4 channel rows of 1 KB each as 16-byte stores (lane = 8 consecutive pixels of one group: its a1 and its a2 octet).
+// The tile's column index is pix + pix / 8 over an odd row stride, which makes both phases bank-conflict free.  (Round 2's first version
+// moved 32 x 32 tiles with 2-byte stores: 147 K CTAs for a 128-channel 256x256 conv, about a tenth of the HBM rate.)
+constexpr int WG_PIX = 256, WG_STRIDE = WG_PIX + WG_PIX / 8 + 1;
+
 __global__ void __launch_bounds__(256) im2col_t_operand_kernel(const float* __restrict__ x, int B, int H, int W, int C, int k, int stride, int pad,
-                                                               int Ho, int Wo, long long P, int chunk, __nv_bfloat16* __restrict__ out) {
-    __shared__ float tile[32][33];
+                                                               int Ho, int Wo, long long P, int chunk, long long groups,
+                                                               __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[32 * WG_STRIDE];
     const int tap = blockIdx.z, dy = tap / k, dx = tap - dy * k;
     const int c0 = blockIdx.y * 32;
-    const long long p0 = (long long)blockIdx.x * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    // load: 32 pixels x 32 channels, coalesced over the channels of a pixel; taps outside the image and pixels past P read as zero
-#pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const long long p = p0 + r;
-        float v = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // gather: warp = pixel group; lane j resolves pixel j's source once, the warp then reads the 32 channels of each pixel
+    {
+        const long long p = ((long long)blockIdx.x * 8 + warp) * 32 + lane;
+        long long src = -1;
         if (p < P) {
             const long long hw = (long long)Ho * Wo;
             const int b = (int)(p / hw);
             const int rem = (int)(p - (long long)b * hw);
             const int oy = rem / Wo, ox = rem - oy * Wo;
             const int iy = oy * stride + dy - pad, ix = ox * stride + dx - pad;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long long)b * H + iy) * W + ix) * C + c0 + tx);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) src = (((long long)b * H + iy) * W + ix) * C + c0;
         }
-        tile[r][tx] = v;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const long long s = __shfl_sync(0xffffffffu, src, j);
+            const int pix = warp * 32 + j;
+            tile[lane * WG_STRIDE + pix + (pix >> 3)] = s >= 0 ? __ldg(x + s + lane) : 0.f;
+        }
     }
     __syncthreads();
-    // store: row m = tap * C + c, 32 consecutive pixels of one K group: a1 pieces then a2 pieces (64 bytes each)
-    const int ci = (int)(p0 / chunk);
-    const int j0 = (int)(p0 - (long long)ci * chunk);                       // multiple of 32
+    // scatter: lane -> (pixel group g, octet q); rows warp * 4 .. + 3
+    const int g = lane >> 2, q = lane & 3;
+    const long long gi = (long long)blockIdx.x * 8 + g;
+    if (gi >= groups) return;
+    const long long p0 = gi * 32;
+    const long long ci = p0 / chunk;
+    const int j0 = (int)(p0 - ci * chunk);                                  // multiple of 32
     const long long M = (long long)k * k * C;
+    const int col = (g * 32 + q * 8) + (g * 4 + q);                           // pix + pix / 8 of the octet's first pixel
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const float v = tile[tx][r];                                          // pixel tx, channel c0 + r
-        __nv_bfloat16 a1, a2;
-        split_b3(v, a1, a2);
-        __nv_bfloat16* row = out + (((long long)ci * M + (long long)tap * C + c0 + r) * chunk + j0) * 2;
-        row[tx] = a1;
-        row[32 + tx] = a2;
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp * 4 + rr;
+        const float* t = tile + r * WG_STRIDE + col;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat16 a1, a2, b1, b2;
+            split_b3(t[2 * i], a1, a2);
+            split_b3(t[2 * i + 1], b1, b2);
+            hi[i] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+            lo[i] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+        }
+        __nv_bfloat16* row = out + ((ci * M + (long long)tap * C + c0 + r) * chunk + j0) * 2 + q * 8;
+        *reinterpret_cast<uint4*>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(row + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -68,8 +91,9 @@ GLARE_API int glare_im2col_t_operand_bf16x3(const float* x, int B, int H, int W,
     const long long nch = (P + chunk - 1) / chunk;
     const long long groups = nch * (chunk / 32);
     if (groups > 0x7fffffffLL || C / 32 > 65535) return GLARE_ERR_UNSUPPORTED;
-    im2col_t_operand_kernel<<<dim3((unsigned)groups, (unsigned)(C / 32), (unsigned)(k * k)), dim3(32, 8), 0, stream>>>(
-        x, B, H, W, C, k, stride, pad, Ho, Wo, P, chunk, reinterpret_cast<__nv_bfloat16*>(out));
+    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return GLARE_ERR_BAD_ARG;
+    im2col_t_operand_kernel<<<dim3((unsigned)((groups + 7) / 8), (unsigned)(C / 32), (unsigned)(k * k)), 256, 0, stream>>>(
+        x, B, H, W, C, k, stride, pad, Ho, Wo, P, chunk, groups, reinterpret_cast<__nv_bfloat16*>(out));
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }

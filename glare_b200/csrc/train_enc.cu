@@ -132,6 +132,39 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __re
     for (int j = threadIdx.x; j < n_keys; j += blockDim.x) o[j] = scale * __ldg(p + j) * (__ldg(d + j) - dot);
 }
 
+// out[c] += sum_p x[p][c]: the bias gradient of a convolution (dY summed over the pixels of the batch).  grid (C / 128 rounded up, row chunks),
+// 256 threads = 32 column quads x 8 row lanes; 512-byte row segments per warp, fp32 partials reduced through shared memory, one atomicAdd per
+// column and CTA.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long P, int C, long long rows_per_cta, float* __restrict__ out) {
+    __shared__ float4 part[8][32];
+    const int quad = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + quad) * 4;
+    const long long p0 = (long long)blockIdx.y * rows_per_cta, p1 = (p0 + rows_per_cta < P) ? p0 + rows_per_cta : P;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C)
+        for (long long p = p0 + lane_r; p < p1; p += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(x + p * C + c);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+    part[lane_r][quad] = acc;
+    __syncthreads();
+    if (lane_r == 0 && c < C) {
+        for (int r = 1; r < 8; ++r) {
+            acc.x += part[r][quad].x;
+            acc.y += part[r][quad].y;
+            acc.z += part[r][quad].z;
+            acc.w += part[r][quad].w;
+        }
+        atomicAdd(out + c, acc.x);
+        atomicAdd(out + c + 1, acc.y);
+        atomicAdd(out + c + 2, acc.z);
+        atomicAdd(out + c + 3, acc.w);
+    }
+}
+
 }  // namespace glare
 
 using namespace glare;
@@ -181,6 +214,23 @@ GLARE_API int glare_attn_softmax_bwd_f32(const float* P, const float* dP, long l
     if (rows == 0) return GLARE_OK;
     if (!P || !dP || !dS || rows > 0x7fffffffLL) return GLARE_ERR_BAD_ARG;
     TE_LAUNCH(attn_softmax_bwd_kernel, dim3((unsigned)rows), 256, stream, P, dP, ld, n_keys, scale, dS);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// x [P][C] fp32 contiguous, C % 4 == 0 -> out[C] += column sums (out zero-filled by the caller for a plain sum): bias gradients of the
+// encoder / decoder convolutions (torch autograd of nn.Conv2d's bias, encoder_decoder.py:88-115)
+GLARE_API int glare_colsum_f32(const float* x, long long P, int C, float* out, cudaStream_t stream) {
+    if (P < 0 || C <= 0 || (C & 3)) return GLARE_ERR_BAD_ARG;
+    if (P == 0) return GLARE_OK;
+    if (!x || !out) return GLARE_ERR_BAD_ARG;
+    const int col_tiles = (C + 127) / 128;
+    long long chunks = (P + 255) / 256;                                  // >= 32 sequential loads per thread
+    const long long cap = (148LL * 8 + col_tiles - 1) / col_tiles;
+    if (chunks > cap) chunks = cap;
+    const long long per = (P + chunks - 1) / chunks;
+    chunks = (P + per - 1) / per;
+    TE_LAUNCH(colsum_kernel, dim3((unsigned)col_tiles, (unsigned)chunks), 256, stream, x, P, C, per, out);
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }

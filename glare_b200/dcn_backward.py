@@ -4,11 +4,13 @@ forward : the fp32 operator (glare_dcnv2_fwd_f32) -- same semantics and argument
 backward: for the configuration GLARE trains with (3x3, stride 1, pad 1, dilation 1, groups 1; stage 3, VQLLFLOWD_model.py:187-232):
     dcol   = W^T grad_out            1x1 conv on the tcgen05 path (fp32-grade mode)
     grad_input / grad_offset / grad_mask / col   one fused gather-scatter kernel (glare_dcnv2_bwd_data_f32)
-    grad_weight = col^T grad_out     split-K fp32 GEMM over the pixels of the batch (glare_dcnv2_bwd_weight_f32)
+    grad_weight = col^T grad_out     batched tcgen05 GEMM over pixel chunks (ops.wgrad_conv_tc; fp32 split-K GEMM when 9C % 32 != 0)
     grad_bias   = sum grad_out
 Unlike the reference there is no per-sample host loop and no `columns` buffer shared between calls; `chunk` bounds the two
 [n,H,W,9C] scratch tensors (1.2 GB per sample at 128 channels, 420x620).
 """
+import os
+
 import torch
 
 from . import ops
@@ -43,6 +45,7 @@ class ModulatedDeformConvFunction(torch.autograd.Function):
 
 modulated_deform_conv = ModulatedDeformConvFunction.apply
 _MODE = ops.MODE_TF32_BF16X2                     # fp32-grade tensor-core mode for dcol = W^T grad_out
+_WGRAD_TC = not os.environ.get("GLARE_WGRAD_FMA")   # GLARE_WGRAD_FMA=1: the fp32 split-K GEMM (glare_dcnv2_bwd_weight_f32), the correctness baseline
 
 
 def dcn_backward(x, offset, mask, weight, grad_output, dg, with_bias=True, chunk=2):
@@ -67,7 +70,11 @@ def dcn_backward(x, offset, mask, weight, grad_output, dg, with_bias=True, chunk
         dcol = ops.conv2d_nhwc_tc(_MODE, g_hi, g_lo, w_hi, w_lo, None, None, b1 - b0, H, W, Co, 9 * C, 1)
         col = torch.empty_like(dcol)
         ops.dcnv2_bwd_data(x_n[b0:b1], offset[b0:b1], mask[b0:b1], dcol, dg, grad_x[b0:b1], grad_offset[b0:b1], grad_mask[b0:b1], col)
-        ops.dcnv2_bwd_weight(col, gc, grad_wp)
+        gw = ops.wgrad_conv_tc(col, gc, 1, 1, 0) if _WGRAD_TC else None       # col^T grad_out on the tensor cores (fp32-grade bf16x3)
+        if gw is not None:
+            grad_wp += gw
+        else:
+            ops.dcnv2_bwd_weight(col, gc, grad_wp)
     grad_w = grad_wp.view(3, 3, C, Co).permute(3, 2, 0, 1).contiguous()
     grad_b = g_n.sum(dim=(0, 1, 2)) if with_bias else None
     return grad_x.permute(0, 3, 1, 2), grad_offset, grad_mask, grad_w, grad_b

@@ -89,15 +89,14 @@ class CudaLeaves:
         return out
 
     def colsum(self, x):
-        """x [P][C] -> column sums [C] (bias gradients).  C a multiple of 64: the flow path's column-sum kernel on 64-column slabs; other widths
-        (3-channel heads) are tiny reductions left to torch.  (Round 1 ran these through the 128 x 128-tile split-K GEMM with a ones vector:
-        35 ms of a 194 ms step.)"""
+        """x [P][C] -> column sums [C] (bias gradients): csrc/train_enc.cu colsum_kernel, one launch per tensor; widths that are not a multiple
+        of 4 (3-channel heads) are tiny reductions left to torch.  (Round 1 ran these through the 128 x 128-tile split-K GEMM with a ones
+        vector: 35 ms of a 194 ms step; round 2 first used the flow path's 64-column kernel, C / 64 launches per tensor.)"""
         P, C = x.shape
-        if C % 64 or not x.is_contiguous():
+        if C % 4 or not x.is_contiguous():
             return x.sum(dim=0)
         out = torch.zeros((C,), device=x.device, dtype=torch.float32)
-        for c0 in range(0, C, 64):
-            self._call("glare_flow_train_colsum_f32", ctypes.c_void_p(x.data_ptr() + 4 * c0), C, None, 0, 64, P, ctypes.c_void_p(out.data_ptr() + 4 * c0))
+        self._call("glare_colsum_f32", self._p(x), P, C, self._p(out))
         return out
 
     def gemm_tn_tc(self, a, b, chunk=8192):
@@ -123,25 +122,11 @@ class CudaLeaves:
         return y[:, :, :N].sum(dim=0)
 
     def wgrad_conv(self, x_nhwc, gy_nhwc, k, stride, pad, chunk=8192):
-        """weight gradient of a k x k conv, [k*k*Ci][Co] (tap-major rows), on the tensor cores WITHOUT fp32 im2col columns: the transposed
-        bf16x3 operands of im2col(x) and of dY are written directly (csrc/train_wgrad.cu), then one batched GEMM over the pixel chunks.
+        """weight gradient of a k x k conv, [k*k*Ci][Co] (tap-major rows), on the tensor cores without fp32 im2col columns (ops.wgrad_conv_tc).
         None when the shape is outside that path (the caller uses im2col + gemm_tn)."""
-        B, H, W, Ci = x_nhwc.shape
-        _, Ho, Wo, Co = gy_nhwc.shape
-        M, N, P = k * k * Ci, Co, B * Ho * Wo
-        if not self.wgrad_tc or M < 128 or N < 32 or Ci % 32 or N % 32 or not x_nhwc.is_contiguous() or not gy_nhwc.is_contiguous():
+        if not self.wgrad_tc:
             return None
-        chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
-        nch = (P + chunk - 1) // chunk
-        a_op = torch.empty((nch, M, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
-        b_op = torch.empty((nch, N, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
-        self._call("glare_im2col_t_operand_bf16x3", self._p(x_nhwc), B, H, W, Ci, k, stride, pad, Ho, Wo, chunk, self._p(a_op))
-        self._call("glare_im2col_t_operand_bf16x3", self._p(gy_nhwc), B, Ho, Wo, Co, 1, 1, 0, Ho, Wo, chunk, self._p(b_op))
-        rows_w = 16 if M % 16 == 0 else 1
-        ldy = (N + 3) // 4 * 4
-        y = torch.empty((nch, M, ldy), device=x_nhwc.device, dtype=torch.float32)
-        self.ops.conv2d_nhwc_tc_ex(self.dense.mode, a_op, None, b_op, None, y, nch, M // rows_w, rows_w, chunk, N, ldy, N * chunk)
-        return y[:, :, :N].sum(dim=0)
+        return self.ops.wgrad_conv_tc(x_nhwc, gy_nhwc, k, stride, pad, chunk)
 
     def gemm_nt(self, a, b, rows_hw):
         """a [R][K], b [N][K] -> a b^T [R][N] on the tcgen05 GEMM path (R = rows_hw[0] * rows_hw[1], the tile walk needs the 2-D factorisation)"""

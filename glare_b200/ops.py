@@ -127,6 +127,33 @@ def dcnv2_bwd_weight(col_nhwc, gout_nhwc, grad_w_packed):
                                            stream()), "glare_dcnv2_bwd_weight_f32")
 
 
+def wgrad_conv_tc(x_nhwc, gy_nhwc, k, stride, pad, chunk=8192):
+    """weight gradient of a k x k conv, [k*k*Ci][Co] (tap-major rows), on the tensor cores WITHOUT fp32 im2col columns: the transposed bf16x3
+    operands of im2col(x) and of dY are written directly (csrc/train_wgrad.cu), then one batched tcgen05 GEMM over the pixel chunks, summed
+    in fp32.  Co is zero-padded to a multiple of 32.  None when the shape is outside that path (Ci % 32, fewer than 128 rows)."""
+    import torch.nn.functional as F
+    B, H, W, Ci = x_nhwc.shape
+    _, Ho, Wo, Co = gy_nhwc.shape
+    M, P = k * k * Ci, B * Ho * Wo
+    if M < 128 or Ci % 32 or not x_nhwc.is_contiguous() or not gy_nhwc.is_contiguous() or x_nhwc.dtype != torch.float32:
+        return None
+    N = (Co + 31) // 32 * 32
+    if N != Co:
+        gy_nhwc = F.pad(gy_nhwc, (0, N - Co))
+    chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
+    nch = (P + chunk - 1) // chunk
+    a_op = torch.empty((nch, M, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
+    b_op = torch.empty((nch, N, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
+    check(lib().glare_im2col_t_operand_bf16x3(ptr(x_nhwc), B, H, W, Ci, k, stride, pad, Ho, Wo, chunk, ptr(a_op), stream()),
+          "glare_im2col_t_operand_bf16x3")
+    check(lib().glare_im2col_t_operand_bf16x3(ptr(gy_nhwc), B, Ho, Wo, N, 1, 1, 0, Ho, Wo, chunk, ptr(b_op), stream()),
+          "glare_im2col_t_operand_bf16x3")
+    rows_w = 16 if M % 16 == 0 else 1
+    y = torch.empty((nch, M, N), device=x_nhwc.device, dtype=torch.float32)
+    conv2d_nhwc_tc_ex(MODE_BF16X3, a_op, None, b_op, None, y, nch, M // rows_w, rows_w, chunk, N, N, N * chunk)
+    return y[:, :, :Co].sum(dim=0)
+
+
 # ------------------------------------------------------------------------------------------- flow
 def flow_cond_tail(p, p_strides, nets, n_steps, nout, B, h, w, out, out_batch_stride, out_step_stride):
     """p_strides = (batch, step, channel, pixel) element strides of the pre-activation planes"""

@@ -256,6 +256,8 @@ int glare_im2col_t_operand_bf16x3(const float* x, int B, int H, int W, int C, in
                                   void* out, cudaStream_t stream);
 int glare_attn_softmax_bwd_f32(const float* P, const float* dP, long long rows, long long ld, int n_keys, float scale, float* dS,
                                cudaStream_t stream);
+/* out[C] += column sums of x [P][C] fp32 (C % 4 == 0): the bias gradient of nn.Conv2d (dY summed over the pixels of the batch). */
+int glare_colsum_f32(const float* x, long long P, int C, float* out, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (7) Elementwise glue of the AFT decoder -- deformableDecoder_arch.py:587-590 (Mix: enc * m + h * (1 - m)) and :567

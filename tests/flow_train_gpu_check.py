@@ -161,6 +161,13 @@ def encoder_step_check(dev, dense, conv):
     for (Pp, M, N) in ((5000, 1152, 128), (777, 128, 64)):
         a, b = torch.randn((Pp, M), generator=gen).to(dev), torch.randn((Pp, N), generator=gen).to(dev)
         check("gemm_tn_tc %dx%dx%d" % (Pp, M, N), Lg.gemm_tn_tc(a, b, chunk=1024), (a.double().t() @ b.double()).float(), 1e-4)
+    for (Pp, C) in ((204800, 128), (777, 512), (51, 4)):
+        xs = torch.randn((Pp, C), generator=gen)
+        check("colsum %dx%d" % (Pp, C), Lg.colsum(xs.to(dev)), xs.double().sum(dim=0).float(), 2e-5)
+    # a 3-output-channel conv (residual_conv / color_conv): dY zero-padded to 32 columns inside wgrad_conv
+    xq, gq = torch.randn((2, 20, 24, 128), generator=gen), torch.randn((2, 20, 24, 3), generator=gen)
+    want = (TorchLeaves().im2col(xq, 3, 1, 1, 20, 24).double().t() @ gq.reshape(-1, 3).double()).float()
+    check("wgrad_conv Co=3", Lg.wgrad_conv(xq.to(dev), gq.to(dev), 3, 1, 1), want, 1e-4)
     # im2col-free tensor-core weight gradient (csrc/train_wgrad.cu: transposed operands written directly) against fp64 over the torch im2col
     T = TorchLeaves()
     for (Bq, Hh, Ww, Ci, Co, kk, stride, pad) in ((2, 13, 21, 128, 128, 3, 1, 1), (1, 22, 18, 64, 128, 3, 2, 0), (3, 9, 11, 256, 64, 1, 1, 0),

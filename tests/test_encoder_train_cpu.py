@@ -100,6 +100,10 @@ def test_train_enc_kernel_source_on_the_host():
         x = torch.randn((2, Hh, Ww, C), generator=gen)
         Ho, Wo = (Hh, Ww) if stride == 1 else ((Hh + 1 - 3) // 2 + 1, (Ww + 1 - 3) // 2 + 1)
         close(H.im2col(x, k, stride, pad, Ho, Wo), T.im2col(x, k, stride, pad, Ho, Wo), "im2col %s" % ((Hh, Ww, C, k, stride, pad),), 0.0)
+    # bias gradients: column sums of any width that is a multiple of 4, ragged row counts
+    for (Pp, C) in ((1000, 128), (37, 64), (513, 516), (5, 4)):
+        xs = torch.randn((Pp, C), generator=gen)
+        close(H.colsum(xs), xs.double().sum(dim=0).float(), "colsum %dx%d" % (Pp, C), 1e-5)
     # softmax backward
     P = torch.softmax(torch.randn((9, 20), generator=gen), dim=1)
     dP = torch.randn((9, 20), generator=gen)

@@ -3,8 +3,9 @@
 The reference selects its networks by name through two factories, ``models.networks.define_Flow`` (YAML
 ``network_G.which_model_G``) and ``models.networks.find_vqgan`` (``network_VQGAN.type``)
 (code/models/networks.py:28-53, called from VQLLFLOWD_model.py:28-40), and calls the DCN operator through the
-module-level name ``modulated_deform_conv`` (deformableDecoder_arch.py:151).  ``install()`` rebinds those three
-names; entry points (``infer_unpaired.py``, ``infer_dataset_lol.py``), YAML files, checkpoints and the solver
+module-level name ``modulated_deform_conv`` (deformableDecoder_arch.py:151); stage 3 takes its two loss operators from
+``models.modules.losses.PerceptualNetwork`` and ``models.modules.pytorch_msssim.msssim`` (VQLLFLOWD_model.py:16-17).  ``install()``
+rebinds those names; entry points (``infer_unpaired.py``, ``infer_dataset_lol.py``), YAML files, checkpoints and the solver
 classes stay untouched:
 
     import glare_b200.dropin as dropin
@@ -42,6 +43,12 @@ def find_vqgan(opt):
                            attn_resolutions=o["attn_resolutions"])
 
 
+def PerceptualNetwork():
+    """losses.py:12-18 replacement: no arguments, pretrained torchvision VGG16 weights (or GLARE_VGG16_WEIGHTS), on the GPU"""
+    from . import losses
+    return losses.PerceptualNetwork(pretrained=True).to("cuda")
+
+
 def install(reference_code_dir=None):
     """Rebind the reference's factory / operator names to the glare_b200 implementations.  Returns the patched modules."""
     if reference_code_dir and reference_code_dir not in sys.path:
@@ -60,5 +67,19 @@ def install(reference_code_dir=None):
         dda.DCNv2Pack = modules.DCNv2Pack
         patched.append(dda)
     except Exception:       # the reference module imports its CUDA extension at import time; absence is not fatal here
+        pass
+    try:
+        # stage 3 (VQLLFLOWD_model.py:16-17, 88-90): `from models.modules.losses import l1_loss, PerceptualNetwork` and
+        # `from models.modules.pytorch_msssim import msssim` -- the two loss operators with a gradient for the reconstruction
+        from . import losses
+        ref_losses = importlib.import_module("models.modules.losses")
+        ref_msssim = importlib.import_module("models.modules.pytorch_msssim")
+        ref_losses.PerceptualNetwork = PerceptualNetwork
+        ref_msssim.msssim = losses.msssim
+        patched += [ref_losses, ref_msssim]
+        m = sys.modules.get("models.VQLLFLOWD_model")
+        if m is not None:
+            m.PerceptualNetwork, m.msssim = PerceptualNetwork, losses.msssim
+    except Exception:       # lpips / torchvision missing: the inference entry points do not need the losses
         pass
     return patched

@@ -8,8 +8,10 @@ reference's ``total_loss.backward()`` runs unchanged on top of them.  The VGG co
 tape as the encoder / decoder training code (its weights are frozen: no weight gradients); the SSIM levels are csrc/loss.cu.  ReLU, max-pool
 and avg_pool2d between them are torch elementwise ops on the same stream.
 
-The reference constructs ``vgg16(pretrained=True)`` (a download); there is no network here, so PerceptualNetwork takes a state dict with
-torchvision's keys (``features.N.weight`` or ``N.weight``) and otherwise initialises like torchvision's ``vgg16(weights=None)``.
+The reference constructs ``vgg16(pretrained=True)`` (a download).  PerceptualNetwork takes the weights as a state dict with torchvision's
+keys (``features.N.weight`` or ``N.weight``), from the file named by GLARE_VGG16_WEIGHTS, or -- ``pretrained=True``, what the drop-in binding
+uses -- from torchvision like the reference; otherwise it initialises like torchvision's ``vgg16(weights=None)`` (tests and the bench: there
+is no network on the build / GPU boxes).
 """
 import ctypes
 import math
@@ -216,8 +218,14 @@ class PerceptualNetwork(nn.Module):
     """losses.py:12-40.  ``vgg_model`` holds the seven conv layers of torchvision's vgg16.features[:16] under the reference's keys
     (``vgg_model.<idx>.weight``), frozen."""
 
-    def __init__(self, state_dict=None, leaves=None):
+    def __init__(self, state_dict=None, leaves=None, pretrained=False):
         super().__init__()
+        import os
+        if state_dict is None and os.environ.get("GLARE_VGG16_WEIGHTS"):
+            state_dict = torch.load(os.environ["GLARE_VGG16_WEIGHTS"], map_location="cpu")       # torchvision's vgg16 state dict
+        # pretrained=True: torchvision's weights, the reference's own source (losses.py:15) -- fetched at the first loss evaluation, not at
+        # construction: the reference builds this module for inference too (VQLLFLOWD_model.py:89), where it is never called
+        self._fetch_pretrained = state_dict is None and pretrained
         self.vgg_model = nn.Module()
         for idx, ci, co in VGG_CONVS:
             m = nn.Module()
@@ -247,6 +255,11 @@ class PerceptualNetwork(nn.Module):
         return self._leaves
 
     def _sd(self):
+        if self._fetch_pretrained:
+            from torchvision.models import vgg16
+            sd = {k: v for k, v in vgg16(pretrained=True).features.state_dict().items() if int(k.split(".")[0]) < 16}
+            self.vgg_model.load_state_dict(sd, strict=True)
+            self._fetch_pretrained = False
         return {k: v.detach() for k, v in self.vgg_model.state_dict().items()}
 
     @torch.no_grad()

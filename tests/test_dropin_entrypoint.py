@@ -70,6 +70,9 @@ def test_infer_unpaired_main_through_dropin(tmp_path, sd_g, sd_v, monkeypatch):
     import models.networks as networks
     import models.modules.deformableDecoder_arch as dda
     saved = (networks.define_Flow, networks.find_vqgan, dda.modulated_deform_conv, dda.DCNv2Pack)
+    import models.modules.losses as ref_losses
+    import models.modules.pytorch_msssim as ref_msssim
+    saved_losses = (ref_losses.PerceptualNetwork, ref_msssim.msssim)
     cwd = os.getcwd()
     try:
         dropin.install()
@@ -87,6 +90,10 @@ def test_infer_unpaired_main_through_dropin(tmp_path, sd_g, sd_v, monkeypatch):
     finally:
         os.chdir(cwd)
         networks.define_Flow, networks.find_vqgan, dda.modulated_deform_conv, dda.DCNv2Pack = saved
+        ref_losses.PerceptualNetwork, ref_msssim.msssim = saved_losses
+        vm = sys.modules.get("models.VQLLFLOWD_model")
+        if vm is not None:
+            vm.PerceptualNetwork, vm.msssim = saved_losses
     out_path = os.path.join(tmp, "results-unpair", "LOL", "t", "a.png")
     assert os.path.exists(out_path)
     got = cv2.imread(out_path)[:, :, ::-1]

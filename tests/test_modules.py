@@ -71,6 +71,9 @@ def test_dropin_rebinds_reference_factories(sd_g, sd_v):
     saved = (networks.define_Flow, networks.find_vqgan)
     import models.modules.deformableDecoder_arch as dda
     saved_dcn = (dda.modulated_deform_conv, dda.DCNv2Pack)
+    import models.modules.losses as ref_losses
+    import models.modules.pytorch_msssim as ref_msssim
+    saved_losses = (ref_losses.PerceptualNetwork, ref_msssim.msssim)
     try:
         dropin.install()
         opt = ref_shims.parse_opt("LOL.yml")
@@ -80,9 +83,14 @@ def test_dropin_rebinds_reference_factories(sd_g, sd_v):
         netG.load_state_dict(sd_g, strict=True)
         net_hq.load_state_dict(sd_v, strict=True)
         assert dda.modulated_deform_conv is modules.modulated_deform_conv
+        assert not any(p.requires_grad for p in netG.RRDB.parameters()) and not any(p.requires_grad for p in netG.flowUpsamplerNet.parameters())
+        assert all(p.requires_grad for p in netG.deformable_decoder.parameters())          # VQLLFLOWDeformable_arch.py:49-52
+        from glare_b200 import losses
+        assert ref_msssim.msssim is losses.msssim and ref_losses.PerceptualNetwork is dropin.PerceptualNetwork
     finally:
         networks.define_Flow, networks.find_vqgan = saved
         dda.modulated_deform_conv, dda.DCNv2Pack = saved_dcn
+        ref_losses.PerceptualNetwork, ref_msssim.msssim = saved_losses
 
 
 def test_deform_conv_ext_shim_exports_the_reference_plugin_surface():

@@ -412,7 +412,11 @@ def main():
 
     alt = None
     if not args.no_alt and args.dense in ("auto", "tc-bf16x3"):
-        alt = alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, eng, quick=args.quick_alt)
+        try:
+            alt = alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, eng, quick=args.quick_alt)
+        except Exception as exc:                       # the headline line must survive a failure in the side measurements
+            import traceback
+            alt = {"error": "%s: %s" % (type(exc).__name__, exc), "traceback": traceback.format_exc()[-1500:]}
 
     if rank == 0:
         pk = peaks()

@@ -14,6 +14,7 @@ STATUS (round 2): green on B200 (tests/test_zz_flow_train_gpu.py, profiles/r41_t
 profiles/r40_train_probe*.txt).
 """
 import ctypes
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -35,16 +36,19 @@ _NO_CACHE = False          # set while a training step is being captured into a 
 
 
 def _flipped_transposed(w):
-    """[Co,Ci,k,k] -> [Ci,Co,k,k] with the taps reversed; cached per weight version so that the conv path's packed-weight cache (keyed on the
-    tensor it is given) does not grow with every training step"""
+    """[Co,Ci,k,k] -> [Ci,Co,k,k] with the taps reversed; one cached copy per weight (storage address, shape), REPLACED when the optimizer's
+    in-place update moves the tensor's version -- keying on the version kept a flipped copy (and, through it, a packed operand copy in the
+    conv path's cache) of every weight per training step: 0.18 GB per stage-2 step until the table was cleared"""
     if _NO_CACHE:
         return w.flip(2, 3).transpose(0, 1).contiguous()
-    key = (w.data_ptr(), w._version, tuple(w.shape))
-    if key not in _WT:
-        if len(_WT) > 4096:
-            _WT.clear()
-        _WT[key] = (w, w.flip(2, 3).transpose(0, 1).contiguous())
-    return _WT[key][1]
+    key = (w.data_ptr(), tuple(w.shape))
+    ent = _WT.get(key)
+    if ent is None or ent[0]() is not w or ent[1] != w._version:
+        if ent is None and len(_WT) > 1024:
+            for k in [k for k, e in _WT.items() if e[0]() is None]:
+                del _WT[k]
+        ent = _WT[key] = (weakref.ref(w), w._version, w.flip(2, 3).transpose(0, 1).contiguous())
+    return ent[2]
 
 
 class CudaLeaves:

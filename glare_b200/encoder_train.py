@@ -75,8 +75,7 @@ class CudaLeaves:
         return self.dense.conv2d(x, w, b, stride=1, padding=w.shape[2] // 2, gn_stats=False).float()   # the tape's Normalize takes its own statistics
 
     def conv_down(self, x, w, b=None):
-        y = self.dense.downsample_conv(x, w, b, gn_stats=False)
-        return (y if y is not None else F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)).float()
+        return self.dense.downsample_conv(x, w, b, gn_stats=False).float()          # shapes outside the kernel's coverage raise (no library path)
 
     def attention(self, q, k, v):
         # exact softmax: the fused-softmax fast path relies on a device flag the caller must read and act on (engine.infer does); a training

@@ -37,3 +37,29 @@ for i in range(14):
     torch.cuda.synchronize(); t.append(time.perf_counter())
     print("step %2d: vqgan encode %.1f | objective + gradients %.1f | backward() %.1f | Adam %.1f | total %.1f ms   mem %.1f GB" %
           tuple([i] + [1e3 * (b - a) for a, b in zip(t, t[1:])] + [1e3 * (t[-1] - t[0]), torch.cuda.memory_allocated() / 2 ** 30]), flush=True)
+
+# the same step without host synchronisation (what bench.py times), one event per step
+import gc  # noqa: E402
+
+
+def step():
+    optim.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        encoder_gt, _ = net_hq.encode(real_H)
+    _, nll, _ = netG(gt=encoder_gt.detach(), lr=var_L, reverse=False)
+    nll.mean().backward()
+    optim.step()
+
+
+for label, before in (("as is", lambda: None), ("gc disabled", gc.disable)):
+    before()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(13)]
+    t0 = time.perf_counter()
+    evs[0].record()
+    for i in range(12):
+        step()
+        evs[i + 1].record()
+    host = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    print("unsynchronised, %s: per-step device ms %s | host issue time %.1f ms per step" %
+          (label, [round(evs[i].elapsed_time(evs[i + 1]), 1) for i in range(12)], 1e3 * host / 12), flush=True)

@@ -129,6 +129,9 @@ class DeformableDecoderFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_rec):
+        if ctx.trainer is None:
+            raise RuntimeError("Trying to backward through the deformable decoder a second time: its tape is freed by the first backward pass "
+                               "(the reference's optimize_parameters calls backward once per forward)")
         with torch.no_grad():
             grads = ctx.trainer.backward(g_rec)
         ctx.trainer = None

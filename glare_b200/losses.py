@@ -126,6 +126,8 @@ class MsssimFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
+        if ctx.tape is None:
+            raise RuntimeError("Trying to backward through msssim a second time: its saved levels are freed by the first backward pass")
         dx = None
         for lvl in reversed(range(len(ctx.tape))):
             x, y, win, C1, C2, n_pos = ctx.tape[lvl]
@@ -208,6 +210,8 @@ class PerceptualFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
+        if ctx.graph is None:
+            raise RuntimeError("Trying to backward through the perceptual loss a second time: its tape is freed by the first backward pass")
         with torch.no_grad():
             gx = ctx.graph.backward([s * g_out.float() for s in ctx.seeds])
         ctx.graph = ctx.seeds = None

@@ -66,6 +66,16 @@ def test_decoder_autograd_node_fills_param_grads(sd_g):
         ref = sda[k].grad
         assert float((params[k].grad - ref).abs().max()) <= 1e-3 * float(ref.abs().max()) + 1e-8, k
     assert params["deformable_decoder.conv_out.weight"].grad is None
+    # loss scaling (GradScaler, VQLLFLOWD_model.py:226) is linear in the gradients; a second backward through the freed tape is refused
+    for p in params.values():
+        p.grad = None
+    rec = decoder_train.deformable_decoder(params.items(), z, vq, mid, TorchLeaves())
+    loss = (rec.clamp(0, 1) - gt).abs().mean() * 1024.0
+    loss.backward(retain_graph=True)
+    k = "deformable_decoder.up.0.block.2.conv2.weight"
+    assert float((params[k].grad / 1024.0 - sda[k].grad).abs().max()) <= 1e-3 * float(sda[k].grad.abs().max())
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
 
 
 def test_stage3_evaluation_matches_the_reference_golden(sd_g, sd_v):

@@ -58,6 +58,11 @@ SIGNATURES = {
     "glare_ssim_partials": [_i, _i, _i, _i],
     "glare_ssim_fwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp],
     "glare_ssim_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "glare_relu_f32": [_vp, _vp, _ll, _vp, _vp],
+    "glare_maxpool2_nhwc_f32": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "glare_maxpool2_nhwc_bwd_f32": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "glare_avgpool2_f32": [_vp, _ll, _i, _i, _vp, _vp],
+    "glare_up2_nhwc_f32": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_aft_axpby_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp, _vp],
     "glare_aft_cat_operand": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "glare_preprocess_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],

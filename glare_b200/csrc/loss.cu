@@ -169,6 +169,121 @@ __global__ void __launch_bounds__(T* T) ssim_bwd_apply_kernel(const float* __res
     dx[p] = v;
 }
 
+// ---- elementwise / pooling pieces between the convolutions of the stage-3 step (VGG16 features, Upsample, MS-SSIM pyramid) -----------------
+// 256 threads, grid-stride; NHWC tensors are walked as float4 over the channels (C % 4 == 0).
+
+__global__ void __launch_bounds__(256) relu_fwd_kernel(const float4* __restrict__ x, long long n4, float4* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 v = x[i];
+        y[i] = make_float4(v.x > 0.f ? v.x : 0.f, v.y > 0.f ? v.y : 0.f, v.z > 0.f ? v.z : 0.f, v.w > 0.f ? v.w : 0.f);
+    }
+}
+
+// gx = gy where the forward OUTPUT is positive (nn.ReLU backward)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ gy, long long n4,
+                                                       float4* __restrict__ gx) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 v = y[i], g = gy[i];
+        gx[i] = make_float4(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f, v.z > 0.f ? g.z : 0.f, v.w > 0.f ? g.w : 0.f);
+    }
+}
+
+__device__ __forceinline__ void pool_pick(float v, int k, float& best, unsigned& which) {
+    if (v > best || v != v) {            // strictly greater (the first maximum wins, like ATen's max_pool2d scan order); NaN propagates
+        best = v;
+        which = (unsigned)k;
+    }
+}
+
+// nn.MaxPool2d(2, 2) on NHWC: y [B][H/2][W/2][C]; idx: one byte per element (0..3 = position in the 2 x 2 window, row-major), packed 4 per word
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float4* __restrict__ x, int H, int W, int C4, long long n_out4,
+                                                           float4* __restrict__ y, unsigned* __restrict__ idx) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_out4; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % C4);
+        long long r = i / C4;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho);
+        const long long b = r / Ho;
+        const long long base = ((b * H + 2 * oy) * W + 2 * ox) * C4 + c;
+        float4 best = x[base];
+        unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const float4 v = x[base + ((long long)(k >> 1) * W + (k & 1)) * C4];
+            pool_pick(v.x, k, best.x, w0);
+            pool_pick(v.y, k, best.y, w1);
+            pool_pick(v.z, k, best.z, w2);
+            pool_pick(v.w, k, best.w, w3);
+        }
+        y[i] = best;
+        idx[i] = w0 | (w1 << 8) | (w2 << 16) | (w3 << 24);
+    }
+}
+
+// gx [B][H][W][C]: the pooled gradient routed to the recorded position, zero elsewhere (rows / columns past 2 * (H / 2) are the caller's zeros)
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float4* __restrict__ gy, const unsigned* __restrict__ idx, int H, int W, int C4,
+                                                           long long n_out4, float4* __restrict__ gx) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_out4; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % C4);
+        long long r = i / C4;
+        const int ox = (int)(r % Wo);
+        r /= Wo;
+        const int oy = (int)(r % Ho);
+        const long long b = r / Ho;
+        const long long base = ((b * H + 2 * oy) * W + 2 * ox) * C4 + c;
+        const float4 g = gy[i];
+        const unsigned w = idx[i];
+#pragma unroll
+        for (unsigned k = 0; k < 4; ++k)
+            gx[base + ((long long)(k >> 1) * W + (k & 1)) * C4] =
+                make_float4((w & 255u) == k ? g.x : 0.f, ((w >> 8) & 255u) == k ? g.y : 0.f, ((w >> 16) & 255u) == k ? g.z : 0.f, (w >> 24) == k ? g.w : 0.f);
+    }
+}
+
+// F.avg_pool2d(x, (2, 2)) on [planes][H][W] (the MS-SSIM pyramid, pytorch_msssim/__init__.py:83-84)
+__global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ x, int H, int W, long long n_out, float* __restrict__ y) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_out; i += (long long)gridDim.x * 256) {
+        const int ox = (int)(i % Wo);
+        const long long r = i / Wo;
+        const int oy = (int)(r % Ho);
+        const float* p = x + ((r / Ho) * H + 2 * oy) * W + 2 * ox;
+        y[i] = (p[0] + p[1] + p[W] + p[W + 1]) * 0.25f;
+    }
+}
+
+// nearest x2 on NHWC (Upsample.forward, encoder_decoder.py:46-48): adjoint = 0 -> y [B][2H][2W][C] = x; adjoint = 1 -> y [B][H][W][C] = the 2 x 2
+// sums of x [B][2H][2W][C]
+__global__ void __launch_bounds__(256) up2_kernel(const float4* __restrict__ x, int H, int W, int C4, long long n4, int adjoint, float4* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % C4);
+        long long r = i / C4;
+        const int px = (int)(r % W);
+        r /= W;
+        const int py = (int)(r % H);
+        const long long b = r / H;
+        const long long big = ((b * 2 * H + 2 * py) * 2 * W + 2 * px) * C4 + c;
+        if (!adjoint) {
+            const float4 v = x[i];
+            y[big] = v;
+            y[big + C4] = v;
+            y[big + 2LL * W * C4] = v;
+            y[big + 2LL * W * C4 + C4] = v;
+        } else {
+            const float4 a = x[big], b2 = x[big + C4], c2 = x[big + 2LL * W * C4], d = x[big + 2LL * W * C4 + C4];
+            y[i] = make_float4((a.x + b2.x) + (c2.x + d.x), (a.y + b2.y) + (c2.y + d.y), (a.z + b2.z) + (c2.z + d.z), (a.w + b2.w) + (c2.w + d.w));
+        }
+    }
+}
+
+inline unsigned ew_grid(long long n) {
+    long long g = (n + 255) / 256;
+    return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
 bool make_window(int ws, const float* g, Win* w) {
     if (ws < 1 || ws > MAXW || g == nullptr) return false;
     for (int i = 0; i < MAXW; ++i) w->g[i] = i < ws ? g[i] : 0.f;
@@ -205,6 +320,64 @@ GLARE_API int glare_ssim_bwd_f32(const float* x, const float* y, int planes, int
     LS_LAUNCH(ssim_bwd_maps_kernel, dim3((Wo + T - 1) / T, (Ho + T - 1) / T, planes), T * T, stream, x, y, H, W, ws, w, C1, C2, coef, g_mu, g_e11, g_e12);
     GLARE_CHECK_LAUNCH();
     LS_LAUNCH(ssim_bwd_apply_kernel, dim3((W + T - 1) / T, (H + T - 1) / T, planes), T * T, stream, x, y, H, W, ws, w, g_mu, g_e11, g_e12, coarse, dx);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// ---- elementwise / pooling entry points (section 8b of include/glare_b200.h) ---------------------------------------------------------------
+GLARE_API int glare_relu_f32(const float* x, const float* gy, long long n, float* out, cudaStream_t stream) {
+    if (n < 0 || (n & 3)) return GLARE_ERR_BAD_ARG;
+    if (n == 0) return GLARE_OK;
+    if (!x || !out) return GLARE_ERR_BAD_ARG;
+    if (gy == nullptr)
+        LS_LAUNCH(relu_fwd_kernel, dim3(ew_grid(n / 4)), 256, stream, reinterpret_cast<const float4*>(x), n / 4, reinterpret_cast<float4*>(out));
+    else
+        LS_LAUNCH(relu_bwd_kernel, dim3(ew_grid(n / 4)), 256, stream, reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gy), n / 4,
+                  reinterpret_cast<float4*>(out));
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+GLARE_API int glare_maxpool2_nhwc_f32(const float* x, int B, int H, int W, int C, float* y, void* idx, cudaStream_t stream) {
+    if (B < 0 || H < 2 || W < 2 || C <= 0 || (C & 3)) return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!x || !y || !idx) return GLARE_ERR_BAD_ARG;
+    const long long n = (long long)B * (H / 2) * (W / 2) * (C / 4);
+    LS_LAUNCH(maxpool2_fwd_kernel, dim3(ew_grid(n)), 256, stream, reinterpret_cast<const float4*>(x), H, W, C / 4, n, reinterpret_cast<float4*>(y),
+              reinterpret_cast<unsigned*>(idx));
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+GLARE_API int glare_maxpool2_nhwc_bwd_f32(const float* gy, const void* idx, int B, int H, int W, int C, float* gx, cudaStream_t stream) {
+    if (B < 0 || H < 2 || W < 2 || C <= 0 || (C & 3)) return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!gy || !gx || !idx) return GLARE_ERR_BAD_ARG;
+    if ((H | W) & 1) GLARE_CUDA(cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)B * H * W * C, stream));
+    const long long n = (long long)B * (H / 2) * (W / 2) * (C / 4);
+    LS_LAUNCH(maxpool2_bwd_kernel, dim3(ew_grid(n)), 256, stream, reinterpret_cast<const float4*>(gy), reinterpret_cast<const unsigned*>(idx), H, W, C / 4, n,
+              reinterpret_cast<float4*>(gx));
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+GLARE_API int glare_avgpool2_f32(const float* x, long long planes, int H, int W, float* y, cudaStream_t stream) {
+    if (planes < 0 || H < 2 || W < 2) return GLARE_ERR_BAD_ARG;
+    if (planes == 0) return GLARE_OK;
+    if (!x || !y) return GLARE_ERR_BAD_ARG;
+    const long long n = planes * (H / 2) * (W / 2);
+    LS_LAUNCH(avgpool2_kernel, dim3(ew_grid(n)), 256, stream, x, H, W, n, y);
+    GLARE_CHECK_LAUNCH();
+    return GLARE_OK;
+}
+
+// x NHWC; H, W: the SMALL tensor's size.  adjoint = 0: x [B][H][W][C] -> y [B][2H][2W][C]; adjoint = 1: x [B][2H][2W][C] -> y [B][H][W][C]
+GLARE_API int glare_up2_nhwc_f32(const float* x, int B, int H, int W, int C, int adjoint, float* y, cudaStream_t stream) {
+    if (B < 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return GLARE_ERR_BAD_ARG;
+    if (B == 0) return GLARE_OK;
+    if (!x || !y) return GLARE_ERR_BAD_ARG;
+    const long long n = (long long)B * H * W * (C / 4);
+    LS_LAUNCH(up2_kernel, dim3(ew_grid(n)), 256, stream, reinterpret_cast<const float4*>(x), H, W, C / 4, n, adjoint, reinterpret_cast<float4*>(y));
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
 }

@@ -9,7 +9,6 @@ block-level backward rules in plain Python shared by every backend (tests/test_d
 torch autograd of the oracle and of the reference's own module).
 """
 import torch
-import torch.nn.functional as F
 
 from .encoder_train import BlockGraph
 
@@ -72,9 +71,7 @@ class DecoderTrainer(BlockGraph):
 
     def _upsample(self, p, i):
         """Upsample.forward   encoder_decoder.py:46-50: nearest x2, then the 3x3 conv"""
-        B, C, H, W = self.vals[i].shape
-        up = self._fn(F.interpolate(self.vals[i], scale_factor=2.0, mode="nearest"), (i,),
-                      lambda gy: (gy.reshape(B, C, H, 2, W, 2).sum(dim=(3, 5)),))
+        up = self._fn(self.L.up2(self.vals[i]), (i,), lambda gy: (self.L.up2_adjoint(gy),))
         return self._conv(p + ".conv", up)
 
     # ------------------------------------------------------------------ forward / backward

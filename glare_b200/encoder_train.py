@@ -162,6 +162,55 @@ class CudaLeaves:
         from .dcn_backward import dcn_backward
         return dcn_backward(x, offset, mask, w, gy, dg, True)
 
+    # elementwise / pooling pieces of the stage-3 step (csrc/loss.cu); logical NCHW in and out, NHWC underneath
+    def relu(self, x):
+        xn = _nhwc(x)
+        y = torch.empty_like(xn)
+        self._call("glare_relu_f32", self._p(xn), None, xn.numel(), self._p(y))
+        return _nchw(y)
+
+    def relu_bwd(self, y, gy):
+        yn, gn = _nhwc(y), _nhwc(gy)
+        gx = torch.empty_like(yn)
+        self._call("glare_relu_f32", self._p(yn), self._p(gn), yn.numel(), self._p(gx))
+        return _nchw(gx)
+
+    def maxpool2(self, x):
+        xn = _nhwc(x)
+        B, H, W, C = xn.shape
+        y = torch.empty((B, H // 2, W // 2, C), device=xn.device, dtype=torch.float32)
+        idx = torch.empty((B, H // 2, W // 2, C), device=xn.device, dtype=torch.uint8)
+        self._call("glare_maxpool2_nhwc_f32", self._p(xn), B, H, W, C, self._p(y), self._p(idx))
+        return _nchw(y), (idx, (B, H, W, C))
+
+    def maxpool2_bwd(self, gy, saved):
+        idx, (B, H, W, C) = saved
+        gn = _nhwc(gy)                                                         # held until the call is issued
+        gx = torch.empty((B, H, W, C), device=gy.device, dtype=torch.float32)
+        self._call("glare_maxpool2_nhwc_bwd_f32", self._p(gn), self._p(idx), B, H, W, C, self._p(gx))
+        return _nchw(gx)
+
+    def avgpool2(self, x):
+        x = x.float().contiguous()                                            # [B][C][H][W] planes
+        B, C, H, W = x.shape
+        y = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=torch.float32)
+        self._call("glare_avgpool2_f32", self._p(x), B * C, H, W, self._p(y))
+        return y
+
+    def up2(self, x):
+        xn = _nhwc(x)
+        B, H, W, C = xn.shape
+        y = torch.empty((B, 2 * H, 2 * W, C), device=xn.device, dtype=torch.float32)
+        self._call("glare_up2_nhwc_f32", self._p(xn), B, H, W, C, 0, self._p(y))
+        return _nchw(y)
+
+    def up2_adjoint(self, gy):
+        gn = _nhwc(gy)
+        B, H2, W2, C = gn.shape
+        gx = torch.empty((B, H2 // 2, W2 // 2, C), device=gn.device, dtype=torch.float32)
+        self._call("glare_up2_nhwc_f32", self._p(gn), B, H2 // 2, W2 // 2, C, 1, self._p(gx))
+        return _nchw(gx)
+
     # memory-bound kernels
     def im2col(self, x_nhwc, k, stride, pad, Ho, Wo):
         B, H, W, C = x_nhwc.shape

@@ -5,8 +5,8 @@
 
 Both are single autograd nodes with a gradient for the FIRST image only (the reconstruction; the second is the ground truth), so the
 reference's ``total_loss.backward()`` runs unchanged on top of them.  The VGG convolutions run on the tensor-core conv path through the same
-tape as the encoder / decoder training code (its weights are frozen: no weight gradients); the SSIM levels are csrc/loss.cu.  ReLU, max-pool
-and avg_pool2d between them are torch elementwise ops on the same stream.
+tape as the encoder / decoder training code (its weights are frozen: no weight gradients); the SSIM levels, ReLU, max-pool and the
+avg_pool2d pyramid are csrc/loss.cu.
 
 The reference constructs ``vgg16(pretrained=True)`` (a download).  PerceptualNetwork takes the weights as a state dict with torchvision's
 keys (``features.N.weight`` or ``N.weight``), from the file named by GLARE_VGG16_WEIGHTS, or -- ``pretrained=True``, what the drop-in binding
@@ -18,7 +18,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .encoder_train import BlockGraph
 
@@ -65,6 +64,12 @@ class SsimKernels:
                    self._p(part))
         s = part.double().sum(dim=0)
         return s[0], s[1]
+
+    def avgpool2(self, x):
+        B, C, H, W = x.shape
+        y = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=torch.float32)
+        self._call("glare_avgpool2_f32", self._p(x), B * C, H, W, self._p(y))
+        return y
 
     def bwd(self, x, y, win, C1, C2, coef, coarse):
         B, C, H, W = x.shape
@@ -113,7 +118,7 @@ class MsssimFn(torch.autograd.Function):
             sims.append(s_ss / n_pos)
             tape.append((x, y, win, C1, C2, n_pos))
             if lvl + 1 < levels:
-                x, y = F.avg_pool2d(x, (2, 2)), F.avg_pool2d(y, (2, 2))    # :83-84
+                x, y = kernels.avgpool2(x), kernels.avgpool2(y)            # :83-84
         with torch.enable_grad():
             cs_t = torch.stack(css).float().requires_grad_(True)
             ss_t = torch.stack(sims).float().requires_grad_(True)
@@ -169,14 +174,13 @@ class VGGGraph(BlockGraph):
             if idx in convs:
                 h = self._conv(str(idx), h, need_gx=True, need_gw=False)
             elif idx in VGG_POOLS:
-                xin = self.vals[h]
-                y, where = F.max_pool2d(xin, 2, 2, return_indices=True)
-                self.switches.append(where)
-                h = self._fn(y, (h,), lambda gy, where=where, shape=xin.shape: (F.max_unpool2d(gy, where, 2, 2, output_size=shape[2:]),))
+                y, saved = self.L.maxpool2(self.vals[h])
+                self.switches.append(saved[0])
+                h = self._fn(y, (h,), lambda gy, saved=saved: (self.L.maxpool2_bwd(gy, saved),))
             else:
-                y = F.relu(self.vals[h])
+                y = self.L.relu(self.vals[h])
                 self.switches.append(y)
-                h = self._fn(y, (h,), lambda gy, y=y: (gy * (y > 0),))
+                h = self._fn(y, (h,), lambda gy, y=y: (self.L.relu_bwd(y, gy),))
                 if idx in VGG_TAPS:
                     taps.append(h)
         self.taps = taps

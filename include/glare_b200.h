@@ -284,6 +284,20 @@ int glare_ssim_fwd_f32(const float* x, const float* y, int planes, int H, int W,
 int glare_ssim_bwd_f32(const float* x, const float* y, int planes, int H, int W, int ws, const float* window_host, float C1, float C2,
                        const float* coef, float* g_mu, float* g_e11, float* g_e12, const float* coarse, float* dx, cudaStream_t stream);
 
+/* (8b) The elementwise / pooling pieces between the convolutions of the stage-3 step, fp32, NHWC tensors with C % 4 == 0:
+ *   glare_relu_f32            gy == NULL: out = max(x, 0) (nn.ReLU of vgg16.features);  gy != NULL: out = gy where x > 0 (x = the forward OUTPUT)
+ *   glare_maxpool2_nhwc_f32   nn.MaxPool2d(2, 2): y [B][H/2][W/2][C], idx = one byte per output element (position 0..3 in the window;
+ *                             the first maximum wins, NaN propagates), B * (H/2) * (W/2) * C bytes
+ *   glare_maxpool2_nhwc_bwd_f32  gx [B][H][W][C] = gy routed to the recorded positions, zero elsewhere
+ *   glare_avgpool2_f32        F.avg_pool2d(x, (2, 2)) on [planes][H][W] (pytorch_msssim/__init__.py:83-84)
+ *   glare_up2_nhwc_f32        nearest x2 of Upsample.forward (encoder_decoder.py:46-48) on [B][H][W][C] (adjoint = 0) and its adjoint, the
+ *                             2 x 2 sums of [B][2H][2W][C] (adjoint = 1); H, W are the small tensor's size in both directions */
+int glare_relu_f32(const float* x, const float* gy, long long n, float* out, cudaStream_t stream);
+int glare_maxpool2_nhwc_f32(const float* x, int B, int H, int W, int C, float* y, void* idx, cudaStream_t stream);
+int glare_maxpool2_nhwc_bwd_f32(const float* gy, const void* idx, int B, int H, int W, int C, float* gx, cudaStream_t stream);
+int glare_avgpool2_f32(const float* x, long long planes, int H, int W, float* y, cudaStream_t stream);
+int glare_up2_nhwc_f32(const float* x, int B, int H, int W, int C, int adjoint, float* y, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

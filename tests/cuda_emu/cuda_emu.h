@@ -42,6 +42,8 @@ struct dim3 {
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
+static inline int cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
+
 namespace glare_emu {
 struct WarpState {
     uint32_t buf[32];

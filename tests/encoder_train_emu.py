@@ -24,6 +24,29 @@ class TorchLeaves:
     def colsum(self, x):
         return x.sum(dim=0)
 
+    def relu(self, x):
+        return F.relu(x)
+
+    def relu_bwd(self, y, gy):
+        return gy * (y > 0)
+
+    def maxpool2(self, x):
+        y, where = F.max_pool2d(x, 2, 2, return_indices=True)
+        return y, (where, x.shape)
+
+    def maxpool2_bwd(self, gy, saved):
+        return F.max_unpool2d(gy, saved[0], 2, 2, output_size=saved[1][2:])
+
+    def avgpool2(self, x):
+        return F.avg_pool2d(x, (2, 2))
+
+    def up2(self, x):
+        return F.interpolate(x, scale_factor=2.0, mode="nearest")
+
+    def up2_adjoint(self, gy):
+        B, C, H2, W2 = gy.shape
+        return gy.reshape(B, C, H2 // 2, 2, W2 // 2, 2).sum(dim=(3, 5))
+
     def dcn_fwd(self, x, offmask_raw, w, b, dg):
         from torchvision.ops import deform_conv2d
         n_off = offmask_raw.shape[1] // 3 * 2

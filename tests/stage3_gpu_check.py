@@ -69,6 +69,9 @@ def main():
         gc, gg = losses.VGGGraph(TorchLeaves(), vsd), losses.VGGGraph(leaves, {k: v.to(dev) for k, v in vsd.items()})
         fc, fg = gc.forward(sr), gg.forward(sr.to(dev))
         for sc, sg in zip(gc.switches, gg.switches):
+            if sg.dtype == torch.uint8:                   # pooling choice: ATen's flat input index -> the kernel's position code, NHWC
+                w_in = 2 * sc.shape[3]
+                sc = (((sc // w_in) % 2) * 2 + (sc % w_in) % 2).permute(0, 2, 3, 1).to(torch.uint8)
             sg.copy_(sc.to(dev))
         seeds = [torch.randn(f.shape, generator=torch.Generator().manual_seed(i)) for i, f in enumerate(fc)]
         xc, xg = gc.backward(seeds), gg.backward([t.to(dev) for t in seeds])

@@ -115,6 +115,40 @@ def test_msssim_kernel_source_on_the_host(shape, normalize, val_range):
     assert float((a.grad - b.grad).abs().max()) <= 2e-4 * float(b.grad.abs().max()), float((a.grad - b.grad).abs().max())
 
 
+def test_elementwise_kernel_source_on_the_host():
+    """ReLU / MaxPool2d(2,2) / avg_pool2d / nearest x2 and their backward rules (csrc/loss.cu on the host) against the torch restatements,
+    including odd sizes and ties (all-zero windows after a ReLU: the first position wins, like ATen)"""
+    from glare_b200 import _lib, encoder_train
+    host = _host_lib()
+
+    class HostLeaves(encoder_train.CudaLeaves):
+        def __init__(self):
+            pass
+
+        def _call(self, name, *args):
+            fn = getattr(host, name)
+            fn.argtypes, fn.restype = _lib.SIGNATURES[name], ctypes.c_int
+            assert fn(*args, None) == 0, name
+
+    H, T = HostLeaves(), TorchLeaves()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 8, 7, 10), generator=g)
+    x[0, :, 2:4, 4:6] = 0.0                                                # a tie
+    gy = torch.randn(x.shape, generator=g)
+    y = H.relu(x)
+    assert torch.equal(y, T.relu(x)) and torch.equal(H.relu_bwd(y, gy), T.relu_bwd(y, gy))
+    for xin in (x, T.relu(x)):
+        (yp, saved_h), (yt, saved_t) = H.maxpool2(xin), T.maxpool2(xin)
+        assert torch.equal(yp, yt)
+        gp = torch.randn(yt.shape, generator=g)
+        assert torch.equal(H.maxpool2_bwd(gp, saved_h), T.maxpool2_bwd(gp, saved_t))
+    assert torch.allclose(H.avgpool2(x), T.avgpool2(x), atol=1e-7)
+    up = H.up2(x)
+    assert torch.equal(up, T.up2(x))
+    gu = torch.randn(up.shape, generator=g)
+    assert torch.allclose(H.up2_adjoint(gu), T.up2_adjoint(gu), atol=1e-6)
+
+
 def test_msssim_argument_checks():
     from glare_b200 import losses
     sr, gt = _images(1, 40, 36)

@@ -223,6 +223,14 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
             "algorithmic_tflop_per_step": 12.6, "achieved_tflops_per_gpu": 12.6 / (ms_t / 1e3), "frac_of_bf16_peak": 12.6 / (ms_t / 1e3) / pk["tensor"],
             "nll_last": [round(float(v), 4) for v in last["nll"].cpu()],
             "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else None}
+        # the same step with bf16 tensor-core operands (the precision configs[3] names): convolutions, attention GEMMs and weight gradients on
+        # single-piece bf16 operands, fp32 accumulation, fp32 memory-bound kernels and optimizer
+        netG.dense_name, netG._train_ctx = "tc-bf16", None
+        ms_tb = timed(train_step, 5, 2)
+        out["stage2_training_step_bf16"] = {
+            "workload": "configs[3] at its named precision: the same stage-2 step with bf16 tensor-core operands", "dtype": "bf16",
+            "value": world * 4 / (ms_tb / 1e3), "unit": "samples/s", "ms_per_step": ms_tb,
+            "nll_last": [round(float(v), 4) for v in last["nll"].cpu()]}
         del netG, optim
         torch.cuda.empty_cache()
         # ---- stage 3 (train_stage3_LOL.yml: batch 2 x 256x256): the call sequence of VQLLFLOWDModel.optimize_parameters

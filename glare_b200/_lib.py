@@ -53,6 +53,7 @@ SIGNATURES = {
     "glare_gn_bwd_nhwc_f32": [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _i, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "glare_im2col_nhwc_f32": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_im2col_t_operand_bf16x3": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "glare_im2col_t_operand_bf16": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "glare_colsum_f32": [_vp, _ll, _i, _vp, _vp],
     "glare_attn_softmax_bwd_f32": [_vp, _vp, _ll, _ll, _i, ctypes.c_float, _vp, _vp],
     "glare_ssim_partials": [_i, _i, _i, _i],

@@ -18,6 +18,8 @@ namespace glare {
 // moved 32 x 32 tiles with 2-byte stores: 147 K CTAs for a 128-channel 256x256 conv, about a tenth of the HBM rate.)
 constexpr int WG_PIX = 256, WG_STRIDE = WG_PIX + WG_PIX / 8 + 1;
 
+// X3 = false: the single-piece bf16 operand (mode 0), out [nch][k*k*C][chunk], pixel j of the chunk at element j.
+template <bool X3>
 __global__ void __launch_bounds__(256) im2col_t_operand_kernel(const float* __restrict__ x, int B, int H, int W, int C, int k, int stride, int pad,
                                                                int Ho, int Wo, long long P, int chunk, long long groups,
                                                                __nv_bfloat16* __restrict__ out) {
@@ -61,15 +63,25 @@ __global__ void __launch_bounds__(256) im2col_t_operand_kernel(const float* __re
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            __nv_bfloat16 a1, a2, b1, b2;
-            split_b3(t[2 * i], a1, a2);
-            split_b3(t[2 * i + 1], b1, b2);
-            hi[i] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-            lo[i] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+            if (X3) {
+                __nv_bfloat16 a1, a2, b1, b2;
+                split_b3(t[2 * i], a1, a2);
+                split_b3(t[2 * i + 1], b1, b2);
+                hi[i] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                lo[i] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+            } else {
+                hi[i] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(t[2 * i])) |
+                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(t[2 * i + 1])) << 16);
+            }
         }
-        __nv_bfloat16* row = out + ((ci * M + (long long)tap * C + c0 + r) * chunk + j0) * 2 + q * 8;
-        *reinterpret_cast<uint4*>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(row + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (X3) {
+            __nv_bfloat16* row = out + ((ci * M + (long long)tap * C + c0 + r) * chunk + j0) * 2 + q * 8;
+            *reinterpret_cast<uint4*>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(row + 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        } else {
+            __nv_bfloat16* row = out + (ci * M + (long long)tap * C + c0 + r) * chunk + j0 + q * 8;
+            *reinterpret_cast<uint4*>(row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        }
     }
 }
 
@@ -77,13 +89,11 @@ __global__ void __launch_bounds__(256) im2col_t_operand_kernel(const float* __re
 
 using namespace glare;
 
-// x NHWC [B,H,W,C] fp32 (C % 32 == 0) -> transposed bf16x3 operand of its im2col for a k x k conv (k in {1, 3}) with the given stride and
-// low-side padding, output size Ho x Wo: out [nch][k*k*C][2 * chunk] bf16, nch = ceil(B*Ho*Wo / chunk), chunk % 32 == 0; pixels past
-// B*Ho*Wo are zero.  Feeds the batched GEMM of glare_conv2d_nhwc_tc_ex (per-sample weights = the dY operand built with k = 1).
-GLARE_API int glare_im2col_t_operand_bf16x3(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int chunk,
-                                            void* out, cudaStream_t stream) {
+template <bool X3>
+static int im2col_t_operand(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int chunk, void* out,
+                            cudaStream_t stream) {
     if (B < 0 || H <= 0 || W <= 0 || C <= 0 || (C & 31) || (k != 1 && k != 3) || stride < 1 || stride > 2 || pad < 0 || Ho <= 0 || Wo <= 0 ||
-        chunk <= 0 || (chunk & 31))
+        chunk <= 0 || (chunk & (X3 ? 31 : 63)))
         return GLARE_ERR_BAD_ARG;
     if (B == 0) return GLARE_OK;
     if (!x || !out) return GLARE_ERR_BAD_ARG;
@@ -92,8 +102,22 @@ GLARE_API int glare_im2col_t_operand_bf16x3(const float* x, int B, int H, int W,
     const long long groups = nch * (chunk / 32);
     if (groups > 0x7fffffffLL || C / 32 > 65535) return GLARE_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return GLARE_ERR_BAD_ARG;
-    im2col_t_operand_kernel<<<dim3((unsigned)((groups + 7) / 8), (unsigned)(C / 32), (unsigned)(k * k)), 256, 0, stream>>>(
+    im2col_t_operand_kernel<X3><<<dim3((unsigned)((groups + 7) / 8), (unsigned)(C / 32), (unsigned)(k * k)), 256, 0, stream>>>(
         x, B, H, W, C, k, stride, pad, Ho, Wo, P, chunk, groups, reinterpret_cast<__nv_bfloat16*>(out));
     GLARE_CHECK_LAUNCH();
     return GLARE_OK;
+}
+
+// x NHWC [B,H,W,C] fp32 (C % 32 == 0) -> transposed bf16x3 operand of its im2col for a k x k conv (k in {1, 3}) with the given stride and
+// low-side padding, output size Ho x Wo: out [nch][k*k*C][2 * chunk] bf16, nch = ceil(B*Ho*Wo / chunk), chunk % 32 == 0; pixels past
+// B*Ho*Wo are zero.  Feeds the batched GEMM of glare_conv2d_nhwc_tc_ex (per-sample weights = the dY operand built with k = 1).
+GLARE_API int glare_im2col_t_operand_bf16x3(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int chunk,
+                                            void* out, cudaStream_t stream) {
+    return im2col_t_operand<true>(x, B, H, W, C, k, stride, pad, Ho, Wo, chunk, out, stream);
+}
+
+// the same for the single-piece bf16 operand (mode 0): out [nch][k*k*C][chunk] bf16, chunk % 64 == 0
+GLARE_API int glare_im2col_t_operand_bf16(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int chunk,
+                                          void* out, cudaStream_t stream) {
+    return im2col_t_operand<false>(x, B, H, W, C, k, stride, pad, Ho, Wo, chunk, out, stream);
 }

@@ -61,7 +61,8 @@ class CudaLeaves:
         import os
         # weight gradients on the tensor cores (gemm_tn_tc) unless GLARE_WGRAD_FMA=1 selects the fp32 split-K GEMM (the correctness baseline):
         # 209 vs 228 ms per stage-2 step at batch 4 x 320x320 (profiles/r46_train_probe*.txt)
-        self.wgrad_tc = not os.environ.get("GLARE_WGRAD_FMA") and getattr(dense, "mode", None) == 4
+        # (mode 4 = fp32-grade bf16x3 operands, the default; mode 0 = bf16 operands, the bf16 training configuration of BASELINE config 4)
+        self.wgrad_tc = not os.environ.get("GLARE_WGRAD_FMA") and getattr(dense, "mode", None) in (0, 4)
 
     @staticmethod
     def _p(t):
@@ -129,7 +130,7 @@ class CudaLeaves:
         None when the shape is outside that path (the caller uses im2col + gemm_tn)."""
         if not self.wgrad_tc:
             return None
-        return self.ops.wgrad_conv_tc(x_nhwc, gy_nhwc, k, stride, pad, chunk)
+        return self.ops.wgrad_conv_tc(x_nhwc, gy_nhwc, k, stride, pad, chunk, mode=self.dense.mode)
 
     def gemm_nt(self, a, b, rows_hw):
         """a [R][K], b [N][K] -> a b^T [R][N] on the tcgen05 GEMM path (R = rows_hw[0] * rows_hw[1], the tile walk needs the 2-D factorisation)"""

@@ -26,10 +26,11 @@ NPRE = 128 * len(COUPLING_STEPS)            # channels of the hoisted pre-activa
 class CudaKernels:
     """The library's kernels (include/glare_b200.h section 2b).  Pointers are passed as (tensor, element offset) pairs."""
 
-    def __init__(self):
+    def __init__(self, mode=4):
         from . import ops
         from ._lib import lib, stream
         self.ops, self.lib, self.stream = ops, lib, stream
+        self.mode = mode                 # operand mode of the tensor-core weight gradients: 4 = bf16x3 (fp32-grade), 0 = bf16
 
     @staticmethod
     def _p(t, off=0):
@@ -48,16 +49,8 @@ class CudaKernels:
             return None
         Np = (N + 31) // 32 * 32
         gy = gy_pc if Np == N and gy_pc.is_contiguous() else F.pad(gy_pc, (0, Np - N)).contiguous()
-        M = k * k * Ci
-        chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
-        nch = (P + chunk - 1) // chunk
-        a_op = torch.empty((nch, M, 2 * chunk), device=x_pc.device, dtype=torch.bfloat16)
-        b_op = torch.empty((nch, Np, 2 * chunk), device=x_pc.device, dtype=torch.bfloat16)
-        self._call("glare_im2col_t_operand_bf16x3", self._p(x_pc), B, h, w, Ci, k, 1, k // 2, h, w, chunk, ctypes.c_void_p(a_op.data_ptr()))
-        self._call("glare_im2col_t_operand_bf16x3", self._p(gy), B, h, w, Np, 1, 1, 0, h, w, chunk, ctypes.c_void_p(b_op.data_ptr()))
-        y = torch.empty((nch, M, Np), device=x_pc.device, dtype=torch.float32)
-        self.ops.conv2d_nhwc_tc_ex(4, a_op, None, b_op, None, y, nch, M // 16, 16, chunk, Np, Np, Np * chunk)
-        return y.sum(dim=0)[:, :N]
+        G = self.ops.wgrad_conv_tc(x_pc.view(B, h, w, Ci), gy.view(B, h, w, Np), k, 1, k // 2, chunk, mode=self.mode, min_rows=16)
+        return None if G is None else G[:, :N]
 
     def zeros(self, shape, like):
         return torch.zeros(shape, device=like.device, dtype=torch.float32)

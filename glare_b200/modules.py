@@ -288,8 +288,10 @@ class VQLLFLOWDeformable(nn.Module):
         from . import encoder_train
         from .dense import make_dense
         if self._train_ctx is None:
+            from . import flow_train
             dense = make_dense(self.dense_name)
-            self._train_ctx = (dense, encoder_train.CudaLeaves(dense))
+            kernels = flow_train.CudaKernels(mode=dense.mode if dense.mode in (0, 4) else 4)
+            self._train_ctx = (dense, encoder_train.CudaLeaves(dense), kernels)
         return self._train_ctx
 
     def _reverse_flow_train(self, net_vq, lr):
@@ -319,7 +321,7 @@ class VQLLFLOWDeformable(nn.Module):
         from . import encoder_train
         from .dense import make_dense
         dev = next(self.parameters()).device
-        dense, leaves = self._leaves()
+        dense, leaves, flow_kernels = self._leaves()
         ratio = 0.0
         try:
             ratio = float(self.opt["train_gt_ratio"] or 0.0)
@@ -327,6 +329,6 @@ class VQLLFLOWDeformable(nn.Module):
             pass
         named = [(k, p) for k, p in self.named_parameters() if k.startswith(("RRDB.", "flowUpsamplerNet."))]
         nll = encoder_train.stage2_nll(named, gt.to(dev, torch.float32), lr.to(dev, torch.float32), leaves,
-                                       lambda x, w: dense.conv2d(x, w).float(), train_gt_ratio=ratio,
+                                       lambda x, w: dense.conv2d(x, w).float(), flow_kernels=flow_kernels, train_gt_ratio=ratio,
                                        graph=self._train_graphs if self.train_graph else False)
         return None, nll, None

@@ -127,30 +127,33 @@ def dcnv2_bwd_weight(col_nhwc, gout_nhwc, grad_w_packed):
                                            stream()), "glare_dcnv2_bwd_weight_f32")
 
 
-def wgrad_conv_tc(x_nhwc, gy_nhwc, k, stride, pad, chunk=8192):
+def wgrad_conv_tc(x_nhwc, gy_nhwc, k, stride, pad, chunk=8192, mode=None, min_rows=128):
     """weight gradient of a k x k conv, [k*k*Ci][Co] (tap-major rows), on the tensor cores WITHOUT fp32 im2col columns: the transposed bf16x3
     operands of im2col(x) and of dY are written directly (csrc/train_wgrad.cu), then one batched tcgen05 GEMM over the pixel chunks, summed
-    in fp32.  Co is zero-padded to a multiple of 32.  None when the shape is outside that path (Ci % 32, fewer than 128 rows)."""
+    in fp32.  Co is zero-padded to a multiple of 32.  None when the shape is outside that path (Ci % 32, fewer than 128 rows).
+    mode: MODE_BF16X3 (default, fp32-grade) or MODE_BF16 (single-piece bf16 operands: the bf16 training configuration)."""
     import torch.nn.functional as F
+    mode = MODE_BF16X3 if mode is None else mode
+    if mode not in (MODE_BF16, MODE_BF16X3):
+        return None
+    q, e2 = (32, 2) if mode == MODE_BF16X3 else (64, 1)                 # K granule in pixels, operand entries per pixel
+    build = lib().glare_im2col_t_operand_bf16x3 if mode == MODE_BF16X3 else lib().glare_im2col_t_operand_bf16
     B, H, W, Ci = x_nhwc.shape
     _, Ho, Wo, Co = gy_nhwc.shape
     M, P = k * k * Ci, B * Ho * Wo
-    if M < 128 or Ci % 32 or not x_nhwc.is_contiguous() or not gy_nhwc.is_contiguous() or x_nhwc.dtype != torch.float32:
+    if M < min_rows or M % 16 or Ci % 32 or not x_nhwc.is_contiguous() or not gy_nhwc.is_contiguous() or x_nhwc.dtype != torch.float32:
         return None
     N = (Co + 31) // 32 * 32
     if N != Co:
         gy_nhwc = F.pad(gy_nhwc, (0, N - Co))
-    chunk = max(32, min(chunk, (P + 31) // 32 * 32) // 32 * 32)
+    chunk = max(q, min(chunk, (P + q - 1) // q * q) // q * q)
     nch = (P + chunk - 1) // chunk
-    a_op = torch.empty((nch, M, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
-    b_op = torch.empty((nch, N, 2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
-    check(lib().glare_im2col_t_operand_bf16x3(ptr(x_nhwc), B, H, W, Ci, k, stride, pad, Ho, Wo, chunk, ptr(a_op), stream()),
-          "glare_im2col_t_operand_bf16x3")
-    check(lib().glare_im2col_t_operand_bf16x3(ptr(gy_nhwc), B, Ho, Wo, N, 1, 1, 0, Ho, Wo, chunk, ptr(b_op), stream()),
-          "glare_im2col_t_operand_bf16x3")
-    rows_w = 16 if M % 16 == 0 else 1
+    a_op = torch.empty((nch, M, e2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
+    b_op = torch.empty((nch, N, e2 * chunk), device=x_nhwc.device, dtype=torch.bfloat16)
+    check(build(ptr(x_nhwc), B, H, W, Ci, k, stride, pad, Ho, Wo, chunk, ptr(a_op), stream()), "glare_im2col_t_operand")
+    check(build(ptr(gy_nhwc), B, Ho, Wo, N, 1, 1, 0, Ho, Wo, chunk, ptr(b_op), stream()), "glare_im2col_t_operand")
     y = torch.empty((nch, M, N), device=x_nhwc.device, dtype=torch.float32)
-    conv2d_nhwc_tc_ex(MODE_BF16X3, a_op, None, b_op, None, y, nch, M // rows_w, rows_w, chunk, N, N, N * chunk)
+    conv2d_nhwc_tc_ex(mode, a_op, None, b_op, None, y, nch, M // 16, 16, chunk, N, N, N * chunk)
     return y[:, :, :Co].sum(dim=0)
 
 

@@ -254,6 +254,9 @@ int glare_im2col_nhwc_f32(const float* x, int B, int H, int W, int C, int k, int
  * B*Ho*Wo output pixels as the K dimension in chunks of `chunk` (% 32 == 0; zero past the end).  k = 1: the transposed operand of dY. */
 int glare_im2col_t_operand_bf16x3(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int chunk,
                                   void* out, cudaStream_t stream);
+/* The same for single-piece bf16 operands (mode 0, the bf16 training configuration): out [nch][k*k*C][chunk] bf16, chunk % 64 == 0. */
+int glare_im2col_t_operand_bf16(const float* x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int chunk,
+                                void* out, cudaStream_t stream);
 int glare_attn_softmax_bwd_f32(const float* P, const float* dP, long long rows, long long ld, int n_keys, float scale, float* dS,
                                cudaStream_t stream);
 /* out[C] += column sums of x [P][C] fp32 (C % 4 == 0): the bias gradient of nn.Conv2d (dY summed over the pixels of the batch). */

@@ -189,7 +189,23 @@ def encoder_step_check(dev, dense, conv):
           ("ok" if good else "FAIL", len(grads_c), statistics.median(r[0] for r in rel), len(outliers)))
     for e, k in rel[:10]:
         print("       %.3g  %s" % (e, k))
-    return OK and good
+    # the bf16 training configuration (BASELINE config 4 names bf16): single-piece bf16 operands in every convolution, attention GEMM and
+    # weight gradient (csrc/train_wgrad.cu's mode-0 operand), fp32 accumulation and fp32 memory-bound kernels.  Against the fp32-grade step
+    # on the same device: the objective within 1e-3, the gradients within bf16's 2^-9 per operand (relative L2 per tensor)
+    from glare_b200 import flow_train
+    from glare_b200.dense import make_dense
+    d16 = make_dense("tc-bf16")
+    with torch.no_grad():
+        nll_b, grads_b = encoder_train.stage2_step(sd_d, flow.FlowPlan(sd, dev), lr.to(dev), gt.to(dev), encoder_train.CudaLeaves(d16),
+                                                   lambda x, wgt: d16.conv2d(x, wgt).float(), flow_kernels=flow_train.CudaKernels(mode=0))
+        torch.cuda.synchronize()
+    check("stage-2 step nll, bf16 operands", nll_b, nll_g, 1e-3)
+    gmax = max(float(v.abs().max()) for v in grads_g.values())
+    rel16 = sorted(float((grads_b[k] - v).norm()) / max(float(v.norm()), 1e-4 * gmax * v.numel() ** 0.5) for k, v in grads_g.items())
+    good16 = sorted(grads_b) == sorted(grads_g) and statistics.median(rel16) < 1e-2 and rel16[len(rel16) * 9 // 10] < 5e-2
+    print("%-4s stage-2 step gradients, bf16 operands vs fp32-grade: relative L2 per tensor median %.3g, 90th percentile %.3g, max %.3g" %
+          ("ok" if good16 else "FAIL", statistics.median(rel16), rel16[len(rel16) * 9 // 10], rel16[-1]))
+    return OK and good and good16
 
 
 if __name__ == "__main__":

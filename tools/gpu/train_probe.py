@@ -14,8 +14,10 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 dev = torch.device("cuda:0")
 sd = {k: v.to(dev) for k, v in synth.synth_state_dict("netG_stage2", 0).items()}
 plan = flow.FlowPlan({k: v.cpu() for k, v in sd.items()}, dev)
-dense = make_dense("auto")
+import os  # noqa: E402
+dense = make_dense(os.environ.get("GLARE_DENSE", "auto"))          # GLARE_DENSE=tc-bf16: the bf16 training configuration
 leaves = encoder_train.CudaLeaves(dense)
+fkern = flow_train.CudaKernels(mode=dense.mode if dense.mode in (0, 4) else 4)
 conv = lambda x, w: dense.conv2d(x, w).float()      # noqa: E731
 gen = torch.Generator().manual_seed(10)             # train_stage2_LOL.yml manual_seed
 lr = synth.preprocess(torch.rand((4, 3, 320, 320), generator=gen)).to(dev)
@@ -27,10 +29,11 @@ def step():
     enc = encoder_train.EncoderTrainer(leaves, sd)
     heads = enc.forward(lr)
     torch.cuda.synchronize(); t.append(time.perf_counter())
-    nll, _, _, g_ft, g_mean, grads = flow_train.nll_forward_backward(plan, sd, gt, heads["cond_feat"], heads["color_map"], conv)
+    nll, _, _, g_ft, g_mean, grads = flow_train.nll_forward_backward(plan, sd, gt, heads["cond_feat"], heads["color_map"], conv, kernels=fkern)
     torch.cuda.synchronize(); t.append(time.perf_counter())
     grads.update(enc.backward(g_ft, g_mean))
     torch.cuda.synchronize(); t.append(time.perf_counter())
+    step.grads = grads
     return nll, [b - a for a, b in zip(t, t[1:])]
 
 
@@ -40,7 +43,16 @@ with torch.no_grad():
     for _ in range(steps):
         nll, dt = step()
         acc = [a + b for a, b in zip(acc, dt)]
-print("stage-2 step, batch 4 x 320x320 (latent 80x80): nll %s" % [round(float(x), 4) for x in nll])
+print("stage-2 step, batch 4 x 320x320 (latent 80x80), dense %s: nll %s" % (dense.dtype_name, [round(float(x), 4) for x in nll]))
+if os.environ.get("GLARE_GRAD_DUMP"):
+    torch.save({k: v.detach().cpu() for k, v in step.grads.items()}, os.environ["GLARE_GRAD_DUMP"])
+if os.environ.get("GLARE_GRAD_COMPARE"):
+    ref = torch.load(os.environ["GLARE_GRAD_COMPARE"])
+    rel = sorted(float((step.grads[k].cpu() - v).norm() / max(float(v.norm()), 1e-12)) for k, v in ref.items() if float(v.norm()) > 0)
+    cos = sorted(float(torch.nn.functional.cosine_similarity(step.grads[k].cpu().flatten(), v.flatten(), dim=0)) for k, v in ref.items()
+                 if float(v.norm()) > 0)
+    print("  gradients against %s: relative L2 error per tensor median %.2e, 90th percentile %.2e, max %.2e; cosine median %.5f, min %.5f"
+          % (os.environ["GLARE_GRAD_COMPARE"], rel[len(rel) // 2], rel[len(rel) * 9 // 10], rel[-1], cos[len(cos) // 2], cos[0]))
 print("  encoder forward %.1f ms | flow forward + backward %.1f ms | encoder backward %.1f ms | total %.1f ms  (peak memory %.1f GB)"
       % tuple([1e3 * a / steps for a in acc] + [1e3 * sum(acc) / steps, torch.cuda.max_memory_allocated() / 2 ** 30]))
 

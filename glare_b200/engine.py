@@ -252,19 +252,24 @@ class GlareEngine:
                          z_flow=z, z_q=zq, idx=idx, vq_feat1=vq_feats[0], vq_feat0=vq_feats[1], out=out)
 
     @torch.no_grad()
-    def stage3_inputs(self, lr):
+    def stage3_inputs(self, lr, graph=False):
         """the frozen part of VQLLFLOWDeformable.reverse_flow (VQLLFLOWDeformable_arch.py:230-248, all under no_grad there): condition encoder
-        -> flow decode -> VQ -> VQGAN decoder features.  -> (z [B,3,h,w], [vq feat @2h, vq feat @4h], encoder mid features by level)"""
+        -> flow decode -> VQ -> VQGAN decoder features.  -> (z [B,3,h,w], [vq feat @2h, vq feat @4h], encoder mid features by level).
+        graph=True: one CUDA-graph replay per input shape (~600 launches at a training crop's size, CPU-launch bound otherwise); the results
+        are copied out of the graph's static buffers, so they stay valid across later calls (a training tape holds them until its backward)."""
         with torch.cuda.device(self.device):
             lr = lr.to(self.device, torch.float32)
 
-            def run():
-                enc = self.cond_encoder(lr)
+            def run(x):
+                enc = self.cond_encoder(x)
                 z = self.flow_decode(enc["color_map"], enc["cond_feat"])
                 zq, _ = self.vector_quantize(z)
-                return z, self.vq_decoder_features(zq), enc["mid_feat"]
+                return z, self.vq_decoder_features(zq), [enc["mid_feat"][0], enc["mid_feat"][1]]
 
-            return self.run_verified(run)
+            if graph:
+                z, vq, mid = self.graphed("stage3_inputs", run, lr)
+                return z.clone(), [t.clone() for t in vq], [t.clone() for t in mid]
+            return self.run_verified(lambda: run(lr))
 
     def _verified(self):
         # the fused-softmax attention (dense.py) verifies its row sums on the device; a tripped flag switches the backend to the exact

@@ -248,6 +248,9 @@ class VQLLFLOWDeformable(nn.Module):
         # buys nothing and holds a second copy of the tape's memory per branch
         self.train_graph = False
         self._train_graphs = {}
+        # True: the frozen stages (encoder, flow, VQGAN) of a stage-3 training call replay as one CUDA graph per input shape.  Off by default:
+        # measured on B200 at batch 2 x 256x256 the step is 62.6 ms either way (the GPU, not the launch rate, bounds those stages)
+        self.stage3_graph = False
 
     def engine(self, net_vq=None):
         key = _fingerprint(self) + (_fingerprint(net_vq) if net_vq is not None else ())
@@ -308,7 +311,7 @@ class VQLLFLOWDeformable(nn.Module):
             self._frozen = (key, GlareEngine(sd, net_vq.state_dict(), device=next(self.parameters()).device, dense=make_dense(self.dense_name),
                                              decoders=False))
         eng = self._frozen[1]
-        z, vq_feats, mid = eng.stage3_inputs(lr)
+        z, vq_feats, mid = eng.stage3_inputs(lr, graph=self.stage3_graph)
         named = [(k, p) for k, p in self.named_parameters() if k.startswith("deformable_decoder.")]
         rec = decoder_train.deformable_decoder(named, z, vq_feats, mid, self._leaves()[1], global_ratio=True)
         return rec, z

@@ -90,6 +90,118 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const float* __restri
     }
 }
 
+// ---- fast path: C / 4 a power of two <= 256 and (C / G) % 4 == 0 (GLARE: 128 / 256 / 512 channels, 32 groups) --------------------------------
+// thread = (walker, channel quad): float4 loads over the channels, 256 / (C / 4) pixel walkers per CTA so that every thread works whatever C
+// is, two pixels in flight per walker.  Per CTA: one shared-memory reduction over the walkers, a shuffle reduction over the quads of a group,
+// then ONE fp64 atomic pair per group and one fp32 atomic pair per channel.  (The per-channel column walkers above left half of the CTA idle
+// at C = 128 and ran at 1 TB/s: 3.8 ms of a 58 ms stage-3 step.)
+__device__ __forceinline__ void te_quad(const float4 xv, const float4 gv, const float4 ga, const float4 be, float mean, float rstd, int swish,
+                                        float& s1, float& s2, float4& sg, float4& sb) {
+    const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd, xh2 = (xv.z - mean) * rstd, xh3 = (xv.w - mean) * rstd;
+    const float d0 = te_dn(fmaf(xh0, ga.x, be.x), gv.x, swish), d1 = te_dn(fmaf(xh1, ga.y, be.y), gv.y, swish);
+    const float d2 = te_dn(fmaf(xh2, ga.z, be.z), gv.z, swish), d3 = te_dn(fmaf(xh3, ga.w, be.w), gv.w, swish);
+    const float e0 = d0 * ga.x, e1 = d1 * ga.y, e2 = d2 * ga.z, e3 = d3 * ga.w;
+    s1 += (e0 + e1) + (e2 + e3);
+    s2 = fmaf(e0, xh0, fmaf(e1, xh1, fmaf(e2, xh2, fmaf(e3, xh3, s2))));
+    sg.x = fmaf(d0, xh0, sg.x);
+    sg.y = fmaf(d1, xh1, sg.y);
+    sg.z = fmaf(d2, xh2, sg.z);
+    sg.w = fmaf(d3, xh3, sg.w);
+    sb.x += d0;
+    sb.y += d1;
+    sb.z += d2;
+    sb.w += d3;
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_stats_quad_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps, int swish, long long HW, int C, int G,
+                                                                double* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float4 red_g[256], red_b[256];
+    __shared__ float red_1[256], red_2[256];
+    const int b = blockIdx.y;
+    const int C4 = C >> 2, cpg = C / G;
+    const int q = threadIdx.x % C4, w = threadIdx.x / C4, nwalk = 256 / C4;
+    const int c = q * 4, g = c / cpg;
+    const double cnt = (double)HW * cpg;
+    float mean, rstd;
+    te_mean_rstd(stats, b, G, g, cnt, eps, mean, rstd);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const long long per = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per, p1 = (p0 + per < HW) ? p0 + per : HW;
+    const float4* xs = reinterpret_cast<const float4*>(x + (long long)b * HW * C) + q;
+    const float4* gs = reinterpret_cast<const float4*>(gy + (long long)b * HW * C) + q;
+    float s1 = 0.f, s2 = 0.f;
+    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long p = p0 + w;
+    for (; p + nwalk < p1; p += 2 * nwalk) {
+        const float4 xa = xs[p * C4], gA = gs[p * C4], xb = xs[(p + nwalk) * C4], gB = gs[(p + nwalk) * C4];
+        te_quad(xa, gA, ga, be, mean, rstd, swish, s1, s2, sg, sb);
+        te_quad(xb, gB, ga, be, mean, rstd, swish, s1, s2, sg, sb);
+    }
+    if (p < p1) te_quad(xs[p * C4], gs[p * C4], ga, be, mean, rstd, swish, s1, s2, sg, sb);
+    red_g[threadIdx.x] = sg;
+    red_b[threadIdx.x] = sb;
+    red_1[threadIdx.x] = s1;
+    red_2[threadIdx.x] = s2;
+    __syncthreads();
+    if (w == 0) {
+        for (int r = 1; r < nwalk; ++r) {
+            const float4 a = red_g[r * C4 + q], bb = red_b[r * C4 + q];
+            sg.x += a.x; sg.y += a.y; sg.z += a.z; sg.w += a.w;
+            sb.x += bb.x; sb.y += bb.y; sb.z += bb.z; sb.w += bb.w;
+            s1 += red_1[r * C4 + q];
+            s2 += red_2[r * C4 + q];
+        }
+        atomicAdd(dgamma + c, sg.x); atomicAdd(dgamma + c + 1, sg.y); atomicAdd(dgamma + c + 2, sg.z); atomicAdd(dgamma + c + 3, sg.w);
+        atomicAdd(dbeta + c, sb.x); atomicAdd(dbeta + c + 1, sb.y); atomicAdd(dbeta + c + 2, sb.z); atomicAdd(dbeta + c + 3, sb.w);
+    }
+    // the quads of a group are cpg / 4 (1, 2 or 4 ... <= 8) adjacent lanes of walker 0's warps; every lane of those warps takes part
+    if (threadIdx.x < ((C4 + 31) & ~31)) {
+        const int qpg = cpg >> 2;
+        for (int o = 1; o < qpg; o <<= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (w == 0 && (q % qpg) == 0) {
+            atomicAdd(sums + ((long long)b * G + g) * 2, (double)s1);
+            atomicAdd(sums + ((long long)b * G + g) * 2 + 1, (double)s2);
+        }
+    }
+}
+
+// gx = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat * xhat)) with the per-group constants (fp64 once per CTA) staged in shared memory
+__global__ void __launch_bounds__(256) gn_bwd_apply_quad_kernel(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps, int swish, long long HW, int C, int G,
+                                                                const double* __restrict__ sums, float* __restrict__ gx) {
+    __shared__ float4 grp[64];                       // (mean, rstd, m1, m2) per group, G <= 64
+    const int b = blockIdx.y;
+    const int C4 = C >> 2, cpg = C / G;
+    if (threadIdx.x < G) {
+        const double cnt = (double)HW * cpg;
+        float mean, rstd;
+        te_mean_rstd(stats, b, G, threadIdx.x, cnt, eps, mean, rstd);
+        grp[threadIdx.x] = make_float4(mean, rstd, (float)(sums[((long long)b * G + threadIdx.x) * 2] / cnt),
+                                       (float)(sums[((long long)b * G + threadIdx.x) * 2 + 1] / cnt));
+    }
+    __syncthreads();
+    const int q = threadIdx.x % C4, w = threadIdx.x / C4, nwalk = 256 / C4;
+    const int c = q * 4;
+    const float4 k = grp[c / cpg];
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const float4* xs = reinterpret_cast<const float4*>(x + (long long)b * HW * C) + q;
+    const float4* gs = reinterpret_cast<const float4*>(gy + (long long)b * HW * C) + q;
+    float4* os = reinterpret_cast<float4*>(gx + (long long)b * HW * C) + q;
+    for (long long p = (long long)blockIdx.x * nwalk + w; p < HW; p += (long long)gridDim.x * nwalk) {
+        const float4 xv = xs[p * C4], gv = gs[p * C4];
+        const float xh0 = (xv.x - k.x) * k.y, xh1 = (xv.y - k.x) * k.y, xh2 = (xv.z - k.x) * k.y, xh3 = (xv.w - k.x) * k.y;
+        const float e0 = te_dn(fmaf(xh0, ga.x, be.x), gv.x, swish) * ga.x, e1 = te_dn(fmaf(xh1, ga.y, be.y), gv.y, swish) * ga.y;
+        const float e2 = te_dn(fmaf(xh2, ga.z, be.z), gv.z, swish) * ga.z, e3 = te_dn(fmaf(xh3, ga.w, be.w), gv.w, swish) * ga.w;
+        os[p * C4] = make_float4(k.y * (e0 - k.z - xh0 * k.w), k.y * (e1 - k.z - xh1 * k.w), k.y * (e2 - k.z - xh2 * k.w), k.y * (e3 - k.z - xh3 * k.w));
+    }
+}
+
 // col[(b, oy, ox)][t * C + c] = x[b][oy * stride + t / k - pad][ox * stride + t % k - pad][c]  (zero outside the H x W image)
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, int k, int stride, int pad, int Ho,
                                                           int Wo, float* __restrict__ col) {
@@ -181,6 +293,24 @@ GLARE_API int glare_gn_bwd_nhwc_f32(const float* x, const float* gy, const doubl
 #else
     memset(sums, 0, sizeof(double) * 2 * (size_t)B * G);
 #endif
+    const int C4 = C / 4, cpg = C / G;
+    const bool quad = (C % 4 == 0) && C4 <= 256 && (C4 & (C4 - 1)) == 0 && (cpg % 4 == 0) && cpg <= 32 && G <= 64 &&
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx) |
+                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    if (quad) {
+        const int nwalk = 256 / C4;
+        long long chunks = (HW + 16LL * nwalk - 1) / (16LL * nwalk);                 // >= 16 pixels per walker
+        const long long cap = (148LL * 8 + B - 1) / B;
+        if (chunks > cap) chunks = cap;
+        TE_LAUNCH(gn_bwd_stats_quad_kernel, dim3((unsigned)chunks, (unsigned)B), 256, stream, x, gy, stats, gamma, beta, eps, swish, HW, C, G, sums, dgamma,
+                  dbeta);
+        long long blocks = (HW + 4LL * nwalk - 1) / (4LL * nwalk);
+        const long long cap2 = (148LL * 16 + B - 1) / B;
+        if (blocks > cap2) blocks = cap2;
+        TE_LAUNCH(gn_bwd_apply_quad_kernel, dim3((unsigned)blocks, (unsigned)B), 256, stream, x, gy, stats, gamma, beta, eps, swish, HW, C, G, sums, gx);
+        GLARE_CHECK_LAUNCH();
+        return GLARE_OK;
+    }
     long long chunks = (HW + 63) / 64;
     const long long cap = (148LL * 8 + B - 1) / B;
     if (chunks > cap) chunks = cap;

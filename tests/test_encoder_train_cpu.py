@@ -88,9 +88,9 @@ def test_train_enc_kernel_source_on_the_host():
         assert a.shape == b.shape and float((a - b).abs().max()) <= tol * sc, (what, float((a - b).abs().max()), sc)
 
     # GroupNorm (+ swish) backward
-    for C, swish in ((64, True), (128, False)):
-        x = torch.randn((2, 3, 4, C), generator=gen) * 1.5 + 0.7
-        gy = torch.randn((2, 3, 4, C), generator=gen)
+    for C, swish, hw in ((64, True, (3, 4)), (128, False, (3, 4)), (128, True, (9, 23)), (256, True, (5, 7)), (512, False, (2, 3))):
+        x = torch.randn((2,) + hw + (C,), generator=gen) * 1.5 + 0.7
+        gy = torch.randn((2,) + hw + (C,), generator=gen)
         gamma, beta = 1 + 0.2 * torch.randn(C, generator=gen), 0.1 * torch.randn(C, generator=gen)
         _, stats = T.gn_fwd(x, gamma, beta, swish)
         for nm, a, b in zip(("gx", "dgamma", "dbeta"), H.gn_bwd(x, gy, stats, gamma, beta, swish), T.gn_bwd(x, gy, stats, gamma, beta, swish)):

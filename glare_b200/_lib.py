@@ -25,6 +25,7 @@ SIGNATURES = {
     "glare_flow_train_net_bwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp],
     "glare_flow_train_point_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "glare_flow_train_im2col3x3_f32": [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp],
+    "glare_gemm_tn_skinny_f32": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "glare_flow_train_colsum_f32": [_vp, _ll, _vp, _ll, _i, _ll, _vp, _vp],
     "glare_dcn_pack_weight_f32": [_vp, _i, _i, _i, _i, _vp, _vp],
     "glare_dcnv2_fwd_f32": [_vp, _vp, _vp, _vp, _vp] + [_i] * 11 + [_vp, _vp],

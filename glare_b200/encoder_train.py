@@ -88,8 +88,12 @@ class CudaLeaves:
         P, M = a.shape
         if self.wgrad_tc and M >= 128 and b.shape[1] >= 32:
             return self.gemm_tn_tc(a, b)
-        out = torch.zeros((M, b.shape[1]), device=a.device, dtype=torch.float32)
-        self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, b.shape[1], self._p(out))
+        N = b.shape[1]
+        out = torch.zeros((M, N), device=a.device, dtype=torch.float32)
+        if M <= 32 and N <= 256 and 256 % N == 0 and a.is_contiguous() and b.is_contiguous():     # conv_in: 27 im2col columns of a 3-channel input
+            self._call("glare_gemm_tn_skinny_f32", self._p(a), self._p(b), P, M, N, self._p(out))
+        else:
+            self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, N, self._p(out))
         return out
 
     def colsum(self, x):

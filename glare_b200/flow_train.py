@@ -102,8 +102,11 @@ class CudaKernels:
         self._call("glare_flow_train_colsum_f32", self._p(a), lda, self._p(b), ldb, Cx, P, self._p(out))
 
     def gemm_tn(self, a, M, b, N, P, out):
-        """out [M][N] += a [P][M]^T b [P][N] (csrc/dcn_bwd.cu split-K fp32 GEMM)"""
-        self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, N, self._p(out))
+        """out [M][N] += a [P][M]^T b [P][N]: the skinny kernel of csrc/flow_bwd.cu for M <= 32, else the split-K fp32 GEMM of csrc/dcn_bwd.cu"""
+        if M <= 32 and N <= 256 and 256 % N == 0:
+            self._call("glare_gemm_tn_skinny_f32", self._p(a), self._p(b), P, M, N, self._p(out))
+        else:
+            self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, N, self._p(out))
 
 
 def _net_param_grads(K, key, net_has_z, bufs, v, B, h, w, P, grads, like):
@@ -203,15 +206,18 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
         grads[p + ".actnorm.bias"] = sums[12:15].view(1, 3, 1, 1).clone()
 
     # hoisted conv over ft: data gradient on the tensor-core conv path (transpose of a stride-1 'same' conv = the conv with the flipped,
-    # transposed filter), weight gradient by the split-K GEMM over im2col(ft)
+    # transposed filter), weight gradient on the tensor cores (fp32 split-K GEMM over im2col(ft) for kernel sets without them)
     if getattr(plan, "_w_pre_t", None) is None:                        # once per plan: the packed-weight cache of the conv path keys on it
         plan._w_pre_t = plan.w_pre.flip(2, 3).transpose(0, 1).contiguous()
     w_t = plan._w_pre_t
     g_ft = conv2d(g_pre.permute(0, 3, 1, 2), w_t).float()
     ftn = ft.float().permute(0, 2, 3, 1).contiguous()
-    K.im2col3x3(ftn, C, C, B, h, w, col576)
-    Gp = K.zeros((9 * C, NPRE), gt)
-    K.gemm_tn(col576, 9 * C, g_pre, NPRE, P, Gp)
+    wg = getattr(K, "wgrad", None)               # [576][3072] over 25 600 pixels: 90 GFLOP, on the tensor cores where the kernel set has them
+    Gp = wg(ftn.view(P, C), g_pre.reshape(P, NPRE), 3, B, h, w) if wg is not None and g_pre.is_contiguous() else None
+    if Gp is None:
+        K.im2col3x3(ftn, C, C, B, h, w, col576)
+        Gp = K.zeros((9 * C, NPRE), gt)
+        K.gemm_tn(col576, 9 * C, g_pre, NPRE, P, Gp)
     g_wpre = Gp.view(9, C, NPRE).permute(2, 1, 0).reshape(NPRE, C, 3, 3)
     for ci, s in enumerate(COUPLING_STEPS):
         p = "%s.layers.%d.affine" % (prefix, s)

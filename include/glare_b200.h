@@ -239,6 +239,9 @@ int glare_flow_train_point_bwd_f32(const float* g_u, const float* t, const float
                                    cudaStream_t stream);
 int glare_flow_train_im2col3x3_f32(const float* x, long long ldx, int C, int relu, int B, int h, int w, float* col, cudaStream_t stream);
 int glare_flow_train_colsum_f32(const float* a, long long lda, const float* b, long long ldb, int C, long long P, float* out, cudaStream_t stream);
+/* out [M][N] += a [P][M]^T b [P][N], fp32, for a skinny left operand (M <= 32; N <= 256, 256 % N == 0): the weight gradient of the z1 input
+ * channel of a coupling net's first conv (FlowAffineCouplingsAblation.py:143-151 under autograd) and of the 3-channel conv_in (27 columns). */
+int glare_gemm_tn_skinny_f32(const float* a, const float* b, long long P, int M, int N, float* out, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (5b) Backward of the condition encoder's blocks for stage-2 training (autograd of encoder_decoder.py:29-35, 68-72, 117-137, 168-192):

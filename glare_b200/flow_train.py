@@ -109,43 +109,65 @@ class CudaKernels:
             self._call("glare_dcnv2_bwd_weight_f32", self._p(a), self._p(b), P, M, N, self._p(out))
 
 
-def _net_param_grads(K, key, net_has_z, bufs, v, B, h, w, P, grads, like):
-    """parameter gradients of one coupling net from the buffers its data backward left (oracle/flow_backward.py nn_backward)"""
+class _NetGrads:
+    """raw parameter-gradient buffers of all coupling nets, filled net by net by the kernels and converted to the reference's parameter
+    layouts ONCE at the end (the per-net views / permutes / clones were ~1 500 tiny torch launches per training step)"""
+
+    def __init__(self, K, like, n_nets):
+        self.G3 = K.zeros((n_nets, 9 * C, 8), like)            # Conv2dZeros weight, rows tap * C + c, 8 padded outputs
+        self.s8 = K.zeros((n_nets, 2, 8), like)                # its bias / logs sums
+        self.G2 = K.zeros((n_nets, C, C), like)                # 1x1 conv weight, [in][out]
+        self.s64 = K.zeros((n_nets, 4, C), like)               # the two ActNorms' bias / logs sums
+        self.G1 = K.zeros((n_nets, 9, C), like)                # z1 channel of the first conv (nets with a z input only)
+        self.keys = [None] * n_nets
+
+    def finish(self, grads):
+        G3 = self.G3.view(-1, 9, C, 8).permute(0, 3, 2, 1).reshape(-1, 8, C, 3, 3)
+        G2 = self.G2.transpose(1, 2).reshape(-1, C, C, 1, 1)
+        G1 = self.G1.transpose(1, 2).reshape(-1, C, 1, 3, 3)
+        logs8 = 3.0 * self.s8[:, 1]
+        for i, (key, has_z) in enumerate(self.keys):
+            nout = 4 if has_z else 6
+            grads[key + ".4.weight"] = G3[i, :nout].contiguous()
+            grads[key + ".4.bias"] = self.s8[i, 0, :nout]
+            grads[key + ".4.logs"] = logs8[i, :nout].view(nout, 1, 1)
+            grads[key + ".2.weight"] = G2[i]
+            grads[key + ".2.actnorm.bias"] = self.s64[i, 0].view(1, C, 1, 1)
+            grads[key + ".2.actnorm.logs"] = self.s64[i, 1].view(1, C, 1, 1)
+            grads[key + ".0.actnorm.bias"] = self.s64[i, 2].view(1, C, 1, 1)
+            grads[key + ".0.actnorm.logs"] = self.s64[i, 3].view(1, C, 1, 1)
+            if has_z:
+                grads[key + ".0.weight.z"] = G1[i]
+
+
+def _net_param_grads(K, acc, i, key, net_has_z, bufs, v, B, h, w, P):
+    """parameter gradients of one coupling net from the buffers its data backward left (oracle/flow_backward.py nn_backward), into slot ``i``
+    of the stacked buffers ``acc``"""
     h1, h2, hout, g_h, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9 = bufs
-    nout = 4 if net_has_z else 6
+    acc.keys[i] = (key, net_has_z)
     # Conv2dZeros: weight [nout][64][3][3], bias, logs (out = (conv + bias) * exp(3 logs))
     wg = getattr(K, "wgrad", None)               # tensor-core weight gradient where the kernel set has one (the GPU kernels)
     G3 = wg(h2, g_a3, 3, B, h, w) if wg is not None else None
     if G3 is None:
         K.im2col3x3(h2, C, C, B, h, w, col576)
-        G3 = K.zeros((9 * C, 8), like)
-        K.gemm_tn(col576, 9 * C, g_a3, 8, P, G3)
-    grads[key + ".4.weight"] = G3.view(9, C, 8).permute(2, 1, 0)[:nout].reshape(nout, C, 3, 3).contiguous()
-    s8 = K.zeros((2, 8), like)
-    K.colsum(g_a3, 8, None, 0, 8, P, s8[0])
-    K.colsum(g_h, 8, hout, 8, 8, P, s8[1])
-    grads[key + ".4.bias"] = s8[0, :nout].clone()
-    grads[key + ".4.logs"] = (3.0 * s8[1, :nout]).view(nout, 1, 1)
+        K.gemm_tn(col576, 9 * C, g_a3, 8, P, acc.G3[i])
+    else:
+        acc.G3[i].copy_(G3)
+    K.colsum(g_a3, 8, None, 0, 8, P, acc.s8[i, 0])
+    K.colsum(g_h, 8, hout, 8, 8, P, acc.s8[i, 1])
     # 1x1 conv + ActNorm
     G2 = wg(h1, g_a2, 1, B, h, w) if wg is not None else None
     if G2 is None:
-        G2 = K.zeros((C, C), like)
-        K.gemm_tn(h1, C, g_a2, C, P, G2)
-    grads[key + ".2.weight"] = G2.t().reshape(C, C, 1, 1).contiguous()
-    s64 = K.zeros((4, C), like)
-    K.colsum(g_a2, C, None, 0, C, P, s64[0])
-    K.colsum(g_n2, C, h2, C, C, P, s64[1])
-    K.colsum(g_a1, C, None, 0, C, P, s64[2])
-    K.colsum(g_n1, C, h1, C, C, P, s64[3])
-    grads[key + ".2.actnorm.bias"] = s64[0].view(1, C, 1, 1).clone()
-    grads[key + ".2.actnorm.logs"] = s64[1].view(1, C, 1, 1).clone()
-    grads[key + ".0.actnorm.bias"] = s64[2].view(1, C, 1, 1).clone()
-    grads[key + ".0.actnorm.logs"] = s64[3].view(1, C, 1, 1).clone()
+        K.gemm_tn(h1, C, g_a2, C, P, acc.G2[i])
+    else:
+        acc.G2[i].copy_(G2)
+    K.colsum(g_a2, C, None, 0, C, P, acc.s64[i, 0])
+    K.colsum(g_n2, C, h2, C, C, P, acc.s64[i, 1])
+    K.colsum(g_a1, C, None, 0, C, P, acc.s64[i, 2])
+    K.colsum(g_n1, C, h1, C, C, P, acc.s64[i, 3])
     if net_has_z:                               # the z1 input channel of the first 3x3 conv; the ft channels come from the hoisted conv
         K.im2col3x3(v, 4, 1, B, h, w, col9)
-        G1 = K.zeros((9, C), like)
-        K.gemm_tn(col9, 9, g_a1, C, P, G1)
-        grads[key + ".0.weight.z"] = G1.t().reshape(C, 1, 3, 3).contiguous()
+        K.gemm_tn(col9, 9, g_a1, C, P, acc.G1[i])
 
 
 def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="flowUpsamplerNet"):
@@ -173,6 +195,7 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
     t, u, v, g_v, g_u = (new(4) for _ in range(5))
     g_z1, col576, col9 = new(1), new(9 * C), new(9)
     grads = {}
+    acc = _NetGrads(K, gt, 2 * len(COUPLING_STEPS))
     for s in range(N_FLOW_STEPS - 1, -1, -1):
         p = "%s.layers.%d" % (prefix, s)
         pw = plan.pw_fwd[s]
@@ -187,10 +210,10 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
             # self coupling -> NN_A -> feature affine -> NN_F
             K.coupling_bwd(0, g_z, None, v, hA, g_ld, B, h, w, g_hA, g_v)
             K.net_bwd(g_hA, h1A, h2A, netA, B, h, w, g_a3, g_n2, g_a2, g_n1, g_a1, g_pre, offA, NPRE, g_z1)
-            _net_param_grads(K, p + ".affine.fAffine", True, (h1A, h2A, hA, g_hA, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9), v, B, h, w, P, grads, gt)
+            _net_param_grads(K, acc, 2 * ci, p + ".affine.fAffine", True, (h1A, h2A, hA, g_hA, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9), v, B, h, w, P)
             K.coupling_bwd(1, g_v, g_z1, u, hF, g_ld, B, h, w, g_hF, g_u)
             K.net_bwd(g_hF, h1F, h2F, netF, B, h, w, g_a3, g_n2, g_a2, g_n1, g_a1, g_pre, offF, NPRE, None)
-            _net_param_grads(K, p + ".affine.fFeatures", False, (h1F, h2F, hF, g_hF, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9), v, B, h, w, P, grads, gt)
+            _net_param_grads(K, acc, 2 * ci + 1, p + ".affine.fFeatures", False, (h1F, h2F, hF, g_hF, g_a3, g_n2, g_a2, g_n1, g_a1, col576, col9), v, B, h, w, P)
             gu = g_u
         else:
             K.point_fwd(zs[s], pw, None, B, h, w, t, u, v)
@@ -205,6 +228,7 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
         grads[p + ".actnorm.logs"] = (sums[9:12] + ld_total).view(1, 3, 1, 1)
         grads[p + ".actnorm.bias"] = sums[12:15].view(1, 3, 1, 1).clone()
 
+    acc.finish(grads)
     # hoisted conv over ft: data gradient on the tensor-core conv path (transpose of a stride-1 'same' conv = the conv with the flipped,
     # transposed filter), weight gradient on the tensor cores (fp32 split-K GEMM over im2col(ft) for kernel sets without them)
     if getattr(plan, "_w_pre_t", None) is None:                        # once per plan: the packed-weight cache of the conv path keys on it

@@ -3,14 +3,16 @@
 // FlowAffineCouplingsAblation.py:50-151, flow.py:13-70).  Every formula follows oracle/flow_backward.py, the CPU specification that
 // tests/test_oracle.py checks against torch autograd and the reference's own gradients (tests/golden/stage2.npz).
 //
-// STATUS: written against the CPU specification and compiled for sm_100a; NOT yet run on hardware (the round's GPU budget was spent on
-// the inference path).  Nothing on the inference path calls into this file; tests/test_zz_flow_train_gpu.py runs it in a child process.
+// STATUS: verified on the CPU (this source through tests/cuda_emu, tests/test_flow_train_cpu.py) and green on B200 since round 2
+// (tests/flow_train_gpu_check.py in a child process of tests/test_zz_flow_train_gpu.py; profiles/r70_train_check.log).  Nothing on the
+// inference path calls into this file.
 //
 // Training shapes are small (latent 80x80, batch 4: P = 25 600 pixels, 24 coupling steps x 2 nets x 9 552 parameters), so the pass is a
 // sequence of simple kernels over NHWC-flattened [P][C] fp32 buffers -- one thread per pixel, parameters of the packed net block
-// (flow.cu NET_* layout) read through the read-only cache or staged in shared memory -- plus the split-K fp32 GEMM of dcn_bwd.cu
-// (glare_dcnv2_bwd_weight_f32: grad[M][N] += a[P][M]^T b[P][N]) for every weight gradient.  The hoisted 64 -> 3072 conv over ft
-// (DESIGN.md "flow") gets its data gradient from the tensor-core conv path and its weight gradient from the same GEMM.
+// (flow.cu NET_* layout) read through the read-only cache or staged in shared memory.  Weight gradients: the tensor-core path of
+// csrc/train_wgrad.cu (glare_b200/flow_train.py CudaKernels.wgrad), the skinny kernel at the end of this file for the 9-column ones, the
+// split-K fp32 GEMM of dcn_bwd.cu for anything else.  The hoisted 64 -> 3072 conv over ft (DESIGN.md "flow") gets its data gradient from
+// the tensor-core conv path and its weight gradient from the same tensor-core path.
 #ifdef GLARE_CUDA_EMU
 #include "cuda_emu.h"        // tests/cuda_emu: the same kernel source executed on the host (CPU check of indexing and arithmetic)
 #define FB_LAUNCH(kern, grid, block, stream, ...) glare_emu::launch(kern, dim3(grid), dim3(block), __VA_ARGS__)

@@ -6,7 +6,7 @@
 //   im2col_nhwc                 : [B,H,W,C] -> [B*Ho*Wo][k*k*C] (tap-major) for any 1x1 / 3x3, stride 1 / 2, low-side padding 0 / 1 conv: the
 //                                 operand of a weight gradient  dW[tap*C + c][co] = sum_p col[p][tap*C + c] * dY[p][co]
 //   attn_softmax_bwd            : dS = scale * P o (dP - rowsum(dP o P))
-// STATUS: like flow_bwd.cu -- verified on the CPU (the same source through tests/cuda_emu), not yet run on hardware.
+// STATUS: verified on the CPU (the same source through tests/cuda_emu) and on B200 (tests/flow_train_gpu_check.py, profiles/r70_train_check.log).
 #ifdef GLARE_CUDA_EMU
 #include "cuda_emu.h"
 #define TE_LAUNCH(kern, grid, block, stream, ...) glare_emu::launch(kern, grid, dim3(block), __VA_ARGS__)

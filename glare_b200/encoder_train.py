@@ -9,9 +9,8 @@ Downsample's becomes a conv over the zero-interleaved gradient, the five matmuls
 every backend, so the CPU test (tests/test_encoder_train_cpu.py) runs exactly this logic with torch / host-compiled leaves against torch
 autograd of the oracle and the reference's own gradients.
 
-STATUS (round 2): green on B200 (tests/test_zz_flow_train_gpu.py, profiles/r41_train_check.log); 240 ms per step at BASELINE config 4
-(batch 4 x 320x320) with the fp32 split-K weight-gradient GEMM, 200 ms with the tensor-core weight gradient (GLARE_WGRAD_TC=1,
-profiles/r40_train_probe*.txt).
+STATUS: green on B200 (tests/test_zz_flow_train_gpu.py, profiles/r70_train_check.log); 98 ms per objective + gradient evaluation at BASELINE
+config 4 (batch 4 x 320x320) with fp32-grade operands, 78 ms with bf16 operands (profiles/r71_train_probe*_kernel_breakdown.txt).
 """
 import ctypes
 import weakref

@@ -3,12 +3,13 @@
 every flow parameter (reference: torch autograd through FlowUpsamplerNet.encode, FlowUpsamplerNet.py:228-274).
 
 Formulas: oracle/flow_backward.py (CPU specification, checked against autograd and the reference's own gradients).  Kernels:
-csrc/flow_bwd.cu + the split-K GEMM of csrc/dcn_bwd.cu + the tensor-core conv path for the hoisted 64 -> 3072 conv.  This module is
-the host side: buffer management, the 28-step loops, and the assembly of the packed gradients into state-dict shaped tensors.
+csrc/flow_bwd.cu, the tensor-core weight gradients of csrc/train_wgrad.cu (skinny / uncovered shapes: the fp32 kernels of flow_bwd.cu and
+dcn_bwd.cu) and the tensor-core conv path for the hoisted 64 -> 3072 conv.  This module is the host side: buffer management, the 28-step
+loops, and the assembly of the packed gradients into state-dict shaped tensors.
 
-STATUS (round 1): the host logic is verified on the CPU against the specification through a torch restatement of every kernel
-contract (tests/flow_train_emu.py, tests/test_flow_train_cpu.py); the CUDA kernels compile for sm_100a and have not run on
-hardware yet (tests/test_zz_flow_train_gpu.py runs them in a child process).
+STATUS: the host logic is verified on the CPU against the specification through a torch restatement of every kernel contract and through
+the kernel source itself run on the host (tests/flow_train_emu.py, tests/test_flow_train_cpu.py); green on B200 since round 2
+(tests/test_zz_flow_train_gpu.py runs tests/flow_train_gpu_check.py in a child process; profiles/r70_train_check.log, 62 checks).
 """
 import ctypes
 import math

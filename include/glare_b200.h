@@ -224,8 +224,9 @@ int glare_postprocess_u8(const float* y, long long sb, long long sc, long long s
  *      net and the backward pass of FlowStep.normal_flow (FlowStep.py:75-98) -- the autograd of FlowActNorms.py:48-100,
  *      Permutations.py:21-59, FlowAffineCouplingsAblation.py:50-151, flow.py:13-70 -- over NHWC-flattened [P][C] fp32 buffers,
  *      P = B*h*w.  Formulas: oracle/flow_backward.py (checked against autograd on the CPU).  Weight gradients are formed from the
- *      buffers below with glare_dcnv2_bwd_weight_f32 (grad[M][N] += a[P][M]^T b[P][N]) and glare_flow_train_colsum_f32; the host side is
- *      glare_b200/flow_train.py.  Not yet run on hardware in round 1 (csrc/flow_bwd.cu header).
+ *      buffers below with glare_im2col_t_operand_bf16x3 + glare_conv2d_nhwc_tc_ex (tensor cores), glare_gemm_tn_skinny_f32 /
+ *      glare_dcnv2_bwd_weight_f32 (grad[M][N] += a[P][M]^T b[P][N]) and glare_flow_train_colsum_f32; the host side is
+ *      glare_b200/flow_train.py.  Green on B200 (tests/flow_train_gpu_check.py).
  * ---------------------------------------------------------------------------------------------------- */
 int glare_flow_train_net_fwd_f32(const float* pre, long long pre_ld, const float* z1, long long z1_ld, const float* net, int B, int h, int w,
                                  float* h1, float* h2, float* hout, cudaStream_t stream);
@@ -247,7 +248,7 @@ int glare_gemm_tn_skinny_f32(const float* a, const float* b, long long P, int M,
  * (5b) Backward of the condition encoder's blocks for stage-2 training (autograd of encoder_decoder.py:29-35, 68-72, 117-137, 168-192):
  *      GroupNorm (+ swish) backward, the im2col operand of a conv weight gradient (dW = col^T dY through glare_dcnv2_bwd_weight_f32), and the
  *      softmax backward of AttnBlock.  Data gradients of the convolutions and the attention matmuls reuse the tensor-core conv path with
- *      flipped / transposed operands (glare_b200/encoder_train.py).  CPU-verified, not yet run on hardware (csrc/train_enc.cu header).
+ *      flipped / transposed operands (glare_b200/encoder_train.py).  Verified on the CPU (kernel source run on the host) and on B200 (tests/flow_train_gpu_check.py).
  * ---------------------------------------------------------------------------------------------------- */
 int glare_gn_bwd_nhwc_f32(const float* x, const float* gy, const double* stats, const float* gamma, const float* beta, float eps, int swish, int B,
                           long long HW, int C, int G, double* sums, float* gx, float* dgamma, float* dbeta, cudaStream_t stream);

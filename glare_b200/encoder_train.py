@@ -13,6 +13,7 @@ STATUS: green on B200 (tests/test_zz_flow_train_gpu.py, profiles/r70_train_check
 config 4 (batch 4 x 320x320) with fp32-grade operands, 78 ms with bf16 operands (profiles/r71_train_probe*_kernel_breakdown.txt).
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -148,6 +149,27 @@ class CudaLeaves:
         ldy = (N + 3) // 4 * 4
         y = torch.empty((R, ldy), device=a.device, dtype=torch.float32)
         self.ops.conv2d_nhwc_tc_ex(mode, a_hi, a_lo, b_hi, b_lo, y, 1, rows_hw[0], rows_hw[1], K + padk, N, ldy, 0)
+        return y[:, :N]
+
+    def gemm_nt_ta(self, at, b, rows_hw):
+        """at [K][R], b [N][K] -> at^T b^T [R][N]: the left operand is given as its TRANSPOSE and its tensor-core operand is written directly
+        from that layout (csrc/train_wgrad.cu with k = 1: pixels = the K index), instead of a transposed fp32 copy followed by the operand
+        conversion -- the two N x N transposes per sample of the attention backward were 4.3 ms of the stage-2 step."""
+        K, R = at.shape
+        N = b.shape[0]
+        mode = self.dense.mode
+        if mode not in (0, 4) or R % 32 or not at.is_contiguous() or os.environ.get("GLARE_NO_GEMM_TA"):     # (the env switch: A/B timing)
+            return self.gemm_nt(at.t().contiguous(), b, rows_hw)
+        q, e2 = (32, 2) if mode == 4 else (64, 1)
+        chunk = (K + q - 1) // q * q
+        a_op = torch.empty((1, R, e2 * chunk), device=at.device, dtype=torch.bfloat16)
+        self._call("glare_im2col_t_operand_bf16x3" if mode == 4 else "glare_im2col_t_operand_bf16", self._p(at), 1, 1, K, R, 1, 1, 0, 1, K, chunk,
+                   self._p(a_op))
+        bp = F.pad(b, (0, chunk - K)) if chunk != K else b
+        b_hi, b_lo = self.ops.conv_prep_act(mode, bp.contiguous())
+        ldy = (N + 3) // 4 * 4
+        y = torch.empty((R, ldy), device=at.device, dtype=torch.float32)
+        self.ops.conv2d_nhwc_tc_ex(mode, a_op, None, b_hi, b_lo, y, 1, rows_hw[0], rows_hw[1], chunk, N, ldy, 0)
         return y[:, :N]
 
     # modulated deformable convolution (stage 3, decoder_train.py)
@@ -330,9 +352,9 @@ class Tape:
             P = self.L.softmax_rows(self.L.gemm_nt(Q, K, hw).contiguous(), scale)       # w_ = softmax(scale q^T k)          :181-183
             dP = self.L.gemm_nt(dO, V, hw).contiguous()                                 # h_[n] = sum_j w_[n][j] v[j]        :186-187
             dS = self.L.softmax_bwd(P, dP, scale)
-            dV = self.L.gemm_nt(P.t().contiguous(), dO.t().contiguous(), hw)
+            dV = self.L.gemm_nt_ta(P, dO.t().contiguous(), hw)                          # P^T dO
             dQ = self.L.gemm_nt(dS, K.t().contiguous(), hw)
-            dK = self.L.gemm_nt(dS.t().contiguous(), Q.t().contiguous(), hw)
+            dK = self.L.gemm_nt_ta(dS, Q.t().contiguous(), hw)                          # dS^T Q
             for dst, src in ((gq, dQ), (gk, dK), (gv, dV)):
                 dst[b] = src.reshape(h, w, C).permute(2, 0, 1)
         return gq, gk, gv

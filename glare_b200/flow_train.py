@@ -9,7 +9,7 @@ loops, and the assembly of the packed gradients into state-dict shaped tensors.
 
 STATUS: the host logic is verified on the CPU against the specification through a torch restatement of every kernel contract and through
 the kernel source itself run on the host (tests/flow_train_emu.py, tests/test_flow_train_cpu.py); green on B200 since round 2
-(tests/test_zz_flow_train_gpu.py runs tests/flow_train_gpu_check.py in a child process; profiles/r70_train_check.log, 62 checks).
+(tests/test_zz_flow_train_gpu.py runs tests/flow_train_gpu_check.py in a child process; profiles/r70_train_check.log, 64 checks).
 """
 import ctypes
 import math

@@ -67,6 +67,9 @@ class TorchLeaves:
     def gemm_nt(self, a, b, rows_hw):
         return a @ b.t()
 
+    def gemm_nt_ta(self, at, b, rows_hw):
+        return at.t() @ b.t()
+
     def im2col(self, x_nhwc, k, stride, pad, Ho, Wo):
         B, H, W, C = x_nhwc.shape
         need_h, need_w = (Ho - 1) * stride + k - pad - H, (Wo - 1) * stride + k - pad - W

@@ -161,6 +161,10 @@ def encoder_step_check(dev, dense, conv):
     for (Pp, M, N) in ((5000, 1152, 128), (777, 128, 64)):
         a, b = torch.randn((Pp, M), generator=gen).to(dev), torch.randn((Pp, N), generator=gen).to(dev)
         check("gemm_tn_tc %dx%dx%d" % (Pp, M, N), Lg.gemm_tn_tc(a, b, chunk=1024), (a.double().t() @ b.double()).float(), 1e-4)
+    # left operand given as its transpose (attention backward: P^T dO, dS^T Q), K not a multiple of the K granule
+    for (Kk, hh, ww, Nn) in ((200, 8, 8, 40), (4096, 16, 16, 512)):
+        at, bq = torch.randn((Kk, hh * ww), generator=gen), torch.randn((Nn, Kk), generator=gen)
+        check("gemm_nt_ta K=%d R=%d N=%d" % (Kk, hh * ww, Nn), Lg.gemm_nt_ta(at.to(dev), bq.to(dev), (hh, ww)), (at.double().t() @ bq.double().t()).float(), 1e-4)
     a27, b128 = torch.randn((5003, 27), generator=gen), torch.randn((5003, 128), generator=gen)
     check("gemm_tn skinny 27 x 128 (conv_in)", Lg.gemm_tn(a27.to(dev), b128.to(dev)), (a27.double().t() @ b128.double()).float(), 2e-5)
     for (Pp, C) in ((204800, 128), (777, 512), (51, 4)):

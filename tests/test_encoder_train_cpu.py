@@ -149,6 +149,8 @@ def test_cuda_leaves_glue_with_fake_ops():
         a, b = torch.randn((h * w, K), generator=gen), torch.randn((N, K), generator=gen)
         got = L.gemm_nt(a, b, (h, w))
         assert got.shape == (h * w, N) and torch.allclose(got, a @ b.t(), atol=1e-5)
+        got = L.gemm_nt_ta(a.t().contiguous(), b, (h, w))                  # modes without a transposed-operand kernel: transposed copy + gemm_nt
+        assert got.shape == (h * w, N) and torch.allclose(got, a @ b.t(), atol=1e-5)
     for (P, M, N, chunk) in ((200, 128, 32, 64), (97, 144, 40, 8192), (64, 9, 64, 32)):
         a, b = torch.randn((P, M), generator=gen), torch.randn((P, N), generator=gen)
         got = L.gemm_tn_tc(a, b, chunk=chunk)

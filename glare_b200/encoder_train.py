@@ -9,7 +9,7 @@ Downsample's becomes a conv over the zero-interleaved gradient, the five matmuls
 every backend, so the CPU test (tests/test_encoder_train_cpu.py) runs exactly this logic with torch / host-compiled leaves against torch
 autograd of the oracle and the reference's own gradients.
 
-STATUS: green on B200 (tests/test_zz_flow_train_gpu.py, profiles/r70_train_check.log); 98 ms per objective + gradient evaluation at BASELINE
+STATUS: green on B200 (tests/test_zz_flow_train_gpu.py, profiles/r70_train_check.log); 94 ms per objective + gradient evaluation at BASELINE
 config 4 (batch 4 x 320x320) with fp32-grade operands, 78 ms with bf16 operands (profiles/r71_train_probe*_kernel_breakdown.txt).
 """
 import ctypes

@@ -197,6 +197,11 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
     g_z1, col576, col9 = new(1), new(9 * C), new(9)
     grads = {}
     acc = _NetGrads(K, gt, 2 * len(COUPLING_STEPS))
+    # d log|det W| / dW = W^-T for all 28 invertible 1x1 convs at once: fp64 cofactor inverse (no LU library call: no error-flag
+    # synchronisation, CUDA-graph capturable; one batch instead of ~25 tiny tensor ops per step)
+    w_all = torch.stack([sd["%s.layers.%d.invconv.weight" % (prefix, s)].to(gt.device, torch.float32) for s in range(N_FLOW_STEPS)])
+    w_inv_t = flowmod._inv_logdet_3x3(w_all)[0].transpose(1, 2)
+    ld_total = g_ld * B * hw                                            # sum over samples of dL/dlogdet, times the pixel count
     for s in range(N_FLOW_STEPS - 1, -1, -1):
         p = "%s.layers.%d" % (prefix, s)
         pw = plan.pw_fwd[s]
@@ -222,10 +227,7 @@ def nll_forward_backward(plan, sd, gt, ft, mean, conv2d, kernels=None, prefix="f
         sums = K.zeros((16,), gt)
         g_z = K.empty((B, 3, h, w), gt)
         K.point_bwd(gu, t, pw, B, h, w, g_z, sums)
-        wmat = sd[p + ".invconv.weight"].to(gt.device, torch.float32)
-        ld_total = g_ld * B * hw                                        # sum over samples of dL/dlogdet, times the pixel count
-        # d log|det W| / dW = W^-T; fp64 cofactor inverse (no LU library call: no error-flag synchronisation, CUDA-graph capturable)
-        grads[p + ".invconv.weight"] = sums[0:9].view(3, 3) + ld_total * flowmod._inv_logdet_3x3(wmat[None])[0][0].t()
+        grads[p + ".invconv.weight"] = sums[0:9].view(3, 3) + ld_total * w_inv_t[s]
         grads[p + ".actnorm.logs"] = (sums[9:12] + ld_total).view(1, 3, 1, 1)
         grads[p + ".actnorm.bias"] = sums[12:15].view(1, 3, 1, 1).clone()
 

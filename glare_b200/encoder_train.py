@@ -571,8 +571,12 @@ class Stage2NLL(torch.autograd.Function):
         if not bool((g_nll == g_nll[0]).all()):
             raise RuntimeError("Stage2NLL supports reductions that weigh every sample equally (nll.mean(), nll.sum())")
         scale = g_nll[0] * ctx.batch                                     # stored gradients are those of nll.mean()
-        saved = iter(ctx.saved_tensors)
-        return (None, None, None) + tuple(next(saved) * scale if h else None for h in ctx.has)
+        try:
+            scaled = torch._foreach_mul(list(ctx.saved_tensors), scale)  # one fused launch instead of one per parameter (628 of them)
+        except (RuntimeError, TypeError):
+            scaled = [g * scale for g in ctx.saved_tensors]
+        saved = iter(scaled)
+        return (None, None, None) + tuple(next(saved) if h else None for h in ctx.has)
 
 
 def stage2_nll(named_parameters, gt_latent, lr, leaves, conv2d, flow_kernels=None, train_gt_ratio=0.0, use_gt_mean=None, graph=False):

@@ -243,9 +243,9 @@ class VQLLFLOWDeformable(nn.Module):
         self._engine = None
         self._frozen = None
         self._train_ctx = None
-        # True: stage-2 training calls replay as one CUDA graph per (shapes, mean branch).  Off by default: measured on B200 the step is
-        # GPU-bound (193 ms of kernel time per replay at batch 4 x 320x320 against 195-245 ms eagerly launched, profiles/r48_*), so the graph
-        # buys nothing and holds a second copy of the tape's memory per branch
+        # True: stage-2 training calls replay as one CUDA graph per (shapes, mean branch): 106 -> 97 ms per step at batch 4 x 320x320 with the
+        # final kernels (nothing while the step was 190 ms of kernels, profiles/r48_*).  Off by default: the gradients handed to autograd are
+        # then the graph's static buffers (valid until the next training call) and every branch holds a second copy of the tape's memory
         self.train_graph = False
         self._train_graphs = {}
         # True: the frozen stages (encoder, flow, VQGAN) of a stage-3 training call replay as one CUDA graph per input shape.  Off by default:

@@ -16,6 +16,7 @@ kernel of libglare_b200.so timed live with CUDA events, `cpu_baseline` = the CPU
 /root/reference does not exist on the GPU box) with all host threads.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -153,6 +154,26 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    def timed_each(fn, steps, warm):
+        """like `timed`, with one event per step: -> (mean ms per step over the ranks' max, {median, max} of this rank's steps) -- the
+        training steps run thousands of small launches from Python, and a collector pause or an allocator refill in one step moves a 8-step mean"""
+        for _ in range(warm):
+            fn()
+            flush.zero_()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        evs[0].record()
+        for i in range(steps):
+            fn()
+            flush.zero_()
+            evs[i + 1].record()
+        barrier()
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        t = torch.tensor([evs[0].elapsed_time(evs[steps])], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, {"ms_per_step_median": per[len(per) // 2], "ms_per_step_max": per[-1]}
+
     out = {}
     pk = peaks()
     # ---- configs[2]: bf16 tensor-core operands (fp32 accumulate, fp32 GroupNorm / softmax / residual stream), 8 images per GPU
@@ -178,7 +199,8 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
         "ceiling_images_per_s_per_gpu": pk["tensor"] / 13.16,
         "dpsnr_vs_fp32_path_db": abs(O.psnr(o16, gtq) - O.psnr(o32, gtq)), "pixel_mean_abs_diff_vs_fp32_path": float((o16 - o32).abs().mean())}
     del enh, lr_dev
-    torch.cuda.empty_cache()
+    gc.collect()                      # engines hold reference cycles (graphs <-> closures): without this their CUDA graphs and pools are torn
+    torch.cuda.empty_cache()          # down by the cyclic collector at a random moment inside the NEXT timed region (seen: +0.5 s in one step)
     # ---- configs[3]: one stage-2 training step through the drop-in mirrors, the call sequence of LLFlow_model.optimize_parameters
     # (LLFlow_model.py:181-232): frozen VQGAN encodes the ground truth, netG(gt=..., lr=..., reverse=False) -> nll.mean().backward()
     # (objective + every gradient from libglare_b200.so), gradient all-reduce over the ranks, Adam step.  Batch 4 x 320x320 per GPU.
@@ -215,23 +237,24 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
             optim.step()
             last["nll"] = nll.detach()
 
-        ms_t = timed(train_step, 5, 2)
+        ms_t, spread_t = timed_each(train_step, 8, 4)    # (the caching allocator needs a few steps to settle after the inference configs)
         out["stage2_training_step"] = {
             "workload": "configs[3]: one stage-2 step (frozen-VQGAN encode of GT, flow NLL forward + backward, Adam) through the drop-in "
                         "mirrors, batch 4 x 320x320 per GPU, fp32-grade tensor-core operands (bf16x3), train_gt_ratio 0.2",
-            "value": world * 4 / (ms_t / 1e3), "unit": "samples/s", "ms_per_step": ms_t, "steps_per_s_per_gpu": 1e3 / ms_t,
+            "value": world * 4 / (ms_t / 1e3), "unit": "samples/s", "ms_per_step": ms_t, **spread_t, "steps_per_s_per_gpu": 1e3 / ms_t,
             "algorithmic_tflop_per_step": 12.6, "achieved_tflops_per_gpu": 12.6 / (ms_t / 1e3), "frac_of_bf16_peak": 12.6 / (ms_t / 1e3) / pk["tensor"],
             "nll_last": [round(float(v), 4) for v in last["nll"].cpu()],
             "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else None}
         # the same step with bf16 tensor-core operands (the precision configs[3] names): convolutions, attention GEMMs and weight gradients on
         # single-piece bf16 operands, fp32 accumulation, fp32 memory-bound kernels and optimizer
         netG.dense_name, netG._train_ctx = "tc-bf16", None
-        ms_tb = timed(train_step, 5, 2)
+        ms_tb, spread_tb = timed_each(train_step, 8, 3)
         out["stage2_training_step_bf16"] = {
             "workload": "configs[3] at its named precision: the same stage-2 step with bf16 tensor-core operands", "dtype": "bf16",
-            "value": world * 4 / (ms_tb / 1e3), "unit": "samples/s", "ms_per_step": ms_tb,
+            "value": world * 4 / (ms_tb / 1e3), "unit": "samples/s", "ms_per_step": ms_tb, **spread_tb,
             "nll_last": [round(float(v), 4) for v in last["nll"].cpu()]}
         del netG, optim
+        gc.collect()
         torch.cuda.empty_cache()
         # ---- stage 3 (train_stage3_LOL.yml: batch 2 x 256x256): the call sequence of VQLLFLOWDModel.optimize_parameters
         # (VQLLFLOWD_model.py:187-232): netG(net_vq=..., lr=..., reverse=True, reverse_with_grad=True) with encoder / flow / VQGAN frozen,
@@ -264,14 +287,15 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
             optim3.step()
             last3["total"] = total.detach()
 
-        ms_3 = timed(train_step3, 5, 3)
+        ms_3, spread_3 = timed_each(train_step3, 8, 4)
         out["stage3_training_step"] = {
             "workload": "one stage-3 step (train_stage3_LOL.yml shape: batch 2 x 256x256 per GPU) through the drop-in mirrors: frozen encoder / "
                         "flow / VQGAN forward, deformable-decoder forward + backward (DCN backward in the loop), L1 + VGG16 perceptual (synthetic "
                         "weights) + MS-SSIM objective, Adam; fp32-grade tensor-core operands (bf16x3)",
-            "value": world * 2 / (ms_3 / 1e3), "unit": "samples/s", "ms_per_step": ms_3, "objective_last": round(float(last3["total"]), 5),
+            "value": world * 2 / (ms_3 / 1e3), "unit": "samples/s", "ms_per_step": ms_3, **spread_3, "objective_last": round(float(last3["total"]), 5),
             "collective": "one flat fp32 gradient all-reduce (NCCL)" if world > 1 else None}
         del netG3, net_hq, optim3, percep
+        gc.collect()
         torch.cuda.empty_cache()
     # ---- single-image latency of the bench shape (infer_dataset_lol.py / infer_unpaired.py run batch 1): host uint8 in -> host uint8 out
     enh1 = GlareEnhancer(sd_g, sd_v, device=dev, pad="lol", dense=fp32_engine.dense)

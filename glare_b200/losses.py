@@ -268,7 +268,12 @@ class PerceptualNetwork(nn.Module):
             sd = {k: v for k, v in vgg16(pretrained=True).features.state_dict().items() if int(k.split(".")[0]) < 16}
             self.vgg_model.load_state_dict(sd, strict=True)
             self._fetch_pretrained = False
-        return {k: v.detach() for k, v in self.vgg_model.state_dict().items()}
+        # the weights are frozen: hand the SAME tensor objects to every call, so that the conv path's packed-weight cache and the flipped
+        # filters of the data gradients (both keyed on the tensor they were made from) are built once, not once per loss evaluation
+        key = tuple((p.data_ptr(), p._version) for p in self.vgg_model.parameters())
+        if getattr(self, "_sd_key", None) != key:
+            self._sd_key, self._sd_cache = key, {k: v.detach() for k, v in self.vgg_model.state_dict().items()}
+        return self._sd_cache
 
     @torch.no_grad()
     def output_features(self, x):

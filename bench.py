@@ -161,13 +161,16 @@ def alt_configs(rank, world, dev, sd_g, sd_v, barrier, flush, fp32_engine, quick
             fn()
             flush.zero_()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        barrier()
+        gc.collect()
+        gc.freeze()                       # the interpreter's old generation (millions of objects of torch and this process) is not re-walked by
+        barrier()                         # a full collection that happens to start inside a timed step; the steps' own garbage still is
         evs[0].record()
         for i in range(steps):
             fn()
             flush.zero_()
             evs[i + 1].record()
         barrier()
+        gc.unfreeze()
         per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
         t = torch.tensor([evs[0].elapsed_time(evs[steps])], device=dev, dtype=torch.float64)
         if world > 1:
